@@ -1,0 +1,118 @@
+/* pdplqr.h -- C ABI of the B200-native parallel dynamic-programming LQ solver (libpdplqr.so).
+ *
+ * This is the drop-in boundary for the reference's OpenMP path.  The reference has no FFI layer: its boundary
+ * is the C++ class lqr::LQRParallelSolver (/root/reference include/clqr/lqr/lqr_solver_parallel.hpp:19-62)
+ * and the duck-typed 4-call protocol it shares with lqr::LQRSolver (lqr_solver.hpp:9-28).  Every entry point
+ * below names the reference interface it replaces.  The header-only C++ host class that restores the
+ * reference's own signatures on top of this ABI is include/pdplqr/lqr_cuda_solver.hpp; the binding a
+ * maintainer of the reference would add is shown in INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; all matrices FP64 column-major (Eigen's default,
+ * typedefs.hpp:8-21); no exceptions cross the ABI; every function returns PDPLQR_OK (0) or a negative error
+ * code, and pdplqr_last_error() returns a description.  There is NO CPU fallback: if no CUDA device is
+ * usable pdplqr_create fails with PDPLQR_ERR_CUDA.
+ *
+ * Flat problem layout (a batch of `batch` problems with identical dimensions; batch = 1 is the reference's
+ * single-model case), s = nu + nx:
+ *   E  [batch][N][nx*s]   E_k = [B_k A_k]                       lqr_model.hpp:12-15
+ *   c  [batch][N][nx]
+ *   H  [batch][N][s*s]    H_k = [R S; S^T Q] (u block first)    lqr_model.hpp:17-19
+ *   h  [batch][N][s]      h_k = [r; q]
+ *   HN [batch][nx*nx], hN [batch][nx]    terminal cost          lqr_model.hpp:32-35
+ *   D  [batch][sum_k nc_k*dim_k]  D_k = [Du Dx] (nc_k x dim_k), dim_k = s for k < N, nx for k = N
+ *                                                                lqr_model.hpp:21-24
+ *   ws [batch][N*s + nx]  w_k = [u_k; x_k] (k < N), w_N = x_N   lqr_example.cpp:30-34
+ *   ys, zs, rho, inv_rho [batch][sum_k nc_k]                    lqr_solver_parallel.hpp:33-39
+ *   x0 [batch][nx]
+ */
+#ifndef PDPLQR_H
+#define PDPLQR_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDPLQR_OK 0
+#define PDPLQR_ERR_INVALID (-1)      /* bad argument / dimensions (reference: std::runtime_error, lqr_model.hpp:75-77) */
+#define PDPLQR_ERR_UNSUPPORTED (-2)  /* (nx, nu) pair not instantiated in this build */
+#define PDPLQR_ERR_CUDA (-3)         /* CUDA runtime failure (incl. no device): no CPU fallback exists */
+#define PDPLQR_ERR_ORDER (-4)        /* call-order contract violated (e.g. forward before backward) */
+#define PDPLQR_ERR_NOT_PD (-5)       /* a stage Quu was not positive definite (the reference never checks,
+                                        lqr_kernel.hpp:89,126; we report it) */
+
+#define PDPLQR_CONDENSED_LU 0        /* CondensedSystemSolverType::LU       lqr_solver_parallel.hpp:14-17 */
+#define PDPLQR_CONDENSED_CHOLESKY 1  /* CondensedSystemSolverType::CHOLESKY (both map to the device tree solve) */
+
+typedef struct pdplqr_solver* pdplqr_handle_t;
+
+/* Replaces LQRParallelSolver::LQRParallelSolver(model, num_segments, load_balancing, solver_type)
+ * (lqr_solver_parallel.hpp:64-113) and LQRSolver::LQRSolver (lqr_solver.hpp:31-39; num_segments = 1).
+ * `ncs` = constraint rows per stage (N+1 entries, LQRModel::ncs lqr_model.hpp:71) or NULL for none.
+ * num_segments >= 1 uses the reference's partition rule (lqr_solver_parallel.hpp:70-80, 1.55 load-balance
+ * factor); num_segments = 0 lets the library choose a GPU-appropriate segmentation.  `device` = CUDA ordinal. */
+int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, int batch, int num_segments,
+                  int load_balancing, int condensed_type, int device);
+int pdplqr_destroy(pdplqr_handle_t h);
+
+/* Run all work of this handle on an existing CUDA stream (cudaStream_t passed as void*). */
+int pdplqr_set_stream(pdplqr_handle_t h, void* cuda_stream);
+
+/* The reference keeps `const LQRModel&` and re-reads it on every call (lqr_solver_parallel.hpp:52).  A device
+ * solver cannot alias host memory, so the model is uploaded explicitly; call again after mutating it.
+ * D may be NULL when there are no constraints.  *_device takes device pointers in the same flat layout. */
+int pdplqr_set_model(pdplqr_handle_t h, const double* E, const double* c, const double* H, const double* hvec,
+                     const double* HN, const double* hN, const double* D);
+int pdplqr_set_model_device(pdplqr_handle_t h, const double* E, const double* c, const double* H,
+                            const double* hvec, const double* HN, const double* hN, const double* D);
+
+/* Replaces update_problem_data(ws, ys, zs, inv_rho_vecs, sigma)   lqr_solver_parallel.hpp:115-140.
+ * The fold-in (H += sigma I, h -= sigma w, g = z - y/rho) is fused into the backward kernels; this call
+ * stages the vectors.  ys/zs/inv_rho may be NULL when there are no constraints; ws may be NULL (zeros). */
+int pdplqr_update_problem_data(pdplqr_handle_t h, const double* ws, const double* ys, const double* zs,
+                               const double* inv_rho, double sigma);
+/* Replaces backward(rho_vecs)                        lqr_solver_parallel.hpp:142-146 (reduction + condensed backward) */
+int pdplqr_backward(pdplqr_handle_t h, const double* rho);
+/* Replaces backward_without_factorization(rho_vecs)  lqr_solver_parallel.hpp:148-154 */
+int pdplqr_backward_without_factorization(pdplqr_handle_t h, const double* rho);
+/* Replaces forward(x0, ws)                           lqr_solver_parallel.hpp:213-238.  Blocks until ws_out is written. */
+int pdplqr_forward(pdplqr_handle_t h, const double* x0, double* ws_out);
+/* Addition (north_star "solve()"): update_problem_data + backward + forward in one call. */
+int pdplqr_solve(pdplqr_handle_t h, const double* ws_in, const double* ys, const double* zs, const double* rho,
+                 const double* inv_rho, double sigma, const double* x0, double* ws_out);
+
+/* Device-pointer variants: arguments are device arrays (same layouts), work is enqueued on the handle's stream
+ * and the call returns without synchronising.  Pointers passed to update_problem_data_device must stay valid
+ * until the following backward has run. */
+int pdplqr_update_problem_data_device(pdplqr_handle_t h, const double* ws, const double* ys, const double* zs,
+                                      const double* inv_rho, double sigma);
+int pdplqr_backward_device(pdplqr_handle_t h, const double* rho);
+int pdplqr_backward_without_factorization_device(pdplqr_handle_t h, const double* rho);
+int pdplqr_forward_device(pdplqr_handle_t h, const double* x0, double* ws_out);
+int pdplqr_synchronize(pdplqr_handle_t h);
+
+/* Accessors (additions; the reference keeps these in a private workspace, lqr_solver_parallel.hpp:55-60).
+ * All outputs are host arrays; any pointer may be NULL to skip it.
+ *   partition: starts[S], lens[S]                                   (lqr_solver_parallel.hpp:73-80)
+ *   gains:     K [batch][N][nu*nx], d [batch][N][nu]                (lqr_kernel_parallel.hpp:105-108; segment-local
+ *              inside non-last segments), Gt [batch][N][nu*nx] = Luu^-T G (lqr_kernel_parallel.hpp:127-128,198)
+ *   interface: xhat, uhat [batch][S][nx]                            (condensed_system.hpp:140-146)
+ *   summaries: P,F,C [batch][S][nx*nx], p,f [batch][S][nx]          (lqr_solver_parallel.hpp:180-187) */
+int pdplqr_num_segments(pdplqr_handle_t h);
+int pdplqr_get_partition(pdplqr_handle_t h, int* starts, int* lens);
+int pdplqr_get_gains(pdplqr_handle_t h, double* K, double* d, double* Gt);
+int pdplqr_get_interface(pdplqr_handle_t h, double* xhat, double* uhat);
+int pdplqr_get_summaries(pdplqr_handle_t h, double* P, double* p, double* F, double* f, double* C);
+/* Number of problems whose last factorising backward met a non-positive pivot; per-problem codes (0 = ok,
+ * else 1 + stage index) are written to `status` ([batch], may be NULL). */
+int pdplqr_last_status(pdplqr_handle_t h, int* status);
+const char* pdplqr_last_error(pdplqr_handle_t h);
+/* Kernels launched by this handle so far (bench.py's gpu_launches). */
+long long pdplqr_launch_count(pdplqr_handle_t h);
+/* Bytes of one device model record / factor record (DESIGN.md data layout), for roofline bookkeeping. */
+int pdplqr_record_doubles(pdplqr_handle_t h, int* model_rec, int* factor_rec);
+int pdplqr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDPLQR_H */

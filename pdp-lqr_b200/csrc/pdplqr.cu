@@ -1,0 +1,577 @@
+// libpdplqr.so -- C ABI (include/pdplqr.h) + host-side orchestration of the sm_100a kernels.
+// One handle = one batch of identically-sized LQ problems resident on one GPU, one CUDA stream.
+#include "../../include/pdplqr.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "batch_kernels.cuh"
+#include "seg_kernels.cuh"
+#include "tree_kernels.cuh"
+
+using namespace pdplqr;
+
+namespace {
+
+struct TreeLevel {
+    int count, R, groups;
+    double *sum, *dd, *x, *lam;  // sum/x/lam of level 0 alias the segment arrays
+};
+
+struct Ops;
+
+}  // namespace
+
+struct pdplqr_solver {
+    int nx = 0, nu = 0, N = 0, batch = 0, S = 1, s = 0, device = 0;
+    bool load_balancing = true;
+    int condensed_type = 1;
+    std::vector<int> ncs, seg_start, seg_len;
+    long long nc_total = 0;
+    const Ops* ops = nullptr;
+    bool thread_path = false;  // thread-per-problem kernels (tiny nx+nu, S == 1)
+    int frec = 0;              // doubles per stage in d_fac for the active path
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // device memory
+    double *d_model = nullptr, *d_HN = nullptr, *d_hN = nullptr;
+    double *d_fac = nullptr, *d_sum = nullptr, *d_xhat = nullptr, *d_uhat = nullptr;
+    double *d_ws_in = nullptr, *d_x0 = nullptr, *d_ws_out = nullptr;
+    int *d_seg_start = nullptr, *d_seg_len = nullptr, *d_status = nullptr;
+    std::vector<TreeLevel> levels;
+    std::vector<void*> owned;  // everything to cudaFree
+    // per-iteration state
+    const double* cur_ws = nullptr;  // device pointer used by the next backward (nullptr == zeros)
+    double sigma = 0.0;
+    bool model_set = false, updated = false, factorized = false, backward_done = false;
+    long long launches = 0;
+    std::string err;
+};
+
+namespace {
+
+using Solver = pdplqr_solver;
+
+struct Ops {
+    int nx, nu, T;
+    int REC, FREC, SREC, DREC, FRECT;
+    bool has_thread_path;
+    int (*backward)(Solver&);
+    int (*forward)(Solver&, const double* d_x0, double* d_ws_out);
+    int (*tree_up)(Solver&, const TreeParams&);
+    int (*tree_down)(Solver&, const TreeParams&);
+};
+
+int fail(Solver* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+#define CU_TRY(h, expr)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return fail(h, PDPLQR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+
+template <class K>
+int set_smem(Solver& h, K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) CU_TRY(&h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PDPLQR_OK;
+}
+
+SegParams seg_params(Solver& h) {
+    SegParams p{};
+    p.N = h.N; p.S = h.S; p.batch = h.batch;
+    p.seg_start = h.d_seg_start; p.seg_len = h.d_seg_len;
+    p.model = h.d_model; p.HN = h.d_HN; p.hN = h.d_hN;
+    p.ws_prev = h.cur_ws; p.sigma = h.sigma;
+    p.fac = h.d_fac; p.sum = h.d_sum; p.status = h.d_status;
+    p.xhat = h.d_xhat; p.uhat = h.d_uhat;
+    return p;
+}
+
+template <int NX, int NU, int T>
+int backward_impl(Solver& h) {
+    SegParams p = seg_params(h);
+    if constexpr (BatchDims<NX, NU>::ENABLED) {
+        if (h.thread_path) {
+            auto kern = batch_backward_kernel<NX, NU>;
+            constexpr size_t bytes = BatchBwdSmem<NX, NU>::BYTES;
+            int rc = set_smem(h, kern, bytes);
+            if (rc) return rc;
+            const int blocks = (h.batch + BATCH_WARPS * 32 - 1) / (BATCH_WARPS * 32);
+            kern<<<blocks, BATCH_WARPS * 32, bytes, h.stream>>>(p);
+            h.launches++;
+            CU_TRY(&h, cudaGetLastError());
+            return PDPLQR_OK;
+        }
+    }
+    auto kern = seg_backward_kernel<NX, NU, T>;
+    constexpr size_t bytes = BwdSmem<NX, NU>::BYTES;
+    int rc = set_smem(h, kern, bytes);
+    if (rc) return rc;
+    kern<<<h.batch * h.S, T, bytes, h.stream>>>(p);
+    h.launches++;
+    CU_TRY(&h, cudaGetLastError());
+    return PDPLQR_OK;
+}
+
+template <int NX, int NU, int T>
+int forward_impl(Solver& h, const double* d_x0, double* d_ws_out) {
+    SegParams p = seg_params(h);
+    p.ws_out = d_ws_out;
+    if (h.S == 1) p.xhat = d_x0;
+    if constexpr (BatchDims<NX, NU>::ENABLED) {
+        if (h.thread_path) {
+            auto kern = batch_forward_kernel<NX, NU>;
+            constexpr size_t bytes = BatchFwdSmem<NX, NU>::BYTES;
+            int rc = set_smem(h, kern, bytes);
+            if (rc) return rc;
+            const int blocks = (h.batch + BATCH_WARPS * 32 - 1) / (BATCH_WARPS * 32);
+            kern<<<blocks, BATCH_WARPS * 32, bytes, h.stream>>>(p);
+            h.launches++;
+            CU_TRY(&h, cudaGetLastError());
+            return PDPLQR_OK;
+        }
+    }
+    auto kern = seg_forward_kernel<NX, NU, 32>;
+    constexpr size_t bytes = FwdSmem<NX, NU>::BYTES;
+    int rc = set_smem(h, kern, bytes);
+    if (rc) return rc;
+    kern<<<h.batch * h.S, 32, bytes, h.stream>>>(p);
+    h.launches++;
+    CU_TRY(&h, cudaGetLastError());
+    return PDPLQR_OK;
+}
+
+template <int NX>
+int tree_up_impl(Solver& h, const TreeParams& p) {
+    auto kern = tree_up_kernel<NX>;
+    constexpr size_t bytes = TreeSmem<NX>::BYTES;
+    int rc = set_smem(h, kern, bytes);
+    if (rc) return rc;
+    kern<<<p.batch * p.groups, 32, bytes, h.stream>>>(p);
+    h.launches++;
+    CU_TRY(&h, cudaGetLastError());
+    return PDPLQR_OK;
+}
+template <int NX>
+int tree_down_impl(Solver& h, const TreeParams& p) {
+    auto kern = tree_down_kernel<NX>;
+    kern<<<p.batch * p.groups, 32, 4 * NX * sizeof(double), h.stream>>>(p);
+    h.launches++;
+    CU_TRY(&h, cudaGetLastError());
+    return PDPLQR_OK;
+}
+
+template <int NX, int NU, int T>
+constexpr Ops make_ops() {
+    return Ops{NX, NU, T, SegDims<NX, NU>::REC, SegDims<NX, NU>::FREC, SegDims<NX, NU>::SREC, TreeDims<NX>::DREC,
+               BatchDims<NX, NU>::FRECT, BatchDims<NX, NU>::ENABLED,
+               &backward_impl<NX, NU, T>, &forward_impl<NX, NU, T>, &tree_up_impl<NX>, &tree_down_impl<NX>};
+}
+
+// Instantiated (nx, nu) pairs.  The BASELINE.json configs use (12,4), (4,1) and (30,10); the rest cover the
+// generic-size parity tests (odd sizes, nu > nx/2, ...).
+const Ops g_ops[] = {
+    make_ops<12, 4, 32>(), make_ops<4, 1, 32>(), make_ops<30, 10, 128>(),
+    make_ops<2, 1, 32>(),  make_ops<3, 2, 32>(), make_ops<6, 3, 32>(), make_ops<8, 8, 32>(),
+};
+
+const Ops* find_ops(int nx, int nu) {
+    for (const Ops& o : g_ops)
+        if (o.nx == nx && o.nu == nu) return &o;
+    return nullptr;
+}
+
+__global__ void pack_model_kernel(const double* __restrict__ E, const double* __restrict__ c,
+                                  const double* __restrict__ H, const double* __restrict__ hv, double* __restrict__ rec,
+                                  long long nstages, int nx, int s, int REC) {
+    const long long total = nstages * REC;
+    const int oC = nx * s, oH = oC + nx, oh = oH + s * s, oend = oh + s;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long st = idx / REC;
+        const int e = (int)(idx - st * REC);
+        double v = 0.0;
+        if (e < oC) v = E[st * oC + e];
+        else if (e < oH) v = c[st * nx + (e - oC)];
+        else if (e < oh) v = H[st * (long long)(s * s) + (e - oH)];
+        else if (e < oend) v = hv[st * s + (e - oh)];
+        rec[idx] = v;
+    }
+}
+
+template <class Tp>
+int dev_alloc(Solver& h, Tp** p, size_t count) {
+    void* q = nullptr;
+    CU_TRY(&h, cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(Tp)));
+    h.owned.push_back(q);
+    *p = static_cast<Tp*>(q);
+    return PDPLQR_OK;
+}
+
+int set_model_common(Solver& h, const double* E, const double* c, const double* H, const double* hv,
+                     const double* HN, const double* hN, bool on_device) {
+    const size_t nst = (size_t)h.batch * h.N;
+    const size_t nE = nst * h.nx * h.s, nc = nst * h.nx, nH = nst * h.s * h.s, nh = nst * h.s;
+    const double *dE = E, *dc = c, *dH = H, *dh = hv;
+    double* stage = nullptr;
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (!on_device) {
+        CU_TRY(&h, cudaMalloc((void**)&stage, (nE + nc + nH + nh) * sizeof(double)));
+        cudaError_t e1 = cudaMemcpyAsync(stage, E, nE * 8, kind, h.stream);
+        cudaError_t e2 = cudaMemcpyAsync(stage + nE, c, nc * 8, kind, h.stream);
+        cudaError_t e3 = cudaMemcpyAsync(stage + nE + nc, H, nH * 8, kind, h.stream);
+        cudaError_t e4 = cudaMemcpyAsync(stage + nE + nc + nH, hv, nh * 8, kind, h.stream);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+            cudaFree(stage);
+            return fail(&h, PDPLQR_ERR_CUDA, "model upload failed");
+        }
+        dE = stage; dc = stage + nE; dH = stage + nE + nc; dh = stage + nE + nc + nH;
+    }
+    const long long total = (long long)nst * h.ops->REC;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+    pack_model_kernel<<<blocks, 256, 0, h.stream>>>(dE, dc, dH, dh, h.d_model, (long long)nst, h.nx, h.s, h.ops->REC);
+    h.launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h.d_HN, HN, (size_t)h.batch * h.nx * h.nx * 8, kind, h.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h.d_hN, hN, (size_t)h.batch * h.nx * 8, kind, h.stream);
+    if (e == cudaSuccess && stage) e = cudaStreamSynchronize(h.stream);
+    if (stage) cudaFree(stage);
+    if (e != cudaSuccess) return fail(&h, PDPLQR_ERR_CUDA, std::string("set_model: ") + cudaGetErrorString(e));
+    h.model_set = true;
+    h.factorized = false;
+    return PDPLQR_OK;
+}
+
+int run_backward(Solver& h) {
+    if (!h.model_set) return fail(&h, PDPLQR_ERR_ORDER, "backward before set_model");
+    if (!h.updated) return fail(&h, PDPLQR_ERR_ORDER, "backward before update_problem_data (lqr_solver_parallel.hpp:115)");
+    CU_TRY(&h, cudaMemsetAsync(h.d_status, 0, sizeof(int) * h.batch, h.stream));
+    int rc = h.ops->backward(h);
+    if (rc) return rc;
+    if (h.S > 1) {
+        for (size_t l = 0; l < h.levels.size(); ++l) {
+            TreeLevel& lv = h.levels[l];
+            TreeParams tp{};
+            tp.batch = h.batch; tp.count = lv.count; tp.R = lv.R; tp.groups = lv.groups;
+            tp.sum_in = lv.sum; tp.dd = lv.dd;
+            tp.sum_out = (l + 1 < h.levels.size()) ? h.levels[l + 1].sum : nullptr;
+            rc = h.ops->tree_up(h, tp);
+            if (rc) return rc;
+        }
+    }
+    h.updated = false;  // backward consumes the staged data (in-place accumulation in the reference)
+    h.factorized = true;
+    h.backward_done = true;
+    return PDPLQR_OK;
+}
+
+int run_forward(Solver& h, const double* d_x0, double* d_ws_out) {
+    if (!h.backward_done) return fail(&h, PDPLQR_ERR_ORDER, "forward before backward (one forward per backward)");
+    if (h.S > 1) {
+        for (int l = (int)h.levels.size() - 1; l >= 0; --l) {
+            TreeLevel& lv = h.levels[l];
+            const bool top = (l + 1 == (int)h.levels.size());
+            TreeParams tp{};
+            tp.batch = h.batch; tp.count = lv.count; tp.R = lv.R; tp.groups = lv.groups;
+            tp.dd = lv.dd;
+            tp.x_parent = top ? d_x0 : h.levels[l + 1].x;
+            tp.lam_parent = top ? nullptr : h.levels[l + 1].lam;
+            tp.x_node = lv.x; tp.lam_node = lv.lam;
+            int rc = h.ops->tree_down(h, tp);
+            if (rc) return rc;
+        }
+    }
+    int rc = h.ops->forward(h, d_x0, d_ws_out);
+    if (rc) return rc;
+    h.backward_done = false;
+    return PDPLQR_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int pdplqr_version(void) { return 100; }
+
+int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, int batch, int num_segments,
+                  int load_balancing, int condensed_type, int device) {
+    if (!out) return PDPLQR_ERR_INVALID;
+    *out = nullptr;
+    if (nx < 1 || nu < 1 || N < 1 || batch < 1 || num_segments < 0) return PDPLQR_ERR_INVALID;  // lqr_model.hpp:75-77
+    if (condensed_type != PDPLQR_CONDENSED_LU && condensed_type != PDPLQR_CONDENSED_CHOLESKY)
+        return PDPLQR_ERR_INVALID;  // lqr_solver_parallel.hpp:98-99
+    const Ops* ops = find_ops(nx, nu);
+    if (!ops) return PDPLQR_ERR_UNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) return PDPLQR_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return PDPLQR_ERR_CUDA;
+
+    Solver* h = new Solver();
+    h->nx = nx; h->nu = nu; h->N = N; h->batch = batch; h->s = nx + nu; h->device = device;
+    h->load_balancing = load_balancing != 0; h->condensed_type = condensed_type; h->ops = ops;
+    h->ncs.assign(N + 1, 0);
+    if (ncs) h->ncs.assign(ncs, ncs + N + 1);
+    for (int v : h->ncs) {
+        if (v < 0) { delete h; return PDPLQR_ERR_INVALID; }
+        h->nc_total += v;
+    }
+    if (h->nc_total > 0) { delete h; return PDPLQR_ERR_UNSUPPORTED; }  // constraint fold-in: see DESIGN.md status
+
+    // ---- segmentation (lqr_solver_parallel.hpp:70-80)
+    int S = num_segments;
+    if (S == 0) {
+        // GPU-appropriate default: enough (problem, segment) groups to fill the machine, segments >= 8 stages
+        const int target_groups = 148 * 8;
+        S = std::max(1, std::min(N / 8, (target_groups + batch - 1) / batch));
+    }
+    S = std::min(S, N);
+    h->S = S;
+    const double scale = h->load_balancing ? 1.55 : 1.0;
+    h->seg_start.resize(S); h->seg_len.resize(S);
+    for (int i = 0; i < S; ++i) {
+        const int st = (i == 0) ? 0 : h->seg_start[i - 1] + h->seg_len[i - 1];
+        int len = (i < S - 1) ? int(N / (scale + S - 1)) : N - st;
+        if (i < S - 1 && len < 1) len = 1;
+        h->seg_start[i] = st; h->seg_len[i] = len;
+    }
+    if (h->seg_len[S - 1] < 1) { delete h; return PDPLQR_ERR_INVALID; }
+    h->thread_path = (S == 1) && ops->has_thread_path;
+    h->frec = h->thread_path ? ops->FRECT : ops->FREC;
+
+    auto bail = [&](int rc) { std::string e = h->err; pdplqr_destroy(h); (void)e; return rc; };
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PDPLQR_ERR_CUDA);
+    h->own_stream = true;
+    const size_t B = batch, ws_len = (size_t)N * h->s + nx;
+    int rc = 0;
+    rc |= dev_alloc(*h, &h->d_model, B * N * ops->REC);
+    rc |= dev_alloc(*h, &h->d_HN, B * nx * nx);
+    rc |= dev_alloc(*h, &h->d_hN, B * nx);
+    rc |= dev_alloc(*h, &h->d_fac, B * N * ops->FREC);
+    rc |= dev_alloc(*h, &h->d_sum, B * S * ops->SREC);
+    rc |= dev_alloc(*h, &h->d_xhat, B * S * nx);
+    rc |= dev_alloc(*h, &h->d_uhat, B * S * nx);
+    rc |= dev_alloc(*h, &h->d_ws_in, ws_len * B);
+    rc |= dev_alloc(*h, &h->d_ws_out, ws_len * B);
+    rc |= dev_alloc(*h, &h->d_x0, B * nx);
+    rc |= dev_alloc(*h, &h->d_seg_start, S);
+    rc |= dev_alloc(*h, &h->d_seg_len, S);
+    rc |= dev_alloc(*h, &h->d_status, B);
+    if (rc) return bail(PDPLQR_ERR_CUDA);
+    cudaMemcpy(h->d_seg_start, h->seg_start.data(), sizeof(int) * S, cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_seg_len, h->seg_len.data(), sizeof(int) * S, cudaMemcpyHostToDevice);
+    cudaMemset(h->d_fac, 0, B * N * ops->FREC * sizeof(double));
+    cudaMemset(h->d_uhat, 0, B * S * nx * sizeof(double));
+    cudaMemset(h->d_status, 0, B * sizeof(int));
+
+    // ---- interface tree plan
+    if (S > 1) {
+        const int RTOP = 12, RGRP = 8;
+        int cnt = S;
+        for (int l = 0;; ++l) {
+            TreeLevel lv{};
+            lv.count = cnt;
+            lv.R = (cnt <= RTOP) ? cnt : RGRP;
+            lv.groups = (cnt + lv.R - 1) / lv.R;
+            if (l == 0) { lv.sum = h->d_sum; lv.x = h->d_xhat; lv.lam = h->d_uhat; }
+            else {
+                rc |= dev_alloc(*h, &lv.sum, B * cnt * ops->SREC);
+                rc |= dev_alloc(*h, &lv.x, B * cnt * nx);
+                rc |= dev_alloc(*h, &lv.lam, B * cnt * nx);
+            }
+            rc |= dev_alloc(*h, &lv.dd, B * cnt * ops->DREC);
+            h->levels.push_back(lv);
+            if (lv.groups == 1) break;
+            cnt = lv.groups;
+        }
+        if (rc) return bail(PDPLQR_ERR_CUDA);
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail(PDPLQR_ERR_CUDA);
+    *out = h;
+    return PDPLQR_OK;
+}
+
+int pdplqr_destroy(pdplqr_handle_t h) {
+    if (!h) return PDPLQR_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->owned) cudaFree(p);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PDPLQR_OK;
+}
+
+int pdplqr_set_stream(pdplqr_handle_t h, void* cuda_stream) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    h->own_stream = false;
+    return PDPLQR_OK;
+}
+
+int pdplqr_set_model(pdplqr_handle_t h, const double* E, const double* c, const double* H, const double* hvec,
+                     const double* HN, const double* hN, const double* D) {
+    if (!h || !E || !c || !H || !hvec || !HN || !hN) return fail(h, PDPLQR_ERR_INVALID, "set_model: null pointer");
+    (void)D;
+    cudaSetDevice(h->device);
+    return set_model_common(*h, E, c, H, hvec, HN, hN, false);
+}
+int pdplqr_set_model_device(pdplqr_handle_t h, const double* E, const double* c, const double* H,
+                            const double* hvec, const double* HN, const double* hN, const double* D) {
+    if (!h || !E || !c || !H || !hvec || !HN || !hN) return fail(h, PDPLQR_ERR_INVALID, "set_model: null pointer");
+    (void)D;
+    cudaSetDevice(h->device);
+    return set_model_common(*h, E, c, H, hvec, HN, hN, true);
+}
+
+int pdplqr_update_problem_data_device(pdplqr_handle_t h, const double* ws, const double* ys, const double* zs,
+                                      const double* inv_rho, double sigma) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    (void)ys; (void)zs; (void)inv_rho;
+    h->cur_ws = ws;
+    h->sigma = sigma;
+    h->updated = true;
+    return PDPLQR_OK;
+}
+int pdplqr_update_problem_data(pdplqr_handle_t h, const double* ws, const double* ys, const double* zs,
+                               const double* inv_rho, double sigma) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    cudaSetDevice(h->device);
+    const size_t ws_len = (size_t)h->N * h->s + h->nx;
+    if (ws) CU_TRY(h, cudaMemcpyAsync(h->d_ws_in, ws, ws_len * h->batch * 8, cudaMemcpyHostToDevice, h->stream));
+    return pdplqr_update_problem_data_device(h, ws ? h->d_ws_in : nullptr, ys, zs, inv_rho, sigma);
+}
+
+int pdplqr_backward_device(pdplqr_handle_t h, const double* rho) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    (void)rho;
+    cudaSetDevice(h->device);
+    return run_backward(*h);
+}
+int pdplqr_backward(pdplqr_handle_t h, const double* rho) { return pdplqr_backward_device(h, rho); }
+
+int pdplqr_backward_without_factorization_device(pdplqr_handle_t h, const double* rho) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    (void)rho;
+    return fail(h, PDPLQR_ERR_UNSUPPORTED, "backward_without_factorization: not built yet (DESIGN.md status)");
+}
+int pdplqr_backward_without_factorization(pdplqr_handle_t h, const double* rho) {
+    return pdplqr_backward_without_factorization_device(h, rho);
+}
+
+int pdplqr_forward_device(pdplqr_handle_t h, const double* x0, double* ws_out) {
+    if (!h || !x0 || !ws_out) return fail(h, PDPLQR_ERR_INVALID, "forward: null pointer");
+    cudaSetDevice(h->device);
+    return run_forward(*h, x0, ws_out);
+}
+int pdplqr_forward(pdplqr_handle_t h, const double* x0, double* ws_out) {
+    if (!h || !x0 || !ws_out) return fail(h, PDPLQR_ERR_INVALID, "forward: null pointer");
+    cudaSetDevice(h->device);
+    const size_t ws_len = (size_t)h->N * h->s + h->nx;
+    CU_TRY(h, cudaMemcpyAsync(h->d_x0, x0, (size_t)h->batch * h->nx * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = run_forward(*h, h->d_x0, h->d_ws_out);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(ws_out, h->d_ws_out, ws_len * h->batch * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return PDPLQR_OK;
+}
+int pdplqr_solve(pdplqr_handle_t h, const double* ws_in, const double* ys, const double* zs, const double* rho,
+                 const double* inv_rho, double sigma, const double* x0, double* ws_out) {
+    int rc = pdplqr_update_problem_data(h, ws_in, ys, zs, inv_rho, sigma);
+    if (rc) return rc;
+    rc = pdplqr_backward(h, rho);
+    if (rc) return rc;
+    return pdplqr_forward(h, x0, ws_out);
+}
+int pdplqr_synchronize(pdplqr_handle_t h) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return PDPLQR_OK;
+}
+
+int pdplqr_num_segments(pdplqr_handle_t h) { return h ? h->S : PDPLQR_ERR_INVALID; }
+int pdplqr_get_partition(pdplqr_handle_t h, int* starts, int* lens) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    for (int i = 0; i < h->S; ++i) {
+        if (starts) starts[i] = h->seg_start[i];
+        if (lens) lens[i] = h->seg_len[i];
+    }
+    return PDPLQR_OK;
+}
+int pdplqr_get_gains(pdplqr_handle_t h, double* K, double* d, double* Gt) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    cudaSetDevice(h->device);
+    const int nx = h->nx, nu = h->nu, FREC = h->frec;
+    const size_t nst = (size_t)h->batch * h->N;
+    std::vector<double> host(nst * FREC);
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaMemcpy(host.data(), h->d_fac, host.size() * 8, cudaMemcpyDeviceToHost));
+    for (size_t st = 0; st < nst; ++st) {
+        const double* z = host.data() + st * FREC;
+        const int k = (int)(st % h->N);
+        const bool in_last = k >= h->seg_start[h->S - 1];
+        if (K) std::memcpy(K + st * nu * nx, z, sizeof(double) * nu * nx);
+        if (d) std::memcpy(d + st * nu, z + nu * nx, sizeof(double) * nu);
+        if (Gt) {
+            if (in_last || h->S == 1) std::memset(Gt + st * nu * nx, 0, sizeof(double) * nu * nx);
+            else std::memcpy(Gt + st * nu * nx, z + nu * (nx + 1), sizeof(double) * nu * nx);
+        }
+    }
+    return PDPLQR_OK;
+}
+int pdplqr_get_interface(pdplqr_handle_t h, double* xhat, double* uhat) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    cudaSetDevice(h->device);
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    const size_t n = (size_t)h->batch * h->S * h->nx;
+    if (xhat) CU_TRY(h, cudaMemcpy(xhat, h->d_xhat, n * 8, cudaMemcpyDeviceToHost));
+    if (uhat) CU_TRY(h, cudaMemcpy(uhat, h->d_uhat, n * 8, cudaMemcpyDeviceToHost));
+    return PDPLQR_OK;
+}
+int pdplqr_get_summaries(pdplqr_handle_t h, double* P, double* p, double* F, double* f, double* C) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    cudaSetDevice(h->device);
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    const int nx = h->nx, n2 = nx * nx, SREC = h->ops->SREC;
+    const size_t cnt = (size_t)h->batch * h->S;
+    std::vector<double> host(cnt * SREC);
+    CU_TRY(h, cudaMemcpy(host.data(), h->d_sum, host.size() * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < cnt; ++i) {
+        const double* r = host.data() + i * SREC;
+        if (P) std::memcpy(P + i * n2, r, 8 * n2);
+        if (F) std::memcpy(F + i * n2, r + n2, 8 * n2);
+        if (C) std::memcpy(C + i * n2, r + 2 * n2, 8 * n2);
+        if (p) std::memcpy(p + i * nx, r + 3 * n2, 8 * nx);
+        if (f) std::memcpy(f + i * nx, r + 3 * n2 + nx, 8 * nx);
+    }
+    return PDPLQR_OK;
+}
+int pdplqr_last_status(pdplqr_handle_t h, int* status) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    cudaSetDevice(h->device);
+    std::vector<int> host(h->batch);
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaMemcpy(host.data(), h->d_status, sizeof(int) * h->batch, cudaMemcpyDeviceToHost));
+    int bad = 0;
+    for (int b = 0; b < h->batch; ++b) {
+        bad += host[b] != 0;
+        if (status) status[b] = host[b];
+    }
+    return bad;
+}
+const char* pdplqr_last_error(pdplqr_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+long long pdplqr_launch_count(pdplqr_handle_t h) { return h ? h->launches : 0; }
+int pdplqr_record_doubles(pdplqr_handle_t h, int* model_rec, int* factor_rec) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    if (model_rec) *model_rec = h->ops->REC;
+    if (factor_rec) *factor_rec = h->frec;
+    return PDPLQR_OK;
+}
+
+}  // extern "C"

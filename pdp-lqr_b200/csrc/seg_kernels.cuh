@@ -1,0 +1,426 @@
+// Segment kernels: one group of T threads (a warp, or a CTA for large nx+nu) owns one (problem, segment) and
+// runs the segment-local backward Riccati sweep with sensitivity propagation, resp. the forward rollout.
+//
+// Replaces (B200-first redesign, not a translation):
+//   LQRParallelSolver::update_problem_data      /root/reference include/clqr/lqr/lqr_solver_parallel.hpp:115-140  (fused)
+//   LQRParallelSolver::reduction_per_thread     lqr_solver_parallel.hpp:164-188
+//   LQRKernel::step_with_factorization          lqr_kernel.hpp:103-147
+//   ParallelLQRKernel::step_with_factorization  lqr_kernel_parallel.hpp:87-136
+//   ParallelLQRKernel::forward_step / LQRKernel::forward_step   lqr_kernel_parallel.hpp:170-218 / lqr_kernel.hpp:180-212
+//
+// Algorithmic differences from the reference (same mathematics, results agree to rounding):
+//   * the value function is carried as P_k (Schur complement Qxx - Qxu Quu^-1 Qux) instead of its Cholesky
+//     factor Lxx, so only the nu x nu block Quu is factorised per stage (critical path nu instead of nx+nu);
+//   * the affine terms ride along as an extra column:  [M | g] = [H~ | h~] + E^T (P+ [E c] + [0 p+]);
+//   * F+ [B A c] is formed up front (off the critical path): F = F+A + (F+B) K, f = F+c + (F+B) d + f+;
+//   * what is stored per stage is Z = [K | d | Gt] with K = -Quu^-1 Qux, d = -Quu^-1 Qu, Gt = Luu^-T G
+//     (G as in lqr_kernel_parallel.hpp:127-128), so the rollout is u = K x + d + Gt uhat with no solves.
+#pragma once
+#include "common.cuh"
+
+namespace pdplqr {
+
+constexpr int odd_ld(int n) { return n | 1; }
+constexpr int even_up(int n) { return (n + 1) & ~1; }
+
+template <int NX, int NU>
+struct SegDims {
+    static constexpr int S = NX + NU;
+    // model record (one stage): [E (NX x S) | c (NX) | H (S x S) | h (S)], column-major, padded to 16 bytes
+    static constexpr int REC_E = 0;
+    static constexpr int REC_C = NX * S;
+    static constexpr int REC_H = REC_C + NX;
+    static constexpr int REC_h = REC_H + S * S;
+    static constexpr int REC = even_up(REC_h + S);
+    static constexpr int REC_EC = even_up(NX * S + NX);  // prefix the rollout needs
+    // factor record (one stage): Z = [K (NU x NX) | d (NU) | Gt (NU x NX)], column-major
+    static constexpr int NRHS = 2 * NX + 1;
+    static constexpr int FREC = even_up(NU * NRHS);
+    // segment summary: [P | F | C | p | f]
+    static constexpr int SUM_P = 0, SUM_F = NX * NX, SUM_C = 2 * NX * NX, SUM_p = 3 * NX * NX, SUM_f = 3 * NX * NX + NX;
+    static constexpr int SREC = 3 * NX * NX + 2 * NX;
+};
+
+struct SegParams {
+    int N, S, batch;
+    const int* seg_start;    // [S]
+    const int* seg_len;      // [S]
+    const double* model;     // [batch][N][REC]
+    const double* HN;        // [batch][NX*NX]
+    const double* hN;        // [batch][NX]
+    const double* ws_prev;   // [batch][N*S+NX] or nullptr (== zeros)
+    double sigma;
+    double* fac;             // [batch][N][FREC]
+    double* sum;             // [batch][S][SREC]
+    int* status;             // [batch]
+    const double* xhat;      // [batch][S][NX]  (entry state of each segment; == x0 when S == 1)
+    const double* uhat;      // [batch][S][NX]  (costate at each segment's exit)
+    double* ws_out;          // [batch][N*S+NX]
+};
+
+// compile-time choice of the register tile for an M x N product on T threads
+struct Tile { int tm, tn; };
+constexpr Tile pick_tile(int M, int N, int T) {
+    Tile best{1, 1};
+    double best_cost = 1e30;
+    const int cand[][2] = {{1, 1}, {2, 1}, {1, 2}, {2, 2}, {3, 1}, {1, 3}, {2, 3}, {3, 2}, {4, 1}, {1, 4},
+                           {2, 4}, {4, 2}, {3, 3}, {4, 3}, {3, 4}, {4, 4}};
+    for (auto& c : cand) {
+        int mt = (M + c[0] - 1) / c[0], nt = (N + c[1] - 1) / c[1];
+        int rounds = (mt * nt + T - 1) / T;
+        double cost = rounds * (c[0] * c[1] + 1.0 * (c[0] + c[1]) + 2.0);
+        if (cost < best_cost) { best_cost = cost; best = Tile{c[0], c[1]}; }
+    }
+    return best;
+}
+
+template <int NX, int NU>
+struct BwdSmem {
+    using D = SegDims<NX, NU>;
+    static constexpr int S = D::S;
+    static constexpr int LDT = odd_ld(S + 1);      // ET: (S+1) x NX   (E^T with c^T as last row)
+    static constexpr int LDPF = odd_ld(2 * NX);    // PF: [P+; F+] stacked, (2NX) x NX
+    static constexpr int LDPE = odd_ld(2 * NX);    // PFE: [P+;F+] [E c], (2NX) x (S+1)
+    static constexpr int LDM = odd_ld(S);          // Ma: [M | g], S x (S+1)
+    static constexpr int LDY = odd_ld(D::NRHS);    // YT: NRHS x NU  (Y^T, Y = Luu^-1 [Qux Qu BtFt])
+    static constexpr int o_rec = 0;                                 // 2 x REC (TMA destination, 16B aligned)
+    static constexpr int o_Z = o_rec + 2 * D::REC;                  // FREC
+    static constexpr int o_ET = o_Z + D::FREC;
+    static constexpr int o_PF = o_ET + LDT * NX;
+    static constexpr int o_PFE = o_PF + LDPF * NX;
+    static constexpr int o_Ma = o_PFE + LDPE * (S + 1);
+    static constexpr int o_YT = o_Ma + LDM * (S + 1);
+    static constexpr int o_Cn = o_YT + LDY * NU;
+    static constexpr int o_pn = o_Cn + NX * NX;
+    static constexpr int o_fn = o_pn + NX;
+    static constexpr int o_dinv = o_fn + NX;
+    static constexpr int o_wp = o_dinv + NU;
+    static constexpr int o_bar = even_up(o_wp + S);                 // 2 mbarriers
+    static constexpr int DOUBLES = o_bar + 2;
+    static constexpr size_t BYTES = (size_t)DOUBLES * 8;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Backward: segment-local Riccati sweep (+ sensitivities F, f, C for non-last segments).
+template <int NX, int NU, int T>
+__global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
+    using D = SegDims<NX, NU>;
+    using L = BwdSmem<NX, NU>;
+    constexpr int S = D::S;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    const int g = blockIdx.x;
+    const int b = g / p.S, seg = g % p.S;
+    const int N0 = p.seg_start[seg], LEN = p.seg_len[seg], N1 = N0 + LEN;
+    const bool is_last = (seg == p.S - 1);
+    const bool pdp = !is_last;
+
+    double* rec = smem + L::o_rec;
+    double* Z = smem + L::o_Z;
+    double* ET = smem + L::o_ET;
+    double* PF = smem + L::o_PF;
+    double* PFE = smem + L::o_PFE;
+    double* Ma = smem + L::o_Ma;
+    double* YT = smem + L::o_YT;
+    double* Cn = smem + L::o_Cn;
+    double* pn = smem + L::o_pn;
+    double* fn = smem + L::o_fn;
+    double* dinv = smem + L::o_dinv;
+    double* wp = smem + L::o_wp;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::o_bar);
+
+    const size_t ws_len = (size_t)p.N * S + NX;
+    const double* model_b = p.model + (size_t)b * p.N * D::REC;
+    const double* ws_b = p.ws_prev ? p.ws_prev + (size_t)b * ws_len : nullptr;
+    double* fac_b = p.fac + (size_t)b * p.N * D::FREC;
+    const double sigma = p.sigma;
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    // segment terminal condition (lqr_kernel_parallel.hpp:51-67; lqr_kernel.hpp:79-91 for the last segment)
+    for (int e = tid; e < NX * NX; e += T) {
+        const int i = e % NX, j = e / NX;
+        double Pv = 0.0, Fv = (i == j) ? 1.0 : 0.0;
+        if (is_last) {
+            Pv = p.HN[(size_t)b * NX * NX + e] + ((i == j) ? sigma : 0.0);
+            Fv = 0.0;
+        }
+        PF[i + j * L::LDPF] = Pv;
+        PF[NX + i + j * L::LDPF] = Fv;
+        Cn[e] = 0.0;
+    }
+    for (int i = tid; i < NX; i += T) {
+        double pv = 0.0;
+        if (is_last) pv = p.hN[(size_t)b * NX + i] - (ws_b ? sigma * ws_b[(size_t)p.N * S + i] : 0.0);
+        pn[i] = pv;
+        fn[i] = 0.0;
+    }
+    group_sync<T>();
+    if (tid == 0 && LEN > 0) {
+        mbar_expect_tx(&bar[0], D::REC * 8);
+        bulk_g2s(rec, model_b + (size_t)(N1 - 1) * D::REC, D::REC * 8, &bar[0]);
+    }
+
+    int bad = 0;
+#pragma unroll 1
+    for (int it = 0; it < LEN; ++it) {
+        const int k = N1 - 1 - it;
+        const int buf = it & 1;
+        const double* R = rec + buf * D::REC;
+        if (tid == 0 && it + 1 < LEN) {  // prefetch stage k-1 (its buffer was last read before the previous sync)
+            fence_proxy_async();
+            mbar_expect_tx(&bar[buf ^ 1], D::REC * 8);
+            bulk_g2s(rec + (buf ^ 1) * D::REC, model_b + (size_t)(k - 1) * D::REC, D::REC * 8, &bar[buf ^ 1]);
+        }
+        if (tid < S) wp[tid] = ws_b ? ws_b[(size_t)k * S + tid] : 0.0;
+        if constexpr (S > T) {
+            for (int i = tid + T; i < S; i += T) wp[i] = ws_b ? ws_b[(size_t)k * S + i] : 0.0;
+        }
+        mbar_wait(&bar[buf], (it >> 1) & 1);
+
+        // T0: ET(j,k') = Ea(k',j), Ea = [E c]  ((S+1) x NX, odd leading dimension -> conflict-free operands)
+        for (int e = tid; e < NX * (S + 1); e += T) {
+            const int kk = e % NX, j = e / NX;
+            ET[j + kk * L::LDT] = R[e];
+        }
+        group_sync<T>();
+
+        // S2: PFE = [P+; F+] * [E c]  (+ p+ on the last column of the P rows)
+        {
+            constexpr int MM = 2 * NX;
+            constexpr Tile tl = pick_tile(MM, S + 1, T);
+            auto la = [&](int i, int kk) { return PF[i + kk * L::LDPF]; };
+            auto lb = [&](int kk, int j) { return ET[j + kk * L::LDT]; };
+            auto epi = [&](int i, int j, double v) {
+                if (j == S && i < NX) v += pn[i];
+                PFE[i + j * L::LDPE] = v;
+            };
+            if (pdp) group_mm<MM, S + 1, NX, tl.tm, tl.tn, T>(tid, la, lb, epi);
+            else {
+                constexpr Tile t2 = pick_tile(NX, S + 1, T);
+                group_mm<NX, S + 1, NX, t2.tm, t2.tn, T>(tid, la, lb, epi);
+            }
+        }
+        group_sync<T>();
+
+        // S3: [M | g] = [H + sigma I | h - sigma w_prev] + E^T * PE        (update_problem_data fused in)
+        {
+            constexpr Tile tl = pick_tile(S, S + 1, T);
+            auto la = [&](int i, int kk) { return ET[i + kk * L::LDT]; };
+            auto lb = [&](int kk, int j) { return PFE[kk + j * L::LDPE]; };
+            auto epi = [&](int i, int j, double v) {
+                double base;
+                if (j < S) base = R[D::REC_H + i + j * S] + ((i == j) ? sigma : 0.0);
+                else base = R[D::REC_h + i] - sigma * wp[i];
+                Ma[i + j * L::LDM] = base + v;
+            };
+            group_mm<S, S + 1, NX, tl.tm, tl.tn, T>(tid, la, lb, epi);
+        }
+        group_sync<T>();
+
+        // S4: Luu = chol(Quu) in place (leading NU x NU block of Ma)
+        {
+            const int info = group_chol<NU, T>(tid, Ma, L::LDM, dinv);
+            if (info && !bad) bad = k + 1;
+        }
+
+        // S5: one right-hand side per thread: y = Luu^-1 r, z = -Luu^-T y;  r in [Qux | Qu | (F+B)^T]
+        {
+            const int nrhs = pdp ? D::NRHS : NX + 1;
+            for (int c = tid; c < nrhs; c += T) {
+                double y[NU];
+#pragma unroll
+                for (int m = 0; m < NU; ++m) {
+                    double r;
+                    if (c < NX) r = Ma[(NU + c) + m * L::LDM];               // Qux(m,c) = Qxu(c,m)
+                    else if (c == NX) r = Ma[m + S * L::LDM];                // Qu(m)
+                    else r = PFE[(NX + (c - NX - 1)) + m * L::LDPE];          // (F+ B)(c', m)
+                    y[m] = r;
+                }
+#pragma unroll
+                for (int m = 0; m < NU; ++m) {
+                    double v = y[m];
+#pragma unroll
+                    for (int q = 0; q < m; ++q) v -= Ma[m + q * L::LDM] * y[q];
+                    y[m] = v * dinv[m];
+                    YT[c + m * L::LDY] = y[m];
+                }
+                double z[NU];
+#pragma unroll
+                for (int m = NU - 1; m >= 0; --m) {
+                    double v = y[m];
+#pragma unroll
+                    for (int q = m + 1; q < NU; ++q) v -= Ma[q + m * L::LDM] * z[q];
+                    z[m] = v * dinv[m];
+                }
+#pragma unroll
+                for (int m = 0; m < NU; ++m) Z[m + c * NU] = -z[m];
+            }
+        }
+        group_sync<T>();
+
+        // S6: P = Qxx - Yx^T Yx, p = Qx - Yx^T yu  |  C += Yg^T Yg  |  [F f] = F+[A c] + (F+B)[K d] + [0 f+]
+        {
+            constexpr Tile tl = pick_tile(NX, NX + 1, T);
+            auto la = [&](int i, int m) { return YT[i + m * L::LDY]; };
+            auto lb = [&](int m, int j) { return YT[j + m * L::LDY]; };
+            auto epi = [&](int i, int j, double v) {
+                if (j < NX) {
+                    const int r = max(i, j), c = min(i, j);
+                    PF[i + j * L::LDPF] = Ma[(NU + r) + (NU + c) * L::LDM] - v;
+                } else {
+                    pn[i] = Ma[(NU + i) + S * L::LDM] - v;
+                }
+            };
+            group_mm<NX, NX + 1, NU, tl.tm, tl.tn, T>(tid, la, lb, epi);
+            if (pdp) {
+                constexpr Tile tc = pick_tile(NX, NX, T);
+                auto lga = [&](int i, int m) { return YT[(NX + 1 + i) + m * L::LDY]; };
+                auto lgb = [&](int m, int j) { return YT[(NX + 1 + j) + m * L::LDY]; };
+                auto epc = [&](int i, int j, double v) { Cn[i + j * NX] += v; };
+                group_mm<NX, NX, NU, tc.tm, tc.tn, T>(tid, lga, lgb, epc);
+                auto lfa = [&](int i, int m) { return PFE[(NX + i) + m * L::LDPE]; };     // (F+ B)(i,m)
+                auto lfb = [&](int m, int j) { return Z[m + j * NU]; };                    // [K d](m,j)
+                auto epf = [&](int i, int j, double v) {
+                    if (j < NX) PF[(NX + i) + j * L::LDPF] = PFE[(NX + i) + (NU + j) * L::LDPE] + v;   // F+A + (F+B)K
+                    else fn[i] += PFE[(NX + i) + S * L::LDPE] + v;                                      // F+c + (F+B)d + f+
+                };
+                group_mm<NX, NX + 1, NU, tl.tm, tl.tn, T>(tid, lfa, lfb, epf);
+            }
+            // factor record -> global (coalesced)
+            double* fk = fac_b + (size_t)k * D::FREC;
+            const int nz = pdp ? NU * D::NRHS : NU * (NX + 1);
+            for (int e = tid; e < nz; e += T) fk[e] = Z[e];
+        }
+        group_sync<T>();
+    }
+
+    // segment summary (lqr_solver_parallel.hpp:180-187): P, F, C, p, f at the segment entry
+    double* sm = p.sum + ((size_t)b * p.S + seg) * D::SREC;
+    for (int e = tid; e < NX * NX; e += T) {
+        const int i = e % NX, j = e / NX;
+        sm[D::SUM_P + e] = PF[i + j * L::LDPF];
+        sm[D::SUM_F + e] = PF[NX + i + j * L::LDPF];
+        sm[D::SUM_C + e] = Cn[e];
+    }
+    for (int i = tid; i < NX; i += T) {
+        sm[D::SUM_p + i] = pn[i];
+        sm[D::SUM_f + i] = fn[i];
+    }
+    if (bad && tid == 0) atomicMax(&p.status[b], bad);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward rollout of one segment: u_k = K x_k + d + Gt uhat ; x_{k+1} = c + A x_k + B u_k.
+template <int NX, int NU>
+struct FwdSmem {
+    using D = SegDims<NX, NU>;
+    static constexpr int o_rec = 0;                       // 2 x REC_EC
+    static constexpr int o_fac = o_rec + 2 * D::REC_EC;   // 2 x FREC
+    static constexpr int o_x = o_fac + 2 * D::FREC;
+    static constexpr int o_u = o_x + NX;
+    static constexpr int o_uh = o_u + NU;
+    static constexpr int o_bar = even_up(o_uh + NX);
+    static constexpr int DOUBLES = o_bar + 2;
+    static constexpr size_t BYTES = (size_t)DOUBLES * 8;
+};
+
+template <int NX, int NU, int T>
+__global__ void __launch_bounds__(T) seg_forward_kernel(SegParams p) {
+    using D = SegDims<NX, NU>;
+    using L = FwdSmem<NX, NU>;
+    constexpr int S = D::S;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    const int g = blockIdx.x;
+    const int b = g / p.S, seg = g % p.S;
+    const int N0 = p.seg_start[seg], LEN = p.seg_len[seg], N1 = N0 + LEN;
+    const bool is_last = (seg == p.S - 1);
+
+    double* rec = smem + L::o_rec;
+    double* fac = smem + L::o_fac;
+    double* xs = smem + L::o_x;
+    double* us = smem + L::o_u;
+    double* uh = smem + L::o_uh;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::o_bar);
+
+    const size_t ws_len = (size_t)p.N * S + NX;
+    const double* model_b = p.model + (size_t)b * p.N * D::REC;
+    const double* fac_b = p.fac + (size_t)b * p.N * D::FREC;
+    double* ws_b = p.ws_out + (size_t)b * ws_len;
+    constexpr uint32_t TX = (D::REC_EC + D::FREC) * 8;
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < NX; i += T) {
+        xs[i] = p.xhat[((size_t)b * p.S + seg) * NX + i];
+        uh[i] = is_last ? 0.0 : p.uhat[((size_t)b * p.S + seg) * NX + i];
+    }
+    group_sync<T>();
+    if (tid == 0 && LEN > 0) {
+        mbar_expect_tx(&bar[0], TX);
+        bulk_g2s(rec, model_b + (size_t)N0 * D::REC, D::REC_EC * 8, &bar[0]);
+        bulk_g2s(fac, fac_b + (size_t)N0 * D::FREC, D::FREC * 8, &bar[0]);
+    }
+#pragma unroll 1
+    for (int it = 0; it < LEN; ++it) {
+        const int k = N0 + it;
+        const int buf = it & 1;
+        const double* R = rec + buf * D::REC_EC;
+        const double* Zk = fac + buf * D::FREC;
+        if (tid == 0 && it + 1 < LEN) {
+            fence_proxy_async();
+            mbar_expect_tx(&bar[buf ^ 1], TX);
+            bulk_g2s(rec + (buf ^ 1) * D::REC_EC, model_b + (size_t)(k + 1) * D::REC, D::REC_EC * 8, &bar[buf ^ 1]);
+            bulk_g2s(fac + (buf ^ 1) * D::FREC, fac_b + (size_t)(k + 1) * D::FREC, D::FREC * 8, &bar[buf ^ 1]);
+        }
+        mbar_wait(&bar[buf], (it >> 1) & 1);
+        // u = K x + d (+ Gt uhat)
+        for (int i = tid; i < NU; i += T) {
+            double acc = Zk[NU * NX + i];
+#pragma unroll 4
+            for (int j = 0; j < NX; ++j) acc = fma(Zk[i + j * NU], xs[j], acc);
+            if (!is_last) {
+#pragma unroll 4
+                for (int j = 0; j < NX; ++j) acc = fma(Zk[NU * (NX + 1) + i + j * NU], uh[j], acc);
+            }
+            us[i] = acc;
+            ws_b[(size_t)k * S + i] = acc;
+        }
+        for (int i = tid; i < NX; i += T) ws_b[(size_t)k * S + NU + i] = xs[i];
+        group_sync<T>();
+        // x+ = c + B u + A x
+        double xn[(NX + T - 1) / T];
+#pragma unroll
+        for (int r = 0; r < (NX + T - 1) / T; ++r) {
+            const int i = tid + r * T;
+            if (i < NX) {
+                double acc = R[D::REC_C + i];
+#pragma unroll
+                for (int j = 0; j < NU; ++j) acc = fma(R[i + j * NX], us[j], acc);
+#pragma unroll 4
+                for (int j = 0; j < NX; ++j) acc = fma(R[i + (NU + j) * NX], xs[j], acc);
+                xn[r] = acc;
+            }
+        }
+        group_sync<T>();
+#pragma unroll
+        for (int r = 0; r < (NX + T - 1) / T; ++r) {
+            const int i = tid + r * T;
+            if (i < NX) xs[i] = xn[r];
+        }
+        group_sync<T>();
+    }
+    // the last segment owns x_N; other segments leave their exit state to the next segment's entry
+    // (lqr_solver_parallel.hpp:224,235-236)
+    if (is_last)
+        for (int i = tid; i < NX; i += T) ws_b[(size_t)p.N * S + i] = xs[i];
+}
+
+}  // namespace pdplqr

@@ -52,7 +52,7 @@ def kkt_solve(prob, b=0, ws_prev=None, sigma=1e-6, ys=None, zs=None, rho=None, i
         rows.append(N * nx + i); cols.append(nu + i); vals.append(1.0)
     rhs_c[N * nx:] = x0
     Cm = sp.csc_matrix((vals, (rows, cols)), shape=(N * nx + nx, nw))
-    Hb = sp.block_diag(Hs, format="csc")
+    Hb = sp.block_diag([sp.csc_matrix(Hk) for Hk in Hs], format="csc")
     K = sp.bmat([[Hb, Cm.T], [Cm, None]], format="csc")
     rhs = np.concatenate([-np.concatenate(hs), rhs_c])
     sol = spla.spsolve(K, rhs)

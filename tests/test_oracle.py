@@ -1,0 +1,133 @@
+"""CPU tests pinning the oracle (oracle/pdp_oracle.cpp): the reference ships no tests or golden vectors
+(SURVEY.md section 4), so the oracle is pinned by (i) committed golden fixtures, (ii) sequential == parallel for
+every partition / condensed variant, (iii) an independent sparse KKT solve (rho_dyn = 0), (iv) KKT residuals."""
+import os
+
+import numpy as np
+import pytest
+
+import pdplqr_b200 as P
+from conftest import rel_err
+from kkt_ref import augmented_cost, kkt_solve
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_c1_golden_and_survey_probe(oracle):
+    g = np.load(os.path.join(GOLD, "c1_quadrotor.npz"))
+    p = P.problems.quadrotor_example()
+    ws = oracle.OracleSolver(p).solve()
+    assert rel_err(ws, g["ws_seq"]) < 1e-13
+    assert rel_err(ws, g["ws_kkt"]) < 1e-12
+    # first five controls (lqr_example.cpp:206-209 prints them); sign pattern -+-+ ; survey probe values
+    for k in range(5):
+        u = ws[k * 16:k * 16 + 4]
+        assert abs(abs(u[0]) - abs(g["survey_probe"][k])) < 1e-10
+        assert np.allclose(u, u[0] * np.array([1, -1, 1, -1]), atol=1e-12)
+    xN = ws[-12:]
+    assert abs(xN[2] - 0.9999999) < 1e-9 and np.max(np.abs(np.delete(xN, 2))) < 1e-13
+
+
+@pytest.mark.parametrize("S", [2, 4, 8])
+@pytest.mark.parametrize("ctype", [0, 1])
+@pytest.mark.parametrize("lb", [True, False])
+def test_parallel_equals_sequential(oracle, S, ctype, lb):
+    p = P.problems.quadrotor_example()
+    seq = oracle.OracleSolver(p).solve()
+    o = oracle.OracleSolver(p, parallel=True, num_segments=S, load_balancing=lb, condensed=ctype, nthreads=4)
+    par = o.solve()
+    assert o.status() == 0
+    assert rel_err(par, seq) < 1e-12
+
+
+def test_partition_rule(oracle):
+    # lqr_solver_parallel.hpp:70-80 ; SURVEY.md section 3.1 probe values
+    p = P.problems.quadrotor_example()
+    for S, want in ((2, [39, 61]), (4, [21, 21, 21, 37]), (8, [11] * 7 + [23])):
+        o = oracle.OracleSolver(p, parallel=True, num_segments=S)
+        assert list(o.partition()[1]) == want
+
+
+def test_random_golden_and_kkt(oracle):
+    g = np.load(os.path.join(GOLD, "random_6_3_40.npz"))
+    q = P.problems.random_lq(6, 3, 40, batch=1, seed=11)
+    ws = oracle.OracleSolver(q).solve(ws_in=g["wprev"], sigma=0.05)
+    assert rel_err(ws, g["ws_seq"]) < 1e-13
+    assert rel_err(ws, g["ws_kkt"]) < 1e-11
+    for S in (2, 5):
+        for ct in (0, 1):
+            par = oracle.OracleSolver(q, parallel=True, num_segments=S, condensed=ct).solve(ws_in=g["wprev"], sigma=0.05)
+            assert rel_err(par, ws) < 1e-11
+
+
+def test_constrained_fold_in_matches_kkt(oracle):
+    """a2/a3 with nc > 0: H += D^T rho D, h -= D^T (rho o (z - y/rho))  (lqr_kernel.hpp:106-112)."""
+    q = P.problems.random_lq(4, 2, 12, batch=1, seed=3, nc=5)
+    rng = np.random.default_rng(0)
+    nct = q.nc_total
+    ys, zs = rng.standard_normal(nct), rng.standard_normal(nct)
+    rho = rng.uniform(0.05, 2.0, nct)
+    inv_rho = 1.0 / rho
+    wprev = rng.standard_normal(q.ws_len)
+    ref = kkt_solve(q, 0, wprev, 1e-3, ys, zs, rho, inv_rho)
+    for par, S in ((False, 1), (True, 3)):
+        o = oracle.OracleSolver(q, parallel=par, num_segments=S, condensed=0)
+        o.update_problem_data(wprev, ys, zs, inv_rho, 1e-3)
+        o.backward(rho)
+        ws = o.forward(q.x0[0], np.zeros(q.ws_len))
+        assert rel_err(ws, ref) < 1e-10
+
+
+def test_backward_without_factorization(oracle):
+    """a6: affine-only re-solve with cached factors equals a full re-solve when only h/ws/z/y changed."""
+    q = P.problems.random_lq(4, 2, 16, batch=1, seed=4, nc=3)
+    rng = np.random.default_rng(1)
+    nct = q.nc_total
+    rho = rng.uniform(0.1, 1.0, nct)
+    inv_rho = 1.0 / rho
+    for par, S in ((False, 1), (True, 4)):
+        o = oracle.OracleSolver(q, parallel=par, num_segments=S, condensed=1 if par else 0)
+        w1, y1, z1 = rng.standard_normal(q.ws_len), rng.standard_normal(nct), rng.standard_normal(nct)
+        o.update_problem_data(w1, y1, z1, inv_rho, 1e-2)
+        o.backward(rho)
+        o.forward(q.x0[0], np.zeros(q.ws_len))
+        w2, y2, z2 = rng.standard_normal(q.ws_len), rng.standard_normal(nct), rng.standard_normal(nct)
+        o.update_problem_data(w2, y2, z2, inv_rho, 1e-2)
+        o.backward_without_factorization(rho)
+        fast = o.forward(q.x0[0], np.zeros(q.ws_len))
+        ref = kkt_solve(q, 0, w2, 1e-2, y2, z2, rho, inv_rho)
+        assert rel_err(fast, ref) < 1e-10
+
+
+def test_kkt_residuals_c2_small(oracle):
+    """Dynamics + stationarity residual of the returned trajectory (SURVEY.md section 4 pin iv)."""
+    p = P.problems.quadrotor_ltv(64)
+    o = oracle.OracleSolver(p, parallel=True, num_segments=4)
+    ws = o.solve()
+    nx, nu, s, N = p.nx, p.nu, p.s, p.N
+    x = np.zeros((N + 1, nx))
+    for k in range(N):
+        x[k] = ws[k * s + nu:(k + 1) * s]
+    x[N] = ws[N * s:]
+    dyn = 0.0
+    for k in range(N):
+        Ek = p.E[0, k].reshape(nx, s, order="F")
+        dyn = max(dyn, np.max(np.abs(x[k + 1] - Ek @ ws[k * s:(k + 1) * s] - p.c[0, k])))
+    assert dyn < 1e-12
+    assert rel_err(ws, kkt_solve(p)) < 1e-10
+
+
+def test_batch_pool_matches_single(oracle):
+    p = P.problems.cartpole_batch(batch=16, N=32)
+    ws, bad = oracle.OracleBatch(p).solve(nthreads=2)
+    assert bad == 0
+    for b in (0, 7, 15):
+        assert rel_err(ws[b], oracle.OracleSolver(p, b=b).solve()) < 1e-13
+        assert rel_err(ws[b], kkt_solve(p, b)) < 1e-9
+
+
+def test_augmented_cost_helper():
+    q = P.problems.random_lq(3, 2, 4, seed=2)
+    Hs, hs = augmented_cost(q, 0, np.ones(q.ws_len), 0.5)
+    assert Hs[0].shape == (5, 5) and Hs[-1].shape == (3, 3)
+    assert np.allclose(hs[0], q.h[0, 0] - 0.5)

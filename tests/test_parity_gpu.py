@@ -1,0 +1,179 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/pdplqr.h via pdplqr_b200.LQRCudaSolver),
+against the CPU oracle on identical seeded inputs.  Tolerance: 1e-9 relative (BASELINE.json north_star) --
+states, controls and gains in FP64."""
+import os
+
+import numpy as np
+import pytest
+
+import pdplqr_b200 as P
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gpu_solve(prob, S=1, lb=True, ws_in=None, sigma=1e-6, ctype=P.CHOLESKY):
+    sol = P.LQRCudaSolver.from_problem(prob, num_segments=S, load_balancing=lb, solver_type=ctype)
+    ws_in = prob.zeros_ws() if ws_in is None else ws_in
+    sol.update_problem_data(ws_in, sigma=sigma)
+    sol.backward()
+    out = sol.forward(prob.x0, np.zeros_like(ws_in))
+    return sol, out
+
+
+def test_c1_example_matches_golden_and_oracle(oracle):
+    """Config 1: examples/lqr_example.cpp as shipped (S = 4, load balancing, Cholesky)."""
+    g = np.load(os.path.join(GOLD, "c1_quadrotor.npz"))
+    p = P.problems.quadrotor_example()
+    sol, ws = gpu_solve(p, S=4)
+    assert list(sol.partition()[1]) == [21, 21, 21, 37]
+    assert rel_err(ws[0], g["ws_seq"]) < TOL
+    assert rel_err(ws[0], g["ws_kkt"]) < TOL
+    for k in range(5):
+        assert abs(abs(ws[0, k * 16]) - abs(g["survey_probe"][k])) < 1e-9
+    xh, uh = sol.interface()
+    assert rel_err(xh[0], g["xhat4"]) < TOL
+    assert rel_err(uh[0, :3], g["uhat4"][:3]) < TOL
+    assert sol.last_status()[0] == 0
+
+
+@pytest.mark.parametrize("S,lb", [(1, True), (2, True), (2, False), (4, False), (8, True), (8, False), (13, False)])
+def test_c1_partitions_gains_and_interface(oracle, S, lb):
+    p = P.problems.quadrotor_example()
+    seq = oracle.OracleSolver(p).solve()
+    sol, ws = gpu_solve(p, S=S, lb=lb)
+    assert rel_err(ws[0], seq) < TOL
+    o = oracle.OracleSolver(p, parallel=S > 1, num_segments=S, load_balancing=lb, condensed=oracle.LU)
+    o.solve()
+    if S > 1:
+        assert list(sol.partition()[0]) == list(o.partition()[0])
+    K, d, Gt = sol.gains()
+    Ko, do, Gto = o.gains()
+    assert rel_err(K[0], Ko) < TOL and rel_err(d[0], do) < TOL
+    if S > 1:
+        assert rel_err(Gt[0], Gto) < TOL
+        xh, uh = sol.interface()
+        xo, uo = o.interface()
+        assert rel_err(xh[0], xo) < TOL and rel_err(uh[0, :S - 1], uo[:S - 1]) < TOL
+        Ps, ps, Fs, fs, Cs = sol.summaries()
+        for i in range(S):
+            Po, po, Fo, fo, Co = o.summary(i)
+            assert rel_err(Ps[0, i], Po) < TOL and rel_err(ps[0, i], po) < TOL
+            if i < S - 1:
+                assert rel_err(Fs[0, i], Fo) < TOL and rel_err(Cs[0, i], Co) < TOL
+                assert np.max(np.abs(fs[0, i] - fo)) < TOL * max(1.0, np.max(np.abs(fo)))
+
+
+@pytest.mark.parametrize("N,S", [(256, 16), (1024, 64), (1024, 128), (500, 100)])
+def test_c2_quadrotor_ltv_multilevel_tree(oracle, N, S):
+    """Config 2 shape (nx=12, nu=4, LTV, single problem), many segments -> multi-level interface tree."""
+    p = P.problems.quadrotor_ltv(N)
+    seq = oracle.OracleSolver(p).solve()
+    sol, ws = gpu_solve(p, S=S, lb=False)
+    assert rel_err(ws[0], seq) < TOL
+    sol0, ws0 = gpu_solve(p, S=0)          # library-chosen segmentation
+    assert rel_err(ws0[0], seq) < TOL
+    assert sol.last_status()[0] == 0
+
+
+@pytest.mark.parametrize("batch", [1, 33, 1000])
+def test_c3_cartpole_batch_thread_path(oracle, batch):
+    """Config 3 shape (nx=4, nu=1, N=128), thread-per-problem kernels, ragged batch sizes."""
+    p = P.problems.cartpole_batch(batch=batch, N=128)
+    ref, bad = oracle.OracleBatch(p).solve()
+    assert bad == 0
+    sol, ws = gpu_solve(p)
+    assert ws.shape == ref.shape
+    assert rel_err(ws, ref) < TOL
+    for b in {0, batch // 2, batch - 1}:
+        assert rel_err(ws[b], ref[b]) < TOL
+    K, d, _ = sol.gains()
+    o = oracle.OracleSolver(p, b=batch - 1)
+    o.solve()
+    Ko, do, _ = o.gains()
+    assert rel_err(K[batch - 1], Ko) < TOL and rel_err(d[batch - 1], do) < TOL
+
+
+def test_c3_batch_segmented_warp_path(oracle):
+    """Same tiny systems through the warp-per-segment kernels (S > 1) with a batch dimension."""
+    p = P.problems.cartpole_batch(batch=7, N=128)
+    ref, _ = oracle.OracleBatch(p).solve()
+    sol, ws = gpu_solve(p, S=4)
+    assert rel_err(ws, ref) < TOL
+
+
+@pytest.mark.parametrize("nx,nu", [(2, 1), (3, 2), (6, 3), (8, 8), (4, 1), (12, 4)])
+@pytest.mark.parametrize("S", [1, 3])
+def test_random_dense_problems_with_sigma_term(oracle, nx, nu, S):
+    """Dense H with cross terms, nonzero h and c, sigma * w_prev active (update_problem_data fused in)."""
+    p = P.problems.random_lq(nx, nu, 30, batch=3, seed=nx * 10 + nu)
+    rng = np.random.default_rng(1)
+    wprev = rng.standard_normal((p.batch, p.ws_len))
+    sol, ws = gpu_solve(p, S=S, ws_in=wprev, sigma=0.05)
+    for b in range(p.batch):
+        ref = oracle.OracleSolver(p, b=b).solve(ws_in=wprev[b], sigma=0.05)
+        assert rel_err(ws[b], ref) < TOL
+
+
+def test_random_golden_fixture():
+    g = np.load(os.path.join(GOLD, "random_6_3_40.npz"))
+    q = P.problems.random_lq(6, 3, 40, batch=1, seed=11)
+    for S in (1, 5):
+        _, ws = gpu_solve(q, S=S, ws_in=g["wprev"][None].copy(), sigma=0.05)
+        assert rel_err(ws[0], g["ws_seq"]) < TOL and rel_err(ws[0], g["ws_kkt"]) < TOL
+
+
+@pytest.mark.parametrize("S", [1, 2])
+def test_c4_dims_cta_path_unconstrained(oracle, S):
+    """Config 4 dimensions (nx=30, nu=10): CTA-per-problem kernels (128 threads), unconstrained part."""
+    p = P.problems.random_lq(30, 10, 24, batch=3, seed=5)
+    sol, ws = gpu_solve(p, S=S)
+    for b in range(p.batch):
+        assert rel_err(ws[b], oracle.OracleSolver(p, b=b).solve()) < TOL
+
+
+def test_repeated_solves_and_call_order():
+    p = P.problems.quadrotor_example()
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=4)
+    with pytest.raises(P.PdplqrError) as e:
+        sol.backward()                      # update_problem_data must precede every backward
+    assert e.value.code == P.capi.ERR_ORDER
+    ws0 = p.zeros_ws()
+    sol.update_problem_data(ws0, sigma=1e-6)
+    sol.backward()
+    a = sol.forward(p.x0, np.zeros_like(ws0)).copy()
+    with pytest.raises(P.PdplqrError):
+        sol.forward(p.x0, np.zeros_like(ws0))   # exactly one forward per backward
+    sol.update_problem_data(ws0, sigma=1e-6)
+    sol.backward()
+    b = sol.forward(p.x0, np.zeros_like(ws0))
+    assert np.array_equal(a, b)                 # deterministic
+    out = sol.solve(ws0, p.x0, np.zeros_like(ws0))
+    assert np.array_equal(a, out)
+    assert sol.launch_count() > 0
+
+
+def test_not_positive_definite_is_reported():
+    p = P.problems.random_lq(4, 1, 10, batch=4, seed=9, dense_cost=False)
+    p.H[2, :, 0] = -50.0          # R < 0 for problem 2  (H[.,.,0] is the (0,0) entry = R)
+    sol, _ = gpu_solve(p)
+    bad, st = sol.last_status()
+    assert bad == 1 and st[2] != 0 and st[0] == 0
+
+
+def test_device_pointer_variants_match_host_variants():
+    import torch
+    p = P.problems.cartpole_batch(batch=64, N=128)
+    sol = P.LQRCudaSolver.from_problem(p)
+    sol.set_stream(torch.cuda.current_stream().cuda_stream)
+    ws_in = torch.zeros(p.batch, p.ws_len, dtype=torch.float64, device="cuda")
+    x0 = torch.from_numpy(p.x0).cuda()
+    out = torch.empty_like(ws_in)
+    sol.update_problem_data_device(ws_in, sigma=1e-6)
+    sol.backward_device()
+    sol.forward_device(x0, out)
+    torch.cuda.synchronize()
+    _, ws = gpu_solve(p)
+    assert np.array_equal(out.cpu().numpy(), ws)
