@@ -90,6 +90,13 @@ int pdplqr_backward_without_factorization_device(pdplqr_handle_t h, const double
 int pdplqr_forward_device(pdplqr_handle_t h, const double* x0, double* ws_out);
 int pdplqr_synchronize(pdplqr_handle_t h);
 
+/* Options (addition).  PDPLQR_OPT_AFFINE_CACHE: keep per stage Quu^-1, P+c, F+c, F+B during the factorising
+ * backward so that backward_without_factorization is an affine-only sweep (the reference always keeps its whole
+ * workspace, lqr_kernel.hpp:8-75).  Default: on when the problem has constraints (ADMM use), off otherwise; when
+ * off, backward_without_factorization transparently runs the factorising sweep (same result). */
+#define PDPLQR_OPT_AFFINE_CACHE 1
+int pdplqr_set_option(pdplqr_handle_t h, int option, int value);
+
 /* Accessors (additions; the reference keeps these in a private workspace, lqr_solver_parallel.hpp:55-60).
  * All outputs are host arrays; any pointer may be NULL to skip it.
  *   partition: starts[S], lens[S]                                   (lqr_solver_parallel.hpp:73-80)

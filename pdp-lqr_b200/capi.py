@@ -9,6 +9,7 @@ from . import _build
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_ORDER, ERR_NOT_PD = 0, -1, -2, -3, -4, -5
 CONDENSED_LU, CONDENSED_CHOLESKY = 0, 1
+OPT_AFFINE_CACHE = 1
 
 _dp = C.c_void_p   # double* (host or device address)
 _ip = C.POINTER(C.c_int)
@@ -30,6 +31,7 @@ SIGNATURES = {
     "pdplqr_backward_without_factorization_device": (C.c_int, [C.c_void_p, _dp]),
     "pdplqr_forward_device": (C.c_int, [C.c_void_p, _dp, _dp]),
     "pdplqr_synchronize": (C.c_int, [C.c_void_p]),
+    "pdplqr_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "pdplqr_num_segments": (C.c_int, [C.c_void_p]),
     "pdplqr_get_partition": (C.c_int, [C.c_void_p, _ip, _ip]),
     "pdplqr_get_gains": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),

@@ -1,64 +1,86 @@
 // Thread-per-problem kernels for batches of tiny LQ problems (nx + nu <= 8, one segment per problem):
 // the whole Riccati state of a problem lives in one thread's registers; every lane streams its own problem's
-// stage records from HBM with TMA 1-D bulk copies (cp.async.bulk) into a private shared-memory slot, double
-// buffered on one mbarrier pair per warp.  Records stay in the reference's per-problem, per-stage layout
-// ([batch][N][E|c|H|h]) -- no batch interleaving / repacking of the model is needed.
+// stage records from HBM with TMA 1-D bulk copies (cp.async.bulk) into a private shared-memory slot, in a
+// DEPTH-deep ring completed on one mbarrier per warp and ring slot.
 //
 // Replaces, for the batched sequential case (BASELINE.json config 3):
 //   LQRSolver::update_problem_data / backward / forward      /root/reference include/clqr/lqr/lqr_solver.hpp:41-77
 //   LQRKernel::step_with_factorization / forward_step        lqr_kernel.hpp:103-147, :180-204
+//
+// Device record of one stage on this path ("thread record", written by pack_model_kernel):
+//   [E (NX x S) | c (NX) | lower(H) packed by columns (S(S+1)/2) | h (S)]   -- H is symmetric (lqr_model.hpp:18),
+// so only its lower triangle is kept in HBM: 44 instead of 54 doubles per stage at nx=4, nu=1.
 #pragma once
 #include "common.cuh"
 #include "seg_kernels.cuh"
 
 namespace pdplqr {
 
-constexpr int BATCH_WARPS = 4;  // warps per CTA
-
 template <int NX, int NU>
 struct BatchDims {
-    static constexpr bool ENABLED = (NX + NU) <= 8;
+    static constexpr int S = NX + NU;
+    static constexpr bool ENABLED = S <= 8;
     static constexpr int FRECT = even_up(NU * (NX + 1));  // compact factor record [K | d] (no Gt: single segment)
+    static constexpr int TR_E = 0;
+    static constexpr int TR_C = NX * S;
+    static constexpr int TR_H = TR_C + NX;                 // packed lower triangle, column by column
+    static constexpr int TR_h = TR_H + S * (S + 1) / 2;
+    static constexpr int TREC = even_up(TR_h + S);
+    static constexpr int TREC_EC = even_up(NX * S + NX);
+    // index of H(i,j), i >= j, in the packed lower triangle
+    static constexpr int hl(int i, int j) { return j * S - j * (j - 1) / 2 + (i - j); }
 };
 
-// per-lane slot: 16-byte multiples whose count is odd -> 128-bit shared loads of 32 lanes are conflict-free
+// per-lane slot: a multiple of 16 bytes whose 16-byte count is odd -> 128-bit shared loads of the 32 lanes
+// (each from its own slot) are bank-conflict free
 constexpr int slot_doubles(int rec) { return ((rec / 2) % 2 == 1) ? rec : rec + 2; }
 
-template <int NX, int NU>
+template <int NX, int NU, int WARPS, int DEPTH>
 struct BatchBwdSmem {
-    using D = SegDims<NX, NU>;
-    static constexpr int SLOT = slot_doubles(D::REC);
-    static constexpr int WARP_DOUBLES = 2 * 32 * SLOT;
-    static constexpr int o_bar = BATCH_WARPS * WARP_DOUBLES;
-    static constexpr size_t BYTES = (size_t)(o_bar + 2 * BATCH_WARPS) * 8;
+    static constexpr int SLOT = slot_doubles(BatchDims<NX, NU>::TREC);
+    static constexpr int WARP_DOUBLES = DEPTH * 32 * SLOT;
+    static constexpr int o_bar = WARPS * WARP_DOUBLES;
+    static constexpr size_t BYTES = (size_t)(o_bar + DEPTH * WARPS) * 8;
 };
 
-template <int NX, int NU>
-__global__ void __launch_bounds__(BATCH_WARPS * 32) batch_backward_kernel(SegParams p) {
+template <int NX, int NU, int WARPS, int DEPTH, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) batch_backward_kernel(SegParams p) {
     using D = SegDims<NX, NU>;
-    using L = BatchBwdSmem<NX, NU>;
+    using B = BatchDims<NX, NU>;
+    using L = BatchBwdSmem<NX, NU, WARPS, DEPTH>;
     constexpr int S = D::S;
-    constexpr int FRECT = BatchDims<NX, NU>::FRECT;
+    constexpr int FRECT = B::FRECT;
+    constexpr uint32_t REC_BYTES = B::TREC * 8;
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long bg = (long long)blockIdx.x * (BATCH_WARPS * 32) + threadIdx.x;
+    const long long bg = (long long)blockIdx.x * (WARPS * 32) + threadIdx.x;
     const bool active = bg < p.batch;
     const size_t b = active ? (size_t)bg : (size_t)(p.batch - 1);  // idle lanes shadow the last problem
 
     double* slots = smem + warp * L::WARP_DOUBLES;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::o_bar) + 2 * warp;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::o_bar) + DEPTH * warp;
     const size_t ws_len = (size_t)p.N * S + NX;
-    const double* model_b = p.model + b * p.N * D::REC;
+    const double* model_b = p.model + b * p.N * B::TREC;
     const double* ws_b = p.ws_prev ? p.ws_prev + b * ws_len : nullptr;
     double* fac_b = p.fac + b * p.N * FRECT;
     const double sigma = p.sigma;
+    const int N = p.N;
 
     if (lane == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) mbar_init(&bar[d], 1);
         mbar_fence_init();
     }
     __syncwarp();
+    // prologue: fill DEPTH-1 ring slots (stages N-1, N-2, ...)
+#pragma unroll
+    for (int d = 0; d < DEPTH - 1; ++d) {
+        if (d < N) {
+            if (lane == 0) mbar_expect_tx(&bar[d], 32 * REC_BYTES);
+            __syncwarp();
+            bulk_g2s(slots + (d * 32 + lane) * L::SLOT, model_b + (size_t)(N - 1 - d) * B::TREC, REC_BYTES, &bar[d]);
+        }
+    }
 
     // terminal condition  (lqr_kernel.hpp:79-91):  P_N = H_N + sigma I,  p_N = h_N - sigma w_N
     double P[NX][NX], pv[NX];
@@ -67,61 +89,68 @@ __global__ void __launch_bounds__(BATCH_WARPS * 32) batch_backward_kernel(SegPar
 #pragma unroll
         for (int i = 0; i < NX; ++i) P[i][j] = p.HN[b * NX * NX + i + j * NX] + ((i == j) ? sigma : 0.0);
 #pragma unroll
-    for (int i = 0; i < NX; ++i) pv[i] = p.hN[b * NX + i] - (ws_b ? sigma * ws_b[(size_t)p.N * S + i] : 0.0);
-
-    const int N = p.N;
-    if (lane == 0) mbar_expect_tx(&bar[0], 32 * D::REC * 8);
-    __syncwarp();
-    bulk_g2s(slots + lane * L::SLOT, model_b + (size_t)(N - 1) * D::REC, D::REC * 8, &bar[0]);
+    for (int i = 0; i < NX; ++i) pv[i] = p.hN[b * NX + i] - (ws_b ? sigma * ws_b[(size_t)N * S + i] : 0.0);
+    // w_prev of the first stage; later stages are fetched one stage ahead (register prefetch)
+    double wnext[S];
+#pragma unroll
+    for (int i = 0; i < S; ++i) wnext[i] = ws_b ? ws_b[(size_t)(N - 1) * S + i] : 0.0;
 
     int bad = 0;
+    int slot = 0, phase = 0;          // ring position of stage `it`
+    int pslot = DEPTH - 1;            // ring position the next prefetch goes to
 #pragma unroll 1
     for (int it = 0; it < N; ++it) {
         const int k = N - 1 - it;
-        const int buf = it & 1;
-        if (it + 1 < N) {
-            __syncwarp();  // all lanes are done reading buffer buf^1 (previous iteration)
-            if (lane == 0) mbar_expect_tx(&bar[buf ^ 1], 32 * D::REC * 8);
+        if (it + DEPTH - 1 < N) {
+            __syncwarp();  // every lane has finished with ring slot `pslot` (consumed in the previous iteration)
+            if (lane == 0) mbar_expect_tx(&bar[pslot], 32 * REC_BYTES);
             __syncwarp();
-            bulk_g2s(slots + ((buf ^ 1) * 32 + lane) * L::SLOT, model_b + (size_t)(k - 1) * D::REC, D::REC * 8,
-                     &bar[buf ^ 1]);
+            bulk_g2s(slots + (pslot * 32 + lane) * L::SLOT, model_b + (size_t)(k - (DEPTH - 1)) * B::TREC, REC_BYTES,
+                     &bar[pslot]);
         }
+        pslot = (pslot + 1 == DEPTH) ? 0 : pslot + 1;
         double wprev[S];
 #pragma unroll
-        for (int i = 0; i < S; ++i) wprev[i] = ws_b ? ws_b[(size_t)k * S + i] : 0.0;
-        mbar_wait(&bar[buf], (it >> 1) & 1);
-        const double2* r2 = reinterpret_cast<const double2*>(slots + (buf * 32 + lane) * L::SLOT);
+        for (int i = 0; i < S; ++i) wprev[i] = wnext[i];
+        if (k > 0) {
+#pragma unroll
+            for (int i = 0; i < S; ++i) wnext[i] = ws_b ? ws_b[(size_t)(k - 1) * S + i] : 0.0;
+        }
+        mbar_wait(&bar[slot], phase);
+        const double2* r2 = reinterpret_cast<const double2*>(slots + (slot * 32 + lane) * L::SLOT);
+        slot = (slot + 1 == DEPTH) ? 0 : slot + 1;
+        phase ^= (slot == 0);
         auto ld = [&](int e) {
             const double2 v = r2[e >> 1];
             return (e & 1) ? v.y : v.x;
         };
-        // PEa = P [E c] + [0 p]      (NX x (S+1))
-        double PE[NX][S + 1];
+        // E (and c as column S) into registers
+        double Ea[NX][S + 1];
+#pragma unroll
+        for (int j = 0; j <= S; ++j)
+#pragma unroll
+            for (int i = 0; i < NX; ++i) Ea[i][j] = ld(B::TR_E + i + j * NX);
+        // [M | g] = [H + sigma I | h - sigma w] + E^T (P [E c] + [0 p]) : lower triangle of M and the last column,
+        // one column of P [E c] at a time
+        double M[S][S + 1];
 #pragma unroll
         for (int j = 0; j <= S; ++j) {
             double col[NX];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) col[i] = ld(D::REC_E + i + j * NX);  // c follows E in the record
-#pragma unroll
             for (int i = 0; i < NX; ++i) {
                 double acc = (j == S) ? pv[i] : 0.0;
 #pragma unroll
-                for (int q = 0; q < NX; ++q) acc = fma(P[i][q], col[q], acc);
-                PE[i][j] = acc;
+                for (int q = 0; q < NX; ++q) acc = fma(P[i][q], Ea[q][j], acc);
+                col[i] = acc;
             }
-        }
-        // [M | g] = [H + sigma I | h - sigma w] + E^T PEa   (lower triangle of M and the last column)
-        double M[S][S + 1];
-#pragma unroll
-        for (int j = 0; j <= S; ++j) {
 #pragma unroll
             for (int i = 0; i < S; ++i) {
                 if (j < S && i < j) continue;
                 double acc;
-                if (j < S) acc = ld(D::REC_H + i + j * S) + ((i == j) ? sigma : 0.0);
-                else acc = ld(D::REC_h + i) - sigma * wprev[i];
+                if (j < S) acc = ld(B::TR_H + B::hl(i, j)) + ((i == j) ? sigma : 0.0);
+                else acc = fma(-sigma, wprev[i], ld(B::TR_h + i));
 #pragma unroll
-                for (int q = 0; q < NX; ++q) acc = fma(ld(D::REC_E + q + i * NX), PE[q][j], acc);
+                for (int q = 0; q < NX; ++q) acc = fma(Ea[q][i], col[q], acc);
                 M[i][j] = acc;
             }
         }
@@ -206,64 +235,73 @@ __global__ void __launch_bounds__(BATCH_WARPS * 32) batch_backward_kernel(SegPar
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int NX, int NU>
+template <int NX, int NU, int WARPS, int DEPTH>
 struct BatchFwdSmem {
-    using D = SegDims<NX, NU>;
-    static constexpr int FRECT = BatchDims<NX, NU>::FRECT;
-    static constexpr int SLOT = slot_doubles(D::REC_EC + FRECT);  // [E c (pad) | K d]
-    static constexpr int WARP_DOUBLES = 2 * 32 * SLOT;
-    static constexpr int o_bar = BATCH_WARPS * WARP_DOUBLES;
-    static constexpr size_t BYTES = (size_t)(o_bar + 2 * BATCH_WARPS) * 8;
+    using B = BatchDims<NX, NU>;
+    static constexpr int SLOT = slot_doubles(B::TREC_EC + B::FRECT);  // [E c (pad) | K d]
+    static constexpr int WARP_DOUBLES = DEPTH * 32 * SLOT;
+    static constexpr int o_bar = WARPS * WARP_DOUBLES;
+    static constexpr size_t BYTES = (size_t)(o_bar + DEPTH * WARPS) * 8;
 };
 
-template <int NX, int NU>
-__global__ void __launch_bounds__(BATCH_WARPS * 32) batch_forward_kernel(SegParams p) {
+template <int NX, int NU, int WARPS, int DEPTH, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) batch_forward_kernel(SegParams p) {
     using D = SegDims<NX, NU>;
-    using L = BatchFwdSmem<NX, NU>;
+    using B = BatchDims<NX, NU>;
+    using L = BatchFwdSmem<NX, NU, WARPS, DEPTH>;
     constexpr int S = D::S;
-    constexpr int FRECT = L::FRECT;
+    constexpr int FRECT = B::FRECT;
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long bg = (long long)blockIdx.x * (BATCH_WARPS * 32) + threadIdx.x;
+    const long long bg = (long long)blockIdx.x * (WARPS * 32) + threadIdx.x;
     const bool active = bg < p.batch;
     const size_t b = active ? (size_t)bg : (size_t)(p.batch - 1);
 
     double* slots = smem + warp * L::WARP_DOUBLES;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::o_bar) + 2 * warp;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::o_bar) + DEPTH * warp;
     const size_t ws_len = (size_t)p.N * S + NX;
-    const double* model_b = p.model + b * p.N * D::REC;
+    const double* model_b = p.model + b * p.N * B::TREC;
     const double* fac_b = p.fac + b * p.N * FRECT;
     double* ws_b = p.ws_out + b * ws_len;
-    constexpr uint32_t TX = (D::REC_EC + FRECT) * 8;
+    constexpr uint32_t TX = (B::TREC_EC + FRECT) * 8;
+    const int N = p.N;
 
     if (lane == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) mbar_init(&bar[d], 1);
         mbar_fence_init();
     }
     __syncwarp();
+#pragma unroll
+    for (int d = 0; d < DEPTH - 1; ++d) {
+        if (d < N) {
+            if (lane == 0) mbar_expect_tx(&bar[d], 32 * TX);
+            __syncwarp();
+            double* dst = slots + (d * 32 + lane) * L::SLOT;
+            bulk_g2s(dst, model_b + (size_t)d * B::TREC, B::TREC_EC * 8, &bar[d]);
+            bulk_g2s(dst + B::TREC_EC, fac_b + (size_t)d * FRECT, FRECT * 8, &bar[d]);
+        }
+    }
     double x[NX];
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = p.xhat[b * NX + i];  // S == 1: xhat aliases x0
 
-    const int N = p.N;
-    if (lane == 0) mbar_expect_tx(&bar[0], 32 * TX);
-    __syncwarp();
-    bulk_g2s(slots + lane * L::SLOT, model_b, D::REC_EC * 8, &bar[0]);
-    bulk_g2s(slots + lane * L::SLOT + D::REC_EC, fac_b, FRECT * 8, &bar[0]);
+    int slot = 0, phase = 0, pslot = DEPTH - 1;
 #pragma unroll 1
     for (int k = 0; k < N; ++k) {
-        const int buf = k & 1;
-        if (k + 1 < N) {
+        if (k + DEPTH - 1 < N) {
             __syncwarp();
-            if (lane == 0) mbar_expect_tx(&bar[buf ^ 1], 32 * TX);
+            if (lane == 0) mbar_expect_tx(&bar[pslot], 32 * TX);
             __syncwarp();
-            double* dst = slots + ((buf ^ 1) * 32 + lane) * L::SLOT;
-            bulk_g2s(dst, model_b + (size_t)(k + 1) * D::REC, D::REC_EC * 8, &bar[buf ^ 1]);
-            bulk_g2s(dst + D::REC_EC, fac_b + (size_t)(k + 1) * FRECT, FRECT * 8, &bar[buf ^ 1]);
+            double* dst = slots + (pslot * 32 + lane) * L::SLOT;
+            bulk_g2s(dst, model_b + (size_t)(k + DEPTH - 1) * B::TREC, B::TREC_EC * 8, &bar[pslot]);
+            bulk_g2s(dst + B::TREC_EC, fac_b + (size_t)(k + DEPTH - 1) * FRECT, FRECT * 8, &bar[pslot]);
         }
-        mbar_wait(&bar[buf], (k >> 1) & 1);
-        const double2* r2 = reinterpret_cast<const double2*>(slots + (buf * 32 + lane) * L::SLOT);
+        pslot = (pslot + 1 == DEPTH) ? 0 : pslot + 1;
+        mbar_wait(&bar[slot], phase);
+        const double2* r2 = reinterpret_cast<const double2*>(slots + (slot * 32 + lane) * L::SLOT);
+        slot = (slot + 1 == DEPTH) ? 0 : slot + 1;
+        phase ^= (slot == 0);
         auto ld = [&](int e) {
             const double2 v = r2[e >> 1];
             return (e & 1) ? v.y : v.x;
@@ -271,19 +309,19 @@ __global__ void __launch_bounds__(BATCH_WARPS * 32) batch_forward_kernel(SegPara
         double u[NU];
 #pragma unroll
         for (int m = 0; m < NU; ++m) {
-            double acc = ld(D::REC_EC + NU * NX + m);  // d
+            double acc = ld(B::TREC_EC + NU * NX + m);  // d
 #pragma unroll
-            for (int j = 0; j < NX; ++j) acc = fma(ld(D::REC_EC + m + j * NU), x[j], acc);
+            for (int j = 0; j < NX; ++j) acc = fma(ld(B::TREC_EC + m + j * NU), x[j], acc);
             u[m] = acc;
         }
         double xn[NX];
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
-            double acc = ld(D::REC_C + i);
+            double acc = ld(B::TR_C + i);
 #pragma unroll
-            for (int m = 0; m < NU; ++m) acc = fma(ld(D::REC_E + i + m * NX), u[m], acc);
+            for (int m = 0; m < NU; ++m) acc = fma(ld(B::TR_E + i + m * NX), u[m], acc);
 #pragma unroll
-            for (int j = 0; j < NX; ++j) acc = fma(ld(D::REC_E + i + (NU + j) * NX), x[j], acc);
+            for (int j = 0; j < NX; ++j) acc = fma(ld(B::TR_E + i + (NU + j) * NX), x[j], acc);
             xn[i] = acc;
         }
         if (active) {

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -34,6 +35,8 @@ struct pdplqr_solver {
     const Ops* ops = nullptr;
     bool thread_path = false;  // thread-per-problem kernels (tiny nx+nu, S == 1)
     int frec = 0;              // doubles per stage in d_fac for the active path
+    int mrec = 0;              // doubles per stage in d_model for the active path
+    int bwd_variant = 0, fwd_variant = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     // device memory
@@ -41,6 +44,17 @@ struct pdplqr_solver {
     double *d_fac = nullptr, *d_sum = nullptr, *d_xhat = nullptr, *d_uhat = nullptr;
     double *d_ws_in = nullptr, *d_x0 = nullptr, *d_ws_out = nullptr;
     int *d_seg_start = nullptr, *d_seg_len = nullptr, *d_status = nullptr;
+    // constraints
+    int ncmax = 0;
+    long long d_total_host = 0, d_total_dev = 0;
+    std::vector<long long> coff, doff_host, doff_dev;
+    int* d_ncs = nullptr;
+    long long *d_coff = nullptr, *d_doff = nullptr, *d_doff_host = nullptr;
+    double *d_D = nullptr, *d_ys = nullptr, *d_zs = nullptr, *d_rho = nullptr, *d_inv_rho = nullptr;
+    const double *cur_ys = nullptr, *cur_zs = nullptr, *cur_inv_rho = nullptr, *cur_rho = nullptr;
+    // affine cache for backward_without_factorization
+    bool keep_affine = false;
+    double* d_aff = nullptr;
     std::vector<TreeLevel> levels;
     std::vector<void*> owned;  // everything to cudaFree
     // per-iteration state
@@ -57,12 +71,14 @@ using Solver = pdplqr_solver;
 
 struct Ops {
     int nx, nu, T;
-    int REC, FREC, SREC, DREC, FRECT;
+    int REC, FREC, SREC, DREC, FRECT, TREC, AREC;
     bool has_thread_path;
     int (*backward)(Solver&);
     int (*forward)(Solver&, const double* d_x0, double* d_ws_out);
     int (*tree_up)(Solver&, const TreeParams&);
     int (*tree_down)(Solver&, const TreeParams&);
+    int (*affine)(Solver&);
+    int (*tree_up_affine)(Solver&, const TreeParams&);
 };
 
 int fail(Solver* h, int code, const std::string& msg) {
@@ -90,7 +106,39 @@ SegParams seg_params(Solver& h) {
     p.ws_prev = h.cur_ws; p.sigma = h.sigma;
     p.fac = h.d_fac; p.sum = h.d_sum; p.status = h.d_status;
     p.xhat = h.d_xhat; p.uhat = h.d_uhat;
+    p.aff = h.keep_affine ? h.d_aff : nullptr;
+    p.ncmax = h.ncmax; p.nc_total = h.nc_total; p.d_total = h.d_total_dev;
+    p.ncs = h.d_ncs; p.coff = h.d_coff; p.doff = h.d_doff; p.Dm = h.d_D;
+    p.ys = h.cur_ys; p.zs = h.cur_zs; p.rho = h.cur_rho; p.inv_rho = h.cur_inv_rho;
     return p;
+}
+
+// Thread-path launch variants (warps per CTA, TMA ring depth, min CTAs per SM).  The default is chosen so that a
+// 65,536-problem batch runs in whole waves on 148 SMs (DESIGN.md "grid sizing"); PDPLQR_BWD_VARIANT /
+// PDPLQR_FWD_VARIANT select another one for tuning sweeps.
+template <int NX, int NU, int WARPS, int DEPTH, int MINB>
+int launch_batch_bwd(Solver& h, const SegParams& p) {
+    auto kern = batch_backward_kernel<NX, NU, WARPS, DEPTH, MINB>;
+    constexpr size_t bytes = BatchBwdSmem<NX, NU, WARPS, DEPTH>::BYTES;
+    int rc = set_smem(h, kern, bytes);
+    if (rc) return rc;
+    const int blocks = (h.batch + WARPS * 32 - 1) / (WARPS * 32);
+    kern<<<blocks, WARPS * 32, bytes, h.stream>>>(p);
+    h.launches++;
+    CU_TRY(&h, cudaGetLastError());
+    return PDPLQR_OK;
+}
+template <int NX, int NU, int WARPS, int DEPTH, int MINB>
+int launch_batch_fwd(Solver& h, const SegParams& p) {
+    auto kern = batch_forward_kernel<NX, NU, WARPS, DEPTH, MINB>;
+    constexpr size_t bytes = BatchFwdSmem<NX, NU, WARPS, DEPTH>::BYTES;
+    int rc = set_smem(h, kern, bytes);
+    if (rc) return rc;
+    const int blocks = (h.batch + WARPS * 32 - 1) / (WARPS * 32);
+    kern<<<blocks, WARPS * 32, bytes, h.stream>>>(p);
+    h.launches++;
+    CU_TRY(&h, cudaGetLastError());
+    return PDPLQR_OK;
 }
 
 template <int NX, int NU, int T>
@@ -98,19 +146,17 @@ int backward_impl(Solver& h) {
     SegParams p = seg_params(h);
     if constexpr (BatchDims<NX, NU>::ENABLED) {
         if (h.thread_path) {
-            auto kern = batch_backward_kernel<NX, NU>;
-            constexpr size_t bytes = BatchBwdSmem<NX, NU>::BYTES;
-            int rc = set_smem(h, kern, bytes);
-            if (rc) return rc;
-            const int blocks = (h.batch + BATCH_WARPS * 32 - 1) / (BATCH_WARPS * 32);
-            kern<<<blocks, BATCH_WARPS * 32, bytes, h.stream>>>(p);
-            h.launches++;
-            CU_TRY(&h, cudaGetLastError());
-            return PDPLQR_OK;
+            switch (h.bwd_variant) {
+                case 1: return launch_batch_bwd<NX, NU, 2, 1, 7>(h, p);
+                case 2: return launch_batch_bwd<NX, NU, 4, 2, 2>(h, p);
+                case 3: return launch_batch_bwd<NX, NU, 14, 1, 1>(h, p);
+                case 4: return launch_batch_bwd<NX, NU, 5, 3, 1>(h, p);
+                default: return launch_batch_bwd<NX, NU, 7, 2, 1>(h, p);
+            }
         }
     }
     auto kern = seg_backward_kernel<NX, NU, T>;
-    constexpr size_t bytes = BwdSmem<NX, NU>::BYTES;
+    const size_t bytes = BwdSmem<NX, NU>::bytes(h.ncmax);
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
     kern<<<h.batch * h.S, T, bytes, h.stream>>>(p);
@@ -126,15 +172,13 @@ int forward_impl(Solver& h, const double* d_x0, double* d_ws_out) {
     if (h.S == 1) p.xhat = d_x0;
     if constexpr (BatchDims<NX, NU>::ENABLED) {
         if (h.thread_path) {
-            auto kern = batch_forward_kernel<NX, NU>;
-            constexpr size_t bytes = BatchFwdSmem<NX, NU>::BYTES;
-            int rc = set_smem(h, kern, bytes);
-            if (rc) return rc;
-            const int blocks = (h.batch + BATCH_WARPS * 32 - 1) / (BATCH_WARPS * 32);
-            kern<<<blocks, BATCH_WARPS * 32, bytes, h.stream>>>(p);
-            h.launches++;
-            CU_TRY(&h, cudaGetLastError());
-            return PDPLQR_OK;
+            switch (h.fwd_variant) {
+                case 1: return launch_batch_fwd<NX, NU, 2, 2, 7>(h, p);
+                case 2: return launch_batch_fwd<NX, NU, 4, 2, 3>(h, p);
+                case 3: return launch_batch_fwd<NX, NU, 14, 2, 1>(h, p);
+                case 4: return launch_batch_fwd<NX, NU, 7, 3, 1>(h, p);
+                default: return launch_batch_fwd<NX, NU, 7, 4, 1>(h, p);
+            }
         }
     }
     auto kern = seg_forward_kernel<NX, NU, 32>;
@@ -167,11 +211,35 @@ int tree_down_impl(Solver& h, const TreeParams& p) {
     return PDPLQR_OK;
 }
 
+template <int NX, int NU>
+int affine_impl(Solver& h) {
+    SegParams p = seg_params(h);
+    auto kern = seg_affine_kernel<NX, NU>;
+    const size_t bytes = AffSmem<NX, NU>::bytes(h.ncmax);
+    int rc = set_smem(h, kern, bytes);
+    if (rc) return rc;
+    kern<<<h.batch * h.S, 32, bytes, h.stream>>>(p);
+    h.launches++;
+    CU_TRY(&h, cudaGetLastError());
+    return PDPLQR_OK;
+}
+template <int NX>
+int tree_up_affine_impl(Solver& h, const TreeParams& p) {
+    static_assert(NX <= 32, "tree_up_affine_kernel keeps one row per lane");
+    auto kern = tree_up_affine_kernel<NX>;
+    kern<<<p.batch * p.groups, 32, 5 * NX * sizeof(double), h.stream>>>(p);
+    h.launches++;
+    CU_TRY(&h, cudaGetLastError());
+    return PDPLQR_OK;
+}
+
 template <int NX, int NU, int T>
 constexpr Ops make_ops() {
     return Ops{NX, NU, T, SegDims<NX, NU>::REC, SegDims<NX, NU>::FREC, SegDims<NX, NU>::SREC, TreeDims<NX>::DREC,
-               BatchDims<NX, NU>::FRECT, BatchDims<NX, NU>::ENABLED,
-               &backward_impl<NX, NU, T>, &forward_impl<NX, NU, T>, &tree_up_impl<NX>, &tree_down_impl<NX>};
+               BatchDims<NX, NU>::FRECT, BatchDims<NX, NU>::TREC, SegDims<NX, NU>::AREC,
+               BatchDims<NX, NU>::ENABLED,
+               &backward_impl<NX, NU, T>, &forward_impl<NX, NU, T>, &tree_up_impl<NX>, &tree_down_impl<NX>,
+               &affine_impl<NX, NU>, &tree_up_affine_impl<NX>};
 }
 
 // Instantiated (nx, nu) pairs.  The BASELINE.json configs use (12,4), (4,1) and (30,10); the rest cover the
@@ -187,11 +255,14 @@ const Ops* find_ops(int nx, int nu) {
     return nullptr;
 }
 
+// flat (E, c, H, h) -> device stage records.  sym = 0: [E | c | H | h] (segment kernels);
+// sym = 1: [E | c | lower(H) packed by columns | h] (thread-per-problem kernels, BatchDims::TR_*).
 __global__ void pack_model_kernel(const double* __restrict__ E, const double* __restrict__ c,
                                   const double* __restrict__ H, const double* __restrict__ hv, double* __restrict__ rec,
-                                  long long nstages, int nx, int s, int REC) {
+                                  long long nstages, int nx, int s, int REC, int sym) {
     const long long total = nstages * REC;
-    const int oC = nx * s, oH = oC + nx, oh = oH + s * s, oend = oh + s;
+    const int nH = sym ? s * (s + 1) / 2 : s * s;
+    const int oC = nx * s, oH = oC + nx, oh = oH + nH, oend = oh + s;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const long long st = idx / REC;
@@ -199,10 +270,28 @@ __global__ void pack_model_kernel(const double* __restrict__ E, const double* __
         double v = 0.0;
         if (e < oC) v = E[st * oC + e];
         else if (e < oH) v = c[st * nx + (e - oC)];
-        else if (e < oh) v = H[st * (long long)(s * s) + (e - oH)];
-        else if (e < oend) v = hv[st * s + (e - oh)];
+        else if (e < oh) {
+            int q = e - oH;
+            if (sym) {  // q -> (i, j), i >= j, columns packed one after the other
+                int j = 0;
+                while (q >= s - j) { q -= s - j; ++j; }
+                q = (j + q) + j * s;
+            }
+            v = H[st * (long long)(s * s) + q];
+        } else if (e < oend) v = hv[st * s + (e - oh)];
         rec[idx] = v;
     }
+}
+
+// flat D (reference layout, stage chunks back to back) -> device copy with every stage chunk padded to 16 bytes
+__global__ void pad_D_kernel(const double* __restrict__ src, double* __restrict__ dst, const long long* __restrict__ soff,
+                             const long long* __restrict__ doff, long long s_total, long long d_total, int nstages) {
+    const int b = blockIdx.y, k = blockIdx.x;
+    if (k >= nstages) return;
+    const long long n = soff[k + 1] - soff[k], nd = doff[k + 1] - doff[k];
+    const double* s = src + (long long)b * s_total + soff[k];
+    double* d = dst + (long long)b * d_total + doff[k];
+    for (long long e = threadIdx.x; e < nd; e += blockDim.x) d[e] = e < n ? s[e] : 0.0;
 }
 
 template <class Tp>
@@ -215,7 +304,8 @@ int dev_alloc(Solver& h, Tp** p, size_t count) {
 }
 
 int set_model_common(Solver& h, const double* E, const double* c, const double* H, const double* hv,
-                     const double* HN, const double* hN, bool on_device) {
+                     const double* HN, const double* hN, const double* Dflat, bool on_device) {
+    if (h.nc_total > 0 && !Dflat) return fail(&h, PDPLQR_ERR_INVALID, "set_model: D is required when ncs has non-zero entries");
     const size_t nst = (size_t)h.batch * h.N;
     const size_t nE = nst * h.nx * h.s, nc = nst * h.nx, nH = nst * h.s * h.s, nh = nst * h.s;
     const double *dE = E, *dc = c, *dH = H, *dh = hv;
@@ -233,15 +323,32 @@ int set_model_common(Solver& h, const double* E, const double* c, const double* 
         }
         dE = stage; dc = stage + nE; dH = stage + nE + nc; dh = stage + nE + nc + nH;
     }
-    const long long total = (long long)nst * h.ops->REC;
+    const long long total = (long long)nst * h.mrec;
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
-    pack_model_kernel<<<blocks, 256, 0, h.stream>>>(dE, dc, dH, dh, h.d_model, (long long)nst, h.nx, h.s, h.ops->REC);
+    pack_model_kernel<<<blocks, 256, 0, h.stream>>>(dE, dc, dH, dh, h.d_model, (long long)nst, h.nx, h.s, h.mrec,
+                                                    h.thread_path ? 1 : 0);
     h.launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(h.d_HN, HN, (size_t)h.batch * h.nx * h.nx * 8, kind, h.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(h.d_hN, hN, (size_t)h.batch * h.nx * 8, kind, h.stream);
-    if (e == cudaSuccess && stage) e = cudaStreamSynchronize(h.stream);
+    double* dstage = nullptr;
+    if (e == cudaSuccess && h.nc_total > 0) {
+        const double* dsrc = Dflat;
+        if (!on_device) {
+            e = cudaMalloc((void**)&dstage, (size_t)h.batch * h.d_total_host * 8);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(dstage, Dflat, (size_t)h.batch * h.d_total_host * 8, kind, h.stream);
+            dsrc = dstage;
+        }
+        if (e == cudaSuccess) {
+            pad_D_kernel<<<dim3(h.N + 1, h.batch), 128, 0, h.stream>>>(dsrc, h.d_D, h.d_doff_host, h.d_doff, h.d_total_host,
+                                                                     h.d_total_dev, h.N + 1);
+            h.launches++;
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess && (stage || dstage)) e = cudaStreamSynchronize(h.stream);
     if (stage) cudaFree(stage);
+    if (dstage) cudaFree(dstage);
     if (e != cudaSuccess) return fail(&h, PDPLQR_ERR_CUDA, std::string("set_model: ") + cudaGetErrorString(e));
     h.model_set = true;
     h.factorized = false;
@@ -267,6 +374,32 @@ int run_backward(Solver& h) {
     }
     h.updated = false;  // backward consumes the staged data (in-place accumulation in the reference)
     h.factorized = true;
+    h.backward_done = true;
+    return PDPLQR_OK;
+}
+
+// backward_without_factorization: affine-only sweeps with the cached factors.  When the affine cache is not kept
+// (thread-per-problem path, or PDPLQR_OPT_AFFINE_CACHE = 0) the full factorising sweep is run instead -- same
+// result, since only affine data may have changed between the two calls.
+int run_backward_nofact(Solver& h) {
+    if (!h.factorized)
+        return fail(&h, PDPLQR_ERR_ORDER, "backward_without_factorization before any backward (lqr_solver_parallel.hpp:148)");
+    if (!h.keep_affine || h.thread_path) return run_backward(h);
+    if (!h.updated) return fail(&h, PDPLQR_ERR_ORDER, "backward_without_factorization before update_problem_data");
+    int rc = h.ops->affine(h);
+    if (rc) return rc;
+    if (h.S > 1) {
+        for (size_t l = 0; l < h.levels.size(); ++l) {
+            TreeLevel& lv = h.levels[l];
+            TreeParams tp{};
+            tp.batch = h.batch; tp.count = lv.count; tp.R = lv.R; tp.groups = lv.groups;
+            tp.sum_in = lv.sum; tp.dd = lv.dd;
+            tp.sum_out = (l + 1 < h.levels.size()) ? h.levels[l + 1].sum : nullptr;
+            rc = h.ops->tree_up_affine(h, tp);
+            if (rc) return rc;
+        }
+    }
+    h.updated = false;
     h.backward_done = true;
     return PDPLQR_OK;
 }
@@ -322,11 +455,22 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
         if (v < 0) { delete h; return PDPLQR_ERR_INVALID; }
         h->nc_total += v;
     }
-    if (h->nc_total > 0) { delete h; return PDPLQR_ERR_UNSUPPORTED; }  // constraint fold-in: see DESIGN.md status
+    h->coff.assign(N + 2, 0); h->doff_host.assign(N + 2, 0); h->doff_dev.assign(N + 2, 0);
+    for (int k = 0; k <= N; ++k) {
+        const long long dim = (k < N) ? nx + nu : nx;
+        h->coff[k + 1] = h->coff[k] + h->ncs[k];
+        h->doff_host[k + 1] = h->doff_host[k] + h->ncs[k] * dim;
+        h->doff_dev[k + 1] = h->doff_dev[k] + ((h->ncs[k] * dim + 1) & ~1LL);
+        h->ncmax = std::max(h->ncmax, h->ncs[k]);
+    }
+    h->d_total_host = h->doff_host[N + 1];
+    h->d_total_dev = h->doff_dev[N + 1];
+    h->keep_affine = h->nc_total > 0;
 
     // ---- segmentation (lqr_solver_parallel.hpp:70-80)
     int S = num_segments;
-    if (S == 0) {
+    const bool auto_seg = (S == 0);
+    if (auto_seg) {
         // GPU-appropriate default: enough (problem, segment) groups to fill the machine, segments >= 8 stages
         const int target_groups = 148 * 8;
         S = std::max(1, std::min(N / 8, (target_groups + batch - 1) / batch));
@@ -337,13 +481,18 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     h->seg_start.resize(S); h->seg_len.resize(S);
     for (int i = 0; i < S; ++i) {
         const int st = (i == 0) ? 0 : h->seg_start[i - 1] + h->seg_len[i - 1];
-        int len = (i < S - 1) ? int(N / (scale + S - 1)) : N - st;
+        int len;
+        if (auto_seg) len = N / S + (i < N % S ? 1 : 0);  // equal lengths (the 1.55 rule targets <= #cores segments)
+        else len = (i < S - 1) ? int(N / (scale + S - 1)) : N - st;
         if (i < S - 1 && len < 1) len = 1;
         h->seg_start[i] = st; h->seg_len[i] = len;
     }
     if (h->seg_len[S - 1] < 1) { delete h; return PDPLQR_ERR_INVALID; }
-    h->thread_path = (S == 1) && ops->has_thread_path;
+    h->thread_path = (S == 1) && ops->has_thread_path && h->nc_total == 0;
     h->frec = h->thread_path ? ops->FRECT : ops->FREC;
+    h->mrec = h->thread_path ? ops->TREC : ops->REC;
+    if (const char* e = getenv("PDPLQR_BWD_VARIANT")) h->bwd_variant = atoi(e);
+    if (const char* e = getenv("PDPLQR_FWD_VARIANT")) h->fwd_variant = atoi(e);
 
     auto bail = [&](int rc) { std::string e = h->err; pdplqr_destroy(h); (void)e; return rc; };
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PDPLQR_ERR_CUDA);
@@ -363,7 +512,25 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     rc |= dev_alloc(*h, &h->d_seg_start, S);
     rc |= dev_alloc(*h, &h->d_seg_len, S);
     rc |= dev_alloc(*h, &h->d_status, B);
+    if (h->nc_total > 0) {
+        rc |= dev_alloc(*h, &h->d_ncs, N + 1);
+        rc |= dev_alloc(*h, &h->d_coff, N + 2);
+        rc |= dev_alloc(*h, &h->d_doff, N + 2);
+        rc |= dev_alloc(*h, &h->d_doff_host, N + 2);
+        rc |= dev_alloc(*h, &h->d_D, B * h->d_total_dev);
+        rc |= dev_alloc(*h, &h->d_ys, B * h->nc_total);
+        rc |= dev_alloc(*h, &h->d_zs, B * h->nc_total);
+        rc |= dev_alloc(*h, &h->d_rho, B * h->nc_total);
+        rc |= dev_alloc(*h, &h->d_inv_rho, B * h->nc_total);
+    }
+    if (h->keep_affine) rc |= dev_alloc(*h, &h->d_aff, B * N * ops->AREC);
     if (rc) return bail(PDPLQR_ERR_CUDA);
+    if (h->nc_total > 0) {
+        cudaMemcpy(h->d_ncs, h->ncs.data(), sizeof(int) * (N + 1), cudaMemcpyHostToDevice);
+        cudaMemcpy(h->d_coff, h->coff.data(), sizeof(long long) * (N + 2), cudaMemcpyHostToDevice);
+        cudaMemcpy(h->d_doff, h->doff_dev.data(), sizeof(long long) * (N + 2), cudaMemcpyHostToDevice);
+        cudaMemcpy(h->d_doff_host, h->doff_host.data(), sizeof(long long) * (N + 2), cudaMemcpyHostToDevice);
+    }
     cudaMemcpy(h->d_seg_start, h->seg_start.data(), sizeof(int) * S, cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_seg_len, h->seg_len.data(), sizeof(int) * S, cudaMemcpyHostToDevice);
     cudaMemset(h->d_fac, 0, B * N * ops->FREC * sizeof(double));
@@ -418,23 +585,23 @@ int pdplqr_set_stream(pdplqr_handle_t h, void* cuda_stream) {
 int pdplqr_set_model(pdplqr_handle_t h, const double* E, const double* c, const double* H, const double* hvec,
                      const double* HN, const double* hN, const double* D) {
     if (!h || !E || !c || !H || !hvec || !HN || !hN) return fail(h, PDPLQR_ERR_INVALID, "set_model: null pointer");
-    (void)D;
     cudaSetDevice(h->device);
-    return set_model_common(*h, E, c, H, hvec, HN, hN, false);
+    return set_model_common(*h, E, c, H, hvec, HN, hN, D, false);
 }
 int pdplqr_set_model_device(pdplqr_handle_t h, const double* E, const double* c, const double* H,
                             const double* hvec, const double* HN, const double* hN, const double* D) {
     if (!h || !E || !c || !H || !hvec || !HN || !hN) return fail(h, PDPLQR_ERR_INVALID, "set_model: null pointer");
-    (void)D;
     cudaSetDevice(h->device);
-    return set_model_common(*h, E, c, H, hvec, HN, hN, true);
+    return set_model_common(*h, E, c, H, hvec, HN, hN, D, true);
 }
 
 int pdplqr_update_problem_data_device(pdplqr_handle_t h, const double* ws, const double* ys, const double* zs,
                                       const double* inv_rho, double sigma) {
     if (!h) return PDPLQR_ERR_INVALID;
-    (void)ys; (void)zs; (void)inv_rho;
+    if (h->nc_total > 0 && (!ys || !zs || !inv_rho))
+        return fail(h, PDPLQR_ERR_INVALID, "update_problem_data: ys, zs, inv_rho are required when the problem has constraints");
     h->cur_ws = ws;
+    h->cur_ys = ys; h->cur_zs = zs; h->cur_inv_rho = inv_rho;
     h->sigma = sigma;
     h->updated = true;
     return PDPLQR_OK;
@@ -445,24 +612,67 @@ int pdplqr_update_problem_data(pdplqr_handle_t h, const double* ws, const double
     cudaSetDevice(h->device);
     const size_t ws_len = (size_t)h->N * h->s + h->nx;
     if (ws) CU_TRY(h, cudaMemcpyAsync(h->d_ws_in, ws, ws_len * h->batch * 8, cudaMemcpyHostToDevice, h->stream));
+    if (h->nc_total > 0) {
+        if (!ys || !zs || !inv_rho)
+            return fail(h, PDPLQR_ERR_INVALID, "update_problem_data: ys, zs, inv_rho are required when the problem has constraints");
+        const size_t nb = (size_t)h->batch * h->nc_total * 8;
+        CU_TRY(h, cudaMemcpyAsync(h->d_ys, ys, nb, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(h->d_zs, zs, nb, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaMemcpyAsync(h->d_inv_rho, inv_rho, nb, cudaMemcpyHostToDevice, h->stream));
+        ys = h->d_ys; zs = h->d_zs; inv_rho = h->d_inv_rho;
+    }
     return pdplqr_update_problem_data_device(h, ws ? h->d_ws_in : nullptr, ys, zs, inv_rho, sigma);
 }
 
+static int stage_rho(pdplqr_handle_t h, const double* rho, const double** dev) {
+    *dev = nullptr;
+    if (h->nc_total == 0) return PDPLQR_OK;
+    if (!rho) return fail(h, PDPLQR_ERR_INVALID, "backward: rho_vecs is required when the problem has constraints");
+    CU_TRY(h, cudaMemcpyAsync(h->d_rho, rho, (size_t)h->batch * h->nc_total * 8, cudaMemcpyHostToDevice, h->stream));
+    *dev = h->d_rho;
+    return PDPLQR_OK;
+}
 int pdplqr_backward_device(pdplqr_handle_t h, const double* rho) {
     if (!h) return PDPLQR_ERR_INVALID;
-    (void)rho;
+    if (h->nc_total > 0 && !rho) return fail(h, PDPLQR_ERR_INVALID, "backward: rho_vecs is required when the problem has constraints");
     cudaSetDevice(h->device);
+    h->cur_rho = rho;
     return run_backward(*h);
 }
-int pdplqr_backward(pdplqr_handle_t h, const double* rho) { return pdplqr_backward_device(h, rho); }
-
+int pdplqr_backward(pdplqr_handle_t h, const double* rho) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    cudaSetDevice(h->device);
+    const double* dev = nullptr;
+    int rc = stage_rho(h, rho, &dev);
+    if (rc) return rc;
+    return pdplqr_backward_device(h, dev);
+}
 int pdplqr_backward_without_factorization_device(pdplqr_handle_t h, const double* rho) {
     if (!h) return PDPLQR_ERR_INVALID;
-    (void)rho;
-    return fail(h, PDPLQR_ERR_UNSUPPORTED, "backward_without_factorization: not built yet (DESIGN.md status)");
+    if (h->nc_total > 0 && !rho) return fail(h, PDPLQR_ERR_INVALID, "backward: rho_vecs is required when the problem has constraints");
+    cudaSetDevice(h->device);
+    h->cur_rho = rho;
+    return run_backward_nofact(*h);
 }
 int pdplqr_backward_without_factorization(pdplqr_handle_t h, const double* rho) {
-    return pdplqr_backward_without_factorization_device(h, rho);
+    if (!h) return PDPLQR_ERR_INVALID;
+    cudaSetDevice(h->device);
+    const double* dev = nullptr;
+    int rc = stage_rho(h, rho, &dev);
+    if (rc) return rc;
+    return pdplqr_backward_without_factorization_device(h, dev);
+}
+int pdplqr_set_option(pdplqr_handle_t h, int option, int value) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    if (option == PDPLQR_OPT_AFFINE_CACHE) {
+        if (value && !h->d_aff) {
+            if (dev_alloc(*h, &h->d_aff, (size_t)h->batch * h->N * h->ops->AREC)) return PDPLQR_ERR_CUDA;
+        }
+        h->keep_affine = value != 0;
+        h->factorized = false;
+        return PDPLQR_OK;
+    }
+    return fail(h, PDPLQR_ERR_INVALID, "unknown option");
 }
 
 int pdplqr_forward_device(pdplqr_handle_t h, const double* x0, double* ws_out) {
@@ -569,7 +779,7 @@ const char* pdplqr_last_error(pdplqr_handle_t h) { return h ? h->err.c_str() : "
 long long pdplqr_launch_count(pdplqr_handle_t h) { return h ? h->launches : 0; }
 int pdplqr_record_doubles(pdplqr_handle_t h, int* model_rec, int* factor_rec) {
     if (!h) return PDPLQR_ERR_INVALID;
-    if (model_rec) *model_rec = h->ops->REC;
+    if (model_rec) *model_rec = h->mrec;
     if (factor_rec) *factor_rec = h->frec;
     return PDPLQR_OK;
 }

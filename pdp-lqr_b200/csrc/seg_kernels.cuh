@@ -36,6 +36,9 @@ struct SegDims {
     // factor record (one stage): Z = [K (NU x NX) | d (NU) | Gt (NU x NX)], column-major
     static constexpr int NRHS = 2 * NX + 1;
     static constexpr int FREC = even_up(NU * NRHS);
+    // affine cache (one stage), kept for backward_without_factorization: [Quu^-1 (NU x NU) | P+c | F+c | F+B (NX x NU)]
+    static constexpr int AR_QI = 0, AR_PC = NU * NU, AR_FC = AR_PC + NX, AR_FB = AR_FC + NX;
+    static constexpr int AREC = even_up(AR_FB + NX * NU);
     // segment summary: [P | F | C | p | f]
     static constexpr int SUM_P = 0, SUM_F = NX * NX, SUM_C = 2 * NX * NX, SUM_p = 3 * NX * NX, SUM_f = 3 * NX * NX + NX;
     static constexpr int SREC = 3 * NX * NX + 2 * NX;
@@ -53,6 +56,15 @@ struct SegParams {
     double* fac;             // [batch][N][FREC]
     double* sum;             // [batch][S][SREC]
     int* status;             // [batch]
+    double* aff;             // [batch][N][AREC] affine cache, or nullptr (not kept)
+    // constraints (all nullptr / 0 when the problem has none)
+    const int* ncs;          // [N+1] rows per stage
+    const long long* coff;   // [N+2] prefix offsets of the constraint vectors
+    const long long* doff;   // [N+2] prefix offsets into the (16-byte padded) device copy of D
+    const double* Dm;        // [batch][d_total_dev]
+    long long d_total, nc_total;
+    int ncmax;
+    const double *ys, *zs, *rho, *inv_rho;   // [batch][nc_total]
     const double* xhat;      // [batch][S][NX]  (entry state of each segment; == x0 when S == 1)
     const double* uhat;      // [batch][S][NX]  (costate at each segment's exit)
     double* ws_out;          // [batch][N*S+NX]
@@ -95,9 +107,15 @@ struct BwdSmem {
     static constexpr int o_fn = o_pn + NX;
     static constexpr int o_dinv = o_fn + NX;
     static constexpr int o_wp = o_dinv + NU;
-    static constexpr int o_bar = even_up(o_wp + S);                 // 2 mbarriers
-    static constexpr int DOUBLES = o_bar + 2;
+    static constexpr int o_pc = o_wp + S;                           // P+ c   (NX)
+    static constexpr int o_qi = o_pc + NX;                          // Quu^-1 (NU x NU)
+    static constexpr int o_bar = even_up(o_qi + NU * NU);           // 2 mbarriers
+    static constexpr int DOUBLES = even_up(o_bar + 2);
     static constexpr size_t BYTES = (size_t)DOUBLES * 8;
+    // run-time tail (only when the problem has constraints): D[2][even(ncmax*S)] | rho[ncmax] | rho.*g[ncmax]
+    static size_t bytes(int ncmax) {
+        return BYTES + (ncmax > 0 ? (size_t)(2 * even_up(ncmax * S) + 2 * ncmax) * 8 : 0);
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -127,12 +145,23 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
     double* fn = smem + L::o_fn;
     double* dinv = smem + L::o_dinv;
     double* wp = smem + L::o_wp;
+    double* pc_s = smem + L::o_pc;
+    double* Qi = smem + L::o_qi;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::o_bar);
+    // run-time tail: constraint matrix ring + rho, rho.*g of the current stage
+    const int ncmax = p.ncmax;
+    const int DSTRIDE = even_up(ncmax * S);
+    double* Dbuf = smem + L::DOUBLES;
+    double* rho_s = Dbuf + 2 * DSTRIDE;
+    double* rg_s = rho_s + ncmax;
 
     const size_t ws_len = (size_t)p.N * S + NX;
     const double* model_b = p.model + (size_t)b * p.N * D::REC;
     const double* ws_b = p.ws_prev ? p.ws_prev + (size_t)b * ws_len : nullptr;
     double* fac_b = p.fac + (size_t)b * p.N * D::FREC;
+    double* aff_b = p.aff ? p.aff + (size_t)b * p.N * D::AREC : nullptr;
+    const double* D_b = ncmax > 0 ? p.Dm + (size_t)b * p.d_total : nullptr;
+    const size_t cbase = (size_t)b * p.nc_total;
     const double sigma = p.sigma;
 
     if (tid == 0) {
@@ -158,11 +187,34 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         pn[i] = pv;
         fn[i] = 0.0;
     }
-    group_sync<T>();
-    if (tid == 0 && LEN > 0) {
-        mbar_expect_tx(&bar[0], D::REC * 8);
-        bulk_g2s(rec, model_b + (size_t)(N1 - 1) * D::REC, D::REC * 8, &bar[0]);
+    if (is_last && ncmax > 0 && p.ncs[p.N] > 0) {
+        // terminal fold-in (lqr_kernel.hpp:82-87): P_N += D_N^T rho D_N ; p_N -= D_N^T (rho o (z - y/rho))
+        const int ncN = p.ncs[p.N];
+        const double* DN = D_b + p.doff[p.N];
+        const size_t co = cbase + p.coff[p.N];
+        group_sync<T>();
+        for (int e = tid; e < NX * NX; e += T) {
+            const int i = e % NX, j = e / NX;
+            double acc = 0.0;
+            for (int r = 0; r < ncN; ++r) acc = fma(DN[r + i * ncN] * p.rho[co + r], DN[r + j * ncN], acc);
+            PF[i + j * L::LDPF] += acc;
+        }
+        for (int i = tid; i < NX; i += T) {
+            double acc = 0.0;
+            for (int r = 0; r < ncN; ++r)
+                acc = fma(DN[r + i * ncN], p.rho[co + r] * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]), acc);
+            pn[i] -= acc;
+        }
     }
+    group_sync<T>();
+    auto issue_stage = [&](int kk, int bufi) {   // one elected thread: stage record (+ constraint matrix) of stage kk
+        const int nck = ncmax > 0 ? p.ncs[kk] : 0;
+        const uint32_t dbytes = (uint32_t)even_up(nck * S) * 8;
+        mbar_expect_tx(&bar[bufi], D::REC * 8 + dbytes);
+        bulk_g2s(rec + bufi * D::REC, model_b + (size_t)kk * D::REC, D::REC * 8, &bar[bufi]);
+        if (nck > 0) bulk_g2s(Dbuf + bufi * DSTRIDE, D_b + p.doff[kk], dbytes, &bar[bufi]);
+    };
+    if (tid == 0 && LEN > 0) issue_stage(N1 - 1, 0);
 
     int bad = 0;
 #pragma unroll 1
@@ -172,8 +224,16 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         const double* R = rec + buf * D::REC;
         if (tid == 0 && it + 1 < LEN) {  // prefetch stage k-1 (its buffer was last read before the previous sync)
             fence_proxy_async();
-            mbar_expect_tx(&bar[buf ^ 1], D::REC * 8);
-            bulk_g2s(rec + (buf ^ 1) * D::REC, model_b + (size_t)(k - 1) * D::REC, D::REC * 8, &bar[buf ^ 1]);
+            issue_stage(k - 1, buf ^ 1);
+        }
+        const int nck = ncmax > 0 ? p.ncs[k] : 0;
+        if (nck > 0) {  // g = z - y/rho ; keep rho and rho.*g   (lqr_solver_parallel.hpp:134-137, lqr_kernel.hpp:110)
+            const size_t co = cbase + p.coff[k];
+            for (int r = tid; r < nck; r += T) {
+                const double rr = p.rho[co + r];
+                rho_s[r] = rr;
+                rg_s[r] = rr * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]);
+            }
         }
         if (tid < S) wp[tid] = ws_b ? ws_b[(size_t)k * S + tid] : 0.0;
         if constexpr (S > T) {
@@ -195,7 +255,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
             auto la = [&](int i, int kk) { return PF[i + kk * L::LDPF]; };
             auto lb = [&](int kk, int j) { return ET[j + kk * L::LDT]; };
             auto epi = [&](int i, int j, double v) {
-                if (j == S && i < NX) v += pn[i];
+                if (j == S && i < NX) { pc_s[i] = v; v += pn[i]; }
                 PFE[i + j * L::LDPE] = v;
             };
             if (pdp) group_mm<MM, S + 1, NX, tl.tm, tl.tn, T>(tid, la, lb, epi);
@@ -218,6 +278,13 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 Ma[i + j * L::LDM] = base + v;
             };
             group_mm<S, S + 1, NX, tl.tm, tl.tn, T>(tid, la, lb, epi);
+            if (nck > 0) {  // M += D^T diag(rho) D ; g -= D^T (rho o g_c)      (lqr_kernel.hpp:106-112)
+                const double* Dk = Dbuf + buf * DSTRIDE;
+                auto lda = [&](int i, int r) { return Dk[r + i * nck]; };
+                auto ldb = [&](int r, int j) { return j < S ? rho_s[r] * Dk[r + j * nck] : -rg_s[r]; };
+                auto epd = [&](int i, int j, double v) { Ma[i + j * L::LDM] += v; };
+                group_mm_rt<S, S + 1, tl.tm, tl.tn, T>(tid, nck, lda, ldb, epd);
+            }
         }
         group_sync<T>();
 
@@ -229,15 +296,17 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
 
         // S5: one right-hand side per thread: y = Luu^-1 r, z = -Luu^-T y;  r in [Qux | Qu | (F+B)^T]
         {
-            const int nrhs = pdp ? D::NRHS : NX + 1;
-            for (int c = tid; c < nrhs; c += T) {
+            const int n1 = NX + 1, n2 = pdp ? NX : 0, n3 = aff_b ? NU : 0;
+            for (int q = tid; q < n1 + n2 + n3; q += T) {
+                const int c = (q < n1 + n2) ? q : D::NRHS + (q - n1 - n2);   // >= NRHS: unit vectors -> Quu^-1
                 double y[NU];
 #pragma unroll
                 for (int m = 0; m < NU; ++m) {
                     double r;
                     if (c < NX) r = Ma[(NU + c) + m * L::LDM];               // Qux(m,c) = Qxu(c,m)
                     else if (c == NX) r = Ma[m + S * L::LDM];                // Qu(m)
-                    else r = PFE[(NX + (c - NX - 1)) + m * L::LDPE];          // (F+ B)(c', m)
+                    else if (c < D::NRHS) r = PFE[(NX + (c - NX - 1)) + m * L::LDPE];   // (F+ B)(c', m)
+                    else r = (m == c - D::NRHS) ? 1.0 : 0.0;
                     y[m] = r;
                 }
 #pragma unroll
@@ -246,7 +315,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
 #pragma unroll
                     for (int q = 0; q < m; ++q) v -= Ma[m + q * L::LDM] * y[q];
                     y[m] = v * dinv[m];
-                    YT[c + m * L::LDY] = y[m];
+                    if (c < D::NRHS) YT[c + m * L::LDY] = y[m];
                 }
                 double z[NU];
 #pragma unroll
@@ -256,8 +325,13 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                     for (int q = m + 1; q < NU; ++q) v -= Ma[q + m * L::LDM] * z[q];
                     z[m] = v * dinv[m];
                 }
+                if (c < D::NRHS) {
 #pragma unroll
-                for (int m = 0; m < NU; ++m) Z[m + c * NU] = -z[m];
+                    for (int m = 0; m < NU; ++m) Z[m + c * NU] = -z[m];
+                } else {
+#pragma unroll
+                    for (int m = 0; m < NU; ++m) Qi[m + (c - D::NRHS) * NU] = z[m];
+                }
             }
         }
         group_sync<T>();
@@ -294,6 +368,16 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
             double* fk = fac_b + (size_t)k * D::FREC;
             const int nz = pdp ? NU * D::NRHS : NU * (NX + 1);
             for (int e = tid; e < nz; e += T) fk[e] = Z[e];
+            if (aff_b) {  // what backward_without_factorization needs: Quu^-1, P+c, F+c, F+B
+                double* ak = aff_b + (size_t)k * D::AREC;
+                for (int e = tid; e < NU * NU; e += T) ak[D::AR_QI + e] = Qi[e];
+                for (int i = tid; i < NX; i += T) {
+                    ak[D::AR_PC + i] = pc_s[i];
+                    if (pdp) ak[D::AR_FC + i] = PFE[(NX + i) + S * L::LDPE];
+                }
+                if (pdp)
+                    for (int e = tid; e < NX * NU; e += T) ak[D::AR_FB + e] = PFE[(NX + e % NX) + (e / NX) * L::LDPE];
+            }
         }
         group_sync<T>();
     }
@@ -311,6 +395,177 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         sm[D::SUM_f + i] = fn[i];
     }
     if (bad && tid == 0) atomicMax(&p.status[b], bad);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward without factorisation (affine-only re-solve with the cached K, Quu^-1, P+c, F+c, F+B):
+//     t = P+c + p+ ;  g = h~ + E^T t ;  d = -Quu^-1 g_u ;  p = g_x + K^T g_u ;  f = F+c + (F+B) d + f+
+// Replaces LQRKernel::step_without_factorization (lqr_kernel.hpp:149-178), ParallelLQRKernel::
+// step_without_factorization (lqr_kernel_parallel.hpp:138-168) and reduction_without_factorization
+// (lqr_solver_parallel.hpp:190-211).  One warp per (problem, segment); only d (inside Z) and the segment
+// summary's p, f change.
+template <int NX, int NU>
+struct AffSmem {
+    using D = SegDims<NX, NU>;
+    static constexpr int S = D::S;
+    static constexpr int o_rec = 0;                          // 2 x REC   (TMA)
+    static constexpr int o_fac = o_rec + 2 * D::REC;         // 2 x FREC  (TMA)
+    static constexpr int o_aff = o_fac + 2 * D::FREC;        // 2 x AREC  (TMA)
+    static constexpr int o_t = o_aff + 2 * D::AREC;          // t (NX)
+    static constexpr int o_g = o_t + NX;                     // g (S)
+    static constexpr int o_d = o_g + S;                      // d (NU)
+    static constexpr int o_pn = o_d + NU;
+    static constexpr int o_fn = o_pn + NX;
+    static constexpr int o_bar = even_up(o_fn + NX);
+    static constexpr int DOUBLES = even_up(o_bar + 2);
+    static constexpr size_t BYTES = (size_t)DOUBLES * 8;
+    static size_t bytes(int ncmax) {
+        return BYTES + (ncmax > 0 ? (size_t)(2 * even_up(ncmax * S) + ncmax) * 8 : 0);
+    }
+};
+
+template <int NX, int NU>
+__global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
+    using D = SegDims<NX, NU>;
+    using L = AffSmem<NX, NU>;
+    constexpr int S = D::S;
+    constexpr int T = 32;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    const int gidx = blockIdx.x;
+    const int b = gidx / p.S, seg = gidx % p.S;
+    const int N0 = p.seg_start[seg], LEN = p.seg_len[seg], N1 = N0 + LEN;
+    const bool is_last = (seg == p.S - 1);
+    const bool pdp = !is_last;
+
+    double* rec = smem + L::o_rec;
+    double* fac = smem + L::o_fac;
+    double* aff = smem + L::o_aff;
+    double* tv = smem + L::o_t;
+    double* gv = smem + L::o_g;
+    double* dv = smem + L::o_d;
+    double* pn = smem + L::o_pn;
+    double* fn = smem + L::o_fn;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::o_bar);
+    const int ncmax = p.ncmax;
+    const int DSTRIDE = even_up(ncmax * S);
+    double* Dbuf = smem + L::DOUBLES;
+    double* rg_s = Dbuf + 2 * DSTRIDE;
+
+    const size_t ws_len = (size_t)p.N * S + NX;
+    const double* model_b = p.model + (size_t)b * p.N * D::REC;
+    const double* ws_b = p.ws_prev ? p.ws_prev + (size_t)b * ws_len : nullptr;
+    double* fac_b = p.fac + (size_t)b * p.N * D::FREC;
+    const double* aff_b = p.aff + (size_t)b * p.N * D::AREC;
+    const double* D_b = ncmax > 0 ? p.Dm + (size_t)b * p.d_total : nullptr;
+    const size_t cbase = (size_t)b * p.nc_total;
+    const double sigma = p.sigma;
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        mbar_fence_init();
+    }
+    // terminal: p_N = h_N - sigma w_N - D_N^T (rho o g)   (lqr_kernel.hpp:93-101), zero for interior interfaces
+    for (int i = tid; i < NX; i += T) {
+        double pv = 0.0;
+        if (is_last) {
+            pv = p.hN[(size_t)b * NX + i] - (ws_b ? sigma * ws_b[(size_t)p.N * S + i] : 0.0);
+            if (ncmax > 0 && p.ncs[p.N] > 0) {
+                const int ncN = p.ncs[p.N];
+                const double* DN = D_b + p.doff[p.N];
+                const size_t co = cbase + p.coff[p.N];
+                double acc = 0.0;
+                for (int r = 0; r < ncN; ++r)
+                    acc = fma(DN[r + i * ncN], p.rho[co + r] * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]), acc);
+                pv -= acc;
+            }
+        }
+        pn[i] = pv;
+        fn[i] = 0.0;
+    }
+    __syncwarp();
+    auto issue_stage = [&](int kk, int bufi) {
+        const int nck = ncmax > 0 ? p.ncs[kk] : 0;
+        const uint32_t dbytes = (uint32_t)even_up(nck * S) * 8;
+        mbar_expect_tx(&bar[bufi], (D::REC + D::FREC + D::AREC) * 8 + dbytes);
+        bulk_g2s(rec + bufi * D::REC, model_b + (size_t)kk * D::REC, D::REC * 8, &bar[bufi]);
+        bulk_g2s(fac + bufi * D::FREC, fac_b + (size_t)kk * D::FREC, D::FREC * 8, &bar[bufi]);
+        bulk_g2s(aff + bufi * D::AREC, aff_b + (size_t)kk * D::AREC, D::AREC * 8, &bar[bufi]);
+        if (nck > 0) bulk_g2s(Dbuf + bufi * DSTRIDE, D_b + p.doff[kk], dbytes, &bar[bufi]);
+    };
+    if (tid == 0 && LEN > 0) issue_stage(N1 - 1, 0);
+#pragma unroll 1
+    for (int it = 0; it < LEN; ++it) {
+        const int k = N1 - 1 - it;
+        const int buf = it & 1;
+        const double* R = rec + buf * D::REC;
+        const double* Zk = fac + buf * D::FREC;
+        const double* Ak = aff + buf * D::AREC;
+        if (tid == 0 && it + 1 < LEN) {
+            fence_proxy_async();
+            issue_stage(k - 1, buf ^ 1);
+        }
+        const int nck = ncmax > 0 ? p.ncs[k] : 0;
+        if (nck > 0) {
+            const size_t co = cbase + p.coff[k];
+            for (int r = tid; r < nck; r += T)
+                rg_s[r] = p.rho[co + r] * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]);
+        }
+        double wpv[(S + T - 1) / T];
+#pragma unroll
+        for (int r = 0; r < (S + T - 1) / T; ++r) {
+            const int i = tid + r * T;
+            wpv[r] = (i < S && ws_b) ? ws_b[(size_t)k * S + i] : 0.0;
+        }
+        mbar_wait(&bar[buf], (it >> 1) & 1);
+        for (int i = tid; i < NX; i += T) tv[i] = Ak[D::AR_PC + i] + pn[i];
+        __syncwarp();
+        // g = h - sigma w - D^T (rho o g_c) + E^T t
+#pragma unroll
+        for (int r = 0; r < (S + T - 1) / T; ++r) {
+            const int i = tid + r * T;
+            if (i < S) {
+                double acc = R[D::REC_h + i] - sigma * wpv[r];
+                if (nck > 0) {
+                    const double* Dk = Dbuf + buf * DSTRIDE;
+                    for (int q = 0; q < nck; ++q) acc = fma(-Dk[q + i * nck], rg_s[q], acc);
+                }
+#pragma unroll 4
+                for (int q = 0; q < NX; ++q) acc = fma(R[q + i * NX], tv[q], acc);
+                gv[i] = acc;
+            }
+        }
+        __syncwarp();
+        // d = -Quu^-1 g_u
+        for (int m = tid; m < NU; m += T) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < NU; ++q) acc = fma(-Ak[D::AR_QI + m + q * NU], gv[q], acc);
+            dv[m] = acc;
+            fac_b[(size_t)k * D::FREC + NU * NX + m] = acc;   // the d slot of Z = [K | d | Gt]
+        }
+        __syncwarp();
+        // p = g_x + K^T g_u ;  f = F+c + (F+B) d + f+
+        for (int i = tid; i < NX; i += T) {
+            double acc = gv[NU + i];
+#pragma unroll
+            for (int m = 0; m < NU; ++m) acc = fma(Zk[m + i * NU], gv[m], acc);
+            pn[i] = acc;
+            if (pdp) {
+                double af = Ak[D::AR_FC + i] + fn[i];
+#pragma unroll
+                for (int m = 0; m < NU; ++m) af = fma(Ak[D::AR_FB + i + m * NX], dv[m], af);
+                fn[i] = af;
+            }
+        }
+        __syncwarp();
+    }
+    double* sm = p.sum + ((size_t)b * p.S + seg) * D::SREC;
+    for (int i = tid; i < NX; i += T) {
+        sm[D::SUM_p + i] = pn[i];
+        sm[D::SUM_f + i] = fn[i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

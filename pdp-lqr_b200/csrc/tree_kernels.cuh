@@ -172,17 +172,13 @@ __global__ void __launch_bounds__(32) tree_up_kernel(TreeParams p) {
         }
         // T1 = P_b X_F ; T2 = F_b X_C
         {
-            constexpr Tile tl = pick_tile(2 * NX, NX, 32);
-            auto la = [&](int r, int k) { return r < NX ? Pb[r + k * NX] : Fb[(r - NX) + k * NX]; };
+            constexpr Tile t1 = pick_tile(NX, NX, 32);
             auto lb = [&](int k, int c) { return XF[k + c * LDA]; };
             auto lb2 = [&](int k, int c) { return XC[k + c * LDA]; };
             auto e1 = [&](int r, int c, double v) { T1[r + c * NX] = v; };
             auto e2 = [&](int r, int c, double v) { T2[r + c * NX] = v; };
-            constexpr Tile t1 = pick_tile(NX, NX, 32);
-            (void)tl;
             auto laP = [&](int r, int k) { return Pb[r + k * NX]; };
             auto laF = [&](int r, int k) { return Fb[r + k * NX]; };
-            (void)la;
             group_mm<NX, NX, NX, t1.tm, t1.tn, 32>(lane, laP, lb, e1);
             group_mm<NX, NX, NX, t1.tm, t1.tn, 32>(lane, laF, lb2, e2);
         }
@@ -232,6 +228,83 @@ __global__ void __launch_bounds__(32) tree_up_kernel(TreeParams p) {
     if (p.sum_out) {
         double* out = p.sum_out + ((size_t)b * p.groups + g) * D::SREC;
         for (int e = lane; e < D::SREC; e += 32) out[e] = sb[e];
+    }
+}
+
+// Affine-only up-sweep (after backward_without_factorization): the members' p, f changed, their P, F, C and
+// hence X_F, X_C, P_b, F_b did not.  With W = I - X_C P_b:
+//     x_f = f_a - X_C (P_b f_a + p_b) ;  w_f = x_f + X_C p_b ;  p = p_a + F_a^T (P_b x_f + p_b) ;  f = F_b x_f + f_b
+// Replaces the (p, c)-only update_segment_data + condensed forward's first loop (condensed_system.hpp:76-80,
+// :106-118 / :197-201, :253-271).
+template <int NX>
+__global__ void __launch_bounds__(32) tree_up_affine_kernel(TreeParams p) {
+    using D = TreeDims<NX>;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x;
+    const int b = blockIdx.x / p.groups, g = blockIdx.x % p.groups;
+    const int first = g * p.R, last = min(first + p.R, p.count) - 1;
+    double* pb = smem;            // suffix p
+    double* fb = smem + NX;       // suffix f
+    double* t0 = smem + 2 * NX;   // P_b f_a + p_b
+    double* xf = smem + 3 * NX;
+    double* lv = smem + 4 * NX;
+    const double* in_b = p.sum_in + (size_t)b * p.count * D::SREC;
+    double* dd_b = p.dd + (size_t)b * p.count * D::DREC;
+    for (int r = lane; r < NX; r += 32) {
+        pb[r] = in_b[(size_t)last * D::SREC + D::SUM_p + r];
+        fb[r] = in_b[(size_t)last * D::SREC + D::SUM_f + r];
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int i = last - 1; i >= first; --i) {
+        const double* sa = in_b + (size_t)i * D::SREC;
+        double* ddi = dd_b + (size_t)i * D::DREC;
+        for (int r = lane; r < NX; r += 32) {
+            double acc = pb[r];
+#pragma unroll 4
+            for (int k = 0; k < NX; ++k) acc = fma(ddi[D::DD_PB + r + k * NX], sa[D::SUM_f + k], acc);
+            t0[r] = acc;
+        }
+        __syncwarp();
+        for (int r = lane; r < NX; r += 32) {
+            double acc = sa[D::SUM_f + r], accw = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < NX; ++k) {
+                acc = fma(-ddi[D::DD_XC + r + k * NX], t0[k], acc);
+                accw = fma(ddi[D::DD_XC + r + k * NX], pb[k], accw);
+            }
+            xf[r] = acc;
+            ddi[D::DD_wf + r] = acc + accw;
+            ddi[D::DD_pb + r] = pb[r];
+        }
+        __syncwarp();
+        for (int r = lane; r < NX; r += 32) {
+            double acc = pb[r];
+#pragma unroll 4
+            for (int k = 0; k < NX; ++k) acc = fma(ddi[D::DD_PB + r + k * NX], xf[k], acc);
+            lv[r] = acc;
+        }
+        __syncwarp();
+        double pnew = 0.0, fnew = 0.0;
+        for (int r = lane; r < NX; r += 32) {   // NX <= 32 rows per pass; results kept per lane
+            double ap = sa[D::SUM_p + r], af = fb[r];
+#pragma unroll 4
+            for (int k = 0; k < NX; ++k) {
+                ap = fma(sa[D::SUM_F + k + r * NX], lv[k], ap);
+                af = fma(ddi[D::DD_FB + r + k * NX], xf[k], af);
+            }
+            pnew = ap; fnew = af;
+        }
+        __syncwarp();
+        for (int r = lane; r < NX; r += 32) { pb[r] = pnew; fb[r] = fnew; }
+        __syncwarp();
+    }
+    if (p.sum_out) {
+        double* out = p.sum_out + ((size_t)b * p.groups + g) * D::SREC;
+        for (int r = lane; r < NX; r += 32) {
+            out[D::SUM_p + r] = pb[r];
+            out[D::SUM_f + r] = fb[r];
+        }
     }
 }
 

@@ -97,6 +97,9 @@ class LQRCudaSolver:
     def set_model_device(self, E, c, H, h, HN, hN, D=None):
         self._check(self._lib.pdplqr_set_model_device(self._h, *[_dptr(t) for t in (E, c, H, h, HN, hN)], _dptr(D)))
 
+    def set_option(self, option: int, value: int):
+        self._check(self._lib.pdplqr_set_option(self._h, option, value))
+
     def set_stream(self, cuda_stream_ptr: int):
         self._check(self._lib.pdplqr_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 

@@ -179,3 +179,107 @@ def test_device_pointer_variants_match_host_variants():
     torch.cuda.synchronize()
     _, ws = gpu_solve(p)
     assert np.array_equal(out.cpu().numpy(), ws)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# constraint fold-in (a2/a3 with nc > 0) and backward_without_factorization (a6)
+def _admm_vectors(p, seed):
+    rng = np.random.default_rng(seed)
+    nct = p.nc_total
+    ys = rng.standard_normal((p.batch, nct))
+    zs = rng.standard_normal((p.batch, nct))
+    rho = rng.uniform(0.05, 2.0, (p.batch, nct))
+    wprev = rng.standard_normal((p.batch, p.ws_len))
+    return wprev, ys, zs, rho, np.ascontiguousarray(1.0 / rho)
+
+
+@pytest.mark.parametrize("nx,nu,nc", [(4, 1, 3), (6, 3, 7), (12, 4, 16), (3, 2, 4), (30, 10, 44)])
+@pytest.mark.parametrize("S", [1, 3])
+def test_constraint_fold_in(oracle, nx, nu, nc, S):
+    """H += D^T rho D, h -= D^T (rho o (z - y/rho))  (lqr_kernel.hpp:106-112) incl. the terminal stage."""
+    from kkt_ref import kkt_solve
+    p = P.problems.random_lq(nx, nu, 12, batch=2, seed=100 + nx, nc=nc)
+    wprev, ys, zs, rho, inv_rho = _admm_vectors(p, 3)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=S)
+    sol.update_problem_data(wprev, ys, zs, inv_rho, sigma=1e-3)
+    sol.backward(rho)
+    ws = sol.forward(p.x0, np.zeros_like(wprev))
+    for b in range(p.batch):
+        o = oracle.OracleSolver(p, b=b)
+        o.update_problem_data(wprev[b], ys[b], zs[b], inv_rho[b], 1e-3)
+        o.backward(rho[b])
+        ref = o.forward(p.x0[b], np.zeros(p.ws_len))
+        assert rel_err(ws[b], ref) < TOL
+    assert rel_err(ws[0], kkt_solve(p, 0, wprev[0], 1e-3, ys[0], zs[0], rho[0], inv_rho[0])) < 1e-8
+
+
+def test_c1_with_box_constraints_enabled(oracle):
+    """The example with the constraints it disables by `nc = 0;` switched on (lqr_example.cpp:126-127,157-158):
+    ncs = (nu, nx+nu, ..., nx) -- ragged constraint counts, identity D, rho = 0.01."""
+    p = P.problems.quadrotor_example(constrained=True)
+    rng = np.random.default_rng(8)
+    nct = p.nc_total
+    ys, zs = 0.1 * rng.standard_normal((1, nct)), 0.1 * rng.standard_normal((1, nct))
+    rho = np.full((1, nct), 0.01)
+    inv_rho = np.full((1, nct), 100.0)
+    wprev = np.zeros((1, p.ws_len))
+    o = oracle.OracleSolver(p)
+    o.update_problem_data(wprev[0], ys[0], zs[0], inv_rho[0], 1e-6)
+    o.backward(rho[0])
+    ref = o.forward(p.x0[0], np.zeros(p.ws_len))
+    for S in (1, 4):
+        sol = P.LQRCudaSolver.from_problem(p, num_segments=S)
+        ws = sol.solve(wprev, p.x0, np.zeros_like(wprev), sigma=1e-6, ys=ys, zs=zs, rho=rho, inv_rho=inv_rho)
+        assert rel_err(ws[0], ref) < TOL
+
+
+@pytest.mark.parametrize("nx,nu,nc,S", [(6, 3, 5, 1), (6, 3, 5, 4), (12, 4, 8, 3), (12, 4, 0, 5), (4, 1, 0, 1), (30, 10, 12, 2)])
+def test_backward_without_factorization(oracle, nx, nu, nc, S):
+    """Affine-only re-solve with cached factors (lqr_kernel.hpp:149-178, lqr_solver_parallel.hpp:148-154, :190-211):
+    same protocol on the oracle and on the GPU; also against a fresh factorising solve of the second iterate."""
+    p = P.problems.random_lq(nx, nu, 20, batch=2, seed=7 + nx + S, nc=nc)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=S)
+    if nc == 0 and nx + nu > 8:
+        sol.set_option(P.capi.OPT_AFFINE_CACHE, 1)
+    its = []
+    for seed in (1, 2, 3):
+        if nc > 0:
+            its.append(_admm_vectors(p, seed))
+        else:
+            its.append((np.random.default_rng(seed).standard_normal((p.batch, p.ws_len)), None, None, None, None))
+    rho = its[0][3]
+    outs = []
+    for i, (w, y, z, _, _) in enumerate(its):
+        inv = None if rho is None else np.ascontiguousarray(1.0 / rho)
+        sol.update_problem_data(w, y, z, inv, sigma=1e-2)
+        if i == 0:
+            sol.backward(rho)
+        else:
+            sol.backward_without_factorization(rho)
+        outs.append(sol.forward(p.x0, np.zeros_like(w)).copy())
+    for b in range(p.batch):
+        o = oracle.OracleSolver(p, b=b, parallel=S > 1, num_segments=S, condensed=oracle.LU)
+        for i, (w, y, z, _, _) in enumerate(its):
+            inv = None if rho is None else 1.0 / rho[b]
+            o.update_problem_data(w[b], None if y is None else y[b], None if z is None else z[b], inv, 1e-2)
+            if i == 0:
+                o.backward(None if rho is None else rho[b])
+            else:
+                o.backward_without_factorization(None if rho is None else rho[b])
+            ref = o.forward(p.x0[b], np.zeros(p.ws_len))
+            assert rel_err(outs[i][b], ref) < TOL, (i, b)
+    # a fresh factorising solve of the last iterate gives the same trajectory
+    w, y, z, _, _ = its[-1]
+    sol2 = P.LQRCudaSolver.from_problem(p, num_segments=S)
+    inv = None if rho is None else np.ascontiguousarray(1.0 / rho)
+    ws2 = sol2.solve(w, p.x0, np.zeros_like(w), sigma=1e-2, ys=y, zs=z, rho=rho, inv_rho=inv)
+    assert rel_err(outs[-1], ws2) < TOL
+
+
+def test_nofact_before_backward_is_an_order_error():
+    p = P.problems.random_lq(6, 3, 10, seed=1)
+    sol = P.LQRCudaSolver.from_problem(p)
+    sol.update_problem_data(p.zeros_ws(), sigma=1e-6)
+    with pytest.raises(P.PdplqrError) as e:
+        sol.backward_without_factorization()
+    assert e.value.code == P.capi.ERR_ORDER
