@@ -72,8 +72,9 @@ def algorithmic_bytes_per_stage(nx, nu, pdp: bool):
 
 # --------------------------------------------------------------------------------------------- helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms from before the warm-up until the last timed loop
+    (B200_PROFILING.md recipe); `summary(windows)` keeps the samples that fall inside the timed windows."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -81,11 +82,12 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                       "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "50", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
-    def stop(self):
+    def summary(self, windows):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
@@ -96,22 +98,26 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 9:
                 continue
             try:
-                sm.append(float(parts[1])); mx.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]),
+                             [n for n, v in zip(names, parts[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
         os.unlink(self.f.name)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if any(a - 0.03 <= r[0] <= b + 0.03 for a, b in windows)]
+        if not inside and rows:   # timed windows shorter than the sampling period: nearest samples under load
+            lo, hi = min(a for a, _ in windows), max(b for _, b in windows)
+            inside = [r for r in rows if lo - 0.25 <= r[0] <= hi + 0.25]
+        if inside:
+            out.update(sm_mhz=statistics.median(r[1] for r in inside), sm_max_mhz=max(r[2] for r in inside),
+                       reasons=sorted({n for r in inside for n in r[3]}), samples=len(inside))
         return out
 
 
@@ -188,7 +194,7 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--impl", default="b200")
@@ -214,6 +220,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    sampler = ClockSampler(local_rank)
+    windows = []
     prob, kw, desc = make_workload(args.workload, rank)
     sol = P.LQRCudaSolver.from_problem(prob, device=local_rank, **kw)
     stream = torch.cuda.current_stream()
@@ -245,7 +253,7 @@ def main():
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
+    t_w0 = time.time()
     l0 = sol.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -255,11 +263,12 @@ def main():
     barrier()
     launches = sol.launch_count() - l0
     ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
+    windows.append((t_w0, time.time()))
     bad, _ = sol.last_status()
 
     # dominant kernel alone (backward sweep): CUDA events around back-to-back launches on the same stream
     kb = max(5, args.steps)
+    t_w0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l_b0 = sol.launch_count()
     e0.record(stream)
@@ -270,6 +279,7 @@ def main():
     torch.cuda.synchronize()
     bwd_launches = (sol.launch_count() - l_b0) // kb
     ms_bwd = e0.elapsed_time(e1) / kb
+    windows.append((t_w0, time.time()))
     # leave the handle in a consistent state (one forward per backward)
     sol.forward_device(x0_dev, out_dev)
     torch.cuda.synchronize()
@@ -284,6 +294,8 @@ def main():
         sol.solve(ws_np, x0_np, out_np, sigma=sigma)
     torch.cuda.synchronize()
     t_e2e = (time.perf_counter() - t0) / e2e_steps
+    windows.append((time.time() - t_e2e * e2e_steps, time.time()))
+    clocks = sampler.summary(windows)
     same = bool(np.array_equal(out_np, out_dev.cpu().numpy()))
 
     t = torch.tensor([ms_total, t_e2e * 1e3, ms_bwd], dtype=torch.float64, device=dev)
@@ -313,7 +325,8 @@ def main():
                        "num_segments": sol.num_segments, "sigma": sigma,
                        "l2": "inputs larger than L2 (model records %.2f GB per GPU)" % (B * N * sol.record_doubles()[0] * 8 / 1e9),
                        "sharding": "independent problems per rank, no data-path collective"},
-            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
+                       "samples": clocks["samples"]},
             "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(ws_host.numel() * 8 + x0_host.numel() * 8),
                     "d2h_bytes_per_step": int(out_host.numel() * 8), "ms_per_step": ms_e2e,
@@ -327,7 +340,7 @@ def main():
                          "step_hbm_frac": (bwd_b + fwd_b) * B * N / (ms_step * 1e-3) / 1e9 / peak},
             "non_pd_problems": int(bad),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             v, cores, sample = cpu_baseline(prob)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)

@@ -1,0 +1,45 @@
+"""The C++17 host class lqr::LQRCudaSolver (include/pdplqr/lqr_cuda_solver.hpp) mirrors the reference's solver
+interface on top of the C ABI.  CPU: the example driver compiles and links against libpdplqr.so and fails loudly
+without a GPU.  GPU: it reproduces config 1 (examples/lqr_example.cpp as shipped) to 1e-9."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import pdplqr_b200 as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "examples", "lqr_example_bin")
+
+
+def _compile():
+    libdir = os.path.dirname(P.capi.lib_path())
+    P.capi.load()
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "lqr_example.cpp"), "-L" + libdir, "-lpdplqr",
+                           "-Wl,-rpath," + libdir, "-o", EXE])
+
+
+def test_cpp_example_compiles_and_has_no_cpu_fallback():
+    import torch
+    _compile()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    r = subprocess.run([EXE], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_example_reproduces_config1():
+    _compile()
+    r = subprocess.run([EXE], capture_output=True, text=True, check=True)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "c1_quadrotor.npz"))
+    lines = r.stdout.strip().splitlines()
+    assert len(lines) == 6
+    for k in range(5):
+        u = np.array([float(v) for v in re.findall(r"-?\d+\.\d+", lines[k].split(":")[1])])
+        assert np.max(np.abs(u - g["ws_seq"][k * 16:k * 16 + 4])) < 1e-9
+    xN = np.array([float(v) for v in lines[5].split(":")[1].split()])
+    assert np.max(np.abs(xN - g["ws_seq"][-12:])) < 1e-9
