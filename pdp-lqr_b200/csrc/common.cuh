@@ -141,6 +141,44 @@ PDPLQR_DEVINL void group_mm_rt(int tid, int K, LA la, LB lb, EPI epi) {
     }
 }
 
+// G products of identical shape in ONE pass (tiles of all G products dealt to the group together, so that no
+// lane idles between small products):  C_g(i,j) = epi(g, i, j, sum_k A_g(i,k) B_g(k,j)).
+template <int G, int M, int N, int K, int TM, int TN, int T, class LA, class LB, class EPI>
+PDPLQR_DEVINL void group_mm_multi(int tid, LA la, LB lb, EPI epi) {
+    constexpr int MT = (M + TM - 1) / TM;
+    constexpr int NT = (N + TN - 1) / TN;
+    constexpr int TILES = MT * NT;
+    constexpr bool FULL_M = (M % TM) == 0, FULL_N = (N % TN) == 0;
+#pragma unroll 1
+    for (int t = tid; t < G * TILES; t += T) {
+        const int g = t / TILES, tl = t - g * TILES;
+        const int ti = tl % MT, tj = tl / MT;
+        const int i0 = ti * TM, j0 = tj * TN;
+        double acc[TM][TN];
+#pragma unroll
+        for (int r = 0; r < TM; ++r)
+#pragma unroll
+            for (int c = 0; c < TN; ++c) acc[r][c] = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            double av[TM], bv[TN];
+#pragma unroll
+            for (int r = 0; r < TM; ++r) av[r] = la(g, FULL_M ? i0 + r : min(i0 + r, M - 1), k);
+#pragma unroll
+            for (int c = 0; c < TN; ++c) bv[c] = lb(g, k, FULL_N ? j0 + c : min(j0 + c, N - 1));
+#pragma unroll
+            for (int r = 0; r < TM; ++r)
+#pragma unroll
+                for (int c = 0; c < TN; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+        }
+#pragma unroll
+        for (int r = 0; r < TM; ++r)
+#pragma unroll
+            for (int c = 0; c < TN; ++c)
+                if ((FULL_M || i0 + r < M) && (FULL_N || j0 + c < N)) epi(g, i0 + r, j0 + c, acc[r][c]);
+    }
+}
+
 // Cholesky of the leading NU x NU block of a column-major matrix in shared memory (leading dimension ld),
 // right-looking, cooperative over the group.  On exit the lower triangle holds L and dinv[k] = 1 / L(k,k).
 // Returns (to every thread) 0 or the 1-based index of the first non-positive pivot (factorisation continues

@@ -20,6 +20,7 @@ namespace {
 struct TreeLevel {
     int count, R, groups;
     double *sum, *dd, *x, *lam;  // sum/x/lam of level 0 alias the segment arrays
+    bool in_top;                 // handled inside the single-launch top kernels (binary)
 };
 
 struct Ops;
@@ -79,6 +80,8 @@ struct Ops {
     int (*tree_down)(Solver&, const TreeParams&);
     int (*affine)(Solver&);
     int (*tree_up_affine)(Solver&, const TreeParams&);
+    int (*tree_top_up)(Solver&, const TreeTopParams&);
+    int (*tree_top_down)(Solver&, const TreeTopParams&);
 };
 
 int fail(Solver* h, int code, const std::string& msg) {
@@ -233,13 +236,33 @@ int tree_up_affine_impl(Solver& h, const TreeParams& p) {
     return PDPLQR_OK;
 }
 
+template <int NX>
+int tree_top_up_impl(Solver& h, const TreeTopParams& p) {
+    auto kern = tree_top_up_kernel<NX>;
+    constexpr size_t bytes = TreeTopSmem<NX>::BYTES;
+    int rc = set_smem(h, kern, bytes);
+    if (rc) return rc;
+    kern<<<p.batch, TreeTopSmem<NX>::WARPS * 32, bytes, h.stream>>>(p);
+    h.launches++;
+    CU_TRY(&h, cudaGetLastError());
+    return PDPLQR_OK;
+}
+template <int NX>
+int tree_top_down_impl(Solver& h, const TreeTopParams& p) {
+    auto kern = tree_top_down_kernel<NX>;
+    kern<<<p.batch, TreeTopSmem<NX>::WARPS * 32, TreeTopSmem<NX>::WARPS * 4 * NX * sizeof(double), h.stream>>>(p);
+    h.launches++;
+    CU_TRY(&h, cudaGetLastError());
+    return PDPLQR_OK;
+}
+
 template <int NX, int NU, int T>
 constexpr Ops make_ops() {
     return Ops{NX, NU, T, SegDims<NX, NU>::REC, SegDims<NX, NU>::FREC, SegDims<NX, NU>::SREC, TreeDims<NX>::DREC,
                BatchDims<NX, NU>::FRECT, BatchDims<NX, NU>::TREC, SegDims<NX, NU>::AREC,
                BatchDims<NX, NU>::ENABLED,
                &backward_impl<NX, NU, T>, &forward_impl<NX, NU, T>, &tree_up_impl<NX>, &tree_down_impl<NX>,
-               &affine_impl<NX, NU>, &tree_up_affine_impl<NX>};
+               &affine_impl<NX, NU>, &tree_up_affine_impl<NX>, &tree_top_up_impl<NX>, &tree_top_down_impl<NX>};
 }
 
 // Instantiated (nx, nu) pairs.  The BASELINE.json configs use (12,4), (4,1) and (30,10); the rest cover the
@@ -355,6 +378,32 @@ int set_model_common(Solver& h, const double* E, const double* c, const double* 
     return PDPLQR_OK;
 }
 
+TreeTopParams top_params(Solver& h, const double* d_x0, bool affine_only) {
+    TreeTopParams tp{};
+    tp.batch = h.batch; tp.x0 = d_x0; tp.affine_only = affine_only ? 1 : 0;
+    for (TreeLevel& lv : h.levels)
+        if (lv.in_top) {
+            const int i = tp.nlevels++;
+            tp.count[i] = lv.count; tp.sum[i] = lv.sum; tp.dd[i] = lv.dd; tp.x[i] = lv.x; tp.lam[i] = lv.lam;
+        }
+    return tp;
+}
+
+// up-sweep of the interface tree: one launch per lower level, then one launch for all upper (binary) levels
+int run_tree_up(Solver& h, bool affine_only) {
+    for (size_t l = 0; l < h.levels.size(); ++l) {
+        TreeLevel& lv = h.levels[l];
+        if (lv.in_top) break;
+        TreeParams tp{};
+        tp.batch = h.batch; tp.count = lv.count; tp.R = lv.R; tp.groups = lv.groups;
+        tp.sum_in = lv.sum; tp.dd = lv.dd;
+        tp.sum_out = h.levels[l + 1].sum;
+        int rc = affine_only ? h.ops->tree_up_affine(h, tp) : h.ops->tree_up(h, tp);
+        if (rc) return rc;
+    }
+    return h.ops->tree_top_up(h, top_params(h, nullptr, affine_only));
+}
+
 int run_backward(Solver& h) {
     if (!h.model_set) return fail(&h, PDPLQR_ERR_ORDER, "backward before set_model");
     if (!h.updated) return fail(&h, PDPLQR_ERR_ORDER, "backward before update_problem_data (lqr_solver_parallel.hpp:115)");
@@ -362,15 +411,8 @@ int run_backward(Solver& h) {
     int rc = h.ops->backward(h);
     if (rc) return rc;
     if (h.S > 1) {
-        for (size_t l = 0; l < h.levels.size(); ++l) {
-            TreeLevel& lv = h.levels[l];
-            TreeParams tp{};
-            tp.batch = h.batch; tp.count = lv.count; tp.R = lv.R; tp.groups = lv.groups;
-            tp.sum_in = lv.sum; tp.dd = lv.dd;
-            tp.sum_out = (l + 1 < h.levels.size()) ? h.levels[l + 1].sum : nullptr;
-            rc = h.ops->tree_up(h, tp);
-            if (rc) return rc;
-        }
+        rc = run_tree_up(h, false);
+        if (rc) return rc;
     }
     h.updated = false;  // backward consumes the staged data (in-place accumulation in the reference)
     h.factorized = true;
@@ -389,15 +431,8 @@ int run_backward_nofact(Solver& h) {
     int rc = h.ops->affine(h);
     if (rc) return rc;
     if (h.S > 1) {
-        for (size_t l = 0; l < h.levels.size(); ++l) {
-            TreeLevel& lv = h.levels[l];
-            TreeParams tp{};
-            tp.batch = h.batch; tp.count = lv.count; tp.R = lv.R; tp.groups = lv.groups;
-            tp.sum_in = lv.sum; tp.dd = lv.dd;
-            tp.sum_out = (l + 1 < h.levels.size()) ? h.levels[l + 1].sum : nullptr;
-            rc = h.ops->tree_up_affine(h, tp);
-            if (rc) return rc;
-        }
+        rc = run_tree_up(h, true);
+        if (rc) return rc;
     }
     h.updated = false;
     h.backward_done = true;
@@ -407,16 +442,18 @@ int run_backward_nofact(Solver& h) {
 int run_forward(Solver& h, const double* d_x0, double* d_ws_out) {
     if (!h.backward_done) return fail(&h, PDPLQR_ERR_ORDER, "forward before backward (one forward per backward)");
     if (h.S > 1) {
+        int rc = h.ops->tree_top_down(h, top_params(h, d_x0, false));
+        if (rc) return rc;
         for (int l = (int)h.levels.size() - 1; l >= 0; --l) {
             TreeLevel& lv = h.levels[l];
-            const bool top = (l + 1 == (int)h.levels.size());
+            if (lv.in_top) continue;
             TreeParams tp{};
             tp.batch = h.batch; tp.count = lv.count; tp.R = lv.R; tp.groups = lv.groups;
             tp.dd = lv.dd;
-            tp.x_parent = top ? d_x0 : h.levels[l + 1].x;
-            tp.lam_parent = top ? nullptr : h.levels[l + 1].lam;
+            tp.x_parent = h.levels[l + 1].x;
+            tp.lam_parent = h.levels[l + 1].lam;
             tp.x_node = lv.x; tp.lam_node = lv.lam;
-            int rc = h.ops->tree_down(h, tp);
+            rc = h.ops->tree_down(h, tp);
             if (rc) return rc;
         }
     }
@@ -537,14 +574,15 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     cudaMemset(h->d_uhat, 0, B * S * nx * sizeof(double));
     cudaMemset(h->d_status, 0, B * sizeof(int));
 
-    // ---- interface tree plan
+    // ---- interface tree plan: lower levels (one launch each, fan-in 4) until <= 32 nodes, then binary levels
+    //      that all run inside one launch (tree_top_*_kernel); the last level is the root (1 node)
     if (S > 1) {
-        const int RTOP = 12, RGRP = 8;
         int cnt = S;
         for (int l = 0;; ++l) {
             TreeLevel lv{};
             lv.count = cnt;
-            lv.R = (cnt <= RTOP) ? cnt : RGRP;
+            lv.in_top = cnt <= TREE_TOP_MAX_NODES;
+            lv.R = lv.in_top ? 2 : 4;
             lv.groups = (cnt + lv.R - 1) / lv.R;
             if (l == 0) { lv.sum = h->d_sum; lv.x = h->d_xhat; lv.lam = h->d_uhat; }
             else {
@@ -554,7 +592,7 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
             }
             rc |= dev_alloc(*h, &lv.dd, B * cnt * ops->DREC);
             h->levels.push_back(lv);
-            if (lv.groups == 1) break;
+            if (cnt == 1) break;
             cnt = lv.groups;
         }
         if (rc) return bail(PDPLQR_ERR_CUDA);

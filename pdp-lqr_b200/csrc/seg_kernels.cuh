@@ -215,6 +215,20 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         if (nck > 0) bulk_g2s(Dbuf + bufi * DSTRIDE, D_b + p.doff[kk], dbytes, &bar[bufi]);
     };
     if (tid == 0 && LEN > 0) issue_stage(N1 - 1, 0);
+    // ET(j,k') = Ea(k',j), Ea = [E c]  ((S+1) x NX, odd leading dimension -> conflict-free GEMM operands).  The
+    // transposition of stage k-1 is done in the last phase of stage k, so a stage costs four barriers.
+    auto transpose_stage = [&](int bufi) {
+        const double* Rn = rec + bufi * D::REC;
+        for (int e = tid; e < NX * (S + 1); e += T) {
+            const int kk = e % NX, j = e / NX;
+            ET[j + kk * L::LDT] = Rn[e];
+        }
+    };
+    if (LEN > 0) {
+        mbar_wait(&bar[0], 0);
+        transpose_stage(0);
+    }
+    group_sync<T>();
 
     int bad = 0;
 #pragma unroll 1
@@ -239,15 +253,6 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         if constexpr (S > T) {
             for (int i = tid + T; i < S; i += T) wp[i] = ws_b ? ws_b[(size_t)k * S + i] : 0.0;
         }
-        mbar_wait(&bar[buf], (it >> 1) & 1);
-
-        // T0: ET(j,k') = Ea(k',j), Ea = [E c]  ((S+1) x NX, odd leading dimension -> conflict-free operands)
-        for (int e = tid; e < NX * (S + 1); e += T) {
-            const int kk = e % NX, j = e / NX;
-            ET[j + kk * L::LDT] = R[e];
-        }
-        group_sync<T>();
-
         // S2: PFE = [P+; F+] * [E c]  (+ p+ on the last column of the P rows)
         {
             constexpr int MM = 2 * NX;
@@ -288,15 +293,45 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         }
         group_sync<T>();
 
-        // S4: Luu = chol(Quu) in place (leading NU x NU block of Ma)
-        {
+        // S4: Luu = chol(Quu).  Small NU: every solving thread factorises its own register copy (no barriers);
+        //     larger NU: cooperative in-place factorisation of the leading block of Ma.
+        constexpr bool REG_CHOL = NU <= 8;
+        double Lr[REG_CHOL ? NU : 1][REG_CHOL ? NU : 1];
+        double dr[REG_CHOL ? NU : 1];
+        const int n1 = NX + 1, n2 = pdp ? NX : 0, n3 = aff_b ? NU : 0;
+        if constexpr (REG_CHOL) {
+            if (tid < n1 + n2 + n3) {
+#pragma unroll
+                for (int j = 0; j < NU; ++j)
+#pragma unroll
+                    for (int i = j; i < NU; ++i) Lr[i][j] = Ma[i + j * L::LDM];
+#pragma unroll
+                for (int c = 0; c < NU; ++c) {
+                    double a = Lr[c][c];
+#pragma unroll
+                    for (int q = 0; q < c; ++q) a = fma(-Lr[c][q], Lr[c][q], a);
+                    if (!(a > 0.0)) { if (!bad) bad = k + 1; a = fabs(a) + 1e-300; }
+                    const double r = rsqrt(a);
+                    dr[c] = r;
+                    Lr[c][c] = a * r;
+#pragma unroll
+                    for (int i = c + 1; i < NU; ++i) {
+                        double v = Lr[i][c];
+#pragma unroll
+                        for (int q = 0; q < c; ++q) v = fma(-Lr[i][q], Lr[c][q], v);
+                        Lr[i][c] = v * r;
+                    }
+                }
+            }
+        } else {
             const int info = group_chol<NU, T>(tid, Ma, L::LDM, dinv);
             if (info && !bad) bad = k + 1;
         }
+        auto Lel = [&](int i, int j) { if constexpr (REG_CHOL) return Lr[i][j]; else return Ma[i + j * L::LDM]; };
+        auto Dinv = [&](int m) { if constexpr (REG_CHOL) return dr[m]; else return dinv[m]; };
 
         // S5: one right-hand side per thread: y = Luu^-1 r, z = -Luu^-T y;  r in [Qux | Qu | (F+B)^T]
         {
-            const int n1 = NX + 1, n2 = pdp ? NX : 0, n3 = aff_b ? NU : 0;
             for (int q = tid; q < n1 + n2 + n3; q += T) {
                 const int c = (q < n1 + n2) ? q : D::NRHS + (q - n1 - n2);   // >= NRHS: unit vectors -> Quu^-1
                 double y[NU];
@@ -313,8 +348,8 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 for (int m = 0; m < NU; ++m) {
                     double v = y[m];
 #pragma unroll
-                    for (int q = 0; q < m; ++q) v -= Ma[m + q * L::LDM] * y[q];
-                    y[m] = v * dinv[m];
+                    for (int q = 0; q < m; ++q) v = fma(-Lel(m, q), y[q], v);
+                    y[m] = v * Dinv(m);
                     if (c < D::NRHS) YT[c + m * L::LDY] = y[m];
                 }
                 double z[NU];
@@ -322,8 +357,8 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 for (int m = NU - 1; m >= 0; --m) {
                     double v = y[m];
 #pragma unroll
-                    for (int q = m + 1; q < NU; ++q) v -= Ma[q + m * L::LDM] * z[q];
-                    z[m] = v * dinv[m];
+                    for (int q = m + 1; q < NU; ++q) v = fma(-Lel(q, m), z[q], v);
+                    z[m] = v * Dinv(m);
                 }
                 if (c < D::NRHS) {
 #pragma unroll
@@ -378,6 +413,10 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 if (pdp)
                     for (int e = tid; e < NX * NU; e += T) ak[D::AR_FB + e] = PFE[(NX + e % NX) + (e / NX) * L::LDPE];
             }
+        }
+        if (it + 1 < LEN) {  // the next stage's record was prefetched at the top of this stage: transpose it now
+            mbar_wait(&bar[buf ^ 1], ((it + 1) >> 1) & 1);
+            transpose_stage(buf ^ 1);
         }
         group_sync<T>();
     }

@@ -14,11 +14,14 @@
 //        F = F_b X_F                  f = F_b x_f + f_b               C = C_b + F_b X_C F_b^T
 // (the true-terminal segment has F = 0, f = 0, C = 0, i.e. it is a pure value function).
 //
-// Up-sweep (one warp per group of R consecutive nodes of a level): fold the group right-to-left, keeping for
-// every member i the data the down-sweep needs: X_F, X_C, w_f of the fold step and (P_b, F_b, p_b) of the
-// suffix b = (i+1 .. end of group).  The group total becomes a node of the next level.
+// Up-sweep: groups of R consecutive nodes of a level are folded right-to-left, keeping for every member i the
+// data the down-sweep needs: X_F, X_C, w_f of the fold step and (P_b, F_b, p_b) of the suffix b = (i+1 .. end of
+// group).  The group total becomes a node of the next level.
 // Down-sweep: given the group's entry state x and exit costate lam_e, left-to-right
 //        pt = p_b + F_b^T lam_e ;  x' = X_F x + w_f - X_C pt ;  lam' = P_b x' + pt .
+// Lower levels (many nodes) run one kernel launch per level, one warp per group; the upper levels (<= 32 nodes)
+// run inside ONE launch of a 16-warp CTA per problem (binary tree, __syncthreads between levels), because for a
+// single long-horizon problem the interface solve is pure latency.
 #pragma once
 #include "common.cuh"
 #include "seg_kernels.cuh"
@@ -52,176 +55,282 @@ struct TreeParams {
     double* lam_node;          // [batch][count][NX]
 };
 
+constexpr int TREE_TOP_MAX_LEVELS = 8;
+constexpr int TREE_TOP_MAX_NODES = 32;
+struct TreeTopParams {   // the upper, binary part of the tree: levels[0] is the widest (<= 32 nodes)
+    int batch, nlevels;
+    int count[TREE_TOP_MAX_LEVELS];
+    double* sum[TREE_TOP_MAX_LEVELS];
+    double* dd[TREE_TOP_MAX_LEVELS];
+    double* x[TREE_TOP_MAX_LEVELS];
+    double* lam[TREE_TOP_MAX_LEVELS];
+    const double* x0;      // [batch][NX]
+    int affine_only;
+};
+
 // Gauss-Jordan with partial (row) pivoting on an NX x NCOL augmented matrix in shared memory, one warp.
 // Columns are owned by lanes (column j -> lane j % 32).  On exit columns NX.. hold A^-1 * RHS.
+// The pivot search is redundant per lane (broadcast reads of column k) instead of a shuffle reduction.
 template <int NX, int NCOL, int LDA>
 PDPLQR_DEVINL void warp_gauss_jordan(int lane, double* Aug) {
 #pragma unroll 1
     for (int k = 0; k < NX; ++k) {
-        // pivot search in column k, rows k..NX-1
+        double colk[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) colk[i] = Aug[i + k * LDA];
         double best = -1.0;
         int piv = k;
-        for (int i = k + lane; i < NX; i += 32) {
-            const double v = fabs(Aug[i + k * LDA]);
-            if (v > best) { best = v; piv = i; }
-        }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-            const int op = __shfl_xor_sync(0xffffffffu, piv, off);
-            if (ob > best || (ob == best && op < piv)) { best = ob; piv = op; }
+        for (int i = 0; i < NX; ++i) {
+            const double v = fabs(colk[i]);
+            if (i >= k && v > best) { best = v; piv = i; }
         }
-        // row swap (each lane in its own columns)
-        if (piv != k) {
-            for (int j = k + lane; j < NCOL; j += 32) {
-                const double t = Aug[k + j * LDA];
-                Aug[k + j * LDA] = Aug[piv + j * LDA];
-                Aug[piv + j * LDA] = t;
-            }
+        double pval = 1.0, ck = 0.0;   // selects instead of run-time register indexing
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            if (i == piv) pval = colk[i];
+            if (i == k) ck = colk[i];
         }
-        __syncwarp();
-        const double pinv = 1.0 / Aug[k + k * LDA];
+        const double pinv = 1.0 / pval;
+        // after the swap, row k holds the old row piv and row piv the old row k
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+            if (i == piv) colk[i] = ck;
         for (int j = k + 1 + lane; j < NCOL; j += 32) {
-            const double t = Aug[k + j * LDA] * pinv;
-            Aug[k + j * LDA] = t;
-#pragma unroll 4
-            for (int i = 0; i < NX; ++i)
-                if (i != k) Aug[i + j * LDA] = fma(-Aug[i + k * LDA], t, Aug[i + j * LDA]);
+            double* cj = Aug + j * LDA;
+            const double akj = cj[piv];
+            if (piv != k) cj[piv] = cj[k];
+            const double t = akj * pinv;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) {
+                if (i == k) cj[i] = t;
+                else cj[i] = fma(-colk[i], t, cj[i]);
+            }
         }
         __syncwarp();
     }
 }
 
 template <int NX>
-struct TreeSmem {
+struct CombSmem {   // per-warp workspace of one combine
     using D = TreeDims<NX>;
-    static constexpr int o_a = 0;                     // member summary a (SREC)
-    static constexpr int o_b = o_a + D::SREC;         // suffix summary b (SREC)
-    static constexpr int o_n = o_b + D::SREC;         // new suffix (SREC)
-    static constexpr int o_aug = o_n + D::SREC;       // LDA x NCOL
-    static constexpr int o_t1 = o_aug + D::LDA * D::NCOL;   // P_b X_F  (N2)
-    static constexpr int o_t2 = o_t1 + D::N2;               // F_b X_C  (N2)
-    static constexpr int o_v = o_t2 + D::N2;                // x_f, P_b x_f + p_b   (2 NX)
-    static constexpr int DOUBLES = o_v + 2 * NX;
-    static constexpr size_t BYTES = (size_t)DOUBLES * 8;
+    static constexpr int o_a = 0;                            // member summary a (SREC)
+    static constexpr int o_b = o_a + D::SREC;                // suffix summary b (SREC)
+    static constexpr int o_aug = o_b + D::SREC;              // LDA x NCOL
+    static constexpr int o_t1 = o_aug + D::LDA * D::NCOL;    // P_b X_F  (N2)
+    static constexpr int o_t2 = o_t1 + D::N2;                // F_b X_C  (N2)
+    static constexpr int o_v = o_t2 + D::N2;                 // x_f, P_b x_f + p_b   (2 NX)
+    static constexpr int DOUBLES = even_up(o_v + 2 * NX);
+};
+
+// One combine step by one warp.  a, b: summaries in shared memory (ws + o_a / o_b).  Writes the combined summary to
+// `out` (shared or global) and the down-sweep record of member a to `ddi` (global).
+template <int NX>
+PDPLQR_DEVINL void warp_combine(int lane, double* ws, double* out, double* ddi) {
+    using D = TreeDims<NX>;
+    using L = CombSmem<NX>;
+    constexpr int N2 = D::N2, LDA = D::LDA;
+    const double* sa = ws + L::o_a;
+    const double* sb = ws + L::o_b;
+    double* Aug = ws + L::o_aug;
+    double* T1 = ws + L::o_t1;
+    double* T2 = ws + L::o_t2;
+    double* xf = ws + L::o_v;
+    double* lv = xf + NX;
+    const double *Pa = sa + D::SUM_P, *Fa = sa + D::SUM_F, *Ca = sa + D::SUM_C, *pa = sa + D::SUM_p, *fa = sa + D::SUM_f;
+    const double *Pb = sb + D::SUM_P, *Fb = sb + D::SUM_F, *Cb = sb + D::SUM_C, *pb = sb + D::SUM_p, *fb = sb + D::SUM_f;
+    constexpr Tile t1 = pick_tile(NX, NX, 32);
+    // Aug = [I + C_a P_b | F_a | C_a | f_a]
+    {
+        auto la = [&](int r, int k) { return Ca[r + k * NX]; };
+        auto lb = [&](int k, int c) { return Pb[k + c * NX]; };
+        auto epi = [&](int r, int c, double v) { Aug[r + c * LDA] = v + ((r == c) ? 1.0 : 0.0); };
+        group_mm<NX, NX, NX, t1.tm, t1.tn, 32>(lane, la, lb, epi);
+        for (int e = lane; e < N2; e += 32) {
+            const int r = e % NX, c = e / NX;
+            Aug[r + (NX + c) * LDA] = Fa[e];
+            Aug[r + (2 * NX + c) * LDA] = Ca[e];
+        }
+        for (int r = lane; r < NX; r += 32) Aug[r + 3 * NX * LDA] = fa[r];
+    }
+    __syncwarp();
+    warp_gauss_jordan<NX, D::NCOL, LDA>(lane, Aug);
+    const double* XF = Aug + NX * LDA;
+    const double* XC = Aug + 2 * NX * LDA;
+    const double* wf = Aug + 3 * NX * LDA;
+    // x_f = w_f - X_C p_b ; down-sweep record of member a
+    for (int r = lane; r < NX; r += 32) {
+        double acc = wf[r];
+#pragma unroll 4
+        for (int k = 0; k < NX; ++k) acc = fma(-XC[r + k * LDA], pb[k], acc);
+        xf[r] = acc;
+        ddi[D::DD_wf + r] = wf[r];
+        ddi[D::DD_pb + r] = pb[r];
+    }
+    for (int e = lane; e < N2; e += 32) {
+        const int r = e % NX, c = e / NX;
+        ddi[D::DD_XF + e] = XF[r + c * LDA];
+        ddi[D::DD_XC + e] = XC[r + c * LDA];
+        ddi[D::DD_PB + e] = Pb[e];
+        ddi[D::DD_FB + e] = Fb[e];
+    }
+    // one pass: T1 = P_b X_F ; T2 = F_b X_C ; F = F_b X_F
+    {
+        constexpr Tile t3 = pick_tile(3 * NX, NX, 32);
+        auto la = [&](int g, int r, int k) { return g == 0 ? Pb[r + k * NX] : Fb[r + k * NX]; };
+        auto lb = [&](int g, int k, int c) { return g == 1 ? XC[k + c * LDA] : XF[k + c * LDA]; };
+        auto ep = [&](int g, int r, int c, double v) {
+            if (g == 0) T1[r + c * NX] = v;
+            else if (g == 1) T2[r + c * NX] = v;
+            else out[D::SUM_F + r + c * NX] = v;
+        };
+        group_mm_multi<3, NX, NX, NX, t3.tm, t3.tn, 32>(lane, la, lb, ep);
+    }
+    __syncwarp();
+    // lv = P_b x_f + p_b  (needs xf)
+    for (int r = lane; r < NX; r += 32) {
+        double acc = pb[r];
+#pragma unroll 4
+        for (int k = 0; k < NX; ++k) acc = fma(Pb[r + k * NX], xf[k], acc);
+        lv[r] = acc;
+    }
+    // one pass: P = P_a + F_a^T T1 ; C = C_b + T2 F_b^T
+    {
+        constexpr Tile t2 = pick_tile(2 * NX, NX, 32);
+        auto la = [&](int g, int r, int k) { return g == 0 ? Fa[k + r * NX] : T2[r + k * NX]; };
+        auto lb = [&](int g, int k, int c) { return g == 0 ? T1[k + c * NX] : Fb[c + k * NX]; };
+        auto ep = [&](int g, int r, int c, double v) {
+            if (g == 0) out[D::SUM_P + r + c * NX] = Pa[r + c * NX] + v;
+            else out[D::SUM_C + r + c * NX] = Cb[r + c * NX] + v;
+        };
+        group_mm_multi<2, NX, NX, NX, t2.tm, t2.tn, 32>(lane, la, lb, ep);
+    }
+    __syncwarp();
+    // p = p_a + F_a^T lv ; f = F_b x_f + f_b
+    for (int r = lane; r < NX; r += 32) {
+        double ap = pa[r], af = fb[r];
+#pragma unroll 4
+        for (int k = 0; k < NX; ++k) {
+            ap = fma(Fa[k + r * NX], lv[k], ap);
+            af = fma(Fb[r + k * NX], xf[k], af);
+        }
+        out[D::SUM_p + r] = ap;
+        out[D::SUM_f + r] = af;
+    }
+    __syncwarp();
+}
+
+// affine-only version of one combine step: members' p, f changed, P, F, C (hence X_F, X_C, P_b, F_b) did not.
+// With W = I - X_C P_b:  x_f = f_a - X_C (P_b f_a + p_b) ; w_f = x_f + X_C p_b ; p = p_a + F_a^T (P_b x_f + p_b) ;
+// f = F_b x_f + f_b.   sa: summary of a (global), pb/fb: suffix vectors (shared, NX each, updated in place),
+// tmp: 3*NX doubles of shared scratch.  NX <= 32.
+template <int NX>
+PDPLQR_DEVINL void warp_combine_affine(int lane, const double* sa, double* ddi, double* pb, double* fb, double* tmp) {
+    using D = TreeDims<NX>;
+    double* t0 = tmp;
+    double* xf = tmp + NX;
+    double* lv = tmp + 2 * NX;
+    if (lane < NX) {
+        double acc = pb[lane];
+#pragma unroll 4
+        for (int k = 0; k < NX; ++k) acc = fma(ddi[D::DD_PB + lane + k * NX], sa[D::SUM_f + k], acc);
+        t0[lane] = acc;
+    }
+    __syncwarp();
+    if (lane < NX) {
+        double acc = sa[D::SUM_f + lane], accw = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < NX; ++k) {
+            acc = fma(-ddi[D::DD_XC + lane + k * NX], t0[k], acc);
+            accw = fma(ddi[D::DD_XC + lane + k * NX], pb[k], accw);
+        }
+        xf[lane] = acc;
+        ddi[D::DD_wf + lane] = acc + accw;
+        ddi[D::DD_pb + lane] = pb[lane];
+    }
+    __syncwarp();
+    if (lane < NX) {
+        double acc = pb[lane];
+#pragma unroll 4
+        for (int k = 0; k < NX; ++k) acc = fma(ddi[D::DD_PB + lane + k * NX], xf[k], acc);
+        lv[lane] = acc;
+    }
+    __syncwarp();
+    double pnew = 0.0, fnew = 0.0;
+    if (lane < NX) {
+        double ap = sa[D::SUM_p + lane], af = fb[lane];
+#pragma unroll 4
+        for (int k = 0; k < NX; ++k) {
+            ap = fma(sa[D::SUM_F + k + lane * NX], lv[k], ap);
+            af = fma(ddi[D::DD_FB + lane + k * NX], xf[k], af);
+        }
+        pnew = ap; fnew = af;
+    }
+    __syncwarp();
+    if (lane < NX) { pb[lane] = pnew; fb[lane] = fnew; }
+    __syncwarp();
+}
+
+// one down-sweep step of member i (shared x, le, pt, xn: NX each)
+template <int NX>
+PDPLQR_DEVINL void warp_down_step(int lane, const double* ddi, double* x, const double* le, double* pt, double* xn,
+                                  double* lam_i, double* x_next) {
+    using D = TreeDims<NX>;
+    for (int r = lane; r < NX; r += 32) {
+        double acc = ddi[D::DD_pb + r];
+#pragma unroll 4
+        for (int k = 0; k < NX; ++k) acc = fma(ddi[D::DD_FB + k + r * NX], le[k], acc);   // F_b^T lam_e
+        pt[r] = acc;
+    }
+    __syncwarp();
+    for (int r = lane; r < NX; r += 32) {
+        double acc = ddi[D::DD_wf + r];
+#pragma unroll 4
+        for (int k = 0; k < NX; ++k) {
+            acc = fma(ddi[D::DD_XF + r + k * NX], x[k], acc);
+            acc = fma(-ddi[D::DD_XC + r + k * NX], pt[k], acc);
+        }
+        xn[r] = acc;
+    }
+    __syncwarp();
+    for (int r = lane; r < NX; r += 32) {
+        double acc = pt[r];
+#pragma unroll 4
+        for (int k = 0; k < NX; ++k) acc = fma(ddi[D::DD_PB + r + k * NX], xn[k], acc);
+        lam_i[r] = acc;
+        x_next[r] = xn[r];
+        x[r] = xn[r];
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------- one launch per level, one warp per group
+template <int NX>
+struct TreeSmem {
+    static constexpr int o_n = CombSmem<NX>::DOUBLES;        // new suffix (SREC)
+    static constexpr size_t BYTES = (size_t)(o_n + TreeDims<NX>::SREC) * 8;
 };
 
 template <int NX>
 __global__ void __launch_bounds__(32) tree_up_kernel(TreeParams p) {
     using D = TreeDims<NX>;
-    using L = TreeSmem<NX>;
-    constexpr int N2 = D::N2, LDA = D::LDA;
+    using L = CombSmem<NX>;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x;
     const int b = blockIdx.x / p.groups, g = blockIdx.x % p.groups;
     const int first = g * p.R, last = min(first + p.R, p.count) - 1;
     double* sa = smem + L::o_a;
     double* sb = smem + L::o_b;
-    double* sn = smem + L::o_n;
-    double* Aug = smem + L::o_aug;
-    double* T1 = smem + L::o_t1;
-    double* T2 = smem + L::o_t2;
-    double* xf = smem + L::o_v;
-    double* lv = xf + NX;
+    double* sn = smem + TreeSmem<NX>::o_n;
     const double* in_b = p.sum_in + (size_t)b * p.count * D::SREC;
     double* dd_b = p.dd + (size_t)b * p.count * D::DREC;
-
     for (int e = lane; e < D::SREC; e += 32) sb[e] = in_b[(size_t)last * D::SREC + e];
     __syncwarp();
 #pragma unroll 1
     for (int i = last - 1; i >= first; --i) {
         for (int e = lane; e < D::SREC; e += 32) sa[e] = in_b[(size_t)i * D::SREC + e];
         __syncwarp();
-        const double *Pa = sa + D::SUM_P, *Fa = sa + D::SUM_F, *Ca = sa + D::SUM_C, *pa = sa + D::SUM_p, *fa = sa + D::SUM_f;
-        const double *Pb = sb + D::SUM_P, *Fb = sb + D::SUM_F, *Cb = sb + D::SUM_C, *pb = sb + D::SUM_p, *fb = sb + D::SUM_f;
-        // Aug = [I + C_a P_b | F_a | C_a | f_a]
-        {
-            constexpr Tile tl = pick_tile(NX, NX, 32);
-            auto la = [&](int r, int k) { return Ca[r + k * NX]; };
-            auto lb = [&](int k, int c) { return Pb[k + c * NX]; };
-            auto epi = [&](int r, int c, double v) { Aug[r + c * LDA] = v + ((r == c) ? 1.0 : 0.0); };
-            group_mm<NX, NX, NX, tl.tm, tl.tn, 32>(lane, la, lb, epi);
-            for (int e = lane; e < N2; e += 32) {
-                const int r = e % NX, c = e / NX;
-                Aug[r + (NX + c) * LDA] = Fa[e];
-                Aug[r + (2 * NX + c) * LDA] = Ca[e];
-            }
-            for (int r = lane; r < NX; r += 32) Aug[r + 3 * NX * LDA] = fa[r];
-        }
-        __syncwarp();
-        warp_gauss_jordan<NX, D::NCOL, LDA>(lane, Aug);
-        const double* XF = Aug + NX * LDA;
-        const double* XC = Aug + 2 * NX * LDA;
-        const double* wf = Aug + 3 * NX * LDA;
-        // x_f = w_f - X_C p_b ; down-sweep record of member i
-        double* ddi = dd_b + (size_t)i * D::DREC;
-        for (int r = lane; r < NX; r += 32) {
-            double acc = wf[r];
-#pragma unroll 4
-            for (int k = 0; k < NX; ++k) acc = fma(-XC[r + k * LDA], pb[k], acc);
-            xf[r] = acc;
-            ddi[D::DD_wf + r] = wf[r];
-            ddi[D::DD_pb + r] = pb[r];
-        }
-        for (int e = lane; e < N2; e += 32) {
-            const int r = e % NX, c = e / NX;
-            ddi[D::DD_XF + e] = XF[r + c * LDA];
-            ddi[D::DD_XC + e] = XC[r + c * LDA];
-            ddi[D::DD_PB + e] = Pb[e];
-            ddi[D::DD_FB + e] = Fb[e];
-        }
-        // T1 = P_b X_F ; T2 = F_b X_C
-        {
-            constexpr Tile t1 = pick_tile(NX, NX, 32);
-            auto lb = [&](int k, int c) { return XF[k + c * LDA]; };
-            auto lb2 = [&](int k, int c) { return XC[k + c * LDA]; };
-            auto e1 = [&](int r, int c, double v) { T1[r + c * NX] = v; };
-            auto e2 = [&](int r, int c, double v) { T2[r + c * NX] = v; };
-            auto laP = [&](int r, int k) { return Pb[r + k * NX]; };
-            auto laF = [&](int r, int k) { return Fb[r + k * NX]; };
-            group_mm<NX, NX, NX, t1.tm, t1.tn, 32>(lane, laP, lb, e1);
-            group_mm<NX, NX, NX, t1.tm, t1.tn, 32>(lane, laF, lb2, e2);
-        }
-        __syncwarp();
-        // lv = P_b x_f + p_b
-        for (int r = lane; r < NX; r += 32) {
-            double acc = pb[r];
-#pragma unroll 4
-            for (int k = 0; k < NX; ++k) acc = fma(Pb[r + k * NX], xf[k], acc);
-            lv[r] = acc;
-        }
-        __syncwarp();
-        // new suffix
-        {
-            constexpr Tile t1 = pick_tile(NX, NX, 32);
-            // P = P_a + F_a^T T1
-            auto laFt = [&](int r, int k) { return Fa[k + r * NX]; };
-            auto lbT1 = [&](int k, int c) { return T1[k + c * NX]; };
-            auto eP = [&](int r, int c, double v) { sn[D::SUM_P + r + c * NX] = Pa[r + c * NX] + v; };
-            group_mm<NX, NX, NX, t1.tm, t1.tn, 32>(lane, laFt, lbT1, eP);
-            // F = F_b X_F
-            auto laF = [&](int r, int k) { return Fb[r + k * NX]; };
-            auto lbXF = [&](int k, int c) { return XF[k + c * LDA]; };
-            auto eF = [&](int r, int c, double v) { sn[D::SUM_F + r + c * NX] = v; };
-            group_mm<NX, NX, NX, t1.tm, t1.tn, 32>(lane, laF, lbXF, eF);
-            // C = C_b + T2 F_b^T
-            auto laT2 = [&](int r, int k) { return T2[r + k * NX]; };
-            auto lbFt = [&](int k, int c) { return Fb[c + k * NX]; };
-            auto eC = [&](int r, int c, double v) { sn[D::SUM_C + r + c * NX] = Cb[r + c * NX] + v; };
-            group_mm<NX, NX, NX, t1.tm, t1.tn, 32>(lane, laT2, lbFt, eC);
-            // p = p_a + F_a^T lv ; f = F_b x_f + f_b
-            for (int r = lane; r < NX; r += 32) {
-                double ap = pa[r], af = fb[r];
-#pragma unroll 4
-                for (int k = 0; k < NX; ++k) {
-                    ap = fma(Fa[k + r * NX], lv[k], ap);
-                    af = fma(Fb[r + k * NX], xf[k], af);
-                }
-                sn[D::SUM_p + r] = ap;
-                sn[D::SUM_f + r] = af;
-            }
-        }
-        __syncwarp();
+        warp_combine<NX>(lane, smem, sn, dd_b + (size_t)i * D::DREC);
         for (int e = lane; e < D::SREC; e += 32) sb[e] = sn[e];
         __syncwarp();
     }
@@ -231,11 +340,6 @@ __global__ void __launch_bounds__(32) tree_up_kernel(TreeParams p) {
     }
 }
 
-// Affine-only up-sweep (after backward_without_factorization): the members' p, f changed, their P, F, C and
-// hence X_F, X_C, P_b, F_b did not.  With W = I - X_C P_b:
-//     x_f = f_a - X_C (P_b f_a + p_b) ;  w_f = x_f + X_C p_b ;  p = p_a + F_a^T (P_b x_f + p_b) ;  f = F_b x_f + f_b
-// Replaces the (p, c)-only update_segment_data + condensed forward's first loop (condensed_system.hpp:76-80,
-// :106-118 / :197-201, :253-271).
 template <int NX>
 __global__ void __launch_bounds__(32) tree_up_affine_kernel(TreeParams p) {
     using D = TreeDims<NX>;
@@ -243,11 +347,8 @@ __global__ void __launch_bounds__(32) tree_up_affine_kernel(TreeParams p) {
     const int lane = threadIdx.x;
     const int b = blockIdx.x / p.groups, g = blockIdx.x % p.groups;
     const int first = g * p.R, last = min(first + p.R, p.count) - 1;
-    double* pb = smem;            // suffix p
-    double* fb = smem + NX;       // suffix f
-    double* t0 = smem + 2 * NX;   // P_b f_a + p_b
-    double* xf = smem + 3 * NX;
-    double* lv = smem + 4 * NX;
+    double* pb = smem;
+    double* fb = smem + NX;
     const double* in_b = p.sum_in + (size_t)b * p.count * D::SREC;
     double* dd_b = p.dd + (size_t)b * p.count * D::DREC;
     for (int r = lane; r < NX; r += 32) {
@@ -256,49 +357,8 @@ __global__ void __launch_bounds__(32) tree_up_affine_kernel(TreeParams p) {
     }
     __syncwarp();
 #pragma unroll 1
-    for (int i = last - 1; i >= first; --i) {
-        const double* sa = in_b + (size_t)i * D::SREC;
-        double* ddi = dd_b + (size_t)i * D::DREC;
-        for (int r = lane; r < NX; r += 32) {
-            double acc = pb[r];
-#pragma unroll 4
-            for (int k = 0; k < NX; ++k) acc = fma(ddi[D::DD_PB + r + k * NX], sa[D::SUM_f + k], acc);
-            t0[r] = acc;
-        }
-        __syncwarp();
-        for (int r = lane; r < NX; r += 32) {
-            double acc = sa[D::SUM_f + r], accw = 0.0;
-#pragma unroll 4
-            for (int k = 0; k < NX; ++k) {
-                acc = fma(-ddi[D::DD_XC + r + k * NX], t0[k], acc);
-                accw = fma(ddi[D::DD_XC + r + k * NX], pb[k], accw);
-            }
-            xf[r] = acc;
-            ddi[D::DD_wf + r] = acc + accw;
-            ddi[D::DD_pb + r] = pb[r];
-        }
-        __syncwarp();
-        for (int r = lane; r < NX; r += 32) {
-            double acc = pb[r];
-#pragma unroll 4
-            for (int k = 0; k < NX; ++k) acc = fma(ddi[D::DD_PB + r + k * NX], xf[k], acc);
-            lv[r] = acc;
-        }
-        __syncwarp();
-        double pnew = 0.0, fnew = 0.0;
-        for (int r = lane; r < NX; r += 32) {   // NX <= 32 rows per pass; results kept per lane
-            double ap = sa[D::SUM_p + r], af = fb[r];
-#pragma unroll 4
-            for (int k = 0; k < NX; ++k) {
-                ap = fma(sa[D::SUM_F + k + r * NX], lv[k], ap);
-                af = fma(ddi[D::DD_FB + r + k * NX], xf[k], af);
-            }
-            pnew = ap; fnew = af;
-        }
-        __syncwarp();
-        for (int r = lane; r < NX; r += 32) { pb[r] = pnew; fb[r] = fnew; }
-        __syncwarp();
-    }
+    for (int i = last - 1; i >= first; --i)
+        warp_combine_affine<NX>(lane, in_b + (size_t)i * D::SREC, dd_b + (size_t)i * D::DREC, pb, fb, smem + 2 * NX);
     if (p.sum_out) {
         double* out = p.sum_out + ((size_t)b * p.groups + g) * D::SREC;
         for (int r = lane; r < NX; r += 32) {
@@ -330,34 +390,119 @@ __global__ void __launch_bounds__(32) tree_down_kernel(TreeParams p) {
     }
     __syncwarp();
 #pragma unroll 1
-    for (int i = first; i < last; ++i) {
-        const double* ddi = dd_b + (size_t)i * D::DREC;
-        for (int r = lane; r < NX; r += 32) {
-            double acc = ddi[D::DD_pb + r];
-#pragma unroll 4
-            for (int k = 0; k < NX; ++k) acc = fma(ddi[D::DD_FB + k + r * NX], le[k], acc);   // F_b^T lam_e
-            pt[r] = acc;
-        }
-        __syncwarp();
-        for (int r = lane; r < NX; r += 32) {
-            double acc = ddi[D::DD_wf + r];
-#pragma unroll 4
-            for (int k = 0; k < NX; ++k) {
-                acc = fma(ddi[D::DD_XF + r + k * NX], x[k], acc);
-                acc = fma(-ddi[D::DD_XC + r + k * NX], pt[k], acc);
+    for (int i = first; i < last; ++i)
+        warp_down_step<NX>(lane, dd_b + (size_t)i * D::DREC, x, le, pt, xn, lo + (size_t)i * NX, xo + (size_t)(i + 1) * NX);
+}
+
+// ---------------------------------------------------------------- upper levels: one CTA per problem, one launch
+template <int NX>
+struct TreeTopSmem {
+    static constexpr int WARP_DOUBLES = CombSmem<NX>::DOUBLES;
+    // as many warps as fit in ~220 KB of shared memory (16 at nx = 12)
+    static constexpr int WARPS = (220 * 1024 / 8 / WARP_DOUBLES) >= 16 ? 16 : ((220 * 1024 / 8 / WARP_DOUBLES) < 1 ? 1 : (220 * 1024 / 8 / WARP_DOUBLES));
+    static constexpr size_t BYTES = (size_t)WARPS * WARP_DOUBLES * 8;
+};
+
+template <int NX>
+__global__ void __launch_bounds__(TreeTopSmem<NX>::WARPS * 32) tree_top_up_kernel(TreeTopParams p) {
+    using D = TreeDims<NX>;
+    using L = CombSmem<NX>;
+    constexpr int TREE_TOP_WARPS = TreeTopSmem<NX>::WARPS;
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x;
+    double* ws = smem + warp * TreeTopSmem<NX>::WARP_DOUBLES;
+#pragma unroll 1
+    for (int l = 0; l + 1 < p.nlevels; ++l) {   // level l (count[l] nodes) -> level l+1 (pairs)
+        const int cnt = p.count[l], groups = (cnt + 1) / 2;
+        const double* in_b = p.sum[l] + (size_t)b * cnt * D::SREC;
+        double* out_b = p.sum[l + 1] + (size_t)b * groups * D::SREC;
+        double* dd_b = p.dd[l] + (size_t)b * cnt * D::DREC;
+        for (int g = warp; g < groups; g += TREE_TOP_WARPS) {
+            const int ia = 2 * g, ib = 2 * g + 1;
+            double* out = out_b + (size_t)g * D::SREC;
+            if (ib >= cnt) {                       // odd node out: passes through unchanged
+                if (p.affine_only) {
+                    for (int r = lane; r < NX; r += 32) {
+                        out[D::SUM_p + r] = in_b[(size_t)ia * D::SREC + D::SUM_p + r];
+                        out[D::SUM_f + r] = in_b[(size_t)ia * D::SREC + D::SUM_f + r];
+                    }
+                } else
+                    for (int e = lane; e < D::SREC; e += 32) out[e] = in_b[(size_t)ia * D::SREC + e];
+                continue;
             }
-            xn[r] = acc;
+            if (p.affine_only) {
+                double* pb = ws;
+                double* fb = ws + NX;
+                for (int r = lane; r < NX; r += 32) {
+                    pb[r] = in_b[(size_t)ib * D::SREC + D::SUM_p + r];
+                    fb[r] = in_b[(size_t)ib * D::SREC + D::SUM_f + r];
+                }
+                __syncwarp();
+                warp_combine_affine<NX>(lane, in_b + (size_t)ia * D::SREC, dd_b + (size_t)ia * D::DREC, pb, fb, ws + 2 * NX);
+                for (int r = lane; r < NX; r += 32) {
+                    out[D::SUM_p + r] = pb[r];
+                    out[D::SUM_f + r] = fb[r];
+                }
+            } else {
+                for (int e = lane; e < D::SREC; e += 32) {
+                    ws[L::o_a + e] = in_b[(size_t)ia * D::SREC + e];
+                    ws[L::o_b + e] = in_b[(size_t)ib * D::SREC + e];
+                }
+                __syncwarp();
+                warp_combine<NX>(lane, ws, out, dd_b + (size_t)ia * D::DREC);
+            }
         }
-        __syncwarp();
-        for (int r = lane; r < NX; r += 32) {
-            double acc = pt[r];
-#pragma unroll 4
-            for (int k = 0; k < NX; ++k) acc = fma(ddi[D::DD_PB + r + k * NX], xn[k], acc);
-            lo[(size_t)i * NX + r] = acc;
-            xo[(size_t)(i + 1) * NX + r] = xn[r];
-            x[r] = xn[r];
+        __threadfence_block();
+        __syncthreads();
+    }
+}
+
+template <int NX>
+__global__ void __launch_bounds__(TreeTopSmem<NX>::WARPS * 32) tree_top_down_kernel(TreeTopParams p) {
+    using D = TreeDims<NX>;
+    constexpr int TREE_TOP_WARPS = TreeTopSmem<NX>::WARPS;
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x;
+    double* x = smem + warp * 4 * NX;
+    double* le = x + NX;
+    double* pt = x + 2 * NX;
+    double* xn = x + 3 * NX;
+    // root: the single node of the last level gets x0 and a zero exit costate
+    {
+        const int top = p.nlevels - 1;
+        if (warp == 0)
+            for (int r = lane; r < NX; r += 32) {
+                p.x[top][(size_t)b * NX + r] = p.x0[(size_t)b * NX + r];
+                p.lam[top][(size_t)b * NX + r] = 0.0;
+            }
+        __threadfence_block();
+        __syncthreads();
+    }
+#pragma unroll 1
+    for (int l = p.nlevels - 2; l >= 0; --l) {
+        const int cnt = p.count[l], groups = (cnt + 1) / 2;
+        const double* dd_b = p.dd[l] + (size_t)b * cnt * D::DREC;
+        const double* xp = p.x[l + 1] + (size_t)b * groups * NX;
+        const double* lp = p.lam[l + 1] + (size_t)b * groups * NX;
+        double* xo = p.x[l] + (size_t)b * cnt * NX;
+        double* lo = p.lam[l] + (size_t)b * cnt * NX;
+        for (int g = warp; g < groups; g += TREE_TOP_WARPS) {
+            const int first = 2 * g, last = min(2 * g + 1, cnt - 1);
+            for (int r = lane; r < NX; r += 32) {
+                x[r] = xp[(size_t)g * NX + r];
+                le[r] = lp[(size_t)g * NX + r];
+                xo[(size_t)first * NX + r] = x[r];
+                lo[(size_t)last * NX + r] = le[r];
+            }
+            __syncwarp();
+            if (last > first)
+                warp_down_step<NX>(lane, dd_b + (size_t)first * D::DREC, x, le, pt, xn, lo + (size_t)first * NX,
+                                   xo + (size_t)last * NX);
         }
-        __syncwarp();
+        __threadfence_block();
+        __syncthreads();
     }
 }
 
