@@ -38,6 +38,8 @@ struct pdplqr_solver {
     int frec = 0;              // doubles per stage in d_fac for the active path
     int mrec = 0;              // doubles per stage in d_model for the active path
     int bwd_variant = 0, fwd_variant = 0;
+    int lat_threads = 128;     // 0 disables the 128-thread latency mode of the segment backward kernel
+    int tree_tt = 32;          // threads per tree combine (128 = experimental wide combine; measured slower)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     // device memory
@@ -158,11 +160,21 @@ int backward_impl(Solver& h) {
             }
         }
     }
-    auto kern = seg_backward_kernel<NX, NU, T>;
+    // latency mode: with fewer (problem, segment) groups than SMs a whole 128-thread CTA works on each group
+    constexpr int TL = (T < 128) ? 128 : T;
+    const bool latency_mode = (T < 128) && h.lat_threads > 0 && (long long)h.batch * h.S <= 2 * 148;
     const size_t bytes = BwdSmem<NX, NU>::bytes(h.ncmax);
-    int rc = set_smem(h, kern, bytes);
-    if (rc) return rc;
-    kern<<<h.batch * h.S, T, bytes, h.stream>>>(p);
+    if (latency_mode) {
+        auto kern = seg_backward_kernel<NX, NU, TL>;
+        int rc = set_smem(h, kern, bytes);
+        if (rc) return rc;
+        kern<<<h.batch * h.S, TL, bytes, h.stream>>>(p);
+    } else {
+        auto kern = seg_backward_kernel<NX, NU, T>;
+        int rc = set_smem(h, kern, bytes);
+        if (rc) return rc;
+        kern<<<h.batch * h.S, T, bytes, h.stream>>>(p);
+    }
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -196,11 +208,18 @@ int forward_impl(Solver& h, const double* d_x0, double* d_ws_out) {
 
 template <int NX>
 int tree_up_impl(Solver& h, const TreeParams& p) {
-    auto kern = tree_up_kernel<NX>;
     constexpr size_t bytes = TreeSmem<NX>::BYTES;
-    int rc = set_smem(h, kern, bytes);
-    if (rc) return rc;
-    kern<<<p.batch * p.groups, 32, bytes, h.stream>>>(p);
+    if (h.tree_tt == 128 && (long long)p.batch * p.groups <= 2 * 148) {   // experimental: 128 threads per combine
+        auto kern = tree_up_kernel<NX, 128>;
+        int rc = set_smem(h, kern, bytes);
+        if (rc) return rc;
+        kern<<<p.batch * p.groups, 128, bytes, h.stream>>>(p);
+    } else {
+        auto kern = tree_up_kernel<NX, 32>;
+        int rc = set_smem(h, kern, bytes);
+        if (rc) return rc;
+        kern<<<p.batch * p.groups, 32, bytes, h.stream>>>(p);
+    }
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -238,11 +257,23 @@ int tree_up_affine_impl(Solver& h, const TreeParams& p) {
 
 template <int NX>
 int tree_top_up_impl(Solver& h, const TreeTopParams& p) {
-    auto kern = tree_top_up_kernel<NX>;
     constexpr size_t bytes = TreeTopSmem<NX>::BYTES;
+    constexpr int WARPS = TreeTopSmem<NX>::WARPS;
+    if constexpr (WARPS % 4 == 0) {
+        if (h.tree_tt == 128 && p.batch <= 2 * 148 && !p.affine_only) {   // experimental: 4 warps per combine
+            auto kern = tree_top_up_kernel<NX, 128>;
+            int rc = set_smem(h, kern, bytes);
+            if (rc) return rc;
+            kern<<<p.batch, WARPS * 32, bytes, h.stream>>>(p);
+            h.launches++;
+            CU_TRY(&h, cudaGetLastError());
+            return PDPLQR_OK;
+        }
+    }
+    auto kern = tree_top_up_kernel<NX, 32>;
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
-    kern<<<p.batch, TreeTopSmem<NX>::WARPS * 32, bytes, h.stream>>>(p);
+    kern<<<p.batch, WARPS * 32, bytes, h.stream>>>(p);
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -530,6 +561,8 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     h->mrec = h->thread_path ? ops->TREC : ops->REC;
     if (const char* e = getenv("PDPLQR_BWD_VARIANT")) h->bwd_variant = atoi(e);
     if (const char* e = getenv("PDPLQR_FWD_VARIANT")) h->fwd_variant = atoi(e);
+    if (const char* e = getenv("PDPLQR_LAT_THREADS")) h->lat_threads = atoi(e);
+    if (const char* e = getenv("PDPLQR_TREE_TT")) h->tree_tt = atoi(e);
 
     auto bail = [&](int rc) { std::string e = h->err; pdplqr_destroy(h); (void)e; return rc; };
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PDPLQR_ERR_CUDA);

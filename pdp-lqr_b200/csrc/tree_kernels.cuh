@@ -111,6 +111,54 @@ PDPLQR_DEVINL void warp_gauss_jordan(int lane, double* Aug) {
     }
 }
 
+// barrier among the TT threads of one combine group: a warp, or TT threads on named barrier `bar_id` (1..15)
+template <int TT>
+PDPLQR_DEVINL void sub_sync(int bar_id) {
+    if constexpr (TT == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TT) : "memory");
+}
+
+// Gauss-Jordan with partial pivoting for a TT-thread group (TT > 32): every thread finds the pivot redundantly, then
+// the (NX x remaining-columns) block is updated element-parallel: read phase, barrier, write phase, barrier.
+template <int NX, int NCOL, int LDA, int TT>
+PDPLQR_DEVINL void group_gauss_jordan(int tid, int bar_id, double* Aug) {
+    constexpr int MAXE = (NX * (NCOL - 1) + TT - 1) / TT;
+#pragma unroll 1
+    for (int k = 0; k < NX; ++k) {
+        double best = -1.0, pval = 1.0, akk = 0.0;
+        int piv = k;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            const double c = Aug[i + k * LDA];
+            const double v = fabs(c);
+            if (i == k) akk = c;
+            if (i >= k && v > best) { best = v; piv = i; pval = c; }
+        }
+        const double pinv = 1.0 / pval;
+        const int nelem = NX * (NCOL - 1 - k);
+        double val[MAXE];
+#pragma unroll
+        for (int q = 0; q < MAXE; ++q) {
+            const int e = tid + q * TT;
+            if (e < nelem) {
+                const int i = e % NX, j = k + 1 + e / NX;
+                const double* cj = Aug + j * LDA;
+                const double t = cj[piv] * pinv;              // new row k
+                double mult = Aug[i + k * LDA], aij = cj[i];
+                if (i == piv) { mult = akk; aij = cj[k]; }    // row piv receives the old row k
+                val[q] = (i == k) ? t : fma(-mult, t, aij);
+            }
+        }
+        sub_sync<TT>(bar_id);
+#pragma unroll
+        for (int q = 0; q < MAXE; ++q) {
+            const int e = tid + q * TT;
+            if (e < nelem) Aug[(e % NX) + (k + 1 + e / NX) * LDA] = val[q];
+        }
+        sub_sync<TT>(bar_id);
+    }
+}
+
 template <int NX>
 struct CombSmem {   // per-warp workspace of one combine
     using D = TreeDims<NX>;
@@ -123,10 +171,10 @@ struct CombSmem {   // per-warp workspace of one combine
     static constexpr int DOUBLES = even_up(o_v + 2 * NX);
 };
 
-// One combine step by one warp.  a, b: summaries in shared memory (ws + o_a / o_b).  Writes the combined summary to
+// One combine step by one group of TT threads (a warp, or 4 warps on a named barrier).  a, b: summaries in shared memory (ws + o_a / o_b).  Writes the combined summary to
 // `out` (shared or global) and the down-sweep record of member a to `ddi` (global).
-template <int NX>
-PDPLQR_DEVINL void warp_combine(int lane, double* ws, double* out, double* ddi) {
+template <int NX, int TT>
+PDPLQR_DEVINL void group_combine(int lane, int bar_id, double* ws, double* out, double* ddi) {
     using D = TreeDims<NX>;
     using L = CombSmem<NX>;
     constexpr int N2 = D::N2, LDA = D::LDA;
@@ -139,27 +187,28 @@ PDPLQR_DEVINL void warp_combine(int lane, double* ws, double* out, double* ddi) 
     double* lv = xf + NX;
     const double *Pa = sa + D::SUM_P, *Fa = sa + D::SUM_F, *Ca = sa + D::SUM_C, *pa = sa + D::SUM_p, *fa = sa + D::SUM_f;
     const double *Pb = sb + D::SUM_P, *Fb = sb + D::SUM_F, *Cb = sb + D::SUM_C, *pb = sb + D::SUM_p, *fb = sb + D::SUM_f;
-    constexpr Tile t1 = pick_tile(NX, NX, 32);
+    constexpr Tile t1 = pick_tile(NX, NX, TT);
     // Aug = [I + C_a P_b | F_a | C_a | f_a]
     {
         auto la = [&](int r, int k) { return Ca[r + k * NX]; };
         auto lb = [&](int k, int c) { return Pb[k + c * NX]; };
         auto epi = [&](int r, int c, double v) { Aug[r + c * LDA] = v + ((r == c) ? 1.0 : 0.0); };
-        group_mm<NX, NX, NX, t1.tm, t1.tn, 32>(lane, la, lb, epi);
-        for (int e = lane; e < N2; e += 32) {
+        group_mm<NX, NX, NX, t1.tm, t1.tn, TT>(lane, la, lb, epi);
+        for (int e = lane; e < N2; e += TT) {
             const int r = e % NX, c = e / NX;
             Aug[r + (NX + c) * LDA] = Fa[e];
             Aug[r + (2 * NX + c) * LDA] = Ca[e];
         }
-        for (int r = lane; r < NX; r += 32) Aug[r + 3 * NX * LDA] = fa[r];
+        for (int r = lane; r < NX; r += TT) Aug[r + 3 * NX * LDA] = fa[r];
     }
-    __syncwarp();
-    warp_gauss_jordan<NX, D::NCOL, LDA>(lane, Aug);
+    sub_sync<TT>(bar_id);
+    if constexpr (TT == 32) warp_gauss_jordan<NX, D::NCOL, LDA>(lane, Aug);
+    else group_gauss_jordan<NX, D::NCOL, LDA, TT>(lane, bar_id, Aug);
     const double* XF = Aug + NX * LDA;
     const double* XC = Aug + 2 * NX * LDA;
     const double* wf = Aug + 3 * NX * LDA;
     // x_f = w_f - X_C p_b ; down-sweep record of member a
-    for (int r = lane; r < NX; r += 32) {
+    for (int r = lane; r < NX; r += TT) {
         double acc = wf[r];
 #pragma unroll 4
         for (int k = 0; k < NX; ++k) acc = fma(-XC[r + k * LDA], pb[k], acc);
@@ -167,7 +216,7 @@ PDPLQR_DEVINL void warp_combine(int lane, double* ws, double* out, double* ddi) 
         ddi[D::DD_wf + r] = wf[r];
         ddi[D::DD_pb + r] = pb[r];
     }
-    for (int e = lane; e < N2; e += 32) {
+    for (int e = lane; e < N2; e += TT) {
         const int r = e % NX, c = e / NX;
         ddi[D::DD_XF + e] = XF[r + c * LDA];
         ddi[D::DD_XC + e] = XC[r + c * LDA];
@@ -176,7 +225,7 @@ PDPLQR_DEVINL void warp_combine(int lane, double* ws, double* out, double* ddi) 
     }
     // one pass: T1 = P_b X_F ; T2 = F_b X_C ; F = F_b X_F
     {
-        constexpr Tile t3 = pick_tile(3 * NX, NX, 32);
+        constexpr Tile t3 = pick_tile(3 * NX, NX, TT);
         auto la = [&](int g, int r, int k) { return g == 0 ? Pb[r + k * NX] : Fb[r + k * NX]; };
         auto lb = [&](int g, int k, int c) { return g == 1 ? XC[k + c * LDA] : XF[k + c * LDA]; };
         auto ep = [&](int g, int r, int c, double v) {
@@ -184,11 +233,11 @@ PDPLQR_DEVINL void warp_combine(int lane, double* ws, double* out, double* ddi) 
             else if (g == 1) T2[r + c * NX] = v;
             else out[D::SUM_F + r + c * NX] = v;
         };
-        group_mm_multi<3, NX, NX, NX, t3.tm, t3.tn, 32>(lane, la, lb, ep);
+        group_mm_multi<3, NX, NX, NX, t3.tm, t3.tn, TT>(lane, la, lb, ep);
     }
-    __syncwarp();
+    sub_sync<TT>(bar_id);
     // lv = P_b x_f + p_b  (needs xf)
-    for (int r = lane; r < NX; r += 32) {
+    for (int r = lane; r < NX; r += TT) {
         double acc = pb[r];
 #pragma unroll 4
         for (int k = 0; k < NX; ++k) acc = fma(Pb[r + k * NX], xf[k], acc);
@@ -196,18 +245,18 @@ PDPLQR_DEVINL void warp_combine(int lane, double* ws, double* out, double* ddi) 
     }
     // one pass: P = P_a + F_a^T T1 ; C = C_b + T2 F_b^T
     {
-        constexpr Tile t2 = pick_tile(2 * NX, NX, 32);
+        constexpr Tile t2 = pick_tile(2 * NX, NX, TT);
         auto la = [&](int g, int r, int k) { return g == 0 ? Fa[k + r * NX] : T2[r + k * NX]; };
         auto lb = [&](int g, int k, int c) { return g == 0 ? T1[k + c * NX] : Fb[c + k * NX]; };
         auto ep = [&](int g, int r, int c, double v) {
             if (g == 0) out[D::SUM_P + r + c * NX] = Pa[r + c * NX] + v;
             else out[D::SUM_C + r + c * NX] = Cb[r + c * NX] + v;
         };
-        group_mm_multi<2, NX, NX, NX, t2.tm, t2.tn, 32>(lane, la, lb, ep);
+        group_mm_multi<2, NX, NX, NX, t2.tm, t2.tn, TT>(lane, la, lb, ep);
     }
-    __syncwarp();
+    sub_sync<TT>(bar_id);
     // p = p_a + F_a^T lv ; f = F_b x_f + f_b
-    for (int r = lane; r < NX; r += 32) {
+    for (int r = lane; r < NX; r += TT) {
         double ap = pa[r], af = fb[r];
 #pragma unroll 4
         for (int k = 0; k < NX; ++k) {
@@ -217,7 +266,7 @@ PDPLQR_DEVINL void warp_combine(int lane, double* ws, double* out, double* ddi) 
         out[D::SUM_p + r] = ap;
         out[D::SUM_f + r] = af;
     }
-    __syncwarp();
+    sub_sync<TT>(bar_id);
 }
 
 // affine-only version of one combine step: members' p, f changed, P, F, C (hence X_F, X_C, P_b, F_b) did not.
@@ -311,8 +360,8 @@ struct TreeSmem {
     static constexpr size_t BYTES = (size_t)(o_n + TreeDims<NX>::SREC) * 8;
 };
 
-template <int NX>
-__global__ void __launch_bounds__(32) tree_up_kernel(TreeParams p) {
+template <int NX, int TT>
+__global__ void __launch_bounds__(TT) tree_up_kernel(TreeParams p) {
     using D = TreeDims<NX>;
     using L = CombSmem<NX>;
     extern __shared__ __align__(16) double smem[];
@@ -324,19 +373,19 @@ __global__ void __launch_bounds__(32) tree_up_kernel(TreeParams p) {
     double* sn = smem + TreeSmem<NX>::o_n;
     const double* in_b = p.sum_in + (size_t)b * p.count * D::SREC;
     double* dd_b = p.dd + (size_t)b * p.count * D::DREC;
-    for (int e = lane; e < D::SREC; e += 32) sb[e] = in_b[(size_t)last * D::SREC + e];
-    __syncwarp();
+    for (int e = lane; e < D::SREC; e += TT) sb[e] = in_b[(size_t)last * D::SREC + e];
+    sub_sync<TT>(1);
 #pragma unroll 1
     for (int i = last - 1; i >= first; --i) {
-        for (int e = lane; e < D::SREC; e += 32) sa[e] = in_b[(size_t)i * D::SREC + e];
-        __syncwarp();
-        warp_combine<NX>(lane, smem, sn, dd_b + (size_t)i * D::DREC);
-        for (int e = lane; e < D::SREC; e += 32) sb[e] = sn[e];
-        __syncwarp();
+        for (int e = lane; e < D::SREC; e += TT) sa[e] = in_b[(size_t)i * D::SREC + e];
+        sub_sync<TT>(1);
+        group_combine<NX, TT>(lane, 1, smem, sn, dd_b + (size_t)i * D::DREC);
+        for (int e = lane; e < D::SREC; e += TT) sb[e] = sn[e];
+        sub_sync<TT>(1);
     }
     if (p.sum_out) {
         double* out = p.sum_out + ((size_t)b * p.groups + g) * D::SREC;
-        for (int e = lane; e < D::SREC; e += 32) out[e] = sb[e];
+        for (int e = lane; e < D::SREC; e += TT) out[e] = sb[e];
     }
 }
 
@@ -403,54 +452,59 @@ struct TreeTopSmem {
     static constexpr size_t BYTES = (size_t)WARPS * WARP_DOUBLES * 8;
 };
 
-template <int NX>
+template <int NX, int TT>
 __global__ void __launch_bounds__(TreeTopSmem<NX>::WARPS * 32) tree_top_up_kernel(TreeTopParams p) {
     using D = TreeDims<NX>;
     using L = CombSmem<NX>;
-    constexpr int TREE_TOP_WARPS = TreeTopSmem<NX>::WARPS;
+    constexpr int NGROUPS = TreeTopSmem<NX>::WARPS * 32 / TT;    // combine groups per CTA
+    static_assert(NGROUPS >= 1 && (TT == 32 || NGROUPS <= 15), "one named barrier per group");
     extern __shared__ __align__(16) double smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = threadIdx.x / TT, lane = threadIdx.x % TT;
+    const int bar_id = 1 + grp;
     const int b = blockIdx.x;
-    double* ws = smem + warp * TreeTopSmem<NX>::WARP_DOUBLES;
+    double* ws = smem + grp * TreeTopSmem<NX>::WARP_DOUBLES;   // each group uses one warp-slot of the layout
 #pragma unroll 1
     for (int l = 0; l + 1 < p.nlevels; ++l) {   // level l (count[l] nodes) -> level l+1 (pairs)
         const int cnt = p.count[l], groups = (cnt + 1) / 2;
         const double* in_b = p.sum[l] + (size_t)b * cnt * D::SREC;
         double* out_b = p.sum[l + 1] + (size_t)b * groups * D::SREC;
         double* dd_b = p.dd[l] + (size_t)b * cnt * D::DREC;
-        for (int g = warp; g < groups; g += TREE_TOP_WARPS) {
+        for (int g = grp; g < groups; g += NGROUPS) {
             const int ia = 2 * g, ib = 2 * g + 1;
             double* out = out_b + (size_t)g * D::SREC;
             if (ib >= cnt) {                       // odd node out: passes through unchanged
                 if (p.affine_only) {
-                    for (int r = lane; r < NX; r += 32) {
+                    for (int r = lane; r < NX; r += TT) {
                         out[D::SUM_p + r] = in_b[(size_t)ia * D::SREC + D::SUM_p + r];
                         out[D::SUM_f + r] = in_b[(size_t)ia * D::SREC + D::SUM_f + r];
                     }
                 } else
-                    for (int e = lane; e < D::SREC; e += 32) out[e] = in_b[(size_t)ia * D::SREC + e];
+                    for (int e = lane; e < D::SREC; e += TT) out[e] = in_b[(size_t)ia * D::SREC + e];
                 continue;
             }
             if (p.affine_only) {
-                double* pb = ws;
-                double* fb = ws + NX;
-                for (int r = lane; r < NX; r += 32) {
-                    pb[r] = in_b[(size_t)ib * D::SREC + D::SUM_p + r];
-                    fb[r] = in_b[(size_t)ib * D::SREC + D::SUM_f + r];
-                }
-                __syncwarp();
-                warp_combine_affine<NX>(lane, in_b + (size_t)ia * D::SREC, dd_b + (size_t)ia * D::DREC, pb, fb, ws + 2 * NX);
-                for (int r = lane; r < NX; r += 32) {
-                    out[D::SUM_p + r] = pb[r];
-                    out[D::SUM_f + r] = fb[r];
+                if (lane < 32) {   // matvec-only: the first warp of the group
+                    double* pb = ws;
+                    double* fb = ws + NX;
+                    for (int r = lane; r < NX; r += 32) {
+                        pb[r] = in_b[(size_t)ib * D::SREC + D::SUM_p + r];
+                        fb[r] = in_b[(size_t)ib * D::SREC + D::SUM_f + r];
+                    }
+                    __syncwarp();
+                    warp_combine_affine<NX>(lane, in_b + (size_t)ia * D::SREC, dd_b + (size_t)ia * D::DREC, pb, fb, ws + 2 * NX);
+                    for (int r = lane; r < NX; r += 32) {
+                        out[D::SUM_p + r] = pb[r];
+                        out[D::SUM_f + r] = fb[r];
+                    }
                 }
             } else {
-                for (int e = lane; e < D::SREC; e += 32) {
+                sub_sync<TT>(bar_id);   // previous round's readers of ws are done
+                for (int e = lane; e < D::SREC; e += TT) {
                     ws[L::o_a + e] = in_b[(size_t)ia * D::SREC + e];
                     ws[L::o_b + e] = in_b[(size_t)ib * D::SREC + e];
                 }
-                __syncwarp();
-                warp_combine<NX>(lane, ws, out, dd_b + (size_t)ia * D::DREC);
+                sub_sync<TT>(bar_id);
+                group_combine<NX, TT>(lane, bar_id, ws, out, dd_b + (size_t)ia * D::DREC);
             }
         }
         __threadfence_block();
