@@ -95,7 +95,27 @@ int pdplqr_synchronize(pdplqr_handle_t h);
  * workspace, lqr_kernel.hpp:8-75).  Default: on when the problem has constraints (ADMM use), off otherwise; when
  * off, backward_without_factorization transparently runs the factorising sweep (same result). */
 #define PDPLQR_OPT_AFFINE_CACHE 1
+/* PDPLQR_OPT_INTERIOR_SHARD (set before set_model): this handle owns a time slice of a longer horizon that does
+ * NOT contain the terminal stage, so its last segment ends at an interface like every other segment
+ * (lqr_kernel_parallel.hpp:61-65) and HN / hN are ignored. */
+#define PDPLQR_OPT_INTERIOR_SHARD 2
 int pdplqr_set_option(pdplqr_handle_t h, int option, int value);
+
+/* Horizon sharding across GPUs (addition; the reference's analogue is threads <-> segments with the serial
+ * condensed solve in between, lqr_solver_parallel.hpp:144-145,215).  Every rank owns one handle for its time slice
+ * (all but the last with PDPLQR_OPT_INTERIOR_SHARD).  After backward each rank exports the summary of its whole
+ * slice, `pdplqr_summary_doubles` doubles per problem laid out [P | F | C | p | f] (lqr_solver_parallel.hpp:180-187);
+ * the summaries are all-gathered (NCCL), every rank solves the small interface system of the G slices with a
+ * coupler and feeds its own entry state / exit costate back with pdplqr_set_root_boundary_device before forward.
+ * All pointers are device pointers; work is enqueued on the handle's stream. */
+int pdplqr_summary_doubles(pdplqr_handle_t h);
+int pdplqr_get_root_summary_device(pdplqr_handle_t h, double* summary);
+int pdplqr_set_root_boundary_device(pdplqr_handle_t h, const double* xhat, const double* lam);
+int pdplqr_coupler_create(pdplqr_handle_t* out, int nx, int nu, int num_shards, int batch, int device);
+/* summaries [batch][G][summary_doubles], x0 [batch][nx] -> xhat, lam [batch][G][nx] (entry state / exit costate
+ * of every slice; condensed_system.hpp:140-146).  Destroy the coupler with pdplqr_destroy. */
+int pdplqr_coupler_solve_device(pdplqr_handle_t coupler, const double* summaries, const double* x0, double* xhat,
+                                double* lam);
 
 /* Accessors (additions; the reference keeps these in a private workspace, lqr_solver_parallel.hpp:55-60).
  * All outputs are host arrays; any pointer may be NULL to skip it.

@@ -10,6 +10,7 @@ from . import _build
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_ORDER, ERR_NOT_PD = 0, -1, -2, -3, -4, -5
 CONDENSED_LU, CONDENSED_CHOLESKY = 0, 1
 OPT_AFFINE_CACHE = 1
+OPT_INTERIOR_SHARD = 2
 
 _dp = C.c_void_p   # double* (host or device address)
 _ip = C.POINTER(C.c_int)
@@ -32,6 +33,11 @@ SIGNATURES = {
     "pdplqr_forward_device": (C.c_int, [C.c_void_p, _dp, _dp]),
     "pdplqr_synchronize": (C.c_int, [C.c_void_p]),
     "pdplqr_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "pdplqr_summary_doubles": (C.c_int, [C.c_void_p]),
+    "pdplqr_get_root_summary_device": (C.c_int, [C.c_void_p, _dp]),
+    "pdplqr_set_root_boundary_device": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "pdplqr_coupler_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "pdplqr_coupler_solve_device": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp]),
     "pdplqr_num_segments": (C.c_int, [C.c_void_p]),
     "pdplqr_get_partition": (C.c_int, [C.c_void_p, _ip, _ip]),
     "pdplqr_get_gains": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),

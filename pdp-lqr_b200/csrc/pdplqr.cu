@@ -58,6 +58,11 @@ struct pdplqr_solver {
     // affine cache for backward_without_factorization
     bool keep_affine = false;
     double* d_aff = nullptr;
+    // horizon sharding
+    bool interior = false;         // slice ends at an interface (not the true terminal)
+    bool is_coupler = false;       // handle created by pdplqr_coupler_create (interface tree only)
+    double *d_root_x = nullptr, *d_root_lam = nullptr;
+    bool have_root = false;
     std::vector<TreeLevel> levels;
     std::vector<void*> owned;  // everything to cudaFree
     // per-iteration state
@@ -105,7 +110,7 @@ int set_smem(Solver& h, K kernel, size_t bytes) {
 
 SegParams seg_params(Solver& h) {
     SegParams p{};
-    p.N = h.N; p.S = h.S; p.batch = h.batch;
+    p.N = h.N; p.S = h.S; p.batch = h.batch; p.interior = h.interior ? 1 : 0;
     p.seg_start = h.d_seg_start; p.seg_len = h.d_seg_len;
     p.model = h.d_model; p.HN = h.d_HN; p.hN = h.d_hN;
     p.ws_prev = h.cur_ws; p.sigma = h.sigma;
@@ -184,7 +189,10 @@ template <int NX, int NU, int T>
 int forward_impl(Solver& h, const double* d_x0, double* d_ws_out) {
     SegParams p = seg_params(h);
     p.ws_out = d_ws_out;
-    if (h.S == 1) p.xhat = d_x0;
+    if (h.S == 1) {
+        p.xhat = d_x0;
+        if (h.have_root) p.uhat = h.d_root_lam;
+    }
     if constexpr (BatchDims<NX, NU>::ENABLED) {
         if (h.thread_path) {
             switch (h.fwd_variant) {
@@ -411,7 +419,7 @@ int set_model_common(Solver& h, const double* E, const double* c, const double* 
 
 TreeTopParams top_params(Solver& h, const double* d_x0, bool affine_only) {
     TreeTopParams tp{};
-    tp.batch = h.batch; tp.x0 = d_x0; tp.affine_only = affine_only ? 1 : 0;
+    tp.batch = h.batch; tp.x0 = d_x0; tp.lam0 = nullptr; tp.affine_only = affine_only ? 1 : 0;
     for (TreeLevel& lv : h.levels)
         if (lv.in_top) {
             const int i = tp.nlevels++;
@@ -472,8 +480,13 @@ int run_backward_nofact(Solver& h) {
 
 int run_forward(Solver& h, const double* d_x0, double* d_ws_out) {
     if (!h.backward_done) return fail(&h, PDPLQR_ERR_ORDER, "forward before backward (one forward per backward)");
+    if (h.interior && !h.have_root)
+        return fail(&h, PDPLQR_ERR_ORDER, "forward on an interior horizon shard needs pdplqr_set_root_boundary_device first");
+    if (h.have_root) d_x0 = h.d_root_x;
     if (h.S > 1) {
-        int rc = h.ops->tree_top_down(h, top_params(h, d_x0, false));
+        TreeTopParams ttp = top_params(h, d_x0, false);
+        if (h.have_root) ttp.lam0 = h.d_root_lam;
+        int rc = h.ops->tree_top_down(h, ttp);
         if (rc) return rc;
         for (int l = (int)h.levels.size() - 1; l >= 0; --l) {
             TreeLevel& lv = h.levels[l];
@@ -556,7 +569,7 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
         h->seg_start[i] = st; h->seg_len[i] = len;
     }
     if (h->seg_len[S - 1] < 1) { delete h; return PDPLQR_ERR_INVALID; }
-    h->thread_path = (S == 1) && ops->has_thread_path && h->nc_total == 0;
+    h->thread_path = (S == 1) && ops->has_thread_path && h->nc_total == 0;   // (interior shards switch it off)
     h->frec = h->thread_path ? ops->FRECT : ops->FREC;
     h->mrec = h->thread_path ? ops->TREC : ops->REC;
     if (const char* e = getenv("PDPLQR_BWD_VARIANT")) h->bwd_variant = atoi(e);
@@ -743,7 +756,91 @@ int pdplqr_set_option(pdplqr_handle_t h, int option, int value) {
         h->factorized = false;
         return PDPLQR_OK;
     }
+    if (option == PDPLQR_OPT_INTERIOR_SHARD) {
+        h->interior = value != 0;
+        if (h->interior) {
+            if (h->thread_path) {   // the thread-per-problem records are packed differently: re-plan before set_model
+                if (h->model_set) return fail(h, PDPLQR_ERR_ORDER, "set PDPLQR_OPT_INTERIOR_SHARD before set_model");
+                h->thread_path = false;
+                h->frec = h->ops->FREC;
+                h->mrec = h->ops->REC;
+                if (dev_alloc(*h, &h->d_model, (size_t)h->batch * h->N * h->ops->REC)) return PDPLQR_ERR_CUDA;
+                if (dev_alloc(*h, &h->d_fac, (size_t)h->batch * h->N * h->ops->FREC)) return PDPLQR_ERR_CUDA;
+            }
+            if (!h->d_root_x) {
+                if (dev_alloc(*h, &h->d_root_x, (size_t)h->batch * h->nx)) return PDPLQR_ERR_CUDA;
+                if (dev_alloc(*h, &h->d_root_lam, (size_t)h->batch * h->nx)) return PDPLQR_ERR_CUDA;
+            }
+        }
+        h->factorized = false;
+        return PDPLQR_OK;
+    }
     return fail(h, PDPLQR_ERR_INVALID, "unknown option");
+}
+
+// ---- horizon sharding (one handle per time slice / rank) --------------------------------------------------
+int pdplqr_summary_doubles(pdplqr_handle_t h) { return h ? h->ops->SREC : PDPLQR_ERR_INVALID; }
+
+int pdplqr_get_root_summary_device(pdplqr_handle_t h, double* out) {
+    if (!h || !out) return fail(h, PDPLQR_ERR_INVALID, "get_root_summary: null pointer");
+    if (!h->factorized) return fail(h, PDPLQR_ERR_ORDER, "get_root_summary before backward");
+    cudaSetDevice(h->device);
+    const double* src = (h->S > 1) ? h->levels.back().sum : h->d_sum;
+    CU_TRY(h, cudaMemcpyAsync(out, src, (size_t)h->batch * h->ops->SREC * 8, cudaMemcpyDeviceToDevice, h->stream));
+    return PDPLQR_OK;
+}
+
+int pdplqr_set_root_boundary_device(pdplqr_handle_t h, const double* xhat, const double* lam) {
+    if (!h || !xhat) return fail(h, PDPLQR_ERR_INVALID, "set_root_boundary: null pointer");
+    cudaSetDevice(h->device);
+    if (!h->d_root_x) {
+        if (dev_alloc(*h, &h->d_root_x, (size_t)h->batch * h->nx)) return PDPLQR_ERR_CUDA;
+        if (dev_alloc(*h, &h->d_root_lam, (size_t)h->batch * h->nx)) return PDPLQR_ERR_CUDA;
+    }
+    const size_t nb = (size_t)h->batch * h->nx * 8;
+    CU_TRY(h, cudaMemcpyAsync(h->d_root_x, xhat, nb, cudaMemcpyDeviceToDevice, h->stream));
+    if (lam) CU_TRY(h, cudaMemcpyAsync(h->d_root_lam, lam, nb, cudaMemcpyDeviceToDevice, h->stream));
+    else CU_TRY(h, cudaMemsetAsync(h->d_root_lam, 0, nb, h->stream));
+    h->have_root = true;
+    return PDPLQR_OK;
+}
+
+// Coupler: solves the interface system of G time slices from their (all-gathered) root summaries.
+int pdplqr_coupler_create(pdplqr_handle_t* out, int nx, int nu, int num_shards, int batch, int device) {
+    if (!out) return PDPLQR_ERR_INVALID;
+    *out = nullptr;
+    if (num_shards < 1 || num_shards > TREE_TOP_MAX_NODES) return PDPLQR_ERR_INVALID;
+    // a coupler is a handle whose "segments" are the shards: reuse the tree plan of an S = num_shards handle
+    int rc = pdplqr_create(out, nx, nu, /*N=*/num_shards, nullptr, batch, /*num_segments=*/num_shards, 0,
+                           PDPLQR_CONDENSED_LU, device);
+    if (rc) return rc;
+    (*out)->is_coupler = true;
+    return PDPLQR_OK;
+}
+
+int pdplqr_coupler_solve_device(pdplqr_handle_t c, const double* summaries, const double* x0, double* xhat,
+                                double* lam) {
+    if (!c || !c->is_coupler || !summaries || !x0 || !xhat || !lam)
+        return fail(c, PDPLQR_ERR_INVALID, "coupler_solve: bad arguments");
+    cudaSetDevice(c->device);
+    const int G = c->S;
+    const size_t nb = (size_t)c->batch * G * c->nx * 8;
+    if (G == 1) {
+        CU_TRY(c, cudaMemcpyAsync(xhat, x0, (size_t)c->batch * c->nx * 8, cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(c, cudaMemsetAsync(lam, 0, nb, c->stream));
+        return PDPLQR_OK;
+    }
+    // summaries are laid out [batch][G][SREC] exactly like the level-0 array of the tree
+    CU_TRY(c, cudaMemcpyAsync(c->d_sum, summaries, (size_t)c->batch * G * c->ops->SREC * 8, cudaMemcpyDeviceToDevice,
+                              c->stream));
+    int rc = run_tree_up(*c, false);
+    if (rc) return rc;
+    TreeTopParams ttp = top_params(*c, x0, false);
+    rc = c->ops->tree_top_down(*c, ttp);
+    if (rc) return rc;
+    CU_TRY(c, cudaMemcpyAsync(xhat, c->d_xhat, nb, cudaMemcpyDeviceToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(lam, c->d_uhat, nb, cudaMemcpyDeviceToDevice, c->stream));
+    return PDPLQR_OK;
 }
 
 int pdplqr_forward_device(pdplqr_handle_t h, const double* x0, double* ws_out) {
@@ -796,11 +893,11 @@ int pdplqr_get_gains(pdplqr_handle_t h, double* K, double* d, double* Gt) {
     for (size_t st = 0; st < nst; ++st) {
         const double* z = host.data() + st * FREC;
         const int k = (int)(st % h->N);
-        const bool in_last = k >= h->seg_start[h->S - 1];
+        const bool in_last = !h->interior && k >= h->seg_start[h->S - 1];
         if (K) std::memcpy(K + st * nu * nx, z, sizeof(double) * nu * nx);
         if (d) std::memcpy(d + st * nu, z + nu * nx, sizeof(double) * nu);
         if (Gt) {
-            if (in_last || h->S == 1) std::memset(Gt + st * nu * nx, 0, sizeof(double) * nu * nx);
+            if (in_last || (h->S == 1 && !h->interior)) std::memset(Gt + st * nu * nx, 0, sizeof(double) * nu * nx);
             else std::memcpy(Gt + st * nu * nx, z + nu * (nx + 1), sizeof(double) * nu * nx);
         }
     }

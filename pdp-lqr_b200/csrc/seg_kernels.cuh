@@ -46,6 +46,7 @@ struct SegDims {
 
 struct SegParams {
     int N, S, batch;
+    int interior;            // 1: this handle is a horizon shard whose last segment ends at an interface, not at the terminal
     const int* seg_start;    // [S]
     const int* seg_len;      // [S]
     const double* model;     // [batch][N][REC]
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
     const int g = blockIdx.x;
     const int b = g / p.S, seg = g % p.S;
     const int N0 = p.seg_start[seg], LEN = p.seg_len[seg], N1 = N0 + LEN;
-    const bool is_last = (seg == p.S - 1);
+    const bool is_last = (seg == p.S - 1) && !p.interior;
     const bool pdp = !is_last;
 
     double* rec = smem + L::o_rec;
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
     const int gidx = blockIdx.x;
     const int b = gidx / p.S, seg = gidx % p.S;
     const int N0 = p.seg_start[seg], LEN = p.seg_len[seg], N1 = N0 + LEN;
-    const bool is_last = (seg == p.S - 1);
+    const bool is_last = (seg == p.S - 1) && !p.interior;
     const bool pdp = !is_last;
 
     double* rec = smem + L::o_rec;
@@ -632,7 +633,7 @@ __global__ void __launch_bounds__(T) seg_forward_kernel(SegParams p) {
     const int g = blockIdx.x;
     const int b = g / p.S, seg = g % p.S;
     const int N0 = p.seg_start[seg], LEN = p.seg_len[seg], N1 = N0 + LEN;
-    const bool is_last = (seg == p.S - 1);
+    const bool is_last = (seg == p.S - 1) && !p.interior;
 
     double* rec = smem + L::o_rec;
     double* fac = smem + L::o_fac;

@@ -64,7 +64,8 @@ struct TreeTopParams {   // the upper, binary part of the tree: levels[0] is the
     double* dd[TREE_TOP_MAX_LEVELS];
     double* x[TREE_TOP_MAX_LEVELS];
     double* lam[TREE_TOP_MAX_LEVELS];
-    const double* x0;      // [batch][NX]
+    const double* x0;      // [batch][NX]   entry state of the root
+    const double* lam0;    // [batch][NX]   exit costate of the root (nullptr -> zeros: the root ends at the terminal)
     int affine_only;
 };
 
@@ -529,7 +530,7 @@ __global__ void __launch_bounds__(TreeTopSmem<NX>::WARPS * 32) tree_top_down_ker
         if (warp == 0)
             for (int r = lane; r < NX; r += 32) {
                 p.x[top][(size_t)b * NX + r] = p.x0[(size_t)b * NX + r];
-                p.lam[top][(size_t)b * NX + r] = 0.0;
+                p.lam[top][(size_t)b * NX + r] = p.lam0 ? p.lam0[(size_t)b * NX + r] : 0.0;
             }
         __threadfence_block();
         __syncthreads();

@@ -136,6 +136,17 @@ class LQRCudaSolver:
     def forward_device(self, x0, ws_out):
         self._check(self._lib.pdplqr_forward_device(self._h, _dptr(x0), _dptr(ws_out)))
 
+    # ------------------------------------------------------------------ horizon sharding (one handle per time slice)
+    def summary_doubles(self) -> int:
+        return int(self._lib.pdplqr_summary_doubles(self._h))
+
+    def root_summary_device(self, out):
+        """[batch, summary_doubles] device tensor <- summary (P | F | C | p | f) of this handle's whole slice."""
+        self._check(self._lib.pdplqr_get_root_summary_device(self._h, _dptr(out)))
+
+    def set_root_boundary_device(self, xhat, lam=None):
+        self._check(self._lib.pdplqr_set_root_boundary_device(self._h, _dptr(xhat), _dptr(lam)))
+
     def synchronize(self):
         self._check(self._lib.pdplqr_synchronize(self._h))
 
@@ -179,3 +190,36 @@ class LQRCudaSolver:
         a, b = C.c_int(), C.c_int()
         self._check(self._lib.pdplqr_record_doubles(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+class Coupler:
+    """Interface system of G time slices (ranks): summaries [batch, G, summary_doubles] + x0 -> entry state and exit
+    costate of every slice.  Device tensors only (include/pdplqr.h, pdplqr_coupler_*)."""
+
+    def __init__(self, nx, nu, num_shards, batch=1, device=0):
+        self._lib = capi.load()
+        h = C.c_void_p()
+        rc = self._lib.pdplqr_coupler_create(C.byref(h), nx, nu, num_shards, batch, device)
+        if rc != capi.OK:
+            raise PdplqrError(rc, "coupler_create failed")
+        self._h = h
+        self.nx, self.G, self.batch = nx, num_shards, batch
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._lib.pdplqr_set_stream(self._h, C.c_void_p(cuda_stream_ptr))
+
+    def solve_device(self, summaries, x0, xhat, lam):
+        rc = self._lib.pdplqr_coupler_solve_device(self._h, _dptr(summaries), _dptr(x0), _dptr(xhat), _dptr(lam))
+        if rc != capi.OK:
+            raise PdplqrError(rc, self._lib.pdplqr_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pdplqr_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

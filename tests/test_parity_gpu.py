@@ -283,3 +283,50 @@ def test_nofact_before_backward_is_an_order_error():
     with pytest.raises(P.PdplqrError) as e:
         sol.backward_without_factorization()
     assert e.value.code == P.capi.ERR_ORDER
+
+
+@pytest.mark.parametrize("G,S_local", [(2, 1), (4, 4), (3, 0), (8, 16)])
+def test_horizon_shards_on_one_gpu(oracle, G, S_local):
+    """Horizon sharding (config 5 flow) emulated on ONE GPU: G handles own G time slices (interior shards +
+    the terminal one), their slice summaries feed the coupler, every slice rolls out from its own boundary values.
+    Same calls as sharding.HorizonShardedSolver, with the all_gather replaced by a torch.stack."""
+    import torch
+    from pdplqr_b200 import sharding
+    from pdplqr_b200.solver import Coupler
+    N = 512
+    p = P.problems.quadrotor_ltv(N)
+    ref = oracle.OracleSolver(p).solve()
+    dev = torch.device("cuda", 0)
+    x0 = torch.from_numpy(p.x0).to(dev)
+    sols, outs, sums = [], [], []
+    for r, (start, count) in enumerate(sharding.horizon_slices(N, G)):
+        last = r == G - 1
+        loc = sharding.slice_problem(p, start, count, last)
+        s = P.LQRCudaSolver(p.nx, p.nu, count, num_segments=S_local, load_balancing=False)
+        if not last:
+            s.set_option(P.capi.OPT_INTERIOR_SHARD, 1)
+        s.set_model(loc)
+        s.update_problem_data_device(None, sigma=1e-6)
+        s.backward_device()
+        sm = torch.empty(1, s.summary_doubles(), dtype=torch.float64, device=dev)
+        s.root_summary_device(sm)
+        s.synchronize()
+        sols.append(s); sums.append(sm[0])
+    coup = Coupler(p.nx, p.nu, G)
+    xhat = torch.empty(1, G, p.nx, dtype=torch.float64, device=dev)
+    lam = torch.empty(1, G, p.nx, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    coup.solve_device(torch.stack(sums).unsqueeze(0).contiguous(), x0, xhat, lam)
+    coup._lib.pdplqr_synchronize(coup._h)
+    full = np.zeros(p.ws_len)
+    for r, (start, count) in enumerate(sharding.horizon_slices(N, G)):
+        out = torch.zeros(1, count * p.s + p.nx, dtype=torch.float64, device=dev)
+        sols[r].set_root_boundary_device(xhat[:, r].contiguous(), lam[:, r].contiguous())
+        sols[r].forward_device(x0, out)
+        sols[r].synchronize()
+        o = out.cpu().numpy()[0]
+        n = count * p.s + (p.nx if r == G - 1 else 0)
+        full[start * p.s:start * p.s + n] = o[:n]
+    assert rel_err(full, ref) < TOL
+    xh_ref, _ = sharding.couple_numpy(torch.stack(sums).cpu().numpy(), p.x0[0])
+    assert rel_err(xhat.cpu().numpy()[0], xh_ref) < TOL
