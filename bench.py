@@ -52,6 +52,10 @@ def make_workload(name: str, rank: int):
         prob = P.problems.quadrotor_ltv(1 << 20)
         return prob, dict(num_segments=(1 << 20) // 64, load_balancing=False), \
             "C5: quadrotor LQR nx=12 nu=4 N=2^20, single problem, 16384 segments (configs[4], 1 GPU)"
+    if name == "c5small":
+        prob = P.problems.quadrotor_ltv(1 << 16)
+        return prob, dict(num_segments=(1 << 16) // 64, load_balancing=False), \
+            "C5-small: quadrotor LQR nx=12 nu=4 N=2^16 (debug size)"
     if name == "c1":
         prob = P.problems.quadrotor_example()
         return prob, dict(num_segments=4), "C1: examples/lqr_example.cpp as shipped (configs[0])"
@@ -222,11 +226,23 @@ def main():
 
     sampler = ClockSampler(local_rank)
     windows = []
-    prob, kw, desc = make_workload(args.workload, rank)
-    sol = P.LQRCudaSolver.from_problem(prob, device=local_rank, **kw)
+    horizon_sharded = args.workload in ("c5", "c5small") and world > 1
+    prob, kw, desc = make_workload(args.workload, 0 if horizon_sharded else rank)
     stream = torch.cuda.current_stream()
-    sol.set_stream(stream.cuda_stream)
-    pdp = sol.num_segments > 1
+    if horizon_sharded:
+        # one long problem, contiguous time slices per rank, ONE all_gather of a 3,648-byte summary per solve
+        from pdplqr_b200.sharding import HorizonShardedSolver
+        hs = HorizonShardedSolver(prob, rank, world, num_segments=max(1, kw["num_segments"] // world), device=local_rank)
+        hs.set_stream(stream.cuda_stream)
+        sol = hs.sol
+        full_N = prob.N
+        prob = hs.local
+        prob.x0 = hs.x0.cpu().numpy()
+    else:
+        sol = P.LQRCudaSolver.from_problem(prob, device=local_rank, **kw)
+        sol.set_stream(stream.cuda_stream)
+        full_N = prob.N
+    pdp = sol.num_segments > 1 or horizon_sharded
     B, N, nx, nu, s = prob.batch, prob.N, prob.nx, prob.nu, prob.s
 
     # device-resident iterates (ADMM would update ws between solves; here a fixed seeded iterate)
@@ -240,6 +256,9 @@ def main():
     sigma = 1e-6
 
     def step_device():
+        if horizon_sharded:
+            hs.solve_device(ws_dev, sigma, out_dev)
+            return
         sol.update_problem_data_device(ws_dev, sigma=sigma)
         sol.backward_device()
         sol.forward_device(x0_dev, out_dev)
@@ -281,17 +300,29 @@ def main():
     ms_bwd = e0.elapsed_time(e1) / kb
     windows.append((t_w0, time.time()))
     # leave the handle in a consistent state (one forward per backward)
-    sol.forward_device(x0_dev, out_dev)
+    if horizon_sharded:
+        hs.solve_device(ws_dev, sigma, out_dev)
+    else:
+        sol.forward_device(x0_dev, out_dev)
     torch.cuda.synchronize()
 
     # end-to-end through the host-buffer C ABI (pinned host memory; H2D + kernels + D2H inside the timed region)
     ws_np, x0_np, out_np = ws_host.numpy(), x0_host.numpy(), out_host.numpy()
     e2e_steps = max(3, min(args.steps, 10))
-    sol.solve(ws_np, x0_np, out_np, sigma=sigma)
+
+    def step_e2e():
+        if horizon_sharded:   # host slice in, sharded solve, host slice out (pinned buffers)
+            ws_dev.copy_(ws_host, non_blocking=True)
+            hs.solve_device(ws_dev, sigma, out_dev)
+            out_host.copy_(out_dev, non_blocking=True)
+            torch.cuda.synchronize()
+        else:
+            sol.solve(ws_np, x0_np, out_np, sigma=sigma)
+    step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        sol.solve(ws_np, x0_np, out_np, sigma=sigma)
+        step_e2e()
     torch.cuda.synchronize()
     t_e2e = (time.perf_counter() - t0) / e2e_steps
     windows.append((time.time() - t_e2e * e2e_steps, time.time()))
@@ -305,7 +336,8 @@ def main():
 
     if rank == 0:
         ms_step = ms_total / args.steps
-        value = world * B * 1e3 / ms_step
+        solves_per_step = B if horizon_sharded else world * B   # a sharded long horizon is ONE solve across all ranks
+        value = solves_per_step * 1e3 / ms_step
         bwd_b, fwd_b = algorithmic_bytes_per_stage(nx, nu, pdp)
         peaks = {}
         pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -319,15 +351,19 @@ def main():
             traffic = json.load(open(tr_path)).get(args.workload)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if horizon_sharded else "weak",
+            "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": desc, "problems_per_gpu": B, "nx": nx, "nu": nu, "N": N,
                        "num_segments": sol.num_segments, "sigma": sigma,
                        "l2": "inputs larger than L2 (model records %.2f GB per GPU)" % (B * N * sol.record_doubles()[0] * 8 / 1e9),
-                       "sharding": "independent problems per rank, no data-path collective"},
+                       "sharding": ("horizon: contiguous time slices per rank, one all_gather of a %d-byte slice summary per solve"
+                                    % (sol.summary_doubles() * 8)) if horizon_sharded else
+                                   "independent problems per rank, no data-path collective",
+                       "full_horizon": full_N},
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
                        "samples": clocks["samples"]},
-            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT,
+            "e2e": {"value": solves_per_step / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(ws_host.numel() * 8 + x0_host.numel() * 8),
                     "d2h_bytes_per_step": int(out_host.numel() * 8), "ms_per_step": ms_e2e,
                     "model": "resident (uploaded once by pdplqr_set_model)", "matches_device_path": same},
