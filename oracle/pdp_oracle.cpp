@@ -7,10 +7,10 @@
 // reference file:line it follows; the operation order inside a stage follows the reference.
 //
 // PARITY STATUS: the reference ships no tests / golden vectors, so this oracle is pinned by
-//   (i)   sequential == parallel (S in {2,4,8}, LU and Cholesky condensed variants),
-//   (ii)  an independent dense KKT solve in numpy (tests/test_oracle.py),
-//   (iii) the reference sources themselves compiled against an Eigen-API shim (oracle/_ref,
-//         see oracle/Makefile) when that build is available.
+//   (i)   the reference's own headers compiled unmodified against an Eigen-API shim (oracle/_ref, oracle/Makefile
+//         target `ref`, tests/test_reference_build.py) -- agreement <= 1e-11 incl. constraints / no-refactor,
+//   (ii)  sequential == parallel (S in {2,4,8}, LU and Cholesky condensed variants),
+//   (iii) an independent sparse KKT solve in numpy/scipy (tests/test_oracle.py, tests/kkt_ref.py).
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load this library, and only as the checker / CPU baseline.
 //
