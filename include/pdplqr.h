@@ -117,6 +117,22 @@ int pdplqr_coupler_create(pdplqr_handle_t* out, int nx, int nu, int num_shards, 
 int pdplqr_coupler_solve_device(pdplqr_handle_t coupler, const double* summaries, const double* x0, double* xhat,
                                 double* lam);
 
+/* Conic ADMM outer iteration (addition -- NOT IN THE REFERENCE, which ships only the hooks: the ws/ys/zs/rho/
+ * inv_rho/sigma arguments, lqr_solver_parallel.hpp:33-37, and Node::D_con/e_lb/e_ub, lqr_model.hpp:21-24, with the
+ * example's constraints disabled, lqr_example.cpp:127,158).  OSQP-form ADMM on  D_k w_k in K_k  where every stage's
+ * rows are tiled by cones: type 0 = box [e_lb, e_ub], 1 = second-order cone (first row is t, ||rest|| <= t),
+ * 2 = ball (||rows|| <= e_ub[first row]).  Cones are listed stage by stage.  One factorising backward, then
+ * backward_without_factorization per iteration; everything stays on the device between iterations.
+ * ws (warm start in / solution out), zs, ys: host arrays in the layouts above.  residuals_out[2] = primal, dual. */
+#define PDPLQR_CONE_BOX 0
+#define PDPLQR_CONE_SOC 1
+#define PDPLQR_CONE_BALL 2
+int pdplqr_admm_set_cones(pdplqr_handle_t h, int ncones, const int* stage, const int* row0, const int* dim,
+                          const int* type, const double* e_lb, const double* e_ub);
+int pdplqr_admm_solve(pdplqr_handle_t h, const double* x0, double* ws, double* zs, double* ys, const double* rho,
+                      double sigma, double alpha, int max_iter, double eps_abs, double eps_rel, int check_every,
+                      int* iters_out, double* residuals_out);
+
 /* Accessors (additions; the reference keeps these in a private workspace, lqr_solver_parallel.hpp:55-60).
  * All outputs are host arrays; any pointer may be NULL to skip it.
  *   partition: starts[S], lens[S]                                   (lqr_solver_parallel.hpp:73-80)

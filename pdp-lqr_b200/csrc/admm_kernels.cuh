@@ -1,0 +1,146 @@
+// Conic ADMM outer iteration on top of the LQ solve.
+// NOT IN THE REFERENCE: the reference ships only the hooks -- the ws/ys/zs/rho/inv_rho/sigma arguments of
+// update_problem_data (lqr_solver_parallel.hpp:33-37) and Node::D_con, e_lb, e_ub (lqr_model.hpp:21-24, never read by
+// any solver); its example disables the constraints (lqr_example.cpp:127,158).  The iteration implemented here is
+// the OSQP-form ADMM those hooks are shaped for, with cone projections instead of box clamps only:
+//     w~      = LQ solve with  H + sigma I + D^T rho D ,  h - sigma w - D^T (rho o (z - y/rho))     (the hot path)
+//     z~      = D w~
+//     w       = alpha w~ + (1 - alpha) w_prev ,      z^ = alpha z~ + (1 - alpha) z_prev
+//     z       = Proj_K(z^ + y / rho)                  K = product of boxes [e_lb, e_ub], second-order cones, balls
+//     y       = y + rho o (z^ - z)
+//     r_prim  = || z~ - z ||_inf ,    r_dual = || D^T (rho o (z - z_prev)) ||_inf
+// One warp per (problem, stage): lanes over constraint rows for the mat-vec, lanes over cones for the projections.
+// Parity is pinned against an independent numpy restatement of the same iteration kept with the test infrastructure
+// ("parity unpinned" by the reference by construction).
+#pragma once
+#include "common.cuh"
+
+namespace pdplqr {
+
+enum ConeType { CONE_BOX = 0, CONE_SOC = 1, CONE_BALL = 2 };
+
+struct AdmmParams {
+    int nx, nu, N, batch, ncmax;
+    const int* ncs;            // [N+1]
+    const long long* coff;     // [N+2]
+    const long long* doff;     // [N+2] (padded device layout of D)
+    const double* Dm;          // [batch][d_total]
+    long long d_total, nc_total;
+    // cones: per stage k the cones cone_first[k] .. cone_first[k+1]-1 ; each (type, first row within stage, dim)
+    const int* cone_first;     // [N+2]
+    const int* cone_type;
+    const int* cone_row;
+    const int* cone_dim;
+    const double* e_lb;        // [batch][nc_total]   box bounds (ball: radius in e_ub of the first row)
+    const double* e_ub;
+    const double* w_tilde;     // [batch][ws_len]   LQ solution of this iteration
+    double* w;                 // [batch][ws_len]   in: w_prev, out: relaxed iterate
+    double* z;                 // [batch][nc_total] in: z_prev, out: z
+    double* y;                 // [batch][nc_total] in/out
+    const double* rho;         // [batch][nc_total]
+    double alpha;
+    unsigned long long* res;   // [4] bit patterns of non-negative doubles: r_prim, r_dual, max|z~|,|z| , max|D^T y|
+};
+
+PDPLQR_DEVINL void atomic_max_nonneg(unsigned long long* addr, double v) {
+    // non-negative IEEE doubles order like their bit patterns
+    atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}
+
+__global__ void __launch_bounds__(32) admm_update_kernel(AdmmParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x;
+    const int k = blockIdx.x % (p.N + 1);
+    const int b = blockIdx.x / (p.N + 1);
+    const int s = p.nx + p.nu;
+    const int dim = (k < p.N) ? s : p.nx;
+    const int nc = p.ncs[k];
+    const size_t ws_len = (size_t)p.N * s + p.nx;
+    const size_t wo = (size_t)b * ws_len + (size_t)k * s;
+    double* wt = smem;                 // w~ of this stage   (dim)
+    double* v = smem + s;              // z^ + y/rho         (ncmax)
+    double* zt = v + p.ncmax;          // z~                 (ncmax)
+    double* dz = zt + p.ncmax;         // rho o (z - z_prev) (ncmax)
+    for (int i = lane; i < dim; i += 32) {
+        const double a = p.w_tilde[wo + i];
+        wt[i] = a;
+        p.w[wo + i] = p.alpha * a + (1.0 - p.alpha) * p.w[wo + i];
+    }
+    if (nc == 0) return;
+    __syncwarp();
+    const double* Dk = p.Dm + (size_t)b * p.d_total + p.doff[k];
+    const size_t co = (size_t)b * p.nc_total + p.coff[k];
+    double r_prim = 0.0, nrm = 0.0;
+    for (int r = lane; r < nc; r += 32) {
+        double acc = 0.0;
+        for (int j = 0; j < dim; ++j) acc = fma(Dk[r + (size_t)j * nc], wt[j], acc);
+        zt[r] = acc;
+        const double zh = p.alpha * acc + (1.0 - p.alpha) * p.z[co + r];
+        v[r] = zh + p.y[co + r] / p.rho[co + r];
+    }
+    __syncwarp();
+    // projections: one lane per cone
+    for (int c = p.cone_first[k] + lane; c < p.cone_first[k + 1]; c += 32) {
+        const int r0 = p.cone_row[c], d = p.cone_dim[c], type = p.cone_type[c];
+        if (type == CONE_BOX) {
+            for (int r = r0; r < r0 + d; ++r) v[r] = fmin(fmax(v[r], p.e_lb[co + r]), p.e_ub[co + r]);
+        } else if (type == CONE_SOC) {
+            double nv = 0.0;
+            for (int r = r0 + 1; r < r0 + d; ++r) nv = fma(v[r], v[r], nv);
+            nv = sqrt(nv);
+            const double t = v[r0];
+            if (nv <= t) { /* inside */ }
+            else if (nv <= -t) { for (int r = r0; r < r0 + d; ++r) v[r] = 0.0; }
+            else {
+                const double a = 0.5 * (t + nv), sc = a / nv;
+                v[r0] = a;
+                for (int r = r0 + 1; r < r0 + d; ++r) v[r] *= sc;
+            }
+        } else {  // ball of radius e_ub[first row]
+            double nv = 0.0;
+            for (int r = r0; r < r0 + d; ++r) nv = fma(v[r], v[r], nv);
+            nv = sqrt(nv);
+            const double rad = p.e_ub[co + r0];
+            if (nv > rad) { const double sc = rad / nv; for (int r = r0; r < r0 + d; ++r) v[r] *= sc; }
+        }
+    }
+    __syncwarp();
+    for (int r = lane; r < nc; r += 32) {
+        const double zold = p.z[co + r], znew = v[r], rr = p.rho[co + r];
+        const double zh = p.alpha * zt[r] + (1.0 - p.alpha) * zold;
+        const double ynew = p.y[co + r] + rr * (zh - znew);
+        p.z[co + r] = znew;
+        p.y[co + r] = ynew;
+        dz[r] = rr * (znew - zold);
+        v[r] = ynew;                       // reuse: y for the D^T y norm
+        r_prim = fmax(r_prim, fabs(zt[r] - znew));
+        nrm = fmax(nrm, fmax(fabs(zt[r]), fabs(znew)));
+    }
+    __syncwarp();
+    double r_dual = 0.0, nrm_d = 0.0;
+    for (int j = lane; j < dim; j += 32) {
+        double acc = 0.0, accy = 0.0;
+        for (int r = 0; r < nc; ++r) {
+            const double dv = Dk[r + (size_t)j * nc];
+            acc = fma(dv, dz[r], acc);
+            accy = fma(dv, v[r], accy);
+        }
+        r_dual = fmax(r_dual, fabs(acc));
+        nrm_d = fmax(nrm_d, fabs(accy));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        r_prim = fmax(r_prim, __shfl_xor_sync(0xffffffffu, r_prim, off));
+        r_dual = fmax(r_dual, __shfl_xor_sync(0xffffffffu, r_dual, off));
+        nrm = fmax(nrm, __shfl_xor_sync(0xffffffffu, nrm, off));
+        nrm_d = fmax(nrm_d, __shfl_xor_sync(0xffffffffu, nrm_d, off));
+    }
+    if (lane == 0) {
+        atomic_max_nonneg(&p.res[0], r_prim);
+        atomic_max_nonneg(&p.res[1], r_dual);
+        atomic_max_nonneg(&p.res[2], nrm);
+        atomic_max_nonneg(&p.res[3], nrm_d);
+    }
+}
+
+}  // namespace pdplqr

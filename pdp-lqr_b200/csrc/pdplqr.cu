@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "admm_kernels.cuh"
 #include "batch_kernels.cuh"
 #include "seg_kernels.cuh"
 #include "tree_kernels.cuh"
@@ -58,6 +59,13 @@ struct pdplqr_solver {
     // affine cache for backward_without_factorization
     bool keep_affine = false;
     double* d_aff = nullptr;
+    // conic ADMM outer loop (a11)
+    int ncones = 0;
+    int *d_cone_first = nullptr, *d_cone_type = nullptr, *d_cone_row = nullptr, *d_cone_dim = nullptr;
+    double *d_elb = nullptr, *d_eub = nullptr, *d_wtilde = nullptr, *d_w = nullptr, *d_z = nullptr, *d_y = nullptr, *d_rho_admm = nullptr,
+           *d_invrho_admm = nullptr;
+    unsigned long long* d_res = nullptr;
+    bool cones_set = false;
     // horizon sharding
     bool interior = false;         // slice ends at an interface (not the true terminal)
     bool is_coupler = false;       // handle created by pdplqr_coupler_create (interface tree only)
@@ -949,6 +957,117 @@ int pdplqr_record_doubles(pdplqr_handle_t h, int* model_rec, int* factor_rec) {
     if (!h) return PDPLQR_ERR_INVALID;
     if (model_rec) *model_rec = h->mrec;
     if (factor_rec) *factor_rec = h->frec;
+    return PDPLQR_OK;
+}
+
+// ---- conic ADMM outer iteration (addition; NOT in the reference -- SURVEY.md section 8 row a11) -----------------
+int pdplqr_admm_set_cones(pdplqr_handle_t h, int ncones, const int* stage, const int* row0, const int* dim,
+                          const int* type, const double* e_lb, const double* e_ub) {
+    if (!h || h->nc_total == 0) return fail(h, PDPLQR_ERR_INVALID, "admm_set_cones: the problem has no constraints");
+    if (ncones < 1 || !stage || !row0 || !dim || !type || !e_lb || !e_ub) return fail(h, PDPLQR_ERR_INVALID, "admm_set_cones: bad arguments");
+    cudaSetDevice(h->device);
+    // cones must be given stage by stage (non-decreasing), tile the rows of every stage exactly once
+    std::vector<int> first(h->N + 2, 0);
+    std::vector<int> covered(h->N + 1, 0);
+    for (int c = 0; c < ncones; ++c) {
+        if (stage[c] < 0 || stage[c] > h->N || (c > 0 && stage[c] < stage[c - 1])) return fail(h, PDPLQR_ERR_INVALID, "admm_set_cones: cones must be sorted by stage");
+        if (row0[c] != covered[stage[c]] || dim[c] < 1 || type[c] < 0 || type[c] > 2) return fail(h, PDPLQR_ERR_INVALID, "admm_set_cones: cones must tile the rows of a stage in order");
+        covered[stage[c]] += dim[c];
+        first[stage[c] + 1] = c + 1;
+    }
+    for (int k = 0; k <= h->N; ++k) {
+        if (covered[k] != h->ncs[k]) return fail(h, PDPLQR_ERR_INVALID, "admm_set_cones: rows of a stage not covered");
+        if (first[k + 1] < first[k]) first[k + 1] = first[k];
+    }
+    const size_t B = h->batch, nct = (size_t)h->nc_total, wsl = (size_t)h->N * h->s + h->nx;
+    int rc = 0;
+    if (!h->d_cone_first) {
+        rc |= dev_alloc(*h, &h->d_cone_first, h->N + 2);
+        rc |= dev_alloc(*h, &h->d_elb, B * nct);
+        rc |= dev_alloc(*h, &h->d_eub, B * nct);
+        rc |= dev_alloc(*h, &h->d_wtilde, B * wsl);
+        rc |= dev_alloc(*h, &h->d_w, B * wsl);
+        rc |= dev_alloc(*h, &h->d_z, B * nct);
+        rc |= dev_alloc(*h, &h->d_y, B * nct);
+        rc |= dev_alloc(*h, &h->d_rho_admm, B * nct);
+        rc |= dev_alloc(*h, &h->d_invrho_admm, B * nct);
+        rc |= dev_alloc(*h, &h->d_res, 4);
+    }
+    rc |= dev_alloc(*h, &h->d_cone_type, ncones);
+    rc |= dev_alloc(*h, &h->d_cone_row, ncones);
+    rc |= dev_alloc(*h, &h->d_cone_dim, ncones);
+    if (rc) return PDPLQR_ERR_CUDA;
+    h->ncones = ncones;
+    CU_TRY(h, cudaMemcpy(h->d_cone_first, first.data(), sizeof(int) * (h->N + 2), cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(h->d_cone_type, type, sizeof(int) * ncones, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(h->d_cone_row, row0, sizeof(int) * ncones, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(h->d_cone_dim, dim, sizeof(int) * ncones, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(h->d_elb, e_lb, B * nct * 8, cudaMemcpyHostToDevice));
+    CU_TRY(h, cudaMemcpy(h->d_eub, e_ub, B * nct * 8, cudaMemcpyHostToDevice));
+    h->cones_set = true;
+    return PDPLQR_OK;
+}
+
+int pdplqr_admm_solve(pdplqr_handle_t h, const double* x0, double* ws, double* zs, double* ys, const double* rho,
+                      double sigma, double alpha, int max_iter, double eps_abs, double eps_rel, int check_every,
+                      int* iters_out, double* residuals_out) {
+    if (!h || !x0 || !ws || !zs || !ys || !rho || max_iter < 1)
+        return fail(h, PDPLQR_ERR_INVALID, "admm_solve: bad arguments");
+    if (!h->cones_set) return fail(h, PDPLQR_ERR_ORDER, "admm_solve before admm_set_cones");
+    if (!h->model_set) return fail(h, PDPLQR_ERR_ORDER, "admm_solve before set_model");
+    cudaSetDevice(h->device);
+    const size_t B = h->batch, nct = (size_t)h->nc_total, wsl = (size_t)h->N * h->s + h->nx;
+    CU_TRY(h, cudaMemcpyAsync(h->d_w, ws, B * wsl * 8, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_z, zs, B * nct * 8, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_y, ys, B * nct * 8, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_rho_admm, rho, B * nct * 8, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_x0, x0, B * h->nx * 8, cudaMemcpyHostToDevice, h->stream));
+    {   // inv_rho = 1 / rho on the host side of the protocol (lqr_example.cpp:42-43), computed once
+        std::vector<double> inv(B * nct);
+        for (size_t i = 0; i < inv.size(); ++i) inv[i] = 1.0 / rho[i];
+        CU_TRY(h, cudaMemcpyAsync(h->d_invrho_admm, inv.data(), B * nct * 8, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    if (check_every < 1) check_every = 1;
+    int it = 0, rc = 0;
+    double res[4] = {0, 0, 0, 0};
+    bool converged = false;
+    for (it = 0; it < max_iter && !converged; ++it) {
+        rc = pdplqr_update_problem_data_device(h, h->d_w, h->d_y, h->d_z, h->d_invrho_admm, sigma);
+        if (rc) return rc;
+        rc = (it == 0) ? pdplqr_backward_device(h, h->d_rho_admm)
+                       : pdplqr_backward_without_factorization_device(h, h->d_rho_admm);
+        if (rc) return rc;
+        rc = run_forward(*h, h->d_x0, h->d_wtilde);
+        if (rc) return rc;
+        const bool check = ((it + 1) % check_every == 0) || (it + 1 == max_iter);
+        if (check) CU_TRY(h, cudaMemsetAsync(h->d_res, 0, 4 * sizeof(unsigned long long), h->stream));
+        AdmmParams ap{};
+        ap.nx = h->nx; ap.nu = h->nu; ap.N = h->N; ap.batch = h->batch; ap.ncmax = h->ncmax;
+        ap.ncs = h->d_ncs; ap.coff = h->d_coff; ap.doff = h->d_doff; ap.Dm = h->d_D;
+        ap.d_total = h->d_total_dev; ap.nc_total = h->nc_total;
+        ap.cone_first = h->d_cone_first; ap.cone_type = h->d_cone_type; ap.cone_row = h->d_cone_row; ap.cone_dim = h->d_cone_dim;
+        ap.e_lb = h->d_elb; ap.e_ub = h->d_eub;
+        ap.w_tilde = h->d_wtilde; ap.w = h->d_w; ap.z = h->d_z; ap.y = h->d_y; ap.rho = h->d_rho_admm;
+        ap.alpha = alpha; ap.res = h->d_res;
+        const size_t smem = (size_t)(h->s + 3 * h->ncmax) * sizeof(double);
+        admm_update_kernel<<<h->batch * (h->N + 1), 32, smem, h->stream>>>(ap);
+        h->launches++;
+        CU_TRY(h, cudaGetLastError());
+        if (check) {
+            unsigned long long bits[4];
+            CU_TRY(h, cudaMemcpyAsync(bits, h->d_res, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            for (int i = 0; i < 4; ++i) std::memcpy(&res[i], &bits[i], 8);
+            converged = res[0] <= eps_abs + eps_rel * res[2] && res[1] <= eps_abs + eps_rel * res[3];
+        }
+    }
+    CU_TRY(h, cudaMemcpyAsync(ws, h->d_w, B * wsl * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(zs, h->d_z, B * nct * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(ys, h->d_y, B * nct * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    if (iters_out) *iters_out = it;
+    if (residuals_out) { residuals_out[0] = res[0]; residuals_out[1] = res[1]; }
     return PDPLQR_OK;
 }
 

@@ -34,7 +34,8 @@ class Problem:
     D: np.ndarray | None = None
     e_lb: np.ndarray | None = None
     e_ub: np.ndarray | None = None
-    # SOC cones: list of (stage k, first row, dim); rows outside any cone are box rows.
+    # cones tiling every stage's constraint rows: list of (stage k, first row, dim, type) sorted by stage;
+    # type 0 = box [e_lb, e_ub], 1 = second-order cone (first row t >= ||rest||), 2 = ball (radius e_ub[first row])
     cones: list = field(default_factory=list)
     name: str = ""
 
@@ -152,6 +153,7 @@ def quadrotor_example(N: int = 100, constrained: bool = False) -> Problem:
         p.D = np.concatenate(Ds)[None]
         p.e_lb = np.concatenate(lbs)[None]
         p.e_ub = np.concatenate(ubs)[None]
+        p.cones = [(k, 0, int(ncs[k]), 0) for k in range(N + 1)]
     return p
 
 
@@ -254,17 +256,20 @@ def random_conic_batch(batch: int = 4096, N: int = 256, nx: int = 30, nu: int = 
     for k in range(N + 1):
         if k == N:
             Dk = np.eye(nx); lb, ub = -xmax, xmax
+            cones.append((k, 0, nx, 0))
         else:
             nb = nu if k == 0 else s
             Dk = np.zeros((nb + nsoc, s))
             Dk[:nb, :nb] = np.eye(nb)
             lb = np.concatenate([-umax, -xmax])[:nb]; ub = np.concatenate([umax, xmax])[:nb]
+            cones.append((k, 0, nb, 0))
             if nsoc:
-                # cone rows: (t; u_1..u_3) with t a constant 1.5 supplied through z's affine part:
-                # || (u_1,u_2,u_3) || <= t ; row nb is the all-zero "t" row (t enters via e), rows nb+1.. pick u.
-                Dk[nb + 1, 0] = 1.0; Dk[nb + 2, 1] = 1.0; Dk[nb + 3, 2] = 1.0
-                lb = np.concatenate([lb, [1.5, 0, 0, 0]]); ub = np.concatenate([ub, [1.5, 0, 0, 0]])
-                cones.append((k, nb, 4))
+                # second-order cone on the first four controls:  || (u_1, u_2, u_3) || <= u_0 + 1  is not conic in w,
+                # so the cone is put on the rows (u_0; u_1, u_2, u_3):  || (u_1,u_2,u_3) || <= u_0
+                for r in range(4):
+                    Dk[nb + r, r] = 1.0
+                lb = np.concatenate([lb, np.full(4, -np.inf)]); ub = np.concatenate([ub, np.full(4, np.inf)])
+                cones.append((k, nb, 4, 1))
         Ds.append(_cm(Dk)); lbs.append(lb); ubs.append(ub)
     D1 = np.concatenate(Ds)
     p = Problem(nx, nu, N, batch, E, c, H, h, HN, hN, x0, ncs,
@@ -309,4 +314,5 @@ def random_lq(nx: int, nu: int, N: int, batch: int = 1, seed: int = 0, nc: int =
         nct = int(ncs.sum())
         p.e_lb = -rng.uniform(0.5, 1.5, (batch, nct))
         p.e_ub = rng.uniform(0.5, 1.5, (batch, nct))
+        p.cones = [(k, 0, int(ncs[k]), 0) for k in range(N + 1)]
     return p

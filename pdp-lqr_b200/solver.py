@@ -136,6 +136,26 @@ class LQRCudaSolver:
     def forward_device(self, x0, ws_out):
         self._check(self._lib.pdplqr_forward_device(self._h, _dptr(x0), _dptr(ws_out)))
 
+    # ------------------------------------------------------------------ conic ADMM outer iteration (addition, a11)
+    def admm_set_cones(self, cones, e_lb, e_ub):
+        """cones: list of (stage, first_row, dim, type) sorted by stage, tiling every stage's rows."""
+        arr = np.ascontiguousarray(np.array(cones, dtype=np.int32).reshape(-1, 4))
+        cols = [np.ascontiguousarray(arr[:, i]) for i in range(4)]
+        ip = C.POINTER(C.c_int)
+        self._cone_keep = cols
+        self._check(self._lib.pdplqr_admm_set_cones(self._h, len(arr), *[c.ctypes.data_as(ip) for c in cols],
+                                                     _hp(np.ascontiguousarray(e_lb, dtype=np.float64)),
+                                                     _hp(np.ascontiguousarray(e_ub, dtype=np.float64))))
+
+    def admm_solve(self, x0, ws, zs, ys, rho, sigma=1e-6, alpha=1.6, max_iter=50, eps_abs=1e-4, eps_rel=1e-4,
+                   check_every=10):
+        it = C.c_int()
+        res = np.zeros(2)
+        self._check(self._lib.pdplqr_admm_solve(self._h, _hp(np.ascontiguousarray(x0, dtype=np.float64)), _hp(ws),
+                                                _hp(zs), _hp(ys), _hp(rho), sigma, alpha, max_iter, eps_abs, eps_rel,
+                                                check_every, C.byref(it), _hp(res)))
+        return it.value, res
+
     # ------------------------------------------------------------------ horizon sharding (one handle per time slice)
     def summary_doubles(self) -> int:
         return int(self._lib.pdplqr_summary_doubles(self._h))

@@ -330,3 +330,53 @@ def test_horizon_shards_on_one_gpu(oracle, G, S_local):
     assert rel_err(full, ref) < TOL
     xh_ref, _ = sharding.couple_numpy(torch.stack(sums).cpu().numpy(), p.x0[0])
     assert rel_err(xhat.cpu().numpy()[0], xh_ref) < TOL
+
+
+# ------------------------------------------------------------------------------------------------------------
+# conic ADMM outer iteration (row a11; NOT in the reference -> pinned against oracle/admm_ref.py)
+@pytest.mark.parametrize("S", [1, 3])
+def test_admm_iterates_match_numpy_restatement(oracle, S):
+    from oracle import admm_ref
+    p = P.problems.random_lq(6, 3, 14, batch=2, seed=31, nc=6)
+    # mix cone types: box on rows 0..2, second-order cone on rows 3..5 (terminal stage: all box)
+    p.cones = []
+    for k in range(p.N + 1):
+        nc = int(p.ncs[k])
+        p.cones += [(k, 0, 3, 0), (k, 3, nc - 3, 1)] if k < p.N else [(k, 0, nc, 0)]
+    rho = np.full((p.batch, p.nc_total), 0.7)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=S)
+    sol.admm_set_cones(p.cones, p.e_lb, p.e_ub)
+    ws, zs, ys = p.zeros_ws(), np.zeros((p.batch, p.nc_total)), np.zeros((p.batch, p.nc_total))
+    iters, res = sol.admm_solve(p.x0, ws, zs, ys, rho, sigma=1e-4, alpha=1.6, max_iter=15, eps_abs=0.0, eps_rel=0.0,
+                                check_every=5)
+    assert iters == 15
+    rp = rd = 0.0
+    for b in range(p.batch):
+        w, z, y, r_prim, r_dual = admm_ref.admm(p, b, rho[b], sigma=1e-4, alpha=1.6, iters=15)
+        assert rel_err(ws[b], w) < TOL and rel_err(zs[b], z) < TOL
+        assert np.max(np.abs(ys[b] - y)) < TOL * max(1.0, np.max(np.abs(y)))
+        rp, rd = max(rp, r_prim), max(rd, r_dual)
+    assert abs(res[0] - rp) < 1e-9 * max(1.0, rp) and abs(res[1] - rd) < 1e-9 * max(1.0, rd)
+
+
+def test_admm_quadrotor_mpc_converges_to_feasible_point(oracle):
+    """Config-1 problem with its box constraints switched on (lqr_example.cpp:126-158 minus `nc = 0;`), rho = 0.01
+    as in the example... scaled up for faster convergence; checks feasibility and agreement with the numpy restatement."""
+    from oracle import admm_ref
+    p = P.problems.quadrotor_example(N=20, constrained=True)
+    p.x0[0, 2] = 0.0
+    lb = np.where(np.isfinite(p.e_lb), p.e_lb, -1e20)
+    ub = np.where(np.isfinite(p.e_ub), p.e_ub, 1e20)
+    rho = np.full((1, p.nc_total), 0.1)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=2)
+    sol.admm_set_cones(p.cones, lb, ub)
+    ws, zs, ys = p.zeros_ws(), np.zeros((1, p.nc_total)), np.zeros((1, p.nc_total))
+    iters, res = sol.admm_solve(p.x0, ws, zs, ys, rho, sigma=1e-6, alpha=1.6, max_iter=300, eps_abs=0.0, eps_rel=0.0,
+                                check_every=50)
+    assert iters == 300 and res[0] < 5e-2
+    u = ws[0, :20 * 16].reshape(20, 16)[:, :4]
+    assert np.max(np.abs(u - np.clip(u, -0.9916, 2.4084))) < 5e-2        # ADMM iterate: feasible up to the residual
+    assert np.all(zs >= lb - 1e-12) and np.all(zs <= ub + 1e-12)         # z is exactly feasible by construction
+    p.e_lb, p.e_ub = lb, ub
+    w, z, y, r_prim, _ = admm_ref.admm(p, 0, rho[0], sigma=1e-6, alpha=1.6, iters=300)
+    assert rel_err(ws[0], w) < 1e-8 and abs(res[0] - r_prim) < 1e-8
