@@ -194,6 +194,136 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+
+# --------------------------------------------------------------------------------------------- config 4 (conic ADMM)
+def run_c4(args, rank, world, local_rank):
+    """BASELINE.json configs[3]: conic-constrained (box + SOC) LQ MPC nx=30 nu=10 N=256, batch 4096 per GPU, full outer
+    iterations.  A step = one ADMM solve with a FIXED number of outer iterations (1 factorising + ITERS-1 affine-only
+    LQ solves, projections, residuals), all device-resident.  The outer iteration is not in the reference (hooks only)."""
+    import torch
+    import torch.distributed as dist
+    import pdplqr_b200 as P
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = int(os.environ.get("C4_BATCH", "4096"))
+    N = int(os.environ.get("C4_N", "256"))
+    ITERS = int(os.environ.get("C4_ITERS", "50"))
+    base = 64 if B % 64 == 0 else B
+    sampler = ClockSampler(local_rank)
+    hp = P.problems.random_conic_batch(batch=base, N=N, seed=99 + rank)
+    rep = B // base
+    nx, nu, s = hp.nx, hp.nu, hp.s
+    sol = P.LQRCudaSolver(nx, nu, N, batch=B, num_segments=1, ncs=hp.ncs, device=local_rank)
+    stream = torch.cuda.current_stream()
+    sol.set_stream(stream.cuda_stream)
+
+    def up(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        return t.repeat(rep, *([1] * (t.dim() - 1))).contiguous() if rep > 1 else t
+    dE, dc, dH, dh, dHN, dhN, dD = (up(a) for a in (hp.E, hp.c, hp.H, hp.h, hp.HN, hp.hN, hp.D))
+    sol.set_model_device(dE, dc, dH, dh, dHN, dhN, dD)
+    torch.cuda.synchronize()
+    del dE, dc, dH, dh, dD
+    lb = np.where(np.isfinite(hp.e_lb), hp.e_lb, -1e20)
+    ub = np.where(np.isfinite(hp.e_ub), hp.e_ub, 1e20)
+    sol.admm_set_cones(hp.cones, np.tile(lb, (rep, 1)), np.tile(ub, (rep, 1)))
+    nct = hp.nc_total
+    x0 = up(hp.x0)
+    rho = torch.full((B, nct), 0.1, dtype=torch.float64, device=dev)
+    inv_rho = 1.0 / rho
+    w = torch.zeros(B, hp.ws_len, dtype=torch.float64, device=dev)
+    z = torch.zeros(B, nct, dtype=torch.float64, device=dev)
+    y = torch.zeros(B, nct, dtype=torch.float64, device=dev)
+
+    def step():
+        w.zero_(); z.zero_(); y.zero_()
+        return sol.admm_solve_device(x0, w, z, y, rho, inv_rho, sigma=1e-6, alpha=1.6, max_iter=ITERS, eps_abs=0.0,
+                                     eps_rel=0.0, check_every=ITERS)
+    steps = max(1, min(args.steps, int(os.environ.get("C4_STEPS", "3"))))
+    for _ in range(min(args.warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_w0 = time.time()
+    l0 = sol.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        it, res = step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_step = e0.elapsed_time(e1) / steps
+    launches = sol.launch_count() - l0
+    windows = [(t_w0, time.time())]
+    # affine-only iteration alone (the common ADMM iteration): CUDA events around update + backward_without_factorization
+    ka = 10
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(stream)
+    for _ in range(ka):
+        sol.update_problem_data_device(w, y, z, inv_rho, sigma=1e-6)
+        sol.backward_without_factorization_device(rho)
+    a1.record(stream)
+    torch.cuda.synchronize()
+    ms_aff = a0.elapsed_time(a1) / ka
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    sol.update_problem_data_device(w, y, z, inv_rho, sigma=1e-6)
+    sol.backward_device(rho)
+    f1.record(stream)
+    torch.cuda.synchronize()
+    ms_fact = f0.elapsed_time(f1)
+    clocks = sampler.summary(windows)
+    t = torch.tensor([ms_step, ms_aff, ms_fact], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, ms_aff, ms_fact = (float(v) for v in t.cpu())
+    if rank == 0:
+        nc = int(hp.ncs[1])
+        aff_bytes = 8 * (nx * s + s + nu * nx + nu * nu + 2 * nx + nc * s + 3 * nc + s)   # DESIGN.md section 3
+        fact_bytes = 55488                                                                 # SURVEY.md section 8(d)
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = aff_bytes * B * N / (ms_aff * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": world * B * 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": min(args.warmup, 1), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C4: conic (box + SOC) LQ MPC nx=30 nu=10 N=%d, batch %d per GPU, %d fixed ADMM outer iterations per solve (configs[3])" % (N, B, ITERS),
+                           "problems_per_gpu": B, "nx": nx, "nu": nu, "N": N, "nc": nc, "admm_iterations": ITERS,
+                           "problem_iterations_per_sec": world * B * ITERS * 1e3 / ms_step,
+                           "ms_factorizing_backward": ms_fact, "ms_affine_backward": ms_aff,
+                           "final_residuals": [float(res[0]), float(res[1])],
+                           "l2": "inputs larger than L2", "sharding": "independent problems per rank, no data-path collective"},
+                "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
+                "e2e": None, "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "seg_affine_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": aff_bytes * B * N,
+                             "kernel_ms": ms_aff,
+                             "factorizing_kernel": {"kernel": "seg_backward_kernel<30,10,128>", "ms": ms_fact,
+                                                    "achieved": fact_bytes * B * N / (ms_fact * 1e-3) / 1e9,
+                                                    "frac": fact_bytes * B * N / (ms_fact * 1e-3) / 1e9 / peak}}}
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import oracle as O
+            nb = min(base, 2 * O.max_threads())
+            sub = hp.select(slice(0, nb))
+            pool = O.OracleBatch(sub)
+            rng = np.random.default_rng(0)
+            ys_, zs_ = rng.standard_normal((nb, nct)), rng.standard_normal((nb, nct))
+            rh = np.full((nb, nct), 0.1)
+            t0 = time.perf_counter(); pool.solve(ys=ys_, zs=zs_, rho=rh, inv_rho=1.0 / rh, factorize=True); tf = time.perf_counter() - t0
+            t0 = time.perf_counter(); pool.solve(ys=ys_, zs=zs_, rho=rh, inv_rho=1.0 / rh, factorize=False); tn = time.perf_counter() - t0
+            v = nb / (tf + (ITERS - 1) * tn)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": O.max_threads(), "kind": "port",
+                                    "sample": "%d problems: 1 factorising + 1 affine-only LQ solve timed, extrapolated to %d iterations (projections not counted)" % (nb, ITERS)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
 # --------------------------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
@@ -219,6 +349,9 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    if args.workload == "c4":
+        run_c4(args, rank, world, local_rank)
+        return
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

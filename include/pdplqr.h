@@ -132,6 +132,11 @@ int pdplqr_admm_set_cones(pdplqr_handle_t h, int ncones, const int* stage, const
 int pdplqr_admm_solve(pdplqr_handle_t h, const double* x0, double* ws, double* zs, double* ys, const double* rho,
                       double sigma, double alpha, int max_iter, double eps_abs, double eps_rel, int check_every,
                       int* iters_out, double* residuals_out);
+/* Same loop on device arrays (w, z, y in/out; inv_rho = 1/rho supplied by the caller); no host copies except the
+ * residual read every `check_every` iterations. */
+int pdplqr_admm_solve_device(pdplqr_handle_t h, const double* x0, double* w, double* z, double* y, const double* rho,
+                             const double* inv_rho, double sigma, double alpha, int max_iter, double eps_abs,
+                             double eps_rel, int check_every, int* iters_out, double* residuals_out);
 
 /* Accessors (additions; the reference keeps these in a private workspace, lqr_solver_parallel.hpp:55-60).
  * All outputs are host arrays; any pointer may be NULL to skip it.

@@ -41,6 +41,8 @@ SIGNATURES = {
     "pdplqr_admm_set_cones": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _ip, _ip, _dp, _dp]),
     "pdplqr_admm_solve": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_double,
                                     C.c_double, C.c_int, _ip, _dp]),
+    "pdplqr_admm_solve_device": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int,
+                                           C.c_double, C.c_double, C.c_int, _ip, _dp]),
     "pdplqr_num_segments": (C.c_int, [C.c_void_p]),
     "pdplqr_get_partition": (C.c_int, [C.c_void_p, _ip, _ip]),
     "pdplqr_get_gains": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),

@@ -1008,37 +1008,26 @@ int pdplqr_admm_set_cones(pdplqr_handle_t h, int ncones, const int* stage, const
     return PDPLQR_OK;
 }
 
-int pdplqr_admm_solve(pdplqr_handle_t h, const double* x0, double* ws, double* zs, double* ys, const double* rho,
-                      double sigma, double alpha, int max_iter, double eps_abs, double eps_rel, int check_every,
-                      int* iters_out, double* residuals_out) {
-    if (!h || !x0 || !ws || !zs || !ys || !rho || max_iter < 1)
+// device-resident loop: w, z, y (in/out), rho, inv_rho, x0 are device arrays; no host copies except the 4-double
+// residual read every `check_every` iterations
+int pdplqr_admm_solve_device(pdplqr_handle_t h, const double* x0, double* w, double* z, double* y, const double* rho,
+                             const double* inv_rho, double sigma, double alpha, int max_iter, double eps_abs,
+                             double eps_rel, int check_every, int* iters_out, double* residuals_out) {
+    if (!h || !x0 || !w || !z || !y || !rho || !inv_rho || max_iter < 1)
         return fail(h, PDPLQR_ERR_INVALID, "admm_solve: bad arguments");
     if (!h->cones_set) return fail(h, PDPLQR_ERR_ORDER, "admm_solve before admm_set_cones");
     if (!h->model_set) return fail(h, PDPLQR_ERR_ORDER, "admm_solve before set_model");
     cudaSetDevice(h->device);
-    const size_t B = h->batch, nct = (size_t)h->nc_total, wsl = (size_t)h->N * h->s + h->nx;
-    CU_TRY(h, cudaMemcpyAsync(h->d_w, ws, B * wsl * 8, cudaMemcpyHostToDevice, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(h->d_z, zs, B * nct * 8, cudaMemcpyHostToDevice, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(h->d_y, ys, B * nct * 8, cudaMemcpyHostToDevice, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(h->d_rho_admm, rho, B * nct * 8, cudaMemcpyHostToDevice, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(h->d_x0, x0, B * h->nx * 8, cudaMemcpyHostToDevice, h->stream));
-    {   // inv_rho = 1 / rho on the host side of the protocol (lqr_example.cpp:42-43), computed once
-        std::vector<double> inv(B * nct);
-        for (size_t i = 0; i < inv.size(); ++i) inv[i] = 1.0 / rho[i];
-        CU_TRY(h, cudaMemcpyAsync(h->d_invrho_admm, inv.data(), B * nct * 8, cudaMemcpyHostToDevice, h->stream));
-        CU_TRY(h, cudaStreamSynchronize(h->stream));
-    }
     if (check_every < 1) check_every = 1;
     int it = 0, rc = 0;
     double res[4] = {0, 0, 0, 0};
     bool converged = false;
     for (it = 0; it < max_iter && !converged; ++it) {
-        rc = pdplqr_update_problem_data_device(h, h->d_w, h->d_y, h->d_z, h->d_invrho_admm, sigma);
+        rc = pdplqr_update_problem_data_device(h, w, y, z, inv_rho, sigma);
         if (rc) return rc;
-        rc = (it == 0) ? pdplqr_backward_device(h, h->d_rho_admm)
-                       : pdplqr_backward_without_factorization_device(h, h->d_rho_admm);
+        rc = (it == 0) ? pdplqr_backward_device(h, rho) : pdplqr_backward_without_factorization_device(h, rho);
         if (rc) return rc;
-        rc = run_forward(*h, h->d_x0, h->d_wtilde);
+        rc = run_forward(*h, x0, h->d_wtilde);
         if (rc) return rc;
         const bool check = ((it + 1) % check_every == 0) || (it + 1 == max_iter);
         if (check) CU_TRY(h, cudaMemsetAsync(h->d_res, 0, 4 * sizeof(unsigned long long), h->stream));
@@ -1048,7 +1037,7 @@ int pdplqr_admm_solve(pdplqr_handle_t h, const double* x0, double* ws, double* z
         ap.d_total = h->d_total_dev; ap.nc_total = h->nc_total;
         ap.cone_first = h->d_cone_first; ap.cone_type = h->d_cone_type; ap.cone_row = h->d_cone_row; ap.cone_dim = h->d_cone_dim;
         ap.e_lb = h->d_elb; ap.e_ub = h->d_eub;
-        ap.w_tilde = h->d_wtilde; ap.w = h->d_w; ap.z = h->d_z; ap.y = h->d_y; ap.rho = h->d_rho_admm;
+        ap.w_tilde = h->d_wtilde; ap.w = w; ap.z = z; ap.y = y; ap.rho = rho;
         ap.alpha = alpha; ap.res = h->d_res;
         const size_t smem = (size_t)(h->s + 3 * h->ncmax) * sizeof(double);
         admm_update_kernel<<<h->batch * (h->N + 1), 32, smem, h->stream>>>(ap);
@@ -1062,12 +1051,37 @@ int pdplqr_admm_solve(pdplqr_handle_t h, const double* x0, double* ws, double* z
             converged = res[0] <= eps_abs + eps_rel * res[2] && res[1] <= eps_abs + eps_rel * res[3];
         }
     }
+    if (iters_out) *iters_out = it;
+    if (residuals_out) { residuals_out[0] = res[0]; residuals_out[1] = res[1]; }
+    return PDPLQR_OK;
+}
+
+int pdplqr_admm_solve(pdplqr_handle_t h, const double* x0, double* ws, double* zs, double* ys, const double* rho,
+                      double sigma, double alpha, int max_iter, double eps_abs, double eps_rel, int check_every,
+                      int* iters_out, double* residuals_out) {
+    if (!h || !x0 || !ws || !zs || !ys || !rho || max_iter < 1)
+        return fail(h, PDPLQR_ERR_INVALID, "admm_solve: bad arguments");
+    if (!h->cones_set) return fail(h, PDPLQR_ERR_ORDER, "admm_solve before admm_set_cones");
+    cudaSetDevice(h->device);
+    const size_t B = h->batch, nct = (size_t)h->nc_total, wsl = (size_t)h->N * h->s + h->nx;
+    CU_TRY(h, cudaMemcpyAsync(h->d_w, ws, B * wsl * 8, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_z, zs, B * nct * 8, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_y, ys, B * nct * 8, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_rho_admm, rho, B * nct * 8, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_x0, x0, B * h->nx * 8, cudaMemcpyHostToDevice, h->stream));
+    {   // inv_rho = 1 / rho, as the caller of the reference protocol computes it (lqr_example.cpp:42-43)
+        std::vector<double> inv(B * nct);
+        for (size_t i = 0; i < inv.size(); ++i) inv[i] = 1.0 / rho[i];
+        CU_TRY(h, cudaMemcpyAsync(h->d_invrho_admm, inv.data(), B * nct * 8, cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    int rc = pdplqr_admm_solve_device(h, h->d_x0, h->d_w, h->d_z, h->d_y, h->d_rho_admm, h->d_invrho_admm, sigma, alpha,
+                                      max_iter, eps_abs, eps_rel, check_every, iters_out, residuals_out);
+    if (rc) return rc;
     CU_TRY(h, cudaMemcpyAsync(ws, h->d_w, B * wsl * 8, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaMemcpyAsync(zs, h->d_z, B * nct * 8, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaMemcpyAsync(ys, h->d_y, B * nct * 8, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
-    if (iters_out) *iters_out = it;
-    if (residuals_out) { residuals_out[0] = res[0]; residuals_out[1] = res[1]; }
     return PDPLQR_OK;
 }
 

@@ -156,6 +156,15 @@ class LQRCudaSolver:
                                                 check_every, C.byref(it), _hp(res)))
         return it.value, res
 
+    def admm_solve_device(self, x0, w, z, y, rho, inv_rho, sigma=1e-6, alpha=1.6, max_iter=50, eps_abs=1e-4,
+                          eps_rel=1e-4, check_every=10):
+        it = C.c_int()
+        res = np.zeros(2)
+        self._check(self._lib.pdplqr_admm_solve_device(self._h, _dptr(x0), _dptr(w), _dptr(z), _dptr(y), _dptr(rho),
+                                                       _dptr(inv_rho), sigma, alpha, max_iter, eps_abs, eps_rel,
+                                                       check_every, C.byref(it), _hp(res)))
+        return it.value, res
+
     # ------------------------------------------------------------------ horizon sharding (one handle per time slice)
     def summary_doubles(self) -> int:
         return int(self._lib.pdplqr_summary_doubles(self._h))
