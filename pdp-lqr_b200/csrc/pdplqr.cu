@@ -66,6 +66,12 @@ struct pdplqr_solver {
            *d_invrho_admm = nullptr;
     unsigned long long* d_res = nullptr;
     bool cones_set = false;
+    // pipelined host solve (H2D / compute / D2H overlapped over batch chunks)
+    int chunk_b0 = 0, chunk_nb = 0;   // when chunk_nb > 0 the launchers work on problems [b0, b0 + nb)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_cmp;
+    cudaEvent_t ev_ready = nullptr;
+    int pipeline_chunks = 8;
     // horizon sharding
     bool interior = false;         // slice ends at an interface (not the true terminal)
     bool is_coupler = false;       // handle created by pdplqr_coupler_create (interface tree only)
@@ -128,6 +134,14 @@ SegParams seg_params(Solver& h) {
     p.ncmax = h.ncmax; p.nc_total = h.nc_total; p.d_total = h.d_total_dev;
     p.ncs = h.d_ncs; p.coff = h.d_coff; p.doff = h.d_doff; p.Dm = h.d_D;
     p.ys = h.cur_ys; p.zs = h.cur_zs; p.rho = h.cur_rho; p.inv_rho = h.cur_inv_rho;
+    if (h.chunk_nb > 0) {   // batch chunk [b0, b0 + nb): offset every per-problem array (nc = 0 handles only)
+        const size_t b0 = h.chunk_b0, wsl = (size_t)h.N * h.s + h.nx;
+        p.batch = h.chunk_nb;
+        p.model += b0 * h.N * h.mrec; p.HN += b0 * h.nx * h.nx; p.hN += b0 * h.nx;
+        if (p.ws_prev) p.ws_prev += b0 * wsl;
+        p.fac += b0 * h.N * h.frec; p.sum += b0 * h.S * h.ops->SREC; p.status += b0;
+        p.xhat += b0 * h.S * h.nx; p.uhat += b0 * h.S * h.nx;
+    }
     return p;
 }
 
@@ -140,7 +154,7 @@ int launch_batch_bwd(Solver& h, const SegParams& p) {
     constexpr size_t bytes = BatchBwdSmem<NX, NU, WARPS, DEPTH>::BYTES;
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
-    const int blocks = (h.batch + WARPS * 32 - 1) / (WARPS * 32);
+    const int blocks = (p.batch + WARPS * 32 - 1) / (WARPS * 32);
     kern<<<blocks, WARPS * 32, bytes, h.stream>>>(p);
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
@@ -152,7 +166,7 @@ int launch_batch_fwd(Solver& h, const SegParams& p) {
     constexpr size_t bytes = BatchFwdSmem<NX, NU, WARPS, DEPTH>::BYTES;
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
-    const int blocks = (h.batch + WARPS * 32 - 1) / (WARPS * 32);
+    const int blocks = (p.batch + WARPS * 32 - 1) / (WARPS * 32);
     kern<<<blocks, WARPS * 32, bytes, h.stream>>>(p);
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
@@ -200,6 +214,10 @@ int forward_impl(Solver& h, const double* d_x0, double* d_ws_out) {
     if (h.S == 1) {
         p.xhat = d_x0;
         if (h.have_root) p.uhat = h.d_root_lam;
+    }
+    if (h.chunk_nb > 0) {
+        p.ws_out += (size_t)h.chunk_b0 * ((size_t)h.N * h.s + h.nx);
+        if (h.S == 1) p.xhat += (size_t)h.chunk_b0 * h.nx;
     }
     if constexpr (BatchDims<NX, NU>::ENABLED) {
         if (h.thread_path) {
@@ -584,6 +602,7 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (const char* e = getenv("PDPLQR_FWD_VARIANT")) h->fwd_variant = atoi(e);
     if (const char* e = getenv("PDPLQR_LAT_THREADS")) h->lat_threads = atoi(e);
     if (const char* e = getenv("PDPLQR_TREE_TT")) h->tree_tt = atoi(e);
+    if (const char* e = getenv("PDPLQR_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(1, std::min(64, atoi(e)));
 
     auto bail = [&](int rc) { std::string e = h->err; pdplqr_destroy(h); (void)e; return rc; };
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PDPLQR_ERR_CUDA);
@@ -661,6 +680,11 @@ int pdplqr_destroy(pdplqr_handle_t h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : h->owned) cudaFree(p);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+    for (cudaEvent_t e : h->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_cmp) cudaEventDestroy(e);
+    if (h->ev_ready) cudaEventDestroy(h->ev_ready);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return PDPLQR_OK;
@@ -867,8 +891,59 @@ int pdplqr_forward(pdplqr_handle_t h, const double* x0, double* ws_out) {
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     return PDPLQR_OK;
 }
+// Pipelined host solve for large batches on the thread-per-problem path: the batch is cut into chunks; chunk c's
+// H2D copy (stream s_in), kernels (handle stream) and D2H copy (stream s_out) overlap with the neighbours', so the
+// end-to-end time approaches max(H2D, D2H) instead of H2D + kernels + D2H.  Host buffers should be pinned.
+static int solve_pipelined(Solver& h, const double* ws_in, double sigma, const double* x0, double* ws_out) {
+    const int C = h.pipeline_chunks;
+    if (!h.s_in) {
+        CU_TRY(&h, cudaStreamCreateWithFlags(&h.s_in, cudaStreamNonBlocking));
+        CU_TRY(&h, cudaStreamCreateWithFlags(&h.s_out, cudaStreamNonBlocking));
+        h.ev_in.resize(C); h.ev_cmp.resize(C);
+        for (int c = 0; c < C; ++c) {
+            CU_TRY(&h, cudaEventCreateWithFlags(&h.ev_in[c], cudaEventDisableTiming));
+            CU_TRY(&h, cudaEventCreateWithFlags(&h.ev_cmp[c], cudaEventDisableTiming));
+        }
+        CU_TRY(&h, cudaEventCreateWithFlags(&h.ev_ready, cudaEventDisableTiming));
+    }
+    const size_t wsl = (size_t)h.N * h.s + h.nx;
+    const int per = (((h.batch + C - 1) / C) + 223) / 224 * 224;   // whole CTAs of the default 7-warp launch
+    // copies must not start before earlier work on the handle's stream (e.g. set_model) has finished
+    CU_TRY(&h, cudaEventRecord(h.ev_ready, h.stream));
+    CU_TRY(&h, cudaStreamWaitEvent(h.s_in, h.ev_ready, 0));
+    CU_TRY(&h, cudaStreamWaitEvent(h.s_out, h.ev_ready, 0));
+    CU_TRY(&h, cudaMemsetAsync(h.d_status, 0, sizeof(int) * h.batch, h.stream));
+    h.cur_ws = ws_in ? h.d_ws_in : nullptr;
+    h.sigma = sigma;
+    int rc = PDPLQR_OK;
+    for (int c = 0, b0 = 0; b0 < h.batch && rc == PDPLQR_OK; ++c, b0 += per) {
+        const int nb = std::min(per, h.batch - b0);
+        if (ws_in) CU_TRY(&h, cudaMemcpyAsync(h.d_ws_in + b0 * wsl, ws_in + b0 * wsl, nb * wsl * 8, cudaMemcpyHostToDevice, h.s_in));
+        CU_TRY(&h, cudaMemcpyAsync(h.d_x0 + (size_t)b0 * h.nx, x0 + (size_t)b0 * h.nx, (size_t)nb * h.nx * 8, cudaMemcpyHostToDevice, h.s_in));
+        CU_TRY(&h, cudaEventRecord(h.ev_in[c], h.s_in));
+        CU_TRY(&h, cudaStreamWaitEvent(h.stream, h.ev_in[c], 0));
+        h.chunk_b0 = b0; h.chunk_nb = nb;
+        rc = h.ops->backward(h);
+        if (rc == PDPLQR_OK) rc = h.ops->forward(h, h.d_x0, h.d_ws_out);
+        h.chunk_nb = 0; h.chunk_b0 = 0;
+        if (rc) break;
+        CU_TRY(&h, cudaEventRecord(h.ev_cmp[c], h.stream));
+        CU_TRY(&h, cudaStreamWaitEvent(h.s_out, h.ev_cmp[c], 0));
+        CU_TRY(&h, cudaMemcpyAsync(ws_out + b0 * wsl, h.d_ws_out + b0 * wsl, nb * wsl * 8, cudaMemcpyDeviceToHost, h.s_out));
+    }
+    if (rc) return rc;
+    CU_TRY(&h, cudaStreamSynchronize(h.s_out));
+    CU_TRY(&h, cudaStreamSynchronize(h.stream));
+    h.updated = false; h.factorized = true; h.backward_done = false;
+    return PDPLQR_OK;
+}
+
 int pdplqr_solve(pdplqr_handle_t h, const double* ws_in, const double* ys, const double* zs, const double* rho,
                  const double* inv_rho, double sigma, const double* x0, double* ws_out) {
+    if (h && x0 && ws_out && h->thread_path && h->model_set && h->pipeline_chunks > 1 && h->batch >= 4096 && !h->have_root) {
+        cudaSetDevice(h->device);
+        return solve_pipelined(*h, ws_in, sigma, x0, ws_out);
+    }
     int rc = pdplqr_update_problem_data(h, ws_in, ys, zs, inv_rho, sigma);
     if (rc) return rc;
     rc = pdplqr_backward(h, rho);

@@ -380,3 +380,20 @@ def test_admm_quadrotor_mpc_converges_to_feasible_point(oracle):
     p.e_lb, p.e_ub = lb, ub
     w, z, y, r_prim, _ = admm_ref.admm(p, 0, rho[0], sigma=1e-6, alpha=1.6, iters=300)
     assert rel_err(ws[0], w) < 1e-8 and abs(res[0] - r_prim) < 1e-8
+
+
+def test_pipelined_host_solve_matches_unpipelined(oracle):
+    """pdplqr_solve() on a large thread-path batch overlaps H2D / kernels / D2H over batch chunks; results must be
+    bit-identical to the 3-call protocol (ragged last chunk included)."""
+    p = P.problems.cartpole_batch(batch=5000, N=32)
+    rng = np.random.default_rng(3)
+    w = 0.01 * rng.standard_normal((p.batch, p.ws_len))
+    sol = P.LQRCudaSolver.from_problem(p)
+    a = sol.solve(w, p.x0, np.zeros_like(w), sigma=1e-3).copy()
+    sol.update_problem_data(w, sigma=1e-3)
+    sol.backward()
+    b = sol.forward(p.x0, np.zeros_like(w))
+    assert np.array_equal(a, b)
+    ref, _ = oracle.OracleBatch(p.select(slice(4990, 5000))).solve(ws_in=np.ascontiguousarray(w[4990:]), sigma=1e-3)
+    assert rel_err(a[4990:], ref) < TOL
+    assert sol.last_status()[0] == 0
