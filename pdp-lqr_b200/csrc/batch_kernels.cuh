@@ -1,7 +1,7 @@
 // Thread-per-problem kernels for batches of tiny LQ problems (nx + nu <= 8, one segment per problem):
-// the whole Riccati state of a problem lives in one thread's registers; every lane streams its own problem's
-// stage records from HBM with TMA 1-D bulk copies (cp.async.bulk) into a private shared-memory slot, in a
-// DEPTH-deep ring completed on one mbarrier per warp and ring slot.
+// the whole Riccati state of a problem lives in one thread's registers.  The records of the 32 problems of a warp
+// ("tile") are interleaved in HBM, so ONE TMA 1-D bulk copy (cp.async.bulk) per warp and stage streams a fully
+// contiguous 11 KB block into shared memory, in a DEPTH-deep ring completed on one mbarrier per ring slot.
 //
 // Replaces, for the batched sequential case (BASELINE.json config 3):
 //   LQRSolver::update_problem_data / backward / forward      /root/reference include/clqr/lqr/lqr_solver.hpp:41-77
@@ -10,6 +10,11 @@
 // Device record of one stage on this path ("thread record", written by pack_model_kernel):
 //   [E (NX x S) | c (NX) | lower(H) packed by columns (S(S+1)/2) | h (S)]   -- H is symmetric (lqr_model.hpp:18),
 // so only its lower triangle is kept in HBM: 44 instead of 54 doubles per stage at nx=4, nu=1.
+// Tile layout: element e of problem (tile*32 + lane) at stage k lives at
+//   ((tile*N + k)*TREC + (e & ~1))*32 + lane*2 + (e & 1)
+// i.e. element PAIRS are interleaved across the 32 lanes: a lane reads its pair with one conflict-free 128-bit
+// shared load, the forward kernel copies only the leading [E | c] part of every block (also contiguous), and the
+// factor records [K | d] use the same tiling, so their stores and loads are fully coalesced.
 #pragma once
 #include "common.cuh"
 #include "seg_kernels.cuh"
@@ -31,14 +36,13 @@ struct BatchDims {
     static constexpr int hl(int i, int j) { return j * S - j * (j - 1) / 2 + (i - j); }
 };
 
-// per-lane slot: a multiple of 16 bytes whose 16-byte count is odd -> 128-bit shared loads of the 32 lanes
-// (each from its own slot) are bank-conflict free
-constexpr int slot_doubles(int rec) { return ((rec / 2) % 2 == 1) ? rec : rec + 2; }
+// position of element e of lane `lane` inside a tile block (in doubles)
+PDPLQR_DEVINL constexpr int tile_pos(int e, int lane) { return (e & ~1) * 32 + lane * 2 + (e & 1); }
 
 template <int NX, int NU, int WARPS, int DEPTH>
 struct BatchBwdSmem {
-    static constexpr int SLOT = slot_doubles(BatchDims<NX, NU>::TREC);
-    static constexpr int WARP_DOUBLES = DEPTH * 32 * SLOT;
+    static constexpr int BLOCK = BatchDims<NX, NU>::TREC * 32;   // doubles of one tile block (one warp-stage)
+    static constexpr int WARP_DOUBLES = DEPTH * BLOCK;
     static constexpr int o_bar = WARPS * WARP_DOUBLES;
     static constexpr size_t BYTES = (size_t)(o_bar + DEPTH * WARPS) * 8;
 };
@@ -50,7 +54,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_backward_kernel(SegPar
     using L = BatchBwdSmem<NX, NU, WARPS, DEPTH>;
     constexpr int S = D::S;
     constexpr int FRECT = B::FRECT;
-    constexpr uint32_t REC_BYTES = B::TREC * 8;
+    constexpr uint32_t REC_BYTES = L::BLOCK * 8;
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long bg = (long long)blockIdx.x * (WARPS * 32) + threadIdx.x;
@@ -60,11 +64,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_backward_kernel(SegPar
     double* slots = smem + warp * L::WARP_DOUBLES;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::o_bar) + DEPTH * warp;
     const size_t ws_len = (size_t)p.N * S + NX;
-    const double* model_b = p.model + b * p.N * B::TREC;
+    const size_t tile = (size_t)(blockIdx.x * WARPS + warp);
+    const double* model_t = p.model + tile * p.N * L::BLOCK;
     const double* ws_b = p.ws_prev ? p.ws_prev + b * ws_len : nullptr;
-    double* fac_b = p.fac + b * p.N * FRECT;
+    double* fac_t = p.fac + tile * p.N * (FRECT * 32);
     const double sigma = p.sigma;
     const int N = p.N;
+    const bool tile_live = (long long)tile * 32 < p.batch;   // warps past the batch issue no copies and exit early
+    if (!tile_live) return;
+    auto fetch = [&](int stage, int ring_slot) {   // lane 0: one bulk copy of the whole tile block
+        if (lane == 0) {
+            mbar_expect_tx(&bar[ring_slot], REC_BYTES);
+            bulk_g2s(slots + ring_slot * L::BLOCK, model_t + (size_t)stage * L::BLOCK, REC_BYTES, &bar[ring_slot]);
+        }
+    };
 
     if (lane == 0) {
 #pragma unroll
@@ -75,11 +88,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_backward_kernel(SegPar
     // prologue: fill DEPTH-1 ring slots (stages N-1, N-2, ...)
 #pragma unroll
     for (int d = 0; d < DEPTH - 1; ++d) {
-        if (d < N) {
-            if (lane == 0) mbar_expect_tx(&bar[d], 32 * REC_BYTES);
-            __syncwarp();
-            bulk_g2s(slots + (d * 32 + lane) * L::SLOT, model_b + (size_t)(N - 1 - d) * B::TREC, REC_BYTES, &bar[d]);
-        }
+        if (d < N) fetch(N - 1 - d, d);
     }
 
     // terminal condition  (lqr_kernel.hpp:79-91):  P_N = H_N + sigma I,  p_N = h_N - sigma w_N
@@ -103,10 +112,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_backward_kernel(SegPar
         const int k = N - 1 - it;
         if (it + DEPTH - 1 < N) {
             __syncwarp();  // every lane has finished with ring slot `pslot` (consumed in the previous iteration)
-            if (lane == 0) mbar_expect_tx(&bar[pslot], 32 * REC_BYTES);
-            __syncwarp();
-            bulk_g2s(slots + (pslot * 32 + lane) * L::SLOT, model_b + (size_t)(k - (DEPTH - 1)) * B::TREC, REC_BYTES,
-                     &bar[pslot]);
+            fetch(k - (DEPTH - 1), pslot);
         }
         pslot = (pslot + 1 == DEPTH) ? 0 : pslot + 1;
         double wprev[S];
@@ -117,11 +123,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_backward_kernel(SegPar
             for (int i = 0; i < S; ++i) wnext[i] = ws_b ? ws_b[(size_t)(k - 1) * S + i] : 0.0;
         }
         mbar_wait(&bar[slot], phase);
-        const double2* r2 = reinterpret_cast<const double2*>(slots + (slot * 32 + lane) * L::SLOT);
+        const double2* r2 = reinterpret_cast<const double2*>(slots + slot * L::BLOCK) + lane;
         slot = (slot + 1 == DEPTH) ? 0 : slot + 1;
         phase ^= (slot == 0);
-        auto ld = [&](int e) {
-            const double2 v = r2[e >> 1];
+        auto ld = [&](int e) {   // pair (e>>1) of this lane: one 128-bit load, 32 lanes x 16 B contiguous
+            const double2 v = r2[(e >> 1) * 32];
             return (e & 1) ? v.y : v.x;
         };
         // E (and c as column S) into registers
@@ -213,12 +219,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_backward_kernel(SegPar
             for (int m = 0; m < NU; ++m) acc = fma(-Y[m][i], Y[m][NX], acc);
             pv[i] = acc;
         }
-        if (active) {
-            double* fk = fac_b + (size_t)k * FRECT;
+        {   // factor record [K | d], tile-interleaved: coalesced stores
+            double* fk = fac_t + (size_t)k * (FRECT * 32);
 #pragma unroll
             for (int c = 0; c <= NX; ++c)
 #pragma unroll
-                for (int m = 0; m < NU; ++m) fk[m + c * NU] = Z[m][c];
+                for (int m = 0; m < NU; ++m) fk[tile_pos(m + c * NU, lane)] = Z[m][c];
         }
     }
     // value function at the entry (P_0, p_0) -> summary slot, for the accessors
@@ -238,8 +244,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_backward_kernel(SegPar
 template <int NX, int NU, int WARPS, int DEPTH>
 struct BatchFwdSmem {
     using B = BatchDims<NX, NU>;
-    static constexpr int SLOT = slot_doubles(B::TREC_EC + B::FRECT);  // [E c (pad) | K d]
-    static constexpr int WARP_DOUBLES = DEPTH * 32 * SLOT;
+    static constexpr int BLOCK = (B::TREC_EC + B::FRECT) * 32;   // [E c (pad)] tile block followed by the [K d] tile block
+    static constexpr int WARP_DOUBLES = DEPTH * BLOCK;
     static constexpr int o_bar = WARPS * WARP_DOUBLES;
     static constexpr size_t BYTES = (size_t)(o_bar + DEPTH * WARPS) * 8;
 };
@@ -260,11 +266,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_forward_kernel(SegPara
     double* slots = smem + warp * L::WARP_DOUBLES;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::o_bar) + DEPTH * warp;
     const size_t ws_len = (size_t)p.N * S + NX;
-    const double* model_b = p.model + b * p.N * B::TREC;
-    const double* fac_b = p.fac + b * p.N * FRECT;
+    const size_t tile = (size_t)(blockIdx.x * WARPS + warp);
+    const double* model_t = p.model + tile * p.N * (B::TREC * 32);
+    const double* fac_t = p.fac + tile * p.N * (FRECT * 32);
     double* ws_b = p.ws_out + b * ws_len;
-    constexpr uint32_t TX = (B::TREC_EC + FRECT) * 8;
+    constexpr uint32_t TX = L::BLOCK * 8;
     const int N = p.N;
+    if ((long long)tile * 32 >= p.batch) return;
+    auto fetch = [&](int stage, int ring_slot) {   // lane 0: leading [E | c] part of the record block + factor block
+        if (lane == 0) {
+            double* dst = slots + ring_slot * L::BLOCK;
+            mbar_expect_tx(&bar[ring_slot], TX);
+            bulk_g2s(dst, model_t + (size_t)stage * (B::TREC * 32), B::TREC_EC * 32 * 8, &bar[ring_slot]);
+            bulk_g2s(dst + B::TREC_EC * 32, fac_t + (size_t)stage * (FRECT * 32), FRECT * 32 * 8, &bar[ring_slot]);
+        }
+    };
 
     if (lane == 0) {
 #pragma unroll
@@ -274,13 +290,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_forward_kernel(SegPara
     __syncwarp();
 #pragma unroll
     for (int d = 0; d < DEPTH - 1; ++d) {
-        if (d < N) {
-            if (lane == 0) mbar_expect_tx(&bar[d], 32 * TX);
-            __syncwarp();
-            double* dst = slots + (d * 32 + lane) * L::SLOT;
-            bulk_g2s(dst, model_b + (size_t)d * B::TREC, B::TREC_EC * 8, &bar[d]);
-            bulk_g2s(dst + B::TREC_EC, fac_b + (size_t)d * FRECT, FRECT * 8, &bar[d]);
-        }
+        if (d < N) fetch(d, d);
     }
     double x[NX];
 #pragma unroll
@@ -291,19 +301,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_forward_kernel(SegPara
     for (int k = 0; k < N; ++k) {
         if (k + DEPTH - 1 < N) {
             __syncwarp();
-            if (lane == 0) mbar_expect_tx(&bar[pslot], 32 * TX);
-            __syncwarp();
-            double* dst = slots + (pslot * 32 + lane) * L::SLOT;
-            bulk_g2s(dst, model_b + (size_t)(k + DEPTH - 1) * B::TREC, B::TREC_EC * 8, &bar[pslot]);
-            bulk_g2s(dst + B::TREC_EC, fac_b + (size_t)(k + DEPTH - 1) * FRECT, FRECT * 8, &bar[pslot]);
+            fetch(k + DEPTH - 1, pslot);
         }
         pslot = (pslot + 1 == DEPTH) ? 0 : pslot + 1;
         mbar_wait(&bar[slot], phase);
-        const double2* r2 = reinterpret_cast<const double2*>(slots + (slot * 32 + lane) * L::SLOT);
+        const double2* r2 = reinterpret_cast<const double2*>(slots + slot * L::BLOCK) + lane;
         slot = (slot + 1 == DEPTH) ? 0 : slot + 1;
         phase ^= (slot == 0);
         auto ld = [&](int e) {
-            const double2 v = r2[e >> 1];
+            const double2 v = r2[(e >> 1) * 32];
             return (e & 1) ? v.y : v.x;
         };
         double u[NU];

@@ -225,8 +225,8 @@ int forward_impl(Solver& h, const double* d_x0, double* d_ws_out) {
                 case 1: return launch_batch_fwd<NX, NU, 2, 2, 7>(h, p);
                 case 2: return launch_batch_fwd<NX, NU, 4, 2, 3>(h, p);
                 case 3: return launch_batch_fwd<NX, NU, 14, 2, 1>(h, p);
-                case 4: return launch_batch_fwd<NX, NU, 7, 3, 1>(h, p);
-                default: return launch_batch_fwd<NX, NU, 7, 4, 1>(h, p);
+                case 4: return launch_batch_fwd<NX, NU, 7, 4, 1>(h, p);
+                default: return launch_batch_fwd<NX, NU, 7, 3, 1>(h, p);
             }
         }
     }
@@ -343,18 +343,36 @@ const Ops* find_ops(int nx, int nu) {
     return nullptr;
 }
 
-// flat (E, c, H, h) -> device stage records.  sym = 0: [E | c | H | h] (segment kernels);
-// sym = 1: [E | c | lower(H) packed by columns | h] (thread-per-problem kernels, BatchDims::TR_*).
+// flat (E, c, H, h) -> device stage records.  sym = 0: [E | c | H | h] per (problem, stage) (segment kernels);
+// sym = 1: thread-per-problem path: [E | c | lower(H) packed by columns | h] with the records of the 32 problems of a
+// tile interleaved pair-wise (BatchDims::TR_*, tile_pos): one contiguous block per (tile, stage).  `nprob` is the
+// batch size, the tile count is ceil(nprob / 32) and lanes past the batch replicate the last problem.
 __global__ void pack_model_kernel(const double* __restrict__ E, const double* __restrict__ c,
                                   const double* __restrict__ H, const double* __restrict__ hv, double* __restrict__ rec,
-                                  long long nstages, int nx, int s, int REC, int sym) {
-    const long long total = nstages * REC;
+                                  long long nprob, int N, int nx, int s, int REC, int sym) {
     const int nH = sym ? s * (s + 1) / 2 : s * s;
     const int oC = nx * s, oH = oC + nx, oh = oH + nH, oend = oh + s;
+    const long long npad = sym ? ((nprob + 31) / 32) * 32 : nprob;
+    const long long total = npad * N * REC;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
-        const long long st = idx / REC;
-        const int e = (int)(idx - st * REC);
+        long long b, k;
+        int e;
+        if (!sym) {
+            const long long st = idx / REC;
+            e = (int)(idx - st * REC);
+            b = st / N; k = st - b * N;
+        } else {   // idx = ((tile*N + k)*REC + (e & ~1))*32 + lane*2 + (e & 1)
+            const long long blk = idx / (32LL * REC);
+            const int r = (int)(idx - blk * 32LL * REC);
+            const int pair = r / 64, lane = (r % 64) / 2;
+            e = pair * 2 + (r & 1);
+            const long long tile = blk / N;
+            k = blk - tile * N;
+            b = tile * 32 + lane;
+            if (b >= nprob) b = nprob - 1;
+        }
+        const long long st = b * N + k;
         double v = 0.0;
         if (e < oC) v = E[st * oC + e];
         else if (e < oH) v = c[st * nx + (e - oC)];
@@ -411,9 +429,9 @@ int set_model_common(Solver& h, const double* E, const double* c, const double* 
         }
         dE = stage; dc = stage + nE; dH = stage + nE + nc; dh = stage + nE + nc + nH;
     }
-    const long long total = (long long)nst * h.mrec;
+    const long long total = (long long)(h.thread_path ? ((h.batch + 31) / 32) * 32 : h.batch) * h.N * h.mrec;
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
-    pack_model_kernel<<<blocks, 256, 0, h.stream>>>(dE, dc, dH, dh, h.d_model, (long long)nst, h.nx, h.s, h.mrec,
+    pack_model_kernel<<<blocks, 256, 0, h.stream>>>(dE, dc, dH, dh, h.d_model, (long long)h.batch, h.N, h.nx, h.s, h.mrec,
                                                     h.thread_path ? 1 : 0);
     h.launches++;
     cudaError_t e = cudaGetLastError();
@@ -609,10 +627,11 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     h->own_stream = true;
     const size_t B = batch, ws_len = (size_t)N * h->s + nx;
     int rc = 0;
-    rc |= dev_alloc(*h, &h->d_model, B * N * ops->REC);
+    const size_t Bpad = ((B + 31) / 32) * 32;   // thread-path tiles of 32 problems
+    rc |= dev_alloc(*h, &h->d_model, Bpad * N * ops->REC);
     rc |= dev_alloc(*h, &h->d_HN, B * nx * nx);
     rc |= dev_alloc(*h, &h->d_hN, B * nx);
-    rc |= dev_alloc(*h, &h->d_fac, B * N * ops->FREC);
+    rc |= dev_alloc(*h, &h->d_fac, Bpad * N * ops->FREC);
     rc |= dev_alloc(*h, &h->d_sum, B * S * ops->SREC);
     rc |= dev_alloc(*h, &h->d_xhat, B * S * nx);
     rc |= dev_alloc(*h, &h->d_uhat, B * S * nx);
@@ -643,7 +662,7 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     }
     cudaMemcpy(h->d_seg_start, h->seg_start.data(), sizeof(int) * S, cudaMemcpyHostToDevice);
     cudaMemcpy(h->d_seg_len, h->seg_len.data(), sizeof(int) * S, cudaMemcpyHostToDevice);
-    cudaMemset(h->d_fac, 0, B * N * ops->FREC * sizeof(double));
+    cudaMemset(h->d_fac, 0, Bpad * N * ops->FREC * sizeof(double));
     cudaMemset(h->d_uhat, 0, B * S * nx * sizeof(double));
     cudaMemset(h->d_status, 0, B * sizeof(int));
 
@@ -970,11 +989,19 @@ int pdplqr_get_gains(pdplqr_handle_t h, double* K, double* d, double* Gt) {
     cudaSetDevice(h->device);
     const int nx = h->nx, nu = h->nu, FREC = h->frec;
     const size_t nst = (size_t)h->batch * h->N;
-    std::vector<double> host(nst * FREC);
+    const size_t bpad = h->thread_path ? ((size_t)(h->batch + 31) / 32) * 32 : (size_t)h->batch;
+    std::vector<double> host(bpad * h->N * FREC);
     CU_TRY(h, cudaStreamSynchronize(h->stream));
     CU_TRY(h, cudaMemcpy(host.data(), h->d_fac, host.size() * 8, cudaMemcpyDeviceToHost));
+    std::vector<double> rec(FREC);
     for (size_t st = 0; st < nst; ++st) {
         const double* z = host.data() + st * FREC;
+        if (h->thread_path) {   // tile-interleaved factor records (batch_kernels.cuh, tile_pos)
+            const size_t b = st / h->N, kk = st % h->N, tile = b / 32, lane = b % 32;
+            const double* blk = host.data() + (tile * h->N + kk) * (size_t)FREC * 32;
+            for (int e = 0; e < FREC; ++e) rec[e] = blk[(size_t)(e & ~1) * 32 + lane * 2 + (e & 1)];
+            z = rec.data();
+        }
         const int k = (int)(st % h->N);
         const bool in_last = !h->interior && k >= h->seg_start[h->S - 1];
         if (K) std::memcpy(K + st * nu * nx, z, sizeof(double) * nu * nx);
