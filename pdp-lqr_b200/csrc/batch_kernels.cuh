@@ -245,7 +245,11 @@ template <int NX, int NU, int WARPS, int DEPTH>
 struct BatchFwdSmem {
     using B = BatchDims<NX, NU>;
     static constexpr int BLOCK = (B::TREC_EC + B::FRECT) * 32;   // [E c (pad)] tile block followed by the [K d] tile block
-    static constexpr int WARP_DOUBLES = DEPTH * BLOCK;
+    // output staging: every lane collects OUT_CH stages of its trajectory (OUT_CH * S contiguous doubles of ws) and
+    // writes them with ONE bulk S2G copy instead of OUT_CH * S scattered 8-byte stores
+    static constexpr int OUT_CH = 4;
+    static constexpr int OUT_STRIDE = even_up(OUT_CH * B::S) + 2;   // per-lane slot (16-byte multiple)
+    static constexpr int WARP_DOUBLES = DEPTH * BLOCK + 32 * OUT_STRIDE;
     static constexpr int o_bar = WARPS * WARP_DOUBLES;
     static constexpr size_t BYTES = (size_t)(o_bar + DEPTH * WARPS) * 8;
 };
@@ -270,6 +274,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_forward_kernel(SegPara
     const double* model_t = p.model + tile * p.N * (B::TREC * 32);
     const double* fac_t = p.fac + tile * p.N * (FRECT * 32);
     double* ws_b = p.ws_out + b * ws_len;
+    double* ostage = slots + DEPTH * L::BLOCK + lane * L::OUT_STRIDE;
+    // bulk stores need 16-byte aligned global chunks: even ws_len and an aligned base (else plain stores)
+    const bool out_bulk = (ws_len % 2 == 0) && ((reinterpret_cast<uintptr_t>(p.ws_out) & 15) == 0);
     constexpr uint32_t TX = L::BLOCK * 8;
     const int N = p.N;
     if ((long long)tile * 32 >= p.batch) return;
@@ -330,7 +337,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_forward_kernel(SegPara
             for (int j = 0; j < NX; ++j) acc = fma(ld(B::TR_E + i + (NU + j) * NX), x[j], acc);
             xn[i] = acc;
         }
-        if (active) {
+        if (out_bulk && k - (k % L::OUT_CH) + L::OUT_CH <= N) {   // whole chunk inside the horizon: stage + bulk store
+            const int q = k % L::OUT_CH;
+            if (q == 0) bulk_wait_read<0>();   // the previous chunk's bulk store has finished reading the staging slot
+#pragma unroll
+            for (int m = 0; m < NU; ++m) ostage[q * S + m] = u[m];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) ostage[q * S + NU + i] = x[i];
+            if (q == L::OUT_CH - 1) {
+                fence_proxy_async();
+                if (active) bulk_s2g(ws_b + (size_t)(k - q) * S, ostage, L::OUT_CH * S * 8);
+                bulk_commit();
+            }
+        } else if (active) {
             double* wk = ws_b + (size_t)k * S;
 #pragma unroll
             for (int m = 0; m < NU; ++m) wk[m] = u[m];
@@ -340,6 +359,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_forward_kernel(SegPara
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] = xn[i];
     }
+    bulk_wait<0>();   // all bulk stores of this thread are complete before the CTA may exit
     if (active) {
 #pragma unroll
         for (int i = 0; i < NX; ++i) ws_b[(size_t)N * S + i] = x[i];

@@ -180,10 +180,10 @@ int backward_impl(Solver& h) {
         if (h.thread_path) {
             switch (h.bwd_variant) {
                 case 1: return launch_batch_bwd<NX, NU, 2, 1, 7>(h, p);
-                case 2: return launch_batch_bwd<NX, NU, 4, 2, 2>(h, p);
+                case 2: return launch_batch_bwd<NX, NU, 7, 2, 1>(h, p);
                 case 3: return launch_batch_bwd<NX, NU, 14, 1, 1>(h, p);
                 case 4: return launch_batch_bwd<NX, NU, 5, 3, 1>(h, p);
-                default: return launch_batch_bwd<NX, NU, 7, 2, 1>(h, p);
+                default: return launch_batch_bwd<NX, NU, 4, 2, 2>(h, p);
             }
         }
     }
@@ -223,10 +223,10 @@ int forward_impl(Solver& h, const double* d_x0, double* d_ws_out) {
         if (h.thread_path) {
             switch (h.fwd_variant) {
                 case 1: return launch_batch_fwd<NX, NU, 2, 2, 7>(h, p);
-                case 2: return launch_batch_fwd<NX, NU, 4, 2, 3>(h, p);
-                case 3: return launch_batch_fwd<NX, NU, 14, 2, 1>(h, p);
-                case 4: return launch_batch_fwd<NX, NU, 7, 4, 1>(h, p);
-                default: return launch_batch_fwd<NX, NU, 7, 3, 1>(h, p);
+                case 2: return launch_batch_fwd<NX, NU, 7, 3, 1>(h, p);
+                case 3: return launch_batch_fwd<NX, NU, 10, 2, 1>(h, p);
+                case 4: return launch_batch_fwd<NX, NU, 7, 2, 1>(h, p);
+                default: return launch_batch_fwd<NX, NU, 4, 2, 3>(h, p);
             }
         }
     }
@@ -926,7 +926,7 @@ static int solve_pipelined(Solver& h, const double* ws_in, double sigma, const d
         CU_TRY(&h, cudaEventCreateWithFlags(&h.ev_ready, cudaEventDisableTiming));
     }
     const size_t wsl = (size_t)h.N * h.s + h.nx;
-    const int per = (((h.batch + C - 1) / C) + 223) / 224 * 224;   // whole CTAs of the default 7-warp launch
+    const int per = (((h.batch + C - 1) / C) + 127) / 128 * 128;   // whole CTAs of the default 4-warp launch
     // copies must not start before earlier work on the handle's stream (e.g. set_model) has finished
     CU_TRY(&h, cudaEventRecord(h.ev_ready, h.stream));
     CU_TRY(&h, cudaStreamWaitEvent(h.s_in, h.ev_ready, 0));
