@@ -179,6 +179,90 @@ PDPLQR_DEVINL void group_mm_multi(int tid, LA la, LB lb, EPI epi) {
     }
 }
 
+// ---------------------------------------------------------------- FP64 tensor-core versions (DMMA, mma.sync m8n8k4)
+// Same interface as group_mm / group_mm_rt / group_mm_multi.  Measured on B200 (scripts/micro/dmma_bench.cu): one
+// m8n8k4 per 16 cycles per SM sub-partition (same 37 TFLOP/s peak as the FP64 FMA pipe), latency 26 cycles -- the
+// gain is 8x fewer issued instructions per MAC and two operand loads per 256 MACs, which is what the issue-bound
+// segment kernels need.  Fragment layout: A(row) lane l -> A[l/4][l%4]; B(col) lane l -> B[l%4][l/4];
+// C lane l -> C[l/4][2(l%4) + {0,1}].  Out-of-range rows / columns / k of the padded 8x8x4 tiles are fed zeros.
+PDPLQR_DEVINL void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int G, int M, int N, int T, class LA, class LB, class EPI>
+PDPLQR_DEVINL void group_mm_dmma_impl(int tid, int K, LA la, LB lb, EPI epi) {
+    constexpr int MT = (M + 7) / 8, NT = (N + 7) / 8, TILES = MT * NT, W = T / 32;
+    const int warp = tid >> 5, lane = tid & 31, r = lane >> 2, q = lane & 3;
+    const int KT = (K + 3) >> 2;
+#pragma unroll 1
+    for (int t = warp; t < G * TILES; t += 2 * W) {   // two independent tiles per pass cover the DMMA latency
+        const int t2 = t + W;
+        const bool has2 = t2 < G * TILES;             // warp-uniform
+        const int g0 = t / TILES, l0 = t - g0 * TILES, g1 = has2 ? t2 / TILES : g0, l1 = has2 ? t2 - g1 * TILES : l0;
+        const int i0 = (l0 % MT) * 8, j0 = (l0 / MT) * 8, i1 = (l1 % MT) * 8, j1 = (l1 / MT) * 8;
+        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll 3
+        for (int kt = 0; kt < KT; ++kt) {
+            const int k = kt * 4 + q;
+            const bool kin = k < K;
+            const double a0 = (kin && i0 + r < M) ? la(g0, i0 + r, k) : 0.0;
+            const double b0 = (kin && j0 + r < N) ? lb(g0, k, j0 + r) : 0.0;
+            dmma_m8n8k4(c00, c01, a0, b0);
+            if (has2) {
+                const double a1 = (kin && i1 + r < M) ? la(g1, i1 + r, k) : 0.0;
+                const double b1 = (kin && j1 + r < N) ? lb(g1, k, j1 + r) : 0.0;
+                dmma_m8n8k4(c10, c11, a1, b1);
+            }
+        }
+        if (i0 + r < M) {
+            if (j0 + 2 * q < N) epi(g0, i0 + r, j0 + 2 * q, c00);
+            if (j0 + 2 * q + 1 < N) epi(g0, i0 + r, j0 + 2 * q + 1, c01);
+        }
+        if (has2 && i1 + r < M) {
+            if (j1 + 2 * q < N) epi(g1, i1 + r, j1 + 2 * q, c10);
+            if (j1 + 2 * q + 1 < N) epi(g1, i1 + r, j1 + 2 * q + 1, c11);
+        }
+    }
+}
+template <int M, int N, int K, int T, class LA, class LB, class EPI>
+PDPLQR_DEVINL void group_mm_dmma(int tid, LA la, LB lb, EPI epi) {
+    group_mm_dmma_impl<1, M, N, T>(
+        tid, K, [&](int, int i, int k) { return la(i, k); }, [&](int, int k, int j) { return lb(k, j); },
+        [&](int, int i, int j, double v) { epi(i, j, v); });
+}
+template <int M, int N, int T, class LA, class LB, class EPI>
+PDPLQR_DEVINL void group_mm_dmma_rt(int tid, int K, LA la, LB lb, EPI epi) {
+    group_mm_dmma_impl<1, M, N, T>(
+        tid, K, [&](int, int i, int k) { return la(i, k); }, [&](int, int k, int j) { return lb(k, j); },
+        [&](int, int i, int j, double v) { epi(i, j, v); });
+}
+template <int G, int M, int N, int K, int T, class LA, class LB, class EPI>
+PDPLQR_DEVINL void group_mm_dmma_multi(int tid, LA la, LB lb, EPI epi) {
+    group_mm_dmma_impl<G, M, N, T>(tid, K, la, lb, epi);
+}
+
+#ifndef PDPLQR_DMMA_MIN_MACS
+#define PDPLQR_DMMA_MIN_MACS 20000   // products smaller than this stay on the register-tile FMA path (measured:
+#endif                               // at nx=12/nu=4 the stage kernel is barrier/overhead-bound and DMMA is slower)
+// dispatchers used by the kernels
+template <int M, int N, int K, int TM, int TN, int T, class LA, class LB, class EPI>
+PDPLQR_DEVINL void gmm(int tid, LA la, LB lb, EPI epi) {
+    if constexpr ((long long)M * N * K >= PDPLQR_DMMA_MIN_MACS) group_mm_dmma<M, N, K, T>(tid, la, lb, epi);
+    else group_mm<M, N, K, TM, TN, T>(tid, la, lb, epi);
+}
+template <int M, int N, int TM, int TN, int T, class LA, class LB, class EPI>
+PDPLQR_DEVINL void gmm_rt(int tid, int K, LA la, LB lb, EPI epi) {
+    if constexpr ((long long)M * N * 16 >= PDPLQR_DMMA_MIN_MACS) group_mm_dmma_rt<M, N, T>(tid, K, la, lb, epi);
+    else group_mm_rt<M, N, TM, TN, T>(tid, K, la, lb, epi);
+}
+template <int G, int M, int N, int K, int TM, int TN, int T, class LA, class LB, class EPI>
+PDPLQR_DEVINL void gmm_multi(int tid, LA la, LB lb, EPI epi) {
+    if constexpr ((long long)M * N * K >= PDPLQR_DMMA_MIN_MACS) group_mm_dmma_multi<G, M, N, K, T>(tid, la, lb, epi);
+    else group_mm_multi<G, M, N, K, TM, TN, T>(tid, la, lb, epi);
+}
+
 // Cholesky of the leading NU x NU block of a column-major matrix in shared memory (leading dimension ld),
 // right-looking, cooperative over the group.  On exit the lower triangle holds L and dinv[k] = 1 / L(k,k).
 // Returns (to every thread) 0 or the 1-based index of the first non-positive pivot (factorisation continues

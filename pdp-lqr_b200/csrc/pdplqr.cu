@@ -39,6 +39,7 @@ struct pdplqr_solver {
     int frec = 0;              // doubles per stage in d_fac for the active path
     int mrec = 0;              // doubles per stage in d_model for the active path
     int bwd_variant = 0, fwd_variant = 0;
+    int seg_mode = 0, seg_len0 = 0;   // closed-form partition handed to the kernels
     int lat_threads = 128;     // 0 disables the 128-thread latency mode of the segment backward kernel
     int tree_tt = 32;          // threads per tree combine (128 = experimental wide combine; measured slower)
     cudaStream_t stream = nullptr;
@@ -126,6 +127,7 @@ SegParams seg_params(Solver& h) {
     SegParams p{};
     p.N = h.N; p.S = h.S; p.batch = h.batch; p.interior = h.interior ? 1 : 0;
     p.seg_start = h.d_seg_start; p.seg_len = h.d_seg_len;
+    p.seg_mode = h.seg_mode; p.seg_len0 = h.seg_len0;
     p.model = h.d_model; p.HN = h.d_HN; p.hN = h.d_hN;
     p.ws_prev = h.cur_ws; p.sigma = h.sigma;
     p.fac = h.d_fac; p.sum = h.d_sum; p.status = h.d_status;
@@ -613,6 +615,12 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
         h->seg_start[i] = st; h->seg_len[i] = len;
     }
     if (h->seg_len[S - 1] < 1) { delete h; return PDPLQR_ERR_INVALID; }
+    h->seg_mode = auto_seg ? 0 : 1;
+    h->seg_len0 = h->seg_len[0];
+    if (!auto_seg && S > 1) {   // the reference rule must be expressible in closed form (it is unless len was clamped)
+        for (int i = 0; i < S - 1; ++i)
+            if (h->seg_len[i] != h->seg_len0) { delete h; return PDPLQR_ERR_INVALID; }
+    }
     h->thread_path = (S == 1) && ops->has_thread_path && h->nc_total == 0;   // (interior shards switch it off)
     h->frec = h->thread_path ? ops->FRECT : ops->FREC;
     h->mrec = h->thread_path ? ops->TREC : ops->REC;

@@ -47,7 +47,8 @@ struct SegDims {
 struct SegParams {
     int N, S, batch;
     int interior;            // 1: this handle is a horizon shard whose last segment ends at an interface, not at the terminal
-    const int* seg_start;    // [S]
+    int seg_mode, seg_len0;  // partition in closed form (no global loads in the kernel prologue), see seg_first()
+    const int* seg_start;    // [S]  (kept for reference / debugging)
     const int* seg_len;      // [S]
     const double* model;     // [batch][N][REC]
     const double* HN;        // [batch][NX*NX]
@@ -70,6 +71,16 @@ struct SegParams {
     const double* uhat;      // [batch][S][NX]  (costate at each segment's exit)
     double* ws_out;          // [batch][N*S+NX]
 };
+
+// first stage of segment i (i = S gives N).  seg_mode 0: equal lengths, the first N % S segments one stage longer
+// (library-chosen segmentation); seg_mode 1: the reference's rule -- every segment but the last has seg_len0 stages
+// (lqr_solver_parallel.hpp:73-80).
+PDPLQR_DEVINL int seg_first(const SegParams& p, int i) {
+    if (i >= p.S) return p.N;
+    if (p.seg_mode == 1) return i * p.seg_len0;
+    const int q = p.N / p.S, r = p.N % p.S;
+    return i * q + min(i, r);
+}
 
 // compile-time choice of the register tile for an M x N product on T threads
 struct Tile { int tm, tn; };
@@ -130,7 +141,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
     const int tid = threadIdx.x;
     const int g = blockIdx.x;
     const int b = g / p.S, seg = g % p.S;
-    const int N0 = p.seg_start[seg], LEN = p.seg_len[seg], N1 = N0 + LEN;
+    const int N0 = seg_first(p, seg), LEN = seg_first(p, seg + 1) - N0, N1 = N0 + LEN;
     const bool is_last = (seg == p.S - 1) && !p.interior;
     const bool pdp = !is_last;
 
@@ -264,10 +275,10 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 if (j == S && i < NX) { pc_s[i] = v; v += pn[i]; }
                 PFE[i + j * L::LDPE] = v;
             };
-            if (pdp) group_mm<MM, S + 1, NX, tl.tm, tl.tn, T>(tid, la, lb, epi);
+            if (pdp) gmm<MM, S + 1, NX, tl.tm, tl.tn, T>(tid, la, lb, epi);
             else {
                 constexpr Tile t2 = pick_tile(NX, S + 1, T);
-                group_mm<NX, S + 1, NX, t2.tm, t2.tn, T>(tid, la, lb, epi);
+                gmm<NX, S + 1, NX, t2.tm, t2.tn, T>(tid, la, lb, epi);
             }
         }
         group_sync<T>();
@@ -283,13 +294,13 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 else base = R[D::REC_h + i] - sigma * wp[i];
                 Ma[i + j * L::LDM] = base + v;
             };
-            group_mm<S, S + 1, NX, tl.tm, tl.tn, T>(tid, la, lb, epi);
+            gmm<S, S + 1, NX, tl.tm, tl.tn, T>(tid, la, lb, epi);
             if (nck > 0) {  // M += D^T diag(rho) D ; g -= D^T (rho o g_c)      (lqr_kernel.hpp:106-112)
                 const double* Dk = Dbuf + buf * DSTRIDE;
                 auto lda = [&](int i, int r) { return Dk[r + i * nck]; };
                 auto ldb = [&](int r, int j) { return j < S ? rho_s[r] * Dk[r + j * nck] : -rg_s[r]; };
                 auto epd = [&](int i, int j, double v) { Ma[i + j * L::LDM] += v; };
-                group_mm_rt<S, S + 1, tl.tm, tl.tn, T>(tid, nck, lda, ldb, epd);
+                gmm_rt<S, S + 1, tl.tm, tl.tn, T>(tid, nck, lda, ldb, epd);
             }
         }
         group_sync<T>();
@@ -385,20 +396,20 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                     pn[i] = Ma[(NU + i) + S * L::LDM] - v;
                 }
             };
-            group_mm<NX, NX + 1, NU, tl.tm, tl.tn, T>(tid, la, lb, epi);
+            gmm<NX, NX + 1, NU, tl.tm, tl.tn, T>(tid, la, lb, epi);
             if (pdp) {
                 constexpr Tile tc = pick_tile(NX, NX, T);
                 auto lga = [&](int i, int m) { return YT[(NX + 1 + i) + m * L::LDY]; };
                 auto lgb = [&](int m, int j) { return YT[(NX + 1 + j) + m * L::LDY]; };
                 auto epc = [&](int i, int j, double v) { Cn[i + j * NX] += v; };
-                group_mm<NX, NX, NU, tc.tm, tc.tn, T>(tid, lga, lgb, epc);
+                gmm<NX, NX, NU, tc.tm, tc.tn, T>(tid, lga, lgb, epc);
                 auto lfa = [&](int i, int m) { return PFE[(NX + i) + m * L::LDPE]; };     // (F+ B)(i,m)
                 auto lfb = [&](int m, int j) { return Z[m + j * NU]; };                    // [K d](m,j)
                 auto epf = [&](int i, int j, double v) {
                     if (j < NX) PF[(NX + i) + j * L::LDPF] = PFE[(NX + i) + (NU + j) * L::LDPE] + v;   // F+A + (F+B)K
                     else fn[i] += PFE[(NX + i) + S * L::LDPE] + v;                                      // F+c + (F+B)d + f+
                 };
-                group_mm<NX, NX + 1, NU, tl.tm, tl.tn, T>(tid, lfa, lfb, epf);
+                gmm<NX, NX + 1, NU, tl.tm, tl.tn, T>(tid, lfa, lfb, epf);
             }
             // factor record -> global (coalesced)
             double* fk = fac_b + (size_t)k * D::FREC;
@@ -474,7 +485,7 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
     const int tid = threadIdx.x;
     const int gidx = blockIdx.x;
     const int b = gidx / p.S, seg = gidx % p.S;
-    const int N0 = p.seg_start[seg], LEN = p.seg_len[seg], N1 = N0 + LEN;
+    const int N0 = seg_first(p, seg), LEN = seg_first(p, seg + 1) - N0, N1 = N0 + LEN;
     const bool is_last = (seg == p.S - 1) && !p.interior;
     const bool pdp = !is_last;
 
@@ -632,7 +643,7 @@ __global__ void __launch_bounds__(T) seg_forward_kernel(SegParams p) {
     const int tid = threadIdx.x;
     const int g = blockIdx.x;
     const int b = g / p.S, seg = g % p.S;
-    const int N0 = p.seg_start[seg], LEN = p.seg_len[seg], N1 = N0 + LEN;
+    const int N0 = seg_first(p, seg), LEN = seg_first(p, seg + 1) - N0, N1 = N0 + LEN;
     const bool is_last = (seg == p.S - 1) && !p.interior;
 
     double* rec = smem + L::o_rec;

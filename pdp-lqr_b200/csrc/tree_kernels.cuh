@@ -194,7 +194,7 @@ PDPLQR_DEVINL void group_combine(int lane, int bar_id, double* ws, double* out, 
         auto la = [&](int r, int k) { return Ca[r + k * NX]; };
         auto lb = [&](int k, int c) { return Pb[k + c * NX]; };
         auto epi = [&](int r, int c, double v) { Aug[r + c * LDA] = v + ((r == c) ? 1.0 : 0.0); };
-        group_mm<NX, NX, NX, t1.tm, t1.tn, TT>(lane, la, lb, epi);
+        gmm<NX, NX, NX, t1.tm, t1.tn, TT>(lane, la, lb, epi);
         for (int e = lane; e < N2; e += TT) {
             const int r = e % NX, c = e / NX;
             Aug[r + (NX + c) * LDA] = Fa[e];
@@ -234,7 +234,7 @@ PDPLQR_DEVINL void group_combine(int lane, int bar_id, double* ws, double* out, 
             else if (g == 1) T2[r + c * NX] = v;
             else out[D::SUM_F + r + c * NX] = v;
         };
-        group_mm_multi<3, NX, NX, NX, t3.tm, t3.tn, TT>(lane, la, lb, ep);
+        gmm_multi<3, NX, NX, NX, t3.tm, t3.tn, TT>(lane, la, lb, ep);
     }
     sub_sync<TT>(bar_id);
     // lv = P_b x_f + p_b  (needs xf)
@@ -253,7 +253,7 @@ PDPLQR_DEVINL void group_combine(int lane, int bar_id, double* ws, double* out, 
             if (g == 0) out[D::SUM_P + r + c * NX] = Pa[r + c * NX] + v;
             else out[D::SUM_C + r + c * NX] = Cb[r + c * NX] + v;
         };
-        group_mm_multi<2, NX, NX, NX, t2.tm, t2.tn, TT>(lane, la, lb, ep);
+        gmm_multi<2, NX, NX, NX, t2.tm, t2.tn, TT>(lane, la, lb, ep);
     }
     sub_sync<TT>(bar_id);
     // p = p_a + F_a^T lv ; f = F_b x_f + f_b
