@@ -107,8 +107,9 @@ struct BwdSmem {
     static constexpr int LDPE = odd_ld(2 * NX);    // PFE: [P+;F+] [E c], (2NX) x (S+1)
     static constexpr int LDM = odd_ld(S);          // Ma: [M | g], S x (S+1)
     static constexpr int LDY = odd_ld(D::NRHS);    // YT: NRHS x NU  (Y^T, Y = Luu^-1 [Qux Qu BtFt])
-    static constexpr int o_rec = 0;                                 // 2 x REC (TMA destination, 16B aligned)
-    static constexpr int o_Z = o_rec + 2 * D::REC;                  // FREC
+    static constexpr int o_rec = 0;                                 // REC (TMA destination, 16B aligned), single buffer:
+                                                                    // the next record is fetched right after its last reader (S3)
+    static constexpr int o_Z = o_rec + D::REC;                      // FREC
     static constexpr int o_ET = o_Z + D::FREC;
     static constexpr int o_PF = o_ET + LDT * NX;
     static constexpr int o_PFE = o_PF + LDPF * NX;
@@ -124,9 +125,9 @@ struct BwdSmem {
     static constexpr int o_bar = even_up(o_qi + NU * NU);           // 2 mbarriers
     static constexpr int DOUBLES = even_up(o_bar + 2);
     static constexpr size_t BYTES = (size_t)DOUBLES * 8;
-    // run-time tail (only when the problem has constraints): D[2][even(ncmax*S)] | rho[ncmax] | rho.*g[ncmax]
+    // run-time tail (only when the problem has constraints): D[even(ncmax*S)] | rho[ncmax] | rho.*g[ncmax]
     static size_t bytes(int ncmax) {
-        return BYTES + (ncmax > 0 ? (size_t)(2 * even_up(ncmax * S) + 2 * ncmax) * 8 : 0);
+        return BYTES + (ncmax > 0 ? (size_t)(even_up(ncmax * S) + 2 * ncmax) * 8 : 0);
     }
 };
 
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
     const int ncmax = p.ncmax;
     const int DSTRIDE = even_up(ncmax * S);
     double* Dbuf = smem + L::DOUBLES;
-    double* rho_s = Dbuf + 2 * DSTRIDE;
+    double* rho_s = Dbuf + DSTRIDE;
     double* rg_s = rho_s + ncmax;
 
     const size_t ws_len = (size_t)p.N * S + NX;
@@ -246,12 +247,8 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
 #pragma unroll 1
     for (int it = 0; it < LEN; ++it) {
         const int k = N1 - 1 - it;
-        const int buf = it & 1;
-        const double* R = rec + buf * D::REC;
-        if (tid == 0 && it + 1 < LEN) {  // prefetch stage k-1 (its buffer was last read before the previous sync)
-            fence_proxy_async();
-            issue_stage(k - 1, buf ^ 1);
-        }
+        const int buf = 0;
+        const double* R = rec;
         const int nck = ncmax > 0 ? p.ncs[k] : 0;
         if (nck > 0) {  // g = z - y/rho ; keep rho and rho.*g   (lqr_solver_parallel.hpp:134-137, lqr_kernel.hpp:110)
             const size_t co = cbase + p.coff[k];
@@ -304,6 +301,10 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
             }
         }
         group_sync<T>();
+        if (tid == 0 && it + 1 < LEN) {  // the record (H, h) and D had their last readers in S3: fetch stage k-1 into
+            fence_proxy_async();         // the same buffer; it lands while S4-S6 run and is waited for at the end of S6
+            issue_stage(k - 1, 0);
+        }
 
         // S4: Luu = chol(Quu).  Small NU: every solving thread factorises its own register copy (no barriers);
         //     larger NU: cooperative in-place factorisation of the leading block of Ma.
@@ -427,8 +428,8 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
             }
         }
         if (it + 1 < LEN) {  // the next stage's record was prefetched at the top of this stage: transpose it now
-            mbar_wait(&bar[buf ^ 1], ((it + 1) >> 1) & 1);
-            transpose_stage(buf ^ 1);
+            mbar_wait(&bar[0], (it + 1) & 1);
+            transpose_stage(0);
         }
         group_sync<T>();
     }
@@ -459,8 +460,12 @@ template <int NX, int NU>
 struct AffSmem {
     using D = SegDims<NX, NU>;
     static constexpr int S = D::S;
-    static constexpr int o_rec = 0;                          // 2 x REC   (TMA)
-    static constexpr int o_fac = o_rec + 2 * D::REC;         // 2 x FREC  (TMA)
+    // of the stage record only [E | c] and h are needed (H is 56 % of the record at nx=30): two bulk copies
+    static constexpr int H_OFF = D::REC_h & ~1;              // 16-byte aligned start of the h chunk inside the record
+    static constexpr int H_LEN = (D::REC - H_OFF);           // doubles copied (h plus at most one neighbour)
+    static constexpr int RLITE = D::REC_EC + H_LEN;          // doubles per ring slot
+    static constexpr int o_rec = 0;                          // 2 x RLITE (TMA)
+    static constexpr int o_fac = o_rec + 2 * RLITE;          // 2 x FREC  (TMA)
     static constexpr int o_aff = o_fac + 2 * D::FREC;        // 2 x AREC  (TMA)
     static constexpr int o_t = o_aff + 2 * D::AREC;          // t (NX)
     static constexpr int o_g = o_t + NX;                     // g (S)
@@ -539,8 +544,9 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
     auto issue_stage = [&](int kk, int bufi) {
         const int nck = ncmax > 0 ? p.ncs[kk] : 0;
         const uint32_t dbytes = (uint32_t)even_up(nck * S) * 8;
-        mbar_expect_tx(&bar[bufi], (D::REC + D::FREC + D::AREC) * 8 + dbytes);
-        bulk_g2s(rec + bufi * D::REC, model_b + (size_t)kk * D::REC, D::REC * 8, &bar[bufi]);
+        mbar_expect_tx(&bar[bufi], (L::RLITE + D::FREC + D::AREC) * 8 + dbytes);
+        bulk_g2s(rec + bufi * L::RLITE, model_b + (size_t)kk * D::REC, D::REC_EC * 8, &bar[bufi]);
+        bulk_g2s(rec + bufi * L::RLITE + D::REC_EC, model_b + (size_t)kk * D::REC + L::H_OFF, L::H_LEN * 8, &bar[bufi]);
         bulk_g2s(fac + bufi * D::FREC, fac_b + (size_t)kk * D::FREC, D::FREC * 8, &bar[bufi]);
         bulk_g2s(aff + bufi * D::AREC, aff_b + (size_t)kk * D::AREC, D::AREC * 8, &bar[bufi]);
         if (nck > 0) bulk_g2s(Dbuf + bufi * DSTRIDE, D_b + p.doff[kk], dbytes, &bar[bufi]);
@@ -550,7 +556,8 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
     for (int it = 0; it < LEN; ++it) {
         const int k = N1 - 1 - it;
         const int buf = it & 1;
-        const double* R = rec + buf * D::REC;
+        const double* R = rec + buf * L::RLITE;
+        const double* hrec = R + D::REC_EC + (D::REC_h - L::H_OFF);   // h of this stage
         const double* Zk = fac + buf * D::FREC;
         const double* Ak = aff + buf * D::AREC;
         if (tid == 0 && it + 1 < LEN) {
@@ -577,7 +584,7 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
         for (int r = 0; r < (S + T - 1) / T; ++r) {
             const int i = tid + r * T;
             if (i < S) {
-                double acc = R[D::REC_h + i] - sigma * wpv[r];
+                double acc = hrec[i] - sigma * wpv[r];
                 if (nck > 0) {
                     const double* Dk = Dbuf + buf * DSTRIDE;
                     for (int q = 0; q < nck; ++q) acc = fma(-Dk[q + i * nck], rg_s[q], acc);
