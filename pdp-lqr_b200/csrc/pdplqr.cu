@@ -12,6 +12,7 @@
 #include "admm_kernels.cuh"
 #include "batch_kernels.cuh"
 #include "seg_kernels.cuh"
+#include "seg_km_kernel.cuh"
 #include "tree_kernels.cuh"
 
 using namespace pdplqr;
@@ -41,6 +42,7 @@ struct pdplqr_solver {
     int bwd_variant = 0, fwd_variant = 0;
     int seg_mode = 0, seg_len0 = 0;   // closed-form partition handed to the kernels
     int lat_threads = 128;     // 0 disables the 128-thread latency mode of the segment backward kernel
+    int use_km = 1;            // specialised k-major stage kernel for nx, nu multiples of 4 (PDPLQR_USE_KM=0 disables)
     int tree_tt = 32;          // threads per tree combine (128 = experimental wide combine; measured slower)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -192,6 +194,29 @@ int backward_impl(Solver& h) {
     // latency mode: with fewer (problem, segment) groups than SMs a whole 128-thread CTA works on each group
     constexpr int TL = (T < 128) ? 128 : T;
     const bool latency_mode = (T < 128) && h.lat_threads > 0 && (long long)h.batch * h.S <= 2 * 148;
+    if constexpr (KmSmem<NX, NU>::ELIGIBLE && T == 32) {
+        // quadrotor class (nx, nu multiples of 4), unconstrained, no affine cache: k-major tile kernel
+        // (measured: 3-10 % faster than the generic kernel in the 128-thread latency mode, slower in the one-warp
+        //  throughput mode where padded 4x4 tiles add as many FMAs as the overhead they remove -- DESIGN.md section 4;
+        //  use_km = 2 forces it for both)
+        if (h.use_km && h.ncmax == 0 && !h.keep_affine && (latency_mode || h.use_km == 2)) {
+            constexpr size_t kb = KmSmem<NX, NU>::BYTES;
+            if (latency_mode) {
+                auto kern = seg_backward_km_kernel<NX, NU, 128>;
+                int rc = set_smem(h, kern, kb);
+                if (rc) return rc;
+                kern<<<h.batch * h.S, 128, kb, h.stream>>>(p);
+            } else {
+                auto kern = seg_backward_km_kernel<NX, NU, 32>;
+                int rc = set_smem(h, kern, kb);
+                if (rc) return rc;
+                kern<<<h.batch * h.S, 32, kb, h.stream>>>(p);
+            }
+            h.launches++;
+            CU_TRY(&h, cudaGetLastError());
+            return PDPLQR_OK;
+        }
+    }
     const size_t bytes = BwdSmem<NX, NU>::bytes(h.ncmax);
     if (latency_mode) {
         auto kern = seg_backward_kernel<NX, NU, TL>;
@@ -628,6 +653,7 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (const char* e = getenv("PDPLQR_FWD_VARIANT")) h->fwd_variant = atoi(e);
     if (const char* e = getenv("PDPLQR_LAT_THREADS")) h->lat_threads = atoi(e);
     if (const char* e = getenv("PDPLQR_TREE_TT")) h->tree_tt = atoi(e);
+    if (const char* e = getenv("PDPLQR_USE_KM")) h->use_km = atoi(e);
     if (const char* e = getenv("PDPLQR_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(1, std::min(64, atoi(e)));
 
     auto bail = [&](int rc) { std::string e = h->err; pdplqr_destroy(h); (void)e; return rc; };
