@@ -76,27 +76,26 @@ template <int NX, int NCOL, int LDA>
 PDPLQR_DEVINL void warp_gauss_jordan(int lane, double* Aug) {
 #pragma unroll 1
     for (int k = 0; k < NX; ++k) {
+        // pivot search, redundant per lane (broadcast shared loads of column k, rows k..NX-1)
+        double best = -1.0;
+        int piv = k;
+        for (int i = k; i < NX; ++i) {
+            const double v = fabs(Aug[i + k * LDA]);
+            if (v > best) { best = v; piv = i; }
+        }
+        if (piv != k) {                       // physical swap of column k's two entries (one lane), so that the
+            __syncwarp();                     // multipliers below are simply column k after the row exchange
+            if (lane == 0) {
+                const double t = Aug[k + k * LDA];
+                Aug[k + k * LDA] = Aug[piv + k * LDA];
+                Aug[piv + k * LDA] = t;
+            }
+            __syncwarp();
+        }
         double colk[NX];
 #pragma unroll
         for (int i = 0; i < NX; ++i) colk[i] = Aug[i + k * LDA];
-        double best = -1.0;
-        int piv = k;
-#pragma unroll
-        for (int i = 0; i < NX; ++i) {
-            const double v = fabs(colk[i]);
-            if (i >= k && v > best) { best = v; piv = i; }
-        }
-        double pval = 1.0, ck = 0.0;   // selects instead of run-time register indexing
-#pragma unroll
-        for (int i = 0; i < NX; ++i) {
-            if (i == piv) pval = colk[i];
-            if (i == k) ck = colk[i];
-        }
-        const double pinv = 1.0 / pval;
-        // after the swap, row k holds the old row piv and row piv the old row k
-#pragma unroll
-        for (int i = 0; i < NX; ++i)
-            if (i == piv) colk[i] = ck;
+        const double pinv = 1.0 / Aug[k + k * LDA];
         for (int j = k + 1 + lane; j < NCOL; j += 32) {
             double* cj = Aug + j * LDA;
             const double akj = cj[piv];
