@@ -26,6 +26,8 @@ struct AdmmParams {
     const long long* doff;     // [N+2] (padded device layout of D)
     const double* Dm;          // [batch][d_total]
     long long d_total, nc_total;
+    const int* sel_col;        // selection-matrix constraints (see SegParams): [batch][nc_total] or nullptr (dense D)
+    const double* sel_val;
     // cones: per stage k the cones cone_first[k] .. cone_first[k+1]-1 ; each (type, first row within stage, dim)
     const int* cone_first;     // [N+2]
     const int* cone_type;
@@ -70,10 +72,16 @@ __global__ void __launch_bounds__(32) admm_update_kernel(AdmmParams p) {
     __syncwarp();
     const double* Dk = p.Dm + (size_t)b * p.d_total + p.doff[k];
     const size_t co = (size_t)b * p.nc_total + p.coff[k];
+    const bool sel = p.sel_col != nullptr;
     double r_prim = 0.0, nrm = 0.0;
     for (int r = lane; r < nc; r += 32) {
         double acc = 0.0;
-        for (int j = 0; j < dim; ++j) acc = fma(Dk[r + (size_t)j * nc], wt[j], acc);
+        if (sel) {
+            const int cj = p.sel_col[co + r];
+            if (cj >= 0) acc = p.sel_val[co + r] * wt[cj];
+        } else {
+            for (int j = 0; j < dim; ++j) acc = fma(Dk[r + (size_t)j * nc], wt[j], acc);
+        }
         zt[r] = acc;
         const double zh = p.alpha * acc + (1.0 - p.alpha) * p.z[co + r];
         v[r] = zh + p.y[co + r] / p.rho[co + r];
@@ -120,10 +128,19 @@ __global__ void __launch_bounds__(32) admm_update_kernel(AdmmParams p) {
     double r_dual = 0.0, nrm_d = 0.0;
     for (int j = lane; j < dim; j += 32) {
         double acc = 0.0, accy = 0.0;
-        for (int r = 0; r < nc; ++r) {
-            const double dv = Dk[r + (size_t)j * nc];
-            acc = fma(dv, dz[r], acc);
-            accy = fma(dv, v[r], accy);
+        if (sel) {
+            for (int r = 0; r < nc; ++r)
+                if (p.sel_col[co + r] == j) {
+                    const double dv = p.sel_val[co + r];
+                    acc = fma(dv, dz[r], acc);
+                    accy = fma(dv, v[r], accy);
+                }
+        } else {
+            for (int r = 0; r < nc; ++r) {
+                const double dv = Dk[r + (size_t)j * nc];
+                acc = fma(dv, dz[r], acc);
+                accy = fma(dv, v[r], accy);
+            }
         }
         r_dual = fmax(r_dual, fabs(acc));
         nrm_d = fmax(nrm_d, fabs(accy));

@@ -57,6 +57,12 @@ struct pdplqr_solver {
     std::vector<long long> coff, doff_host, doff_dev;
     int* d_ncs = nullptr;
     long long *d_coff = nullptr, *d_doff = nullptr, *d_doff_host = nullptr;
+    // selection-matrix constraints (every row of D has at most one non-zero): compact (column, value) form
+    int* d_sel_col = nullptr;
+    double* d_sel_val = nullptr;
+    int* d_sel_flag = nullptr;
+    bool sel_mode = false;
+    int allow_sel = 1;   // PDPLQR_SPARSE_D=0 keeps the dense path (A/B tests)
     double *d_D = nullptr, *d_ys = nullptr, *d_zs = nullptr, *d_rho = nullptr, *d_inv_rho = nullptr;
     const double *cur_ys = nullptr, *cur_zs = nullptr, *cur_inv_rho = nullptr, *cur_rho = nullptr;
     // affine cache for backward_without_factorization
@@ -138,6 +144,8 @@ SegParams seg_params(Solver& h) {
     p.ncmax = h.ncmax; p.nc_total = h.nc_total; p.d_total = h.d_total_dev;
     p.ncs = h.d_ncs; p.coff = h.d_coff; p.doff = h.d_doff; p.Dm = h.d_D;
     p.ys = h.cur_ys; p.zs = h.cur_zs; p.rho = h.cur_rho; p.inv_rho = h.cur_inv_rho;
+    p.sel_col = h.sel_mode ? h.d_sel_col : nullptr;
+    p.sel_val = h.sel_mode ? h.d_sel_val : nullptr;
     if (h.chunk_nb > 0) {   // batch chunk [b0, b0 + nb): offset every per-problem array (nc = 0 handles only)
         const size_t b0 = h.chunk_b0, wsl = (size_t)h.N * h.s + h.nx;
         p.batch = h.chunk_nb;
@@ -217,7 +225,7 @@ int backward_impl(Solver& h) {
             return PDPLQR_OK;
         }
     }
-    const size_t bytes = BwdSmem<NX, NU>::bytes(h.ncmax);
+    const size_t bytes = BwdSmem<NX, NU>::bytes(h.ncmax, h.sel_mode);
     if (latency_mode) {
         auto kern = seg_backward_kernel<NX, NU, TL>;
         int rc = set_smem(h, kern, bytes);
@@ -298,7 +306,7 @@ template <int NX, int NU>
 int affine_impl(Solver& h) {
     SegParams p = seg_params(h);
     auto kern = seg_affine_kernel<NX, NU>;
-    const size_t bytes = AffSmem<NX, NU>::bytes(h.ncmax);
+    const size_t bytes = AffSmem<NX, NU>::bytes(h.ncmax, h.sel_mode);
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
     kern<<<h.batch * h.S, 32, bytes, h.stream>>>(p);
@@ -427,6 +435,28 @@ __global__ void pad_D_kernel(const double* __restrict__ src, double* __restrict_
     for (long long e = threadIdx.x; e < nd; e += blockDim.x) d[e] = e < n ? s[e] : 0.0;
 }
 
+// one block per (stage, problem): for every constraint row find its non-zeros; rows with at most one non-zero are
+// recorded as (column, value) (column -1 for an all-zero row), any other row raises the flag (-> dense path)
+__global__ void detect_selection_kernel(const double* __restrict__ D, const long long* __restrict__ doff,
+                                        const long long* __restrict__ coff, const int* __restrict__ ncs, long long d_total,
+                                        long long nc_total, int N, int nx, int s, int* __restrict__ col,
+                                        double* __restrict__ val, int* flag) {
+    const int k = blockIdx.x, b = blockIdx.y;
+    const int nc = ncs[k], dim = (k < N) ? s : nx;
+    const double* Dk = D + (long long)b * d_total + doff[k];
+    for (int r = threadIdx.x; r < nc; r += blockDim.x) {
+        int nnz = 0, cj = -1;
+        double v = 0.0;
+        for (int j = 0; j < dim; ++j) {
+            const double d = Dk[r + (long long)j * nc];
+            if (d != 0.0) { ++nnz; cj = j; v = d; }
+        }
+        col[(long long)b * nc_total + coff[k] + r] = cj;
+        val[(long long)b * nc_total + coff[k] + r] = v;
+        if (nnz > 1) atomicExch(flag, 1);
+    }
+}
+
 template <class Tp>
 int dev_alloc(Solver& h, Tp** p, size_t count) {
     void* q = nullptr;
@@ -477,6 +507,17 @@ int set_model_common(Solver& h, const double* E, const double* c, const double* 
                                                                      h.d_total_dev, h.N + 1);
             h.launches++;
             e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) {   // structure detection: selection-matrix constraints need no dense D in the kernels
+            e = cudaMemsetAsync(h.d_sel_flag, 0, sizeof(int), h.stream);
+            detect_selection_kernel<<<dim3(h.N + 1, h.batch), 64, 0, h.stream>>>(h.d_D, h.d_doff, h.d_coff, h.d_ncs, h.d_total_dev,
+                                                                                h.nc_total, h.N, h.nx, h.s, h.d_sel_col, h.d_sel_val,
+                                                                                h.d_sel_flag);
+            h.launches++;
+            int flag = 1;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, h.d_sel_flag, sizeof(int), cudaMemcpyDeviceToHost, h.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h.stream);
+            h.sel_mode = (e == cudaSuccess) && flag == 0 && h.allow_sel;
         }
     }
     if (e == cudaSuccess && (stage || dstage)) e = cudaStreamSynchronize(h.stream);
@@ -654,6 +695,7 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (const char* e = getenv("PDPLQR_LAT_THREADS")) h->lat_threads = atoi(e);
     if (const char* e = getenv("PDPLQR_TREE_TT")) h->tree_tt = atoi(e);
     if (const char* e = getenv("PDPLQR_USE_KM")) h->use_km = atoi(e);
+    if (const char* e = getenv("PDPLQR_SPARSE_D")) h->allow_sel = atoi(e);
     if (const char* e = getenv("PDPLQR_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(1, std::min(64, atoi(e)));
 
     auto bail = [&](int rc) { std::string e = h->err; pdplqr_destroy(h); (void)e; return rc; };
@@ -685,6 +727,9 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
         rc |= dev_alloc(*h, &h->d_zs, B * h->nc_total);
         rc |= dev_alloc(*h, &h->d_rho, B * h->nc_total);
         rc |= dev_alloc(*h, &h->d_inv_rho, B * h->nc_total);
+        rc |= dev_alloc(*h, &h->d_sel_col, B * h->nc_total);
+        rc |= dev_alloc(*h, &h->d_sel_val, B * h->nc_total);
+        rc |= dev_alloc(*h, &h->d_sel_flag, 1);
     }
     if (h->keep_affine) rc |= dev_alloc(*h, &h->d_aff, B * N * ops->AREC);
     if (rc) return bail(PDPLQR_ERR_CUDA);
@@ -1171,6 +1216,7 @@ int pdplqr_admm_solve_device(pdplqr_handle_t h, const double* x0, double* w, dou
         ap.nx = h->nx; ap.nu = h->nu; ap.N = h->N; ap.batch = h->batch; ap.ncmax = h->ncmax;
         ap.ncs = h->d_ncs; ap.coff = h->d_coff; ap.doff = h->d_doff; ap.Dm = h->d_D;
         ap.d_total = h->d_total_dev; ap.nc_total = h->nc_total;
+        ap.sel_col = h->sel_mode ? h->d_sel_col : nullptr; ap.sel_val = h->sel_mode ? h->d_sel_val : nullptr;
         ap.cone_first = h->d_cone_first; ap.cone_type = h->d_cone_type; ap.cone_row = h->d_cone_row; ap.cone_dim = h->d_cone_dim;
         ap.e_lb = h->d_elb; ap.e_ub = h->d_eub;
         ap.w_tilde = h->d_wtilde; ap.w = w; ap.z = z; ap.y = y; ap.rho = rho;

@@ -67,6 +67,10 @@ struct SegParams {
     long long d_total, nc_total;
     int ncmax;
     const double *ys, *zs, *rho, *inv_rho;   // [batch][nc_total]
+    // selection-matrix constraints (every row of every D_k has at most one non-zero): D is replaced by the column
+    // index (-1 for an all-zero row) and the value of each row; nullptr -> dense D
+    const int* sel_col;      // [batch][nc_total]
+    const double* sel_val;   // [batch][nc_total]
     const double* xhat;      // [batch][S][NX]  (entry state of each segment; == x0 when S == 1)
     const double* uhat;      // [batch][S][NX]  (costate at each segment's exit)
     double* ws_out;          // [batch][N*S+NX]
@@ -125,9 +129,12 @@ struct BwdSmem {
     static constexpr int o_bar = even_up(o_qi + NU * NU);           // 2 mbarriers
     static constexpr int DOUBLES = even_up(o_bar + 2);
     static constexpr size_t BYTES = (size_t)DOUBLES * 8;
-    // run-time tail (only when the problem has constraints): D[even(ncmax*S)] | rho[ncmax] | rho.*g[ncmax]
-    static size_t bytes(int ncmax) {
-        return BYTES + (ncmax > 0 ? (size_t)(even_up(ncmax * S) + 2 * ncmax) * 8 : 0);
+    // run-time tail (only when the problem has constraints):
+    //   dense D:      D[even(ncmax*S)] | rho[ncmax] | rho.*g[ncmax]
+    //   selection D:                     rho[ncmax] | rho.*g[ncmax] | val[ncmax] | col[ncmax] (int)
+    static size_t bytes(int ncmax, bool sel = false) {
+        if (ncmax <= 0) return BYTES;
+        return BYTES + (size_t)((sel ? 0 : even_up(ncmax * S)) + 2 * ncmax + (sel ? ncmax + even_up(ncmax) / 2 + 1 : 0)) * 8;
     }
 };
 
@@ -163,10 +170,13 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::o_bar);
     // run-time tail: constraint matrix ring + rho, rho.*g of the current stage
     const int ncmax = p.ncmax;
-    const int DSTRIDE = even_up(ncmax * S);
+    const bool sel = p.sel_col != nullptr;          // selection-matrix constraints: no dense D at all
+    const int DSTRIDE = sel ? 0 : even_up(ncmax * S);
     double* Dbuf = smem + L::DOUBLES;
     double* rho_s = Dbuf + DSTRIDE;
     double* rg_s = rho_s + ncmax;
+    double* sval_s = rg_s + ncmax;
+    int* scol_s = reinterpret_cast<int*>(sval_s + ncmax);
 
     const size_t ws_len = (size_t)p.N * S + NX;
     const double* model_b = p.model + (size_t)b * p.N * D::REC;
@@ -206,22 +216,36 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         const double* DN = D_b + p.doff[p.N];
         const size_t co = cbase + p.coff[p.N];
         group_sync<T>();
-        for (int e = tid; e < NX * NX; e += T) {
-            const int i = e % NX, j = e / NX;
-            double acc = 0.0;
-            for (int r = 0; r < ncN; ++r) acc = fma(DN[r + i * ncN] * p.rho[co + r], DN[r + j * ncN], acc);
-            PF[i + j * L::LDPF] += acc;
-        }
-        for (int i = tid; i < NX; i += T) {
-            double acc = 0.0;
-            for (int r = 0; r < ncN; ++r)
-                acc = fma(DN[r + i * ncN], p.rho[co + r] * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]), acc);
-            pn[i] -= acc;
+        if (sel) {   // D_N rows are scaled unit vectors: only the diagonal of P_N and p_N change
+            for (int i = tid; i < NX; i += T) {
+                double dgi = 0.0, dhi = 0.0;
+                for (int r = 0; r < ncN; ++r)
+                    if (p.sel_col[co + r] == i) {
+                        const double v = p.sel_val[co + r], rr = p.rho[co + r];
+                        dgi = fma(rr * v, v, dgi);
+                        dhi = fma(v, rr * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]), dhi);
+                    }
+                PF[i + i * L::LDPF] += dgi;
+                pn[i] -= dhi;
+            }
+        } else {
+            for (int e = tid; e < NX * NX; e += T) {
+                const int i = e % NX, j = e / NX;
+                double acc = 0.0;
+                for (int r = 0; r < ncN; ++r) acc = fma(DN[r + i * ncN] * p.rho[co + r], DN[r + j * ncN], acc);
+                PF[i + j * L::LDPF] += acc;
+            }
+            for (int i = tid; i < NX; i += T) {
+                double acc = 0.0;
+                for (int r = 0; r < ncN; ++r)
+                    acc = fma(DN[r + i * ncN], p.rho[co + r] * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]), acc);
+                pn[i] -= acc;
+            }
         }
     }
     group_sync<T>();
     auto issue_stage = [&](int kk, int bufi) {   // one elected thread: stage record (+ constraint matrix) of stage kk
-        const int nck = ncmax > 0 ? p.ncs[kk] : 0;
+        const int nck = (ncmax > 0 && !sel) ? p.ncs[kk] : 0;
         const uint32_t dbytes = (uint32_t)even_up(nck * S) * 8;
         mbar_expect_tx(&bar[bufi], D::REC * 8 + dbytes);
         bulk_g2s(rec + bufi * D::REC, model_b + (size_t)kk * D::REC, D::REC * 8, &bar[bufi]);
@@ -256,6 +280,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 const double rr = p.rho[co + r];
                 rho_s[r] = rr;
                 rg_s[r] = rr * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]);
+                if (sel) { scol_s[r] = p.sel_col[co + r]; sval_s[r] = p.sel_val[co + r]; }
             }
         }
         if (tid < S) wp[tid] = ws_b ? ws_b[(size_t)k * S + tid] : 0.0;
@@ -289,10 +314,17 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 double base;
                 if (j < S) base = R[D::REC_H + i + j * S] + ((i == j) ? sigma : 0.0);
                 else base = R[D::REC_h + i] - sigma * wp[i];
+                if (sel && nck > 0 && (i == j || j == S)) {
+                    // selection-matrix fold-in: D^T rho D is diagonal, D^T (rho o g) picks single entries
+                    double d = 0.0;
+                    for (int r = 0; r < nck; ++r)
+                        if (scol_s[r] == i) d = (j == S) ? fma(-sval_s[r], rg_s[r], d) : fma(rho_s[r] * sval_s[r], sval_s[r], d);
+                    base += d;
+                }
                 Ma[i + j * L::LDM] = base + v;
             };
             gmm<S, S + 1, NX, tl.tm, tl.tn, T>(tid, la, lb, epi);
-            if (nck > 0) {  // M += D^T diag(rho) D ; g -= D^T (rho o g_c)      (lqr_kernel.hpp:106-112)
+            if (nck > 0 && !sel) {  // M += D^T diag(rho) D ; g -= D^T (rho o g_c)      (lqr_kernel.hpp:106-112)
                 const double* Dk = Dbuf + buf * DSTRIDE;
                 auto lda = [&](int i, int r) { return Dk[r + i * nck]; };
                 auto ldb = [&](int r, int j) { return j < S ? rho_s[r] * Dk[r + j * nck] : -rg_s[r]; };
@@ -475,8 +507,9 @@ struct AffSmem {
     static constexpr int o_bar = even_up(o_fn + NX);
     static constexpr int DOUBLES = even_up(o_bar + 2);
     static constexpr size_t BYTES = (size_t)DOUBLES * 8;
-    static size_t bytes(int ncmax) {
-        return BYTES + (ncmax > 0 ? (size_t)(2 * even_up(ncmax * S) + ncmax) * 8 : 0);
+    static size_t bytes(int ncmax, bool sel = false) {
+        if (ncmax <= 0) return BYTES;
+        return BYTES + (size_t)((sel ? 0 : 2 * even_up(ncmax * S)) + ncmax + (sel ? ncmax + even_up(ncmax) / 2 + 1 : 0)) * 8;
     }
 };
 
@@ -504,9 +537,12 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
     double* fn = smem + L::o_fn;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::o_bar);
     const int ncmax = p.ncmax;
-    const int DSTRIDE = even_up(ncmax * S);
+    const bool sel = p.sel_col != nullptr;
+    const int DSTRIDE = sel ? 0 : even_up(ncmax * S);
     double* Dbuf = smem + L::DOUBLES;
     double* rg_s = Dbuf + 2 * DSTRIDE;
+    double* sval_s = rg_s + ncmax;
+    int* scol_s = reinterpret_cast<int*>(sval_s + ncmax);
 
     const size_t ws_len = (size_t)p.N * S + NX;
     const double* model_b = p.model + (size_t)b * p.N * D::REC;
@@ -532,8 +568,10 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
                 const double* DN = D_b + p.doff[p.N];
                 const size_t co = cbase + p.coff[p.N];
                 double acc = 0.0;
-                for (int r = 0; r < ncN; ++r)
-                    acc = fma(DN[r + i * ncN], p.rho[co + r] * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]), acc);
+                for (int r = 0; r < ncN; ++r) {
+                    const double dv = sel ? (p.sel_col[co + r] == i ? p.sel_val[co + r] : 0.0) : DN[r + i * ncN];
+                    acc = fma(dv, p.rho[co + r] * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]), acc);
+                }
                 pv -= acc;
             }
         }
@@ -542,7 +580,7 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
     }
     __syncwarp();
     auto issue_stage = [&](int kk, int bufi) {
-        const int nck = ncmax > 0 ? p.ncs[kk] : 0;
+        const int nck = (ncmax > 0 && !sel) ? p.ncs[kk] : 0;
         const uint32_t dbytes = (uint32_t)even_up(nck * S) * 8;
         mbar_expect_tx(&bar[bufi], (L::RLITE + D::FREC + D::AREC) * 8 + dbytes);
         bulk_g2s(rec + bufi * L::RLITE, model_b + (size_t)kk * D::REC, D::REC_EC * 8, &bar[bufi]);
@@ -567,8 +605,10 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
         const int nck = ncmax > 0 ? p.ncs[k] : 0;
         if (nck > 0) {
             const size_t co = cbase + p.coff[k];
-            for (int r = tid; r < nck; r += T)
+            for (int r = tid; r < nck; r += T) {
                 rg_s[r] = p.rho[co + r] * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]);
+                if (sel) { scol_s[r] = p.sel_col[co + r]; sval_s[r] = p.sel_val[co + r]; }
+            }
         }
         double wpv[(S + T - 1) / T];
 #pragma unroll
@@ -585,7 +625,10 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
             const int i = tid + r * T;
             if (i < S) {
                 double acc = hrec[i] - sigma * wpv[r];
-                if (nck > 0) {
+                if (nck > 0 && sel) {
+                    for (int q = 0; q < nck; ++q)
+                        if (scol_s[q] == i) acc = fma(-sval_s[q], rg_s[q], acc);
+                } else if (nck > 0) {
                     const double* Dk = Dbuf + buf * DSTRIDE;
                     for (int q = 0; q < nck; ++q) acc = fma(-Dk[q + i * nck], rg_s[q], acc);
                 }

@@ -397,3 +397,43 @@ def test_pipelined_host_solve_matches_unpipelined(oracle):
     ref, _ = oracle.OracleBatch(p.select(slice(4990, 5000))).solve(ws_in=np.ascontiguousarray(w[4990:]), sigma=1e-3)
     assert rel_err(a[4990:], ref) < TOL
     assert sol.last_status()[0] == 0
+
+
+@pytest.mark.parametrize("sparse", ["1", "0"])
+def test_selection_matrix_constraints_sparse_and_dense_paths(oracle, sparse, monkeypatch):
+    """Constraint matrices whose rows have at most one non-zero (box / cone rows on single variables: the reference
+    example's own constraint set, lqr_example.cpp:133-147, and config 4) take a structure-exploiting path (no dense D
+    in the kernels); PDPLQR_SPARSE_D=0 forces the dense path.  Both must match the oracle (dense, as the reference)."""
+    from oracle import admm_ref
+    monkeypatch.setenv("PDPLQR_SPARSE_D", sparse)
+    p = P.problems.random_conic_batch(batch=3, N=10, nx=6, nu=3, seed=5, soc=False)
+    # scale some rows so that values other than 1 are exercised
+    p.D[:, ::7] *= 1.5
+    rng = np.random.default_rng(4)
+    nct = p.nc_total
+    wprev, ys, zs = rng.standard_normal((3, p.ws_len)), rng.standard_normal((3, nct)), rng.standard_normal((3, nct))
+    rho = rng.uniform(0.1, 2.0, (3, nct))
+    inv = np.ascontiguousarray(1.0 / rho)
+    for S in (1, 3):
+        sol = P.LQRCudaSolver.from_problem(p, num_segments=S)
+        outs = []
+        for it in range(2):
+            sol.update_problem_data(wprev * (it + 1), ys, zs, inv, sigma=1e-3)
+            (sol.backward if it == 0 else sol.backward_without_factorization)(rho)
+            outs.append(sol.forward(p.x0, np.zeros_like(wprev)).copy())
+        for b in range(3):
+            o = oracle.OracleSolver(p, b=b)
+            for it in range(2):
+                o.update_problem_data(wprev[b] * (it + 1), ys[b], zs[b], inv[b], 1e-3)
+                (o.backward if it == 0 else o.backward_without_factorization)(rho[b])
+                assert rel_err(outs[it][b], o.forward(p.x0[b], np.zeros(p.ws_len))) < TOL
+    # and through the ADMM loop (projection kernel uses the same compact form)
+    lb = np.where(np.isfinite(p.e_lb), p.e_lb, -1e20); ub = np.where(np.isfinite(p.e_ub), p.e_ub, 1e20)
+    p.e_lb, p.e_ub = lb, ub
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=1)
+    sol.admm_set_cones(p.cones, lb, ub)
+    ws, z, y = p.zeros_ws(), np.zeros((3, nct)), np.zeros((3, nct))
+    r2 = np.full((3, nct), 0.5)
+    sol.admm_solve(p.x0, ws, z, y, r2, sigma=1e-4, alpha=1.6, max_iter=8, eps_abs=0.0, eps_rel=0.0, check_every=8)
+    w_ref, z_ref, _, _, _ = admm_ref.admm(p, 1, r2[1], sigma=1e-4, alpha=1.6, iters=8)
+    assert rel_err(ws[1], w_ref) < TOL and rel_err(z[1], z_ref) < TOL
