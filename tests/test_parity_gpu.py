@@ -437,3 +437,57 @@ def test_selection_matrix_constraints_sparse_and_dense_paths(oracle, sparse, mon
     sol.admm_solve(p.x0, ws, z, y, r2, sigma=1e-4, alpha=1.6, max_iter=8, eps_abs=0.0, eps_rel=0.0, check_every=8)
     w_ref, z_ref, _, _, _ = admm_ref.admm(p, 1, r2[1], sigma=1e-4, alpha=1.6, iters=8)
     assert rel_err(ws[1], w_ref) < TOL and rel_err(z[1], z_ref) < TOL
+
+
+@pytest.mark.parametrize("nx,nu,N,S,batch", [(4, 1, 1, 1, 5), (4, 1, 2, 1, 40), (4, 1, 3, 3, 2), (12, 4, 1, 1, 1), (12, 4, 2, 2, 1),
+                                             (12, 4, 5, 5, 2), (6, 3, 7, 0, 3), (3, 2, 129, 1, 70)])
+def test_edge_horizons_and_segment_lengths(oracle, nx, nu, N, S, batch):
+    """Minimum horizon (LQRModel requires N >= 1, lqr_model.hpp:75-77), one-stage segments, thread-path ring shorter
+    than its depth, trajectory chunks that do not divide N."""
+    p = P.problems.random_lq(nx, nu, N, batch=batch, seed=N * 7 + nx)
+    rng = np.random.default_rng(N)
+    w = rng.standard_normal((batch, p.ws_len))
+    sol, ws = gpu_solve(p, S=S, lb=False, ws_in=w, sigma=0.02)
+    for b in range(batch):
+        assert rel_err(ws[b], oracle.OracleSolver(p, b=b).solve(ws_in=w[b], sigma=0.02)) < TOL
+
+
+def test_ragged_constraint_counts_with_empty_stages(oracle):
+    """ncs varies per stage and is zero on some stages (LQRModel::ncs, lqr_model.hpp:71; the reference example itself
+    uses nu rows at k=0, nx+nu inside, nx at k=N)."""
+    nx, nu, N = 6, 3, 9
+    p = P.problems.random_lq(nx, nu, N, batch=2, seed=13)
+    ncs = np.array([3, 0, 5, 0, 0, 9, 1, 0, 4, 2], np.int32)
+    rng = np.random.default_rng(2)
+    dims = np.array([nx + nu] * N + [nx])
+    dtot = int(np.sum(ncs * dims))
+    p.ncs = ncs
+    p.D = rng.standard_normal((2, dtot))
+    nct = int(ncs.sum())
+    ys, zs = rng.standard_normal((2, nct)), rng.standard_normal((2, nct))
+    rho = rng.uniform(0.1, 1.0, (2, nct))
+    inv = np.ascontiguousarray(1.0 / rho)
+    w = rng.standard_normal((2, p.ws_len))
+    for S in (1, 3):
+        sol = P.LQRCudaSolver.from_problem(p, num_segments=S)
+        out = sol.solve(w, p.x0, np.zeros_like(w), sigma=1e-2, ys=ys, zs=zs, rho=rho, inv_rho=inv)
+        for b in range(2):
+            o = oracle.OracleSolver(p, b=b)
+            o.update_problem_data(w[b], ys[b], zs[b], inv[b], 1e-2)
+            o.backward(rho[b])
+            assert rel_err(out[b], o.forward(p.x0[b], np.zeros(p.ws_len))) < TOL
+
+
+def test_invalid_arguments_are_rejected():
+    with pytest.raises(P.PdplqrError) as e:
+        P.LQRCudaSolver(12, 4, 0)                      # N >= 1  (lqr_model.hpp:75-77)
+    assert e.value.code == P.capi.ERR_INVALID
+    with pytest.raises(P.PdplqrError) as e:
+        P.LQRCudaSolver(5, 5, 10)                      # (nx, nu) not instantiated
+    assert e.value.code == P.capi.ERR_UNSUPPORTED
+    with pytest.raises(P.PdplqrError):
+        P.LQRCudaSolver(12, 4, 10, solver_type=7)      # unknown condensed solver type (lqr_solver_parallel.hpp:98-99)
+    p = P.problems.random_lq(6, 3, 8, seed=1, nc=4)
+    sol = P.LQRCudaSolver.from_problem(p)
+    with pytest.raises(P.PdplqrError):
+        sol.update_problem_data(p.zeros_ws(), sigma=1e-6)   # ys / zs / inv_rho missing for a constrained model
