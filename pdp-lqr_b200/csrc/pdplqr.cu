@@ -42,6 +42,7 @@ struct pdplqr_solver {
     int bwd_variant = 0, fwd_variant = 0;
     int seg_mode = 0, seg_len0 = 0;   // closed-form partition handed to the kernels
     int lat_threads = 128;     // 0 disables the 128-thread latency mode of the segment backward kernel
+    int seg_t = 0;             // PDPLQR_SEG_T: threads per (problem, segment) in throughput mode (0 = default 32)
     int use_km = 1;            // specialised k-major stage kernel for nx, nu multiples of 4 (PDPLQR_USE_KM=0 disables)
     int tree_tt = 32;          // threads per tree combine (128 = experimental wide combine; measured slower)
     cudaStream_t stream = nullptr;
@@ -185,6 +186,15 @@ int launch_batch_fwd(Solver& h, const SegParams& p) {
     return PDPLQR_OK;
 }
 
+template <int NX, int NU, int TT, bool CON>
+int launch_seg_bwd(Solver& h, const SegParams& p, size_t bytes) {
+    auto kern = seg_backward_kernel<NX, NU, TT, CON>;
+    int rc = set_smem(h, kern, bytes);
+    if (rc) return rc;
+    kern<<<h.batch * h.S, TT, bytes, h.stream>>>(p);
+    return PDPLQR_OK;
+}
+
 template <int NX, int NU, int T>
 int backward_impl(Solver& h) {
     SegParams p = seg_params(h);
@@ -226,17 +236,24 @@ int backward_impl(Solver& h) {
         }
     }
     const size_t bytes = BwdSmem<NX, NU>::bytes(h.ncmax, h.sel_mode);
-    if (latency_mode) {
-        auto kern = seg_backward_kernel<NX, NU, TL>;
-        int rc = set_smem(h, kern, bytes);
-        if (rc) return rc;
-        kern<<<h.batch * h.S, TL, bytes, h.stream>>>(p);
-    } else {
-        auto kern = seg_backward_kernel<NX, NU, T>;
-        int rc = set_smem(h, kern, bytes);
-        if (rc) return rc;
-        kern<<<h.batch * h.S, T, bytes, h.stream>>>(p);
+    if constexpr (T == 32) {
+        // two warps per (problem, segment) share one shared-memory working set: twice the warps per SM hide more of the
+        // stage's latency (C5: 4.25 -> 4.09 ms).  Default for nx + nu >= 16; PDPLQR_SEG_T = 32 / 64 / 128 overrides.
+        const int seg_t = h.seg_t ? h.seg_t : ((NX + NU) >= 16 ? 64 : 32);
+        if (!latency_mode && seg_t == 64) {
+            int rc = h.ncmax > 0 ? launch_seg_bwd<NX, NU, 64, true>(h, p, bytes) : launch_seg_bwd<NX, NU, 64, false>(h, p, bytes);
+            if (rc) return rc;
+            h.launches++;
+            CU_TRY(&h, cudaGetLastError());
+            return PDPLQR_OK;
+        }
     }
+    int rc;
+    if (latency_mode || (T == 32 && h.seg_t == 128))
+        rc = h.ncmax > 0 ? launch_seg_bwd<NX, NU, TL, true>(h, p, bytes) : launch_seg_bwd<NX, NU, TL, false>(h, p, bytes);
+    else
+        rc = h.ncmax > 0 ? launch_seg_bwd<NX, NU, T, true>(h, p, bytes) : launch_seg_bwd<NX, NU, T, false>(h, p, bytes);
+    if (rc) return rc;
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -695,6 +712,7 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (const char* e = getenv("PDPLQR_LAT_THREADS")) h->lat_threads = atoi(e);
     if (const char* e = getenv("PDPLQR_TREE_TT")) h->tree_tt = atoi(e);
     if (const char* e = getenv("PDPLQR_USE_KM")) h->use_km = atoi(e);
+    if (const char* e = getenv("PDPLQR_SEG_T")) h->seg_t = atoi(e);
     if (const char* e = getenv("PDPLQR_SPARSE_D")) h->allow_sel = atoi(e);
     if (const char* e = getenv("PDPLQR_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(1, std::min(64, atoi(e)));
 

@@ -140,7 +140,8 @@ struct BwdSmem {
 
 // ------------------------------------------------------------------------------------------------
 // Backward: segment-local Riccati sweep (+ sensitivities F, f, C for non-last segments).
-template <int NX, int NU, int T>
+// CON = false compiles every constraint path out (unconstrained problems pay nothing for them).
+template <int NX, int NU, int T, bool CON>
 __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
     using D = SegDims<NX, NU>;
     using L = BwdSmem<NX, NU>;
@@ -169,8 +170,8 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
     double* Qi = smem + L::o_qi;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::o_bar);
     // run-time tail: constraint matrix ring + rho, rho.*g of the current stage
-    const int ncmax = p.ncmax;
-    const bool sel = p.sel_col != nullptr;          // selection-matrix constraints: no dense D at all
+    const int ncmax = CON ? p.ncmax : 0;
+    const bool sel = CON && p.sel_col != nullptr;   // selection-matrix constraints: no dense D at all
     const int DSTRIDE = sel ? 0 : even_up(ncmax * S);
     double* Dbuf = smem + L::DOUBLES;
     double* rho_s = Dbuf + DSTRIDE;
