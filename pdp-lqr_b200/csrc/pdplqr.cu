@@ -387,6 +387,7 @@ constexpr Ops make_ops() {
 const Ops g_ops[] = {
     make_ops<12, 4, 32>(), make_ops<4, 1, 32>(), make_ops<30, 10, 128>(),
     make_ops<2, 1, 32>(),  make_ops<3, 2, 32>(), make_ops<6, 3, 32>(), make_ops<8, 8, 32>(),
+    make_ops<6, 2, 32>(),  make_ops<8, 4, 32>(), make_ops<16, 4, 32>(),
 };
 
 const Ops* find_ops(int nx, int nu) {

@@ -106,7 +106,7 @@ def test_c3_batch_segmented_warp_path(oracle):
     assert rel_err(ws, ref) < TOL
 
 
-@pytest.mark.parametrize("nx,nu", [(2, 1), (3, 2), (6, 3), (8, 8), (4, 1), (12, 4)])
+@pytest.mark.parametrize("nx,nu", [(2, 1), (3, 2), (6, 3), (8, 8), (4, 1), (12, 4), (6, 2), (8, 4), (16, 4)])
 @pytest.mark.parametrize("S", [1, 3])
 def test_random_dense_problems_with_sigma_term(oracle, nx, nu, S):
     """Dense H with cross terms, nonzero h and c, sigma * w_prev active (update_problem_data fused in)."""
