@@ -50,8 +50,8 @@ def make_workload(name: str, rank: int):
         return prob, dict(num_segments=0), "C2: quadrotor LQR nx=12 nu=4 N=1024, single problem, segment-parallel (configs[1])"
     if name == "c5":
         prob = P.problems.quadrotor_ltv(1 << 20)
-        return prob, dict(num_segments=(1 << 20) // 64, load_balancing=False), \
-            "C5: quadrotor LQR nx=12 nu=4 N=2^20, single problem, 16384 segments (configs[4], 1 GPU)"
+        return prob, dict(num_segments=wave_aligned((1 << 20) // 64), load_balancing=2), \
+            "C5: quadrotor LQR nx=12 nu=4 N=2^20, single problem, ~64-stage segments in whole waves of 148x13 CTAs (configs[4])"
     if name == "c5small":
         prob = P.problems.quadrotor_ltv(1 << 16)
         return prob, dict(num_segments=(1 << 16) // 64, load_balancing=False), \
@@ -60,6 +60,14 @@ def make_workload(name: str, rank: int):
         prob = P.problems.quadrotor_example()
         return prob, dict(num_segments=4), "C1: examples/lqr_example.cpp as shipped (configs[0])"
     raise SystemExit(f"unknown workload {name}")
+
+
+def wave_aligned(num_segments: int, wave: int = 148 * 13) -> int:
+    """Round a segment count down to whole waves of the stage kernel's resident CTAs (148 SMs x 13 CTAs of 64 threads at
+    nx12/nu4): a trailing partial wave costs a full wave of time (2048 segments = 1.06 waves ran as 2)."""
+    if num_segments <= wave:
+        return max(1, num_segments)
+    return (num_segments // wave) * wave
 
 
 def algorithmic_bytes_per_stage(nx, nu, pdp: bool):
@@ -366,7 +374,7 @@ def main():
     if horizon_sharded:
         # one long problem, contiguous time slices per rank, ONE all_gather of a 3,648-byte summary per solve
         from pdplqr_b200.sharding import HorizonShardedSolver
-        hs = HorizonShardedSolver(prob, rank, world, num_segments=max(1, kw["num_segments"] // world), device=local_rank)
+        hs = HorizonShardedSolver(prob, rank, world, num_segments=wave_aligned(kw["num_segments"] // world), device=local_rank)
         hs.set_stream(stream.cuda_stream)
         sol = hs.sol
         full_N = prob.N

@@ -48,8 +48,11 @@ typedef struct pdplqr_solver* pdplqr_handle_t;
 /* Replaces LQRParallelSolver::LQRParallelSolver(model, num_segments, load_balancing, solver_type)
  * (lqr_solver_parallel.hpp:64-113) and LQRSolver::LQRSolver (lqr_solver.hpp:31-39; num_segments = 1).
  * `ncs` = constraint rows per stage (N+1 entries, LQRModel::ncs lqr_model.hpp:71) or NULL for none.
- * num_segments >= 1 uses the reference's partition rule (lqr_solver_parallel.hpp:70-80, 1.55 load-balance
- * factor); num_segments = 0 lets the library choose a GPU-appropriate segmentation.  `device` = CUDA ordinal. */
+ * num_segments >= 1 uses the reference's partition rule (lqr_solver_parallel.hpp:70-80): load_balancing = 1 with the
+ * 1.55 factor, 0 without; in both the LAST segment takes the remainder of N.  load_balancing = 2 (addition) splits
+ * the horizon into num_segments equal parts (the first N % S one stage longer) -- the right choice for thousands of
+ * GPU segments.  num_segments = 0 lets the library choose a GPU-appropriate equal segmentation.  `device` = CUDA
+ * ordinal. */
 int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, int batch, int num_segments,
                   int load_balancing, int condensed_type, int device);
 int pdplqr_destroy(pdplqr_handle_t h);

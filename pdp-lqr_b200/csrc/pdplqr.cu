@@ -659,7 +659,7 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
 
     Solver* h = new Solver();
     h->nx = nx; h->nu = nu; h->N = N; h->batch = batch; h->s = nx + nu; h->device = device;
-    h->load_balancing = load_balancing != 0; h->condensed_type = condensed_type; h->ops = ops;
+    h->load_balancing = load_balancing == 1; h->condensed_type = condensed_type; h->ops = ops;
     h->ncs.assign(N + 1, 0);
     if (ncs) h->ncs.assign(ncs, ncs + N + 1);
     for (int v : h->ncs) {
@@ -681,9 +681,11 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     // ---- segmentation (lqr_solver_parallel.hpp:70-80)
     int S = num_segments;
     const bool auto_seg = (S == 0);
+    const bool equal_split = auto_seg || load_balancing == 2;   // GPU-style partition: equal lengths
     if (auto_seg) {
-        // GPU-appropriate default: enough (problem, segment) groups to fill the machine, segments >= 8 stages
-        const int target_groups = 148 * 8;
+        // GPU-appropriate default: one full wave of (problem, segment) groups (148 SMs x ~12 resident stage-kernel
+        // CTAs), segments >= 8 stages
+        const int target_groups = 148 * 12;
         S = std::max(1, std::min(N / 8, (target_groups + batch - 1) / batch));
     }
     S = std::min(S, N);
@@ -693,15 +695,15 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     for (int i = 0; i < S; ++i) {
         const int st = (i == 0) ? 0 : h->seg_start[i - 1] + h->seg_len[i - 1];
         int len;
-        if (auto_seg) len = N / S + (i < N % S ? 1 : 0);  // equal lengths (the 1.55 rule targets <= #cores segments)
+        if (equal_split) len = N / S + (i < N % S ? 1 : 0);  // equal lengths (the 1.55 rule targets <= #cores segments)
         else len = (i < S - 1) ? int(N / (scale + S - 1)) : N - st;
         if (i < S - 1 && len < 1) len = 1;
         h->seg_start[i] = st; h->seg_len[i] = len;
     }
     if (h->seg_len[S - 1] < 1) { delete h; return PDPLQR_ERR_INVALID; }
-    h->seg_mode = auto_seg ? 0 : 1;
+    h->seg_mode = equal_split ? 0 : 1;
     h->seg_len0 = h->seg_len[0];
-    if (!auto_seg && S > 1) {   // the reference rule must be expressible in closed form (it is unless len was clamped)
+    if (!equal_split && S > 1) {   // the reference rule must be expressible in closed form (it is unless len was clamped)
         for (int i = 0; i < S - 1; ++i)
             if (h->seg_len[i] != h->seg_len0) { delete h; return PDPLQR_ERR_INVALID; }
     }

@@ -102,7 +102,7 @@ class HorizonShardedSolver:
         self.is_last = rank == world - 1
         self.local = slice_problem(prob, start, count, self.is_last)
         self.dev = torch.device("cuda", device)
-        self.sol = LQRCudaSolver(prob.nx, prob.nu, count, batch=1, num_segments=num_segments, load_balancing=False,
+        self.sol = LQRCudaSolver(prob.nx, prob.nu, count, batch=1, num_segments=num_segments, load_balancing=2,
                                  device=device)
         if not self.is_last:
             self.sol.set_option(capi.OPT_INTERIOR_SHARD, 1)

@@ -54,7 +54,7 @@ class LQRCudaSolver:
         h = C.c_void_p()
         ncs_arr = None if ncs is None else np.ascontiguousarray(ncs, dtype=np.int32)
         ncs_ptr = None if ncs_arr is None else ncs_arr.ctypes.data_as(C.POINTER(C.c_int))
-        rc = self._lib.pdplqr_create(C.byref(h), nx, nu, N, ncs_ptr, batch, num_segments, int(load_balancing),
+        rc = self._lib.pdplqr_create(C.byref(h), nx, nu, N, ncs_ptr, batch, num_segments, int(load_balancing),  # 2 = equal split
                                      solver_type, device)
         if rc != capi.OK:
             raise PdplqrError(rc, {capi.ERR_INVALID: "invalid dimensions / arguments",

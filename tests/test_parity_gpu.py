@@ -491,3 +491,13 @@ def test_invalid_arguments_are_rejected():
     sol = P.LQRCudaSolver.from_problem(p)
     with pytest.raises(P.PdplqrError):
         sol.update_problem_data(p.zeros_ws(), sigma=1e-6)   # ys / zs / inv_rho missing for a constrained model
+
+
+def test_equal_split_partition_mode(oracle):
+    """load_balancing = 2 (addition): num_segments equal parts instead of the reference rule's long last segment."""
+    p = P.problems.quadrotor_ltv(203)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=10, load_balancing=2)
+    st, ln = sol.partition()
+    assert list(ln) == [21, 21, 21] + [20] * 7 and int(st[-1] + ln[-1]) == 203
+    ws = sol.solve(p.zeros_ws(), p.x0, p.zeros_ws())
+    assert rel_err(ws[0], oracle.OracleSolver(p).solve()) < TOL
