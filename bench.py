@@ -31,6 +31,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout must carry exactly ONE line (the JSON): NCCL_DEBUG=VERSION/INFO makes NCCL print banners to stdout
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO", "TRACE"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "lq_solves_per_sec"
 UNIT = "solves/s"
