@@ -31,9 +31,23 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout must carry exactly ONE line (the JSON): NCCL_DEBUG=VERSION/INFO makes NCCL print banners to stdout
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO", "TRACE"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout must carry exactly ONE line (the JSON).  Libraries (NCCL prints a version banner) write to fd 1 directly, so
+# fd 1 is pointed at stderr for the whole run and emit() writes the JSON line to the saved, real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+def host_cores() -> int:
+    """Cores this process may use (torchrun sets OMP_NUM_THREADS=1, which must not throttle the CPU baseline)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
 
 METRIC = "lq_solves_per_sec"
 UNIT = "solves/s"
@@ -140,7 +154,7 @@ def cpu_baseline(prob, seconds=6.0, max_problems=16384):
     """Time the CPU oracle port (OpenMP over problems, sequential Riccati each -- or the PDP solver for a single
     long problem) on a bounded sample of the workload.  Returns (solves_per_s, cores, sample_description)."""
     from oracle import oracle as O
-    cores = O.max_threads()
+    cores = host_cores()
     if prob.batch > 1:
         nb = min(prob.batch, max_problems)
         sub = prob.select(slice(0, nb))
@@ -203,7 +217,7 @@ def run_reference_arm(args, rank, world):
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "reference needs Eigen3 (absent): timed the CPU oracle port of the same algorithm"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 
@@ -320,18 +334,19 @@ def run_c4(args, rank, world, local_rank):
                                                     "frac": fact_bytes * B * N / (ms_fact * 1e-3) / 1e9 / peak}}}
         if not args.no_cpu_baseline and world == 1:
             from oracle import oracle as O
-            nb = min(base, 2 * O.max_threads())
+            nb = min(base, 2 * host_cores())
             sub = hp.select(slice(0, nb))
             pool = O.OracleBatch(sub)
             rng = np.random.default_rng(0)
             ys_, zs_ = rng.standard_normal((nb, nct)), rng.standard_normal((nb, nct))
             rh = np.full((nb, nct), 0.1)
-            t0 = time.perf_counter(); pool.solve(ys=ys_, zs=zs_, rho=rh, inv_rho=1.0 / rh, factorize=True); tf = time.perf_counter() - t0
-            t0 = time.perf_counter(); pool.solve(ys=ys_, zs=zs_, rho=rh, inv_rho=1.0 / rh, factorize=False); tn = time.perf_counter() - t0
+            nt = host_cores()
+            t0 = time.perf_counter(); pool.solve(ys=ys_, zs=zs_, rho=rh, inv_rho=1.0 / rh, factorize=True, nthreads=nt); tf = time.perf_counter() - t0
+            t0 = time.perf_counter(); pool.solve(ys=ys_, zs=zs_, rho=rh, inv_rho=1.0 / rh, factorize=False, nthreads=nt); tn = time.perf_counter() - t0
             v = nb / (tf + (ITERS - 1) * tn)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": O.max_threads(), "kind": "port",
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": host_cores(), "kind": "port",
                                     "sample": "%d problems: 1 factorising + 1 affine-only LQ solve timed, extrapolated to %d iterations (projections not counted)" % (nb, ITERS)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -524,7 +539,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample = cpu_baseline(prob)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
