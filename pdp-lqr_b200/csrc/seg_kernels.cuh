@@ -131,10 +131,10 @@ struct BwdSmem {
     static constexpr size_t BYTES = (size_t)DOUBLES * 8;
     // run-time tail (only when the problem has constraints):
     //   dense D:      D[even(ncmax*S)] | rho[ncmax] | rho.*g[ncmax]
-    //   selection D:                     rho[ncmax] | rho.*g[ncmax] | val[ncmax] | col[ncmax] (int)
+    //   selection D:                     rho[ncmax] | rho.*g[ncmax] | val[ncmax] | dg[S] | dh[S] | col[ncmax] (int)
     static size_t bytes(int ncmax, bool sel = false) {
         if (ncmax <= 0) return BYTES;
-        return BYTES + (size_t)((sel ? 0 : even_up(ncmax * S)) + 2 * ncmax + (sel ? ncmax + even_up(ncmax) / 2 + 1 : 0)) * 8;
+        return BYTES + (size_t)((sel ? 0 : even_up(ncmax * S)) + 2 * ncmax + (sel ? ncmax + even_up(ncmax) / 2 + 1 + 2 * S : 0)) * 8;
     }
 };
 
@@ -177,7 +177,9 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
     double* rho_s = Dbuf + DSTRIDE;
     double* rg_s = rho_s + ncmax;
     double* sval_s = rg_s + ncmax;
-    int* scol_s = reinterpret_cast<int*>(sval_s + ncmax);
+    double* dg_s = sval_s + ncmax;                  // selection mode: diag(D^T rho D) and D^T (rho o g) of the stage,
+    double* dh_s = dg_s + S;                        // scatter-added by the row threads (shared-memory atomics)
+    int* scol_s = reinterpret_cast<int*>(dh_s + S);
 
     const size_t ws_len = (size_t)p.N * S + NX;
     const double* model_b = p.model + (size_t)b * p.N * D::REC;
@@ -244,6 +246,8 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
             }
         }
     }
+    if (sel)
+        for (int i = tid; i < 2 * S; i += T) dg_s[i] = 0.0;
     group_sync<T>();
     auto issue_stage = [&](int kk, int bufi) {   // one elected thread: stage record (+ constraint matrix) of stage kk
         const int nck = (ncmax > 0 && !sel) ? p.ncs[kk] : 0;
@@ -281,7 +285,14 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 const double rr = p.rho[co + r];
                 rho_s[r] = rr;
                 rg_s[r] = rr * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]);
-                if (sel) { scol_s[r] = p.sel_col[co + r]; sval_s[r] = p.sel_val[co + r]; }
+                if (sel) {   // D_k rows are scaled unit vectors: D^T rho D is diagonal
+                    const int cj = p.sel_col[co + r];
+                    const double v = p.sel_val[co + r];
+                    if (cj >= 0) {
+                        atomicAdd(&dg_s[cj], rr * v * v);
+                        atomicAdd(&dh_s[cj], v * rg_s[r]);
+                    }
+                }
             }
         }
         if (tid < S) wp[tid] = ws_b ? ws_b[(size_t)k * S + tid] : 0.0;
@@ -315,12 +326,9 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 double base;
                 if (j < S) base = R[D::REC_H + i + j * S] + ((i == j) ? sigma : 0.0);
                 else base = R[D::REC_h + i] - sigma * wp[i];
-                if (sel && nck > 0 && (i == j || j == S)) {
-                    // selection-matrix fold-in: D^T rho D is diagonal, D^T (rho o g) picks single entries
-                    double d = 0.0;
-                    for (int r = 0; r < nck; ++r)
-                        if (scol_s[r] == i) d = (j == S) ? fma(-sval_s[r], rg_s[r], d) : fma(rho_s[r] * sval_s[r], sval_s[r], d);
-                    base += d;
+                if (sel && nck > 0) {   // selection-matrix fold-in (dg, dh were scatter-added at the top of the stage)
+                    if (i == j) base += dg_s[i];
+                    else if (j == S) base -= dh_s[i];
                 }
                 Ma[i + j * L::LDM] = base + v;
             };
@@ -338,6 +346,8 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
             fence_proxy_async();         // the same buffer; it lands while S4-S6 run and is waited for at the end of S6
             issue_stage(k - 1, 0);
         }
+        if (sel && nck > 0)
+            for (int i = tid; i < 2 * S; i += T) dg_s[i] = 0.0;   // ready for the next stage's scatter-add
 
         // S4: Luu = chol(Quu).  Small NU: every solving thread factorises its own register copy (no barriers);
         //     larger NU: cooperative in-place factorisation of the leading block of Ma.
@@ -510,7 +520,7 @@ struct AffSmem {
     static constexpr size_t BYTES = (size_t)DOUBLES * 8;
     static size_t bytes(int ncmax, bool sel = false) {
         if (ncmax <= 0) return BYTES;
-        return BYTES + (size_t)((sel ? 0 : 2 * even_up(ncmax * S)) + ncmax + (sel ? ncmax + even_up(ncmax) / 2 + 1 : 0)) * 8;
+        return BYTES + (size_t)((sel ? 0 : 2 * even_up(ncmax * S)) + ncmax + (sel ? ncmax + even_up(ncmax) / 2 + 1 + 2 * S : 0)) * 8;
     }
 };
 
@@ -543,7 +553,7 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
     double* Dbuf = smem + L::DOUBLES;
     double* rg_s = Dbuf + 2 * DSTRIDE;
     double* sval_s = rg_s + ncmax;
-    int* scol_s = reinterpret_cast<int*>(sval_s + ncmax);
+    double* dh_s = sval_s + ncmax + S;              // (same tail layout as the factorising kernel: dg unused here)
 
     const size_t ws_len = (size_t)p.N * S + NX;
     const double* model_b = p.model + (size_t)b * p.N * D::REC;
@@ -579,15 +589,20 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
         pn[i] = pv;
         fn[i] = 0.0;
     }
+    if (sel)
+        for (int i = tid; i < S; i += T) dh_s[i] = 0.0;
     __syncwarp();
     auto issue_stage = [&](int kk, int bufi) {
         const int nck = (ncmax > 0 && !sel) ? p.ncs[kk] : 0;
         const uint32_t dbytes = (uint32_t)even_up(nck * S) * 8;
-        mbar_expect_tx(&bar[bufi], (L::RLITE + D::FREC + D::AREC) * 8 + dbytes);
+        // last / only segments need just [K | d] of the factor record and [Quu^-1 | P+c] of the affine cache
+        const uint32_t fdoubles = pdp ? D::FREC : even_up(NU * (NX + 1));
+        const uint32_t adoubles = pdp ? D::AREC : even_up(D::AR_FC);
+        mbar_expect_tx(&bar[bufi], (L::RLITE + fdoubles + adoubles) * 8 + dbytes);
         bulk_g2s(rec + bufi * L::RLITE, model_b + (size_t)kk * D::REC, D::REC_EC * 8, &bar[bufi]);
         bulk_g2s(rec + bufi * L::RLITE + D::REC_EC, model_b + (size_t)kk * D::REC + L::H_OFF, L::H_LEN * 8, &bar[bufi]);
-        bulk_g2s(fac + bufi * D::FREC, fac_b + (size_t)kk * D::FREC, D::FREC * 8, &bar[bufi]);
-        bulk_g2s(aff + bufi * D::AREC, aff_b + (size_t)kk * D::AREC, D::AREC * 8, &bar[bufi]);
+        bulk_g2s(fac + bufi * D::FREC, fac_b + (size_t)kk * D::FREC, fdoubles * 8, &bar[bufi]);
+        bulk_g2s(aff + bufi * D::AREC, aff_b + (size_t)kk * D::AREC, adoubles * 8, &bar[bufi]);
         if (nck > 0) bulk_g2s(Dbuf + bufi * DSTRIDE, D_b + p.doff[kk], dbytes, &bar[bufi]);
     };
     if (tid == 0 && LEN > 0) issue_stage(N1 - 1, 0);
@@ -607,8 +622,12 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
         if (nck > 0) {
             const size_t co = cbase + p.coff[k];
             for (int r = tid; r < nck; r += T) {
-                rg_s[r] = p.rho[co + r] * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]);
-                if (sel) { scol_s[r] = p.sel_col[co + r]; sval_s[r] = p.sel_val[co + r]; }
+                const double rg = p.rho[co + r] * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]);
+                rg_s[r] = rg;
+                if (sel) {
+                    const int cj = p.sel_col[co + r];
+                    if (cj >= 0) atomicAdd(&dh_s[cj], p.sel_val[co + r] * rg);
+                }
             }
         }
         double wpv[(S + T - 1) / T];
@@ -627,8 +646,8 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
             if (i < S) {
                 double acc = hrec[i] - sigma * wpv[r];
                 if (nck > 0 && sel) {
-                    for (int q = 0; q < nck; ++q)
-                        if (scol_s[q] == i) acc = fma(-sval_s[q], rg_s[q], acc);
+                    acc -= dh_s[i];
+                    dh_s[i] = 0.0;          // ready for the next stage's scatter-add (same thread, next use after a sync)
                 } else if (nck > 0) {
                     const double* Dk = Dbuf + buf * DSTRIDE;
                     for (int q = 0; q < nck; ++q) acc = fma(-Dk[q + i * nck], rg_s[q], acc);
@@ -708,7 +727,8 @@ __global__ void __launch_bounds__(T) seg_forward_kernel(SegParams p) {
     const double* model_b = p.model + (size_t)b * p.N * D::REC;
     const double* fac_b = p.fac + (size_t)b * p.N * D::FREC;
     double* ws_b = p.ws_out + (size_t)b * ws_len;
-    constexpr uint32_t TX = (D::REC_EC + D::FREC) * 8;
+    const uint32_t FD = is_last ? even_up(NU * (NX + 1)) : D::FREC;   // last segment: only [K | d] is needed
+    const uint32_t TX = (D::REC_EC + FD) * 8;
 
     if (tid == 0) {
         mbar_init(&bar[0], 1);
@@ -723,7 +743,7 @@ __global__ void __launch_bounds__(T) seg_forward_kernel(SegParams p) {
     if (tid == 0 && LEN > 0) {
         mbar_expect_tx(&bar[0], TX);
         bulk_g2s(rec, model_b + (size_t)N0 * D::REC, D::REC_EC * 8, &bar[0]);
-        bulk_g2s(fac, fac_b + (size_t)N0 * D::FREC, D::FREC * 8, &bar[0]);
+        bulk_g2s(fac, fac_b + (size_t)N0 * D::FREC, FD * 8, &bar[0]);
     }
 #pragma unroll 1
     for (int it = 0; it < LEN; ++it) {
@@ -735,7 +755,7 @@ __global__ void __launch_bounds__(T) seg_forward_kernel(SegParams p) {
             fence_proxy_async();
             mbar_expect_tx(&bar[buf ^ 1], TX);
             bulk_g2s(rec + (buf ^ 1) * D::REC_EC, model_b + (size_t)(k + 1) * D::REC, D::REC_EC * 8, &bar[buf ^ 1]);
-            bulk_g2s(fac + (buf ^ 1) * D::FREC, fac_b + (size_t)(k + 1) * D::FREC, D::FREC * 8, &bar[buf ^ 1]);
+            bulk_g2s(fac + (buf ^ 1) * D::FREC, fac_b + (size_t)(k + 1) * D::FREC, FD * 8, &bar[buf ^ 1]);
         }
         mbar_wait(&bar[buf], (it >> 1) & 1);
         // u = K x + d (+ Gt uhat)
