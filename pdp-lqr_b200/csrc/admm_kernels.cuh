@@ -41,6 +41,7 @@ struct AdmmParams {
     double* y;                 // [batch][nc_total] in/out
     const double* rho;         // [batch][nc_total]
     double alpha;
+    int compute_res;           // 0: skip the residual norms (only read on check iterations)
     unsigned long long* res;   // [4] bit patterns of non-negative doubles: r_prim, r_dual, max|z~|,|z| , max|D^T y|
 };
 
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(32) admm_update_kernel(AdmmParams p) {
         r_prim = fmax(r_prim, fabs(zt[r] - znew));
         nrm = fmax(nrm, fmax(fabs(zt[r]), fabs(znew)));
     }
+    if (!p.compute_res) return;
     __syncwarp();
     double r_dual = 0.0, nrm_d = 0.0;
     for (int j = lane; j < dim; j += 32) {

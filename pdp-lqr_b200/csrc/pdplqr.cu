@@ -1241,7 +1241,7 @@ int pdplqr_admm_solve_device(pdplqr_handle_t h, const double* x0, double* w, dou
         ap.cone_first = h->d_cone_first; ap.cone_type = h->d_cone_type; ap.cone_row = h->d_cone_row; ap.cone_dim = h->d_cone_dim;
         ap.e_lb = h->d_elb; ap.e_ub = h->d_eub;
         ap.w_tilde = h->d_wtilde; ap.w = w; ap.z = z; ap.y = y; ap.rho = rho;
-        ap.alpha = alpha; ap.res = h->d_res;
+        ap.alpha = alpha; ap.res = h->d_res; ap.compute_res = check ? 1 : 0;
         const size_t smem = (size_t)(h->s + 3 * h->ncmax) * sizeof(double);
         admm_update_kernel<<<h->batch * (h->N + 1), 32, smem, h->stream>>>(ap);
         h->launches++;
