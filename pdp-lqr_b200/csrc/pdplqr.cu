@@ -282,11 +282,12 @@ int forward_impl(Solver& h, const double* d_x0, double* d_ws_out) {
             }
         }
     }
-    auto kern = seg_forward_kernel<NX, NU, 32>;
+    constexpr int TF = (NX + NU >= 32) ? 128 : 32;   // latency-bound rollout: more warps per SM for big stages
+    auto kern = seg_forward_kernel<NX, NU, TF>;
     constexpr size_t bytes = FwdSmem<NX, NU>::BYTES;
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
-    kern<<<h.batch * h.S, 32, bytes, h.stream>>>(p);
+    kern<<<h.batch * h.S, TF, bytes, h.stream>>>(p);
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -322,11 +323,12 @@ int tree_down_impl(Solver& h, const TreeParams& p) {
 template <int NX, int NU>
 int affine_impl(Solver& h) {
     SegParams p = seg_params(h);
-    auto kern = seg_affine_kernel<NX, NU>;
+    constexpr int TA = (NX + NU >= 32) ? 128 : 32;   // the sweep is latency-bound: more warps per SM for big stages
+    auto kern = seg_affine_kernel<NX, NU, TA>;
     const size_t bytes = AffSmem<NX, NU>::bytes(h.ncmax, h.sel_mode);
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
-    kern<<<h.batch * h.S, 32, bytes, h.stream>>>(p);
+    kern<<<h.batch * h.S, TA, bytes, h.stream>>>(p);
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;

@@ -497,8 +497,8 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
 //     t = P+c + p+ ;  g = h~ + E^T t ;  d = -Quu^-1 g_u ;  p = g_x + K^T g_u ;  f = F+c + (F+B) d + f+
 // Replaces LQRKernel::step_without_factorization (lqr_kernel.hpp:149-178), ParallelLQRKernel::
 // step_without_factorization (lqr_kernel_parallel.hpp:138-168) and reduction_without_factorization
-// (lqr_solver_parallel.hpp:190-211).  One warp per (problem, segment); only d (inside Z) and the segment
-// summary's p, f change.
+// (lqr_solver_parallel.hpp:190-211).  One warp (or, for nx + nu >= 32, one 128-thread CTA) per (problem, segment);
+// only d (inside Z) and the segment summary's p, f change.
 template <int NX, int NU>
 struct AffSmem {
     using D = SegDims<NX, NU>;
@@ -524,12 +524,11 @@ struct AffSmem {
     }
 };
 
-template <int NX, int NU>
-__global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
+template <int NX, int NU, int T>
+__global__ void __launch_bounds__(T) seg_affine_kernel(SegParams p) {
     using D = SegDims<NX, NU>;
     using L = AffSmem<NX, NU>;
     constexpr int S = D::S;
-    constexpr int T = 32;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
     const int gidx = blockIdx.x;
@@ -591,7 +590,7 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
     }
     if (sel)
         for (int i = tid; i < S; i += T) dh_s[i] = 0.0;
-    __syncwarp();
+    group_sync<T>();
     auto issue_stage = [&](int kk, int bufi) {
         const int nck = (ncmax > 0 && !sel) ? p.ncs[kk] : 0;
         const uint32_t dbytes = (uint32_t)even_up(nck * S) * 8;
@@ -638,7 +637,7 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
         }
         mbar_wait(&bar[buf], (it >> 1) & 1);
         for (int i = tid; i < NX; i += T) tv[i] = Ak[D::AR_PC + i] + pn[i];
-        __syncwarp();
+        group_sync<T>();
         // g = h - sigma w - D^T (rho o g_c) + E^T t
 #pragma unroll
         for (int r = 0; r < (S + T - 1) / T; ++r) {
@@ -657,7 +656,7 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
                 gv[i] = acc;
             }
         }
-        __syncwarp();
+        group_sync<T>();
         // d = -Quu^-1 g_u
         for (int m = tid; m < NU; m += T) {
             double acc = 0.0;
@@ -666,7 +665,7 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
             dv[m] = acc;
             fac_b[(size_t)k * D::FREC + NU * NX + m] = acc;   // the d slot of Z = [K | d | Gt]
         }
-        __syncwarp();
+        group_sync<T>();
         // p = g_x + K^T g_u ;  f = F+c + (F+B) d + f+
         for (int i = tid; i < NX; i += T) {
             double acc = gv[NU + i];
@@ -680,7 +679,7 @@ __global__ void __launch_bounds__(32) seg_affine_kernel(SegParams p) {
                 fn[i] = af;
             }
         }
-        __syncwarp();
+        group_sync<T>();
     }
     double* sm = p.sum + ((size_t)b * p.S + seg) * D::SREC;
     for (int i = tid; i < NX; i += T) {
