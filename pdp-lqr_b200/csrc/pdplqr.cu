@@ -398,7 +398,7 @@ const Ops* find_ops(int nx, int nu) {
     return nullptr;
 }
 
-// flat (E, c, H, h) -> device stage records.  sym = 0: [E | c | H | h] per (problem, stage) (segment kernels);
+// flat (E, c, H, h) -> device stage records.  sym = 0: [[E c]^T | H | h] per (problem, stage) (segment kernels);
 // sym = 1: thread-per-problem path: [E | c | lower(H) packed by columns | h] with the records of the 32 problems of a
 // tile interleaved pair-wise (BatchDims::TR_*, tile_pos): one contiguous block per (tile, stage).  `nprob` is the
 // batch size, the tile count is ceil(nprob / 32) and lanes past the batch replicate the last problem.
@@ -429,7 +429,10 @@ __global__ void pack_model_kernel(const double* __restrict__ E, const double* __
         }
         const long long st = b * N + k;
         double v = 0.0;
-        if (e < oC) v = E[st * oC + e];
+        if (e < oH && !sym) {      // segment records keep [E c] transposed: ET(j, kk) at j + kk*(s+1)
+            const int j = e % (s + 1), kk = e / (s + 1);
+            v = (j < s) ? E[st * oC + kk + j * nx] : c[st * nx + kk];
+        } else if (e < oC) v = E[st * oC + e];
         else if (e < oH) v = c[st * nx + (e - oC)];
         else if (e < oh) {
             int q = e - oH;

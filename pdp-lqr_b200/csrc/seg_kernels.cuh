@@ -26,10 +26,12 @@ constexpr int even_up(int n) { return (n + 1) & ~1; }
 template <int NX, int NU>
 struct SegDims {
     static constexpr int S = NX + NU;
-    // model record (one stage): [E (NX x S) | c (NX) | H (S x S) | h (S)], column-major, padded to 16 bytes
+    // model record (one stage): [ET ((S+1) x NX) | H (S x S) | h (S)], column-major, padded to 16 bytes, where
+    // ET(j, k) = [E c](k, j): E and c are stored TRANSPOSED so that the backward kernel's products read their operands
+    // straight from the TMA buffer (no per-stage transposition pass) and the affine / rollout kernels read contiguously
     static constexpr int REC_E = 0;
-    static constexpr int REC_C = NX * S;
-    static constexpr int REC_H = REC_C + NX;
+    static constexpr int LDE = S + 1;                 // leading dimension of ET; c is its row S
+    static constexpr int REC_H = NX * (S + 1);
     static constexpr int REC_h = REC_H + S * S;
     static constexpr int REC = even_up(REC_h + S);
     static constexpr int REC_EC = even_up(NX * S + NX);  // prefix the rollout needs
@@ -106,7 +108,7 @@ template <int NX, int NU>
 struct BwdSmem {
     using D = SegDims<NX, NU>;
     static constexpr int S = D::S;
-    static constexpr int LDT = odd_ld(S + 1);      // ET: (S+1) x NX   (E^T with c^T as last row)
+    static constexpr int LDT = D::LDE;             // ET lives in the stage record itself
     static constexpr int LDPF = odd_ld(2 * NX);    // PF: [P+; F+] stacked, (2NX) x NX
     static constexpr int LDPE = odd_ld(2 * NX);    // PFE: [P+;F+] [E c], (2NX) x (S+1)
     static constexpr int LDM = odd_ld(S);          // Ma: [M | g], S x (S+1)
@@ -114,8 +116,7 @@ struct BwdSmem {
     static constexpr int o_rec = 0;                                 // REC (TMA destination, 16B aligned), single buffer:
                                                                     // the next record is fetched right after its last reader (S3)
     static constexpr int o_Z = o_rec + D::REC;                      // FREC
-    static constexpr int o_ET = o_Z + D::FREC;
-    static constexpr int o_PF = o_ET + LDT * NX;
+    static constexpr int o_PF = o_Z + D::FREC;
     static constexpr int o_PFE = o_PF + LDPF * NX;
     static constexpr int o_Ma = o_PFE + LDPE * (S + 1);
     static constexpr int o_YT = o_Ma + LDM * (S + 1);
@@ -156,7 +157,6 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
 
     double* rec = smem + L::o_rec;
     double* Z = smem + L::o_Z;
-    double* ET = smem + L::o_ET;
     double* PF = smem + L::o_PF;
     double* PFE = smem + L::o_PFE;
     double* Ma = smem + L::o_Ma;
@@ -257,20 +257,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         if (nck > 0) bulk_g2s(Dbuf + bufi * DSTRIDE, D_b + p.doff[kk], dbytes, &bar[bufi]);
     };
     if (tid == 0 && LEN > 0) issue_stage(N1 - 1, 0);
-    // ET(j,k') = Ea(k',j), Ea = [E c]  ((S+1) x NX, odd leading dimension -> conflict-free GEMM operands).  The
-    // transposition of stage k-1 is done in the last phase of stage k, so a stage costs four barriers.
-    auto transpose_stage = [&](int bufi) {
-        const double* Rn = rec + bufi * D::REC;
-        for (int e = tid; e < NX * (S + 1); e += T) {
-            const int kk = e % NX, j = e / NX;
-            ET[j + kk * L::LDT] = Rn[e];
-        }
-    };
-    if (LEN > 0) {
-        mbar_wait(&bar[0], 0);
-        transpose_stage(0);
-    }
-    group_sync<T>();
+    // The record holds ET(j,k') = [E c](k',j) ((S+1) x NX): both big products read it in place.
 
     int bad = 0;
 #pragma unroll 1
@@ -278,6 +265,8 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         const int k = N1 - 1 - it;
         const int buf = 0;
         const double* R = rec;
+        const double* ET = rec;                  // [E c]^T of this stage, valid until the refill after S3
+        mbar_wait(&bar[0], it & 1);              // requested after S3 of the previous stage (or in the prologue)
         const int nck = ncmax > 0 ? p.ncs[k] : 0;
         if (nck > 0) {  // g = z - y/rho ; keep rho and rho.*g   (lqr_solver_parallel.hpp:134-137, lqr_kernel.hpp:110)
             const size_t co = cbase + p.coff[k];
@@ -343,7 +332,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         }
         group_sync<T>();
         if (tid == 0 && it + 1 < LEN) {  // the record (H, h) and D had their last readers in S3: fetch stage k-1 into
-            fence_proxy_async();         // the same buffer; it lands while S4-S6 run and is waited for at the end of S6
+            fence_proxy_async();         // the same buffer; it lands while S4-S6 run and is waited for at the top of the next stage
             issue_stage(k - 1, 0);
         }
         if (sel && nck > 0)
@@ -469,10 +458,6 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 if (pdp)
                     for (int e = tid; e < NX * NU; e += T) ak[D::AR_FB + e] = PFE[(NX + e % NX) + (e / NX) * L::LDPE];
             }
-        }
-        if (it + 1 < LEN) {  // the next stage's record was prefetched at the top of this stage: transpose it now
-            mbar_wait(&bar[0], (it + 1) & 1);
-            transpose_stage(0);
         }
         group_sync<T>();
     }
@@ -652,7 +637,7 @@ __global__ void __launch_bounds__(T) seg_affine_kernel(SegParams p) {
                     for (int q = 0; q < nck; ++q) acc = fma(-Dk[q + i * nck], rg_s[q], acc);
                 }
 #pragma unroll 4
-                for (int q = 0; q < NX; ++q) acc = fma(R[q + i * NX], tv[q], acc);
+                for (int q = 0; q < NX; ++q) acc = fma(R[i + q * D::LDE], tv[q], acc);
                 gv[i] = acc;
             }
         }
@@ -777,11 +762,11 @@ __global__ void __launch_bounds__(T) seg_forward_kernel(SegParams p) {
         for (int r = 0; r < (NX + T - 1) / T; ++r) {
             const int i = tid + r * T;
             if (i < NX) {
-                double acc = R[D::REC_C + i];
+                double acc = R[S + i * D::LDE];
 #pragma unroll
-                for (int j = 0; j < NU; ++j) acc = fma(R[i + j * NX], us[j], acc);
+                for (int j = 0; j < NU; ++j) acc = fma(R[j + i * D::LDE], us[j], acc);
 #pragma unroll 4
-                for (int j = 0; j < NX; ++j) acc = fma(R[i + (NU + j) * NX], xs[j], acc);
+                for (int j = 0; j < NX; ++j) acc = fma(R[(NU + j) + i * D::LDE], xs[j], acc);
                 xn[r] = acc;
             }
         }
