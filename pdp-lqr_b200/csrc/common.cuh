@@ -191,10 +191,11 @@ PDPLQR_DEVINL void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-template <int G, int M, int N, int T, class LA, class LB, class EPI>
-PDPLQR_DEVINL void group_mm_dmma_impl(int tid, int K, LA la, LB lb, EPI epi) {
-    constexpr int MT = (M + 7) / 8, NT = (N + 7) / 8, TILES = MT * NT, W = T / 32;
-    const int warp = tid >> 5, lane = tid & 31, r = lane >> 2, q = lane & 3;
+// G products of M x N x K over W warps (W may be a run-time value: the latency-mode tree combines)
+template <int G, int M, int N, class LA, class LB, class EPI>
+PDPLQR_DEVINL void dmma_tiles(int warp, int W, int lane, int K, LA la, LB lb, EPI epi) {
+    constexpr int MT = (M + 7) / 8, NT = (N + 7) / 8, TILES = MT * NT;
+    const int r = lane >> 2, q = lane & 3;
     const int KT = (K + 3) >> 2;
 #pragma unroll 1
     for (int t = warp; t < G * TILES; t += 2 * W) {   // two independent tiles per pass cover the DMMA latency
@@ -225,6 +226,10 @@ PDPLQR_DEVINL void group_mm_dmma_impl(int tid, int K, LA la, LB lb, EPI epi) {
             if (j1 + 2 * q + 1 < N) epi(g1, i1 + r, j1 + 2 * q + 1, c11);
         }
     }
+}
+template <int G, int M, int N, int T, class LA, class LB, class EPI>
+PDPLQR_DEVINL void group_mm_dmma_impl(int tid, int K, LA la, LB lb, EPI epi) {
+    dmma_tiles<G, M, N>(tid >> 5, T / 32, tid & 31, K, la, lb, epi);
 }
 template <int M, int N, int K, int T, class LA, class LB, class EPI>
 PDPLQR_DEVINL void group_mm_dmma(int tid, LA la, LB lb, EPI epi) {

@@ -14,6 +14,7 @@
 #include "seg_kernels.cuh"
 #include "seg_km_kernel.cuh"
 #include "tree_kernels.cuh"
+#include "tree_lat_kernels.cuh"
 
 using namespace pdplqr;
 
@@ -45,6 +46,9 @@ struct pdplqr_solver {
     int seg_t = 0;             // PDPLQR_SEG_T: threads per (problem, segment) in throughput mode (0 = default 32)
     int use_km = 1;            // specialised k-major stage kernel for nx, nu multiples of 4 (PDPLQR_USE_KM=0 disables)
     int tree_tt = 32;          // threads per tree combine (128 = experimental wide combine; measured slower)
+    int tree_lat = 1;          // latency-mode tree kernels when a level has few groups (PDPLQR_TREE_LAT=0 disables)
+    int tree_lat_max = 296;    // ... "few" = at most this many CTAs (PDPLQR_TREE_LAT_MAX)
+    bool top_lat = false;      // the upper tree was planned for the latency kernels (<= top_lat_nodes wide)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     // device memory
@@ -104,6 +108,7 @@ using Solver = pdplqr_solver;
 struct Ops {
     int nx, nu, T;
     int REC, FREC, SREC, DREC, FRECT, TREC, AREC;
+    int top_lat_nodes;   // widest level of the latency-mode upper tree (0: not available for this nx)
     bool has_thread_path;
     int (*backward)(Solver&);
     int (*forward)(Solver&, const double* d_x0, double* d_ws_out);
@@ -296,6 +301,17 @@ int forward_impl(Solver& h, const double* d_x0, double* d_ws_out) {
 template <int NX>
 int tree_up_impl(Solver& h, const TreeParams& p) {
     constexpr size_t bytes = TreeSmem<NX>::BYTES;
+    if constexpr (LatSmem<NX>::UP_OK) {
+        if (h.tree_lat && (long long)p.batch * p.groups <= h.tree_lat_max) {
+            auto kern = tree_up_lat_kernel<NX, LatSmem<NX>::UP_TT>;
+            int rc = set_smem(h, kern, LatSmem<NX>::UP_BYTES);
+            if (rc) return rc;
+            kern<<<p.batch * p.groups, LatSmem<NX>::UP_TT, LatSmem<NX>::UP_BYTES, h.stream>>>(p);
+            h.launches++;
+            CU_TRY(&h, cudaGetLastError());
+            return PDPLQR_OK;
+        }
+    }
     if (h.tree_tt == 128 && (long long)p.batch * p.groups <= 2 * 148) {   // experimental: 128 threads per combine
         auto kern = tree_up_kernel<NX, 128>;
         int rc = set_smem(h, kern, bytes);
@@ -313,6 +329,16 @@ int tree_up_impl(Solver& h, const TreeParams& p) {
 }
 template <int NX>
 int tree_down_impl(Solver& h, const TreeParams& p) {
+    const size_t lat_bytes = ((size_t)(p.R - 1) * TreeDims<NX>::DREC + 4 * NX) * sizeof(double);
+    if (h.tree_lat && (long long)p.batch * p.groups <= h.tree_lat_max && lat_bytes <= 220 * 1024) {
+        auto kern = tree_down_lat_kernel<NX>;
+        int rc = set_smem(h, kern, lat_bytes);
+        if (rc) return rc;
+        kern<<<p.batch * p.groups, 32, lat_bytes, h.stream>>>(p);
+        h.launches++;
+        CU_TRY(&h, cudaGetLastError());
+        return PDPLQR_OK;
+    }
     auto kern = tree_down_kernel<NX>;
     kern<<<p.batch * p.groups, 32, 4 * NX * sizeof(double), h.stream>>>(p);
     h.launches++;
@@ -347,6 +373,17 @@ template <int NX>
 int tree_top_up_impl(Solver& h, const TreeTopParams& p) {
     constexpr size_t bytes = TreeTopSmem<NX>::BYTES;
     constexpr int WARPS = TreeTopSmem<NX>::WARPS;
+    if constexpr (LatSmem<NX>::TOP_NODES >= 2) {
+        if (h.top_lat && !p.affine_only && p.count[0] <= LatSmem<NX>::TOP_NODES) {
+            auto kern = tree_top_up_lat_kernel<NX>;
+            int rc = set_smem(h, kern, LatSmem<NX>::TOP_BYTES);
+            if (rc) return rc;
+            kern<<<p.batch, LatSmem<NX>::TOP_THREADS, LatSmem<NX>::TOP_BYTES, h.stream>>>(p);
+            h.launches++;
+            CU_TRY(&h, cudaGetLastError());
+            return PDPLQR_OK;
+        }
+    }
     if constexpr (WARPS % 4 == 0) {
         if (h.tree_tt == 128 && p.batch <= 2 * 148 && !p.affine_only) {   // experimental: 4 warps per combine
             auto kern = tree_top_up_kernel<NX, 128>;
@@ -368,6 +405,17 @@ int tree_top_up_impl(Solver& h, const TreeTopParams& p) {
 }
 template <int NX>
 int tree_top_down_impl(Solver& h, const TreeTopParams& p) {
+    if constexpr (LatSmem<NX>::DOWN_OK) {
+        if (h.top_lat && p.count[0] <= LatSmem<NX>::TOP_NODES) {
+            auto kern = tree_top_down_lat_kernel<NX>;
+            int rc = set_smem(h, kern, LatSmem<NX>::DOWN_BYTES);
+            if (rc) return rc;
+            kern<<<p.batch, LatSmem<NX>::TOP_THREADS, LatSmem<NX>::DOWN_BYTES, h.stream>>>(p);
+            h.launches++;
+            CU_TRY(&h, cudaGetLastError());
+            return PDPLQR_OK;
+        }
+    }
     auto kern = tree_top_down_kernel<NX>;
     kern<<<p.batch, TreeTopSmem<NX>::WARPS * 32, TreeTopSmem<NX>::WARPS * 4 * NX * sizeof(double), h.stream>>>(p);
     h.launches++;
@@ -379,6 +427,7 @@ template <int NX, int NU, int T>
 constexpr Ops make_ops() {
     return Ops{NX, NU, T, SegDims<NX, NU>::REC, SegDims<NX, NU>::FREC, SegDims<NX, NU>::SREC, TreeDims<NX>::DREC,
                BatchDims<NX, NU>::FRECT, BatchDims<NX, NU>::TREC, SegDims<NX, NU>::AREC,
+               (LatSmem<NX>::DOWN_OK ? LatSmem<NX>::TOP_NODES : 0),
                BatchDims<NX, NU>::ENABLED,
                &backward_impl<NX, NU, T>, &forward_impl<NX, NU, T>, &tree_up_impl<NX>, &tree_down_impl<NX>,
                &affine_impl<NX, NU>, &tree_up_affine_impl<NX>, &tree_top_up_impl<NX>, &tree_top_down_impl<NX>};
@@ -613,28 +662,35 @@ int run_backward_nofact(Solver& h) {
     return PDPLQR_OK;
 }
 
+// down-sweep of the interface tree: the upper levels in one launch, then one launch per lower level
+int run_tree_down(Solver& h, const double* d_x0, const double* d_lam0) {
+    TreeTopParams ttp = top_params(h, d_x0, false);
+    ttp.lam0 = d_lam0;
+    int rc = h.ops->tree_top_down(h, ttp);
+    if (rc) return rc;
+    for (int l = (int)h.levels.size() - 1; l >= 0; --l) {
+        TreeLevel& lv = h.levels[l];
+        if (lv.in_top) continue;
+        TreeParams tp{};
+        tp.batch = h.batch; tp.count = lv.count; tp.R = lv.R; tp.groups = lv.groups;
+        tp.dd = lv.dd;
+        tp.x_parent = h.levels[l + 1].x;
+        tp.lam_parent = h.levels[l + 1].lam;
+        tp.x_node = lv.x; tp.lam_node = lv.lam;
+        rc = h.ops->tree_down(h, tp);
+        if (rc) return rc;
+    }
+    return PDPLQR_OK;
+}
+
 int run_forward(Solver& h, const double* d_x0, double* d_ws_out) {
     if (!h.backward_done) return fail(&h, PDPLQR_ERR_ORDER, "forward before backward (one forward per backward)");
     if (h.interior && !h.have_root)
         return fail(&h, PDPLQR_ERR_ORDER, "forward on an interior horizon shard needs pdplqr_set_root_boundary_device first");
     if (h.have_root) d_x0 = h.d_root_x;
     if (h.S > 1) {
-        TreeTopParams ttp = top_params(h, d_x0, false);
-        if (h.have_root) ttp.lam0 = h.d_root_lam;
-        int rc = h.ops->tree_top_down(h, ttp);
+        int rc = run_tree_down(h, d_x0, h.have_root ? h.d_root_lam : nullptr);
         if (rc) return rc;
-        for (int l = (int)h.levels.size() - 1; l >= 0; --l) {
-            TreeLevel& lv = h.levels[l];
-            if (lv.in_top) continue;
-            TreeParams tp{};
-            tp.batch = h.batch; tp.count = lv.count; tp.R = lv.R; tp.groups = lv.groups;
-            tp.dd = lv.dd;
-            tp.x_parent = h.levels[l + 1].x;
-            tp.lam_parent = h.levels[l + 1].lam;
-            tp.x_node = lv.x; tp.lam_node = lv.lam;
-            rc = h.ops->tree_down(h, tp);
-            if (rc) return rc;
-        }
     }
     int rc = h.ops->forward(h, d_x0, d_ws_out);
     if (rc) return rc;
@@ -719,6 +775,8 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (const char* e = getenv("PDPLQR_FWD_VARIANT")) h->fwd_variant = atoi(e);
     if (const char* e = getenv("PDPLQR_LAT_THREADS")) h->lat_threads = atoi(e);
     if (const char* e = getenv("PDPLQR_TREE_TT")) h->tree_tt = atoi(e);
+    if (const char* e = getenv("PDPLQR_TREE_LAT")) h->tree_lat = atoi(e);
+    if (const char* e = getenv("PDPLQR_TREE_LAT_MAX")) h->tree_lat_max = atoi(e);
     if (const char* e = getenv("PDPLQR_USE_KM")) h->use_km = atoi(e);
     if (const char* e = getenv("PDPLQR_SEG_T")) h->seg_t = atoi(e);
     if (const char* e = getenv("PDPLQR_SPARSE_D")) h->allow_sel = atoi(e);
@@ -775,10 +833,13 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     //      that all run inside one launch (tree_top_*_kernel); the last level is the root (1 node)
     if (S > 1) {
         int cnt = S;
+        // few problems: the upper tree runs on the latency kernels, which take a narrower widest level
+        h->top_lat = h->tree_lat && ops->top_lat_nodes >= 2 && B <= h->tree_lat_max;
+        const int top_max = h->top_lat ? ops->top_lat_nodes : TREE_TOP_MAX_NODES;
         for (int l = 0;; ++l) {
             TreeLevel lv{};
             lv.count = cnt;
-            lv.in_top = cnt <= TREE_TOP_MAX_NODES;
+            lv.in_top = cnt <= top_max;
             lv.R = lv.in_top ? 2 : 4;
             lv.groups = (cnt + lv.R - 1) / lv.R;
             if (l == 0) { lv.sum = h->d_sum; lv.x = h->d_xhat; lv.lam = h->d_uhat; }
@@ -991,8 +1052,7 @@ int pdplqr_coupler_solve_device(pdplqr_handle_t c, const double* summaries, cons
                               c->stream));
     int rc = run_tree_up(*c, false);
     if (rc) return rc;
-    TreeTopParams ttp = top_params(*c, x0, false);
-    rc = c->ops->tree_top_down(*c, ttp);
+    rc = run_tree_down(*c, x0, nullptr);
     if (rc) return rc;
     CU_TRY(c, cudaMemcpyAsync(xhat, c->d_xhat, nb, cudaMemcpyDeviceToDevice, c->stream));
     CU_TRY(c, cudaMemcpyAsync(lam, c->d_uhat, nb, cudaMemcpyDeviceToDevice, c->stream));

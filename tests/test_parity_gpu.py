@@ -68,9 +68,12 @@ def test_c1_partitions_gains_and_interface(oracle, S, lb):
                 assert np.max(np.abs(fs[0, i] - fo)) < TOL * max(1.0, np.max(np.abs(fo)))
 
 
-@pytest.mark.parametrize("N,S", [(256, 16), (1024, 64), (1024, 128), (500, 100)])
-def test_c2_quadrotor_ltv_multilevel_tree(oracle, N, S):
-    """Config 2 shape (nx=12, nu=4, LTV, single problem), many segments -> multi-level interface tree."""
+@pytest.mark.parametrize("tree_lat", ["1", "0"])
+@pytest.mark.parametrize("N,S", [(256, 16), (1024, 64), (1024, 128), (500, 100), (300, 33), (64, 2), (90, 3)])
+def test_c2_quadrotor_ltv_multilevel_tree(oracle, N, S, tree_lat, monkeypatch):
+    """Config 2 shape (nx=12, nu=4, LTV, single problem), many segments -> multi-level interface tree.
+    tree_lat=1: latency-mode tree kernels (few combine groups); 0: the one-warp-per-combine throughput kernels."""
+    monkeypatch.setenv("PDPLQR_TREE_LAT", tree_lat)
     p = P.problems.quadrotor_ltv(N)
     seq = oracle.OracleSolver(p).solve()
     sol, ws = gpu_solve(p, S=S, lb=False)
