@@ -48,7 +48,10 @@ struct pdplqr_solver {
     int tree_tt = 32;          // threads per tree combine (128 = experimental wide combine; measured slower)
     int tree_lat = 1;          // latency-mode tree kernels when a level has few groups (PDPLQR_TREE_LAT=0 disables)
     int tree_lat_max = 296;    // ... "few" = at most this many CTAs (PDPLQR_TREE_LAT_MAX)
-    bool top_lat = false;      // the upper tree was planned for the latency kernels (<= top_lat_nodes wide)
+    int lat_width = 0, lat_tt_cap = 0;   // PDPLQR_TREE_LAT_WIDTH / PDPLQR_TREE_LAT_TT: tuning overrides (0 = default)
+    bool top_lat = false;      // the upper levels are binary and run on the latency-mode sub-tree kernels
+    struct LatGroup { int l0, l1, width; };   // one launch: levels[l0] .. levels[l1], `width` nodes of l0 per CTA
+    std::vector<LatGroup> lat_groups;         // bottom -> top
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     // device memory
@@ -108,7 +111,8 @@ using Solver = pdplqr_solver;
 struct Ops {
     int nx, nu, T;
     int REC, FREC, SREC, DREC, FRECT, TREC, AREC;
-    int top_lat_nodes;   // widest level of the latency-mode upper tree (0: not available for this nx)
+    int top_lat_nodes;   // nodes one CTA of the latency-mode sub-tree kernels reduces (0: not built for this nx)
+    int lat_tt_cap;      // threads per combine at most
     bool has_thread_path;
     int (*backward)(Solver&);
     int (*forward)(Solver&, const double* d_x0, double* d_ws_out);
@@ -118,6 +122,8 @@ struct Ops {
     int (*tree_up_affine)(Solver&, const TreeParams&);
     int (*tree_top_up)(Solver&, const TreeTopParams&);
     int (*tree_top_down)(Solver&, const TreeTopParams&);
+    int (*tree_sub_up)(Solver&, const TreeTopParams&);
+    int (*tree_sub_down)(Solver&, const TreeTopParams&);
 };
 
 int fail(Solver* h, int code, const std::string& msg) {
@@ -301,17 +307,6 @@ int forward_impl(Solver& h, const double* d_x0, double* d_ws_out) {
 template <int NX>
 int tree_up_impl(Solver& h, const TreeParams& p) {
     constexpr size_t bytes = TreeSmem<NX>::BYTES;
-    if constexpr (LatSmem<NX>::UP_OK) {
-        if (h.tree_lat && (long long)p.batch * p.groups <= h.tree_lat_max) {
-            auto kern = tree_up_lat_kernel<NX, LatSmem<NX>::UP_TT>;
-            int rc = set_smem(h, kern, LatSmem<NX>::UP_BYTES);
-            if (rc) return rc;
-            kern<<<p.batch * p.groups, LatSmem<NX>::UP_TT, LatSmem<NX>::UP_BYTES, h.stream>>>(p);
-            h.launches++;
-            CU_TRY(&h, cudaGetLastError());
-            return PDPLQR_OK;
-        }
-    }
     if (h.tree_tt == 128 && (long long)p.batch * p.groups <= 2 * 148) {   // experimental: 128 threads per combine
         auto kern = tree_up_kernel<NX, 128>;
         int rc = set_smem(h, kern, bytes);
@@ -329,16 +324,6 @@ int tree_up_impl(Solver& h, const TreeParams& p) {
 }
 template <int NX>
 int tree_down_impl(Solver& h, const TreeParams& p) {
-    const size_t lat_bytes = ((size_t)(p.R - 1) * TreeDims<NX>::DREC + 4 * NX) * sizeof(double);
-    if (h.tree_lat && (long long)p.batch * p.groups <= h.tree_lat_max && lat_bytes <= 220 * 1024) {
-        auto kern = tree_down_lat_kernel<NX>;
-        int rc = set_smem(h, kern, lat_bytes);
-        if (rc) return rc;
-        kern<<<p.batch * p.groups, 32, lat_bytes, h.stream>>>(p);
-        h.launches++;
-        CU_TRY(&h, cudaGetLastError());
-        return PDPLQR_OK;
-    }
     auto kern = tree_down_kernel<NX>;
     kern<<<p.batch * p.groups, 32, 4 * NX * sizeof(double), h.stream>>>(p);
     h.launches++;
@@ -373,17 +358,6 @@ template <int NX>
 int tree_top_up_impl(Solver& h, const TreeTopParams& p) {
     constexpr size_t bytes = TreeTopSmem<NX>::BYTES;
     constexpr int WARPS = TreeTopSmem<NX>::WARPS;
-    if constexpr (LatSmem<NX>::TOP_NODES >= 2) {
-        if (h.top_lat && !p.affine_only && p.count[0] <= LatSmem<NX>::TOP_NODES) {
-            auto kern = tree_top_up_lat_kernel<NX>;
-            int rc = set_smem(h, kern, LatSmem<NX>::TOP_BYTES);
-            if (rc) return rc;
-            kern<<<p.batch, LatSmem<NX>::TOP_THREADS, LatSmem<NX>::TOP_BYTES, h.stream>>>(p);
-            h.launches++;
-            CU_TRY(&h, cudaGetLastError());
-            return PDPLQR_OK;
-        }
-    }
     if constexpr (WARPS % 4 == 0) {
         if (h.tree_tt == 128 && p.batch <= 2 * 148 && !p.affine_only) {   // experimental: 4 warps per combine
             auto kern = tree_top_up_kernel<NX, 128>;
@@ -405,17 +379,6 @@ int tree_top_up_impl(Solver& h, const TreeTopParams& p) {
 }
 template <int NX>
 int tree_top_down_impl(Solver& h, const TreeTopParams& p) {
-    if constexpr (LatSmem<NX>::DOWN_OK) {
-        if (h.top_lat && p.count[0] <= LatSmem<NX>::TOP_NODES) {
-            auto kern = tree_top_down_lat_kernel<NX>;
-            int rc = set_smem(h, kern, LatSmem<NX>::DOWN_BYTES);
-            if (rc) return rc;
-            kern<<<p.batch, LatSmem<NX>::TOP_THREADS, LatSmem<NX>::DOWN_BYTES, h.stream>>>(p);
-            h.launches++;
-            CU_TRY(&h, cudaGetLastError());
-            return PDPLQR_OK;
-        }
-    }
     auto kern = tree_top_down_kernel<NX>;
     kern<<<p.batch, TreeTopSmem<NX>::WARPS * 32, TreeTopSmem<NX>::WARPS * 4 * NX * sizeof(double), h.stream>>>(p);
     h.launches++;
@@ -423,14 +386,43 @@ int tree_top_down_impl(Solver& h, const TreeTopParams& p) {
     return PDPLQR_OK;
 }
 
+// latency-mode binary sub-tree launches (tree_lat_kernels.cuh)
+template <int NX>
+int tree_sub_up_impl(Solver& h, const TreeTopParams& p) {
+    if constexpr (LatSmem<NX>::DOWN_OK) {
+        auto kern = tree_sub_up_lat_kernel<NX>;
+        int rc = set_smem(h, kern, LatSmem<NX>::TOP_BYTES);
+        if (rc) return rc;
+        kern<<<p.batch * p.ngroups, LatSmem<NX>::TOP_THREADS, LatSmem<NX>::TOP_BYTES, h.stream>>>(p);
+        h.launches++;
+        CU_TRY(&h, cudaGetLastError());
+        return PDPLQR_OK;
+    } else
+        return fail(&h, PDPLQR_ERR_UNSUPPORTED, "latency-mode tree kernels are not built for this nx");
+}
+template <int NX>
+int tree_sub_down_impl(Solver& h, const TreeTopParams& p) {
+    if constexpr (LatSmem<NX>::DOWN_OK) {
+        auto kern = tree_sub_down_lat_kernel<NX>;
+        int rc = set_smem(h, kern, LatSmem<NX>::DOWN_BYTES);
+        if (rc) return rc;
+        kern<<<p.batch * p.ngroups, LatSmem<NX>::TOP_THREADS, LatSmem<NX>::DOWN_BYTES, h.stream>>>(p);
+        h.launches++;
+        CU_TRY(&h, cudaGetLastError());
+        return PDPLQR_OK;
+    } else
+        return fail(&h, PDPLQR_ERR_UNSUPPORTED, "latency-mode tree kernels are not built for this nx");
+}
+
 template <int NX, int NU, int T>
 constexpr Ops make_ops() {
     return Ops{NX, NU, T, SegDims<NX, NU>::REC, SegDims<NX, NU>::FREC, SegDims<NX, NU>::SREC, TreeDims<NX>::DREC,
                BatchDims<NX, NU>::FRECT, BatchDims<NX, NU>::TREC, SegDims<NX, NU>::AREC,
-               (LatSmem<NX>::DOWN_OK ? LatSmem<NX>::TOP_NODES : 0),
+               (LatSmem<NX>::DOWN_OK ? LatSmem<NX>::TOP_NODES : 0), LatSmem<NX>::TT_CAP,
                BatchDims<NX, NU>::ENABLED,
                &backward_impl<NX, NU, T>, &forward_impl<NX, NU, T>, &tree_up_impl<NX>, &tree_down_impl<NX>,
-               &affine_impl<NX, NU>, &tree_up_affine_impl<NX>, &tree_top_up_impl<NX>, &tree_top_down_impl<NX>};
+               &affine_impl<NX, NU>, &tree_up_affine_impl<NX>, &tree_top_up_impl<NX>, &tree_top_down_impl<NX>,
+               &tree_sub_up_impl<NX>, &tree_sub_down_impl<NX>};
 }
 
 // Instantiated (nx, nu) pairs.  The BASELINE.json configs use (12,4), (4,1) and (30,10); the rest cover the
@@ -609,6 +601,23 @@ TreeTopParams top_params(Solver& h, const double* d_x0, bool affine_only) {
             const int i = tp.nlevels++;
             tp.count[i] = lv.count; tp.sum[i] = lv.sum; tp.dd[i] = lv.dd; tp.x[i] = lv.x; tp.lam[i] = lv.lam;
         }
+    tp.width = tp.count[0]; tp.ngroups = 1; tp.is_root = 1;
+    return tp;
+}
+// one latency-mode launch: levels[g.l0] .. levels[g.l1], one CTA per block of g.width nodes of level l0
+TreeTopParams sub_params(Solver& h, const pdplqr_solver::LatGroup& g, const double* d_x0, const double* d_lam0,
+                         bool affine_only) {
+    TreeTopParams tp{};
+    tp.batch = h.batch; tp.x0 = d_x0; tp.lam0 = d_lam0; tp.affine_only = affine_only ? 1 : 0;
+    for (int l = g.l0; l <= g.l1; ++l) {
+        TreeLevel& lv = h.levels[l];
+        const int i = tp.nlevels++;
+        tp.count[i] = lv.count; tp.sum[i] = lv.sum; tp.dd[i] = lv.dd; tp.x[i] = lv.x; tp.lam[i] = lv.lam;
+    }
+    tp.width = g.width;
+    tp.ngroups = (tp.count[0] + g.width - 1) / g.width;
+    tp.is_root = (g.l1 == (int)h.levels.size() - 1) ? 1 : 0;
+    tp.tt_cap = h.lat_tt_cap > 0 ? h.lat_tt_cap : h.ops->lat_tt_cap;
     return tp;
 }
 
@@ -623,6 +632,14 @@ int run_tree_up(Solver& h, bool affine_only) {
         tp.sum_out = h.levels[l + 1].sum;
         int rc = affine_only ? h.ops->tree_up_affine(h, tp) : h.ops->tree_up(h, tp);
         if (rc) return rc;
+    }
+    if (h.top_lat) {
+        for (const auto& g : h.lat_groups) {
+            if (g.l1 == g.l0) continue;   // a lone root: nothing to combine
+            int rc = h.ops->tree_sub_up(h, sub_params(h, g, nullptr, nullptr, affine_only));
+            if (rc) return rc;
+        }
+        return PDPLQR_OK;
     }
     return h.ops->tree_top_up(h, top_params(h, nullptr, affine_only));
 }
@@ -664,10 +681,18 @@ int run_backward_nofact(Solver& h) {
 
 // down-sweep of the interface tree: the upper levels in one launch, then one launch per lower level
 int run_tree_down(Solver& h, const double* d_x0, const double* d_lam0) {
-    TreeTopParams ttp = top_params(h, d_x0, false);
-    ttp.lam0 = d_lam0;
-    int rc = h.ops->tree_top_down(h, ttp);
-    if (rc) return rc;
+    int rc = PDPLQR_OK;
+    if (h.top_lat) {
+        for (int i = (int)h.lat_groups.size() - 1; i >= 0; --i) {
+            rc = h.ops->tree_sub_down(h, sub_params(h, h.lat_groups[i], d_x0, d_lam0, false));
+            if (rc) return rc;
+        }
+    } else {
+        TreeTopParams ttp = top_params(h, d_x0, false);
+        ttp.lam0 = d_lam0;
+        rc = h.ops->tree_top_down(h, ttp);
+        if (rc) return rc;
+    }
     for (int l = (int)h.levels.size() - 1; l >= 0; --l) {
         TreeLevel& lv = h.levels[l];
         if (lv.in_top) continue;
@@ -777,6 +802,8 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (const char* e = getenv("PDPLQR_TREE_TT")) h->tree_tt = atoi(e);
     if (const char* e = getenv("PDPLQR_TREE_LAT")) h->tree_lat = atoi(e);
     if (const char* e = getenv("PDPLQR_TREE_LAT_MAX")) h->tree_lat_max = atoi(e);
+    if (const char* e = getenv("PDPLQR_TREE_LAT_WIDTH")) h->lat_width = atoi(e);
+    if (const char* e = getenv("PDPLQR_TREE_LAT_TT")) h->lat_tt_cap = atoi(e);
     if (const char* e = getenv("PDPLQR_USE_KM")) h->use_km = atoi(e);
     if (const char* e = getenv("PDPLQR_SEG_T")) h->seg_t = atoi(e);
     if (const char* e = getenv("PDPLQR_SPARSE_D")) h->allow_sel = atoi(e);
@@ -833,25 +860,47 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     //      that all run inside one launch (tree_top_*_kernel); the last level is the root (1 node)
     if (S > 1) {
         int cnt = S;
-        // few problems: the upper tree runs on the latency kernels, which take a narrower widest level
-        h->top_lat = h->tree_lat && ops->top_lat_nodes >= 2 && B <= h->tree_lat_max;
-        const int top_max = h->top_lat ? ops->top_lat_nodes : TREE_TOP_MAX_NODES;
-        for (int l = 0;; ++l) {
+        // Few problems (latency mode): fan-in-4 throughput levels only while a level would still need more CTAs than
+        // tree_lat_max, then binary levels, grouped from the top into launches of <= log2(top_lat_nodes) levels that
+        // each reduce blocks of nodes inside one CTA.  Otherwise: fan-in-4 levels until <= 32 nodes, then the binary
+        // upper tree in one launch of one CTA per problem.
+        int W = ops->top_lat_nodes;
+        if (h->lat_width >= 2 && h->lat_width < W) W = h->lat_width;
+        h->top_lat = h->tree_lat && W >= 2 && B <= (size_t)h->tree_lat_max;
+        auto add_level = [&](int count, int R, bool in_top) {
             TreeLevel lv{};
-            lv.count = cnt;
-            lv.in_top = cnt <= top_max;
-            lv.R = lv.in_top ? 2 : 4;
-            lv.groups = (cnt + lv.R - 1) / lv.R;
-            if (l == 0) { lv.sum = h->d_sum; lv.x = h->d_xhat; lv.lam = h->d_uhat; }
+            lv.count = count; lv.R = R; lv.in_top = in_top;
+            lv.groups = (count + R - 1) / R;
+            if (h->levels.empty()) { lv.sum = h->d_sum; lv.x = h->d_xhat; lv.lam = h->d_uhat; }
             else {
-                rc |= dev_alloc(*h, &lv.sum, B * cnt * ops->SREC);
-                rc |= dev_alloc(*h, &lv.x, B * cnt * nx);
-                rc |= dev_alloc(*h, &lv.lam, B * cnt * nx);
+                rc |= dev_alloc(*h, &lv.sum, B * count * ops->SREC);
+                rc |= dev_alloc(*h, &lv.x, B * count * nx);
+                rc |= dev_alloc(*h, &lv.lam, B * count * nx);
             }
-            rc |= dev_alloc(*h, &lv.dd, B * cnt * ops->DREC);
+            rc |= dev_alloc(*h, &lv.dd, B * count * ops->DREC);
             h->levels.push_back(lv);
-            if (cnt == 1) break;
-            cnt = lv.groups;
+        };
+        if (h->top_lat) {
+            while ((long long)B * ((cnt + W - 1) / W) > h->tree_lat_max) { add_level(cnt, 4, false); cnt = (cnt + 3) / 4; }
+            const int first_bin = (int)h->levels.size();
+            for (;; cnt = (cnt + 1) / 2) { add_level(cnt, 2, true); if (cnt == 1) break; }
+            int logw = 0;
+            while ((2 << logw) <= W) ++logw;                       // levels one CTA can climb
+            int hi = (int)h->levels.size() - 1;
+            std::vector<pdplqr_solver::LatGroup> groups;           // top -> bottom
+            do {
+                const int lo = std::max(first_bin, hi - logw);
+                groups.push_back({lo, hi, 1 << (hi - lo)});
+                hi = lo;
+            } while (hi > first_bin);
+            h->lat_groups.assign(groups.rbegin(), groups.rend());
+        } else {
+            for (;;) {
+                const bool in_top = cnt <= TREE_TOP_MAX_NODES;
+                add_level(cnt, in_top ? 2 : 4, in_top);
+                if (cnt == 1) break;
+                cnt = h->levels.back().groups;
+            }
         }
         if (rc) return bail(PDPLQR_ERR_CUDA);
     }

@@ -67,6 +67,8 @@ struct TreeTopParams {   // the upper, binary part of the tree: levels[0] is the
     const double* x0;      // [batch][NX]   entry state of the root
     const double* lam0;    // [batch][NX]   exit costate of the root (nullptr -> zeros: the root ends at the terminal)
     int affine_only;
+    // latency-mode sub-tree launches (tree_lat_kernels.cuh): `ngroups` blocks of `width` level-0 nodes per problem
+    int width, ngroups, is_root, tt_cap;
 };
 
 // Gauss-Jordan with partial (row) pivoting on an NX x NCOL augmented matrix in shared memory, one warp.

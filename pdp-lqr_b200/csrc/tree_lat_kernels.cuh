@@ -1,17 +1,22 @@
-// Latency-mode versions of the interface-tree kernels (tree_kernels.cuh), used when there are fewer combine groups
-// than SMs (one long-horizon problem, horizon shards, the shard coupler): the interface solve is then a chain of
-// dependent small dense steps and what matters is the length of that chain, not throughput.
+// Latency-mode versions of the interface-tree kernels (tree_kernels.cuh), used when there are few problems (one
+// long-horizon problem, horizon shards, the shard coupler): the interface solve is then a chain of dependent small
+// dense steps and what matters is the length of that chain, not throughput.
 //
 // Same mathematics and the same summary / down-sweep records as tree_kernels.cuh (reference: the serial block recursion
 // of /root/reference include/clqr/lqr/condensed_system.hpp:82-146), different mapping:
-//   * a combine is spread element-parallel over tt = 64 .. 256 threads (run-time tt: the upper tree gives every
-//     surviving combine more threads as the level shrinks: 8 x 64, 4 x 128, 2 x 256, 1 x 256);
-//   * Gauss-Jordan: every thread owns a fixed set of matrix elements and keeps them in registers over all pivot steps;
+//   * the tree is binary; one CTA reduces a block of 8 consecutive nodes through all its levels inside one launch
+//     (4 x 256, 2 x 256, 1 x 256 threads), handing each result to its consumer through shared memory; the next launch
+//     does the same one storey up (S = 128: two launches of three and four levels);
+//   * a combine is spread element-parallel over tt = 64 .. 256 threads; its five 12x12x12-class products run on the
+//     FP64 tensor cores (DMMA), one 8x8 output tile per warp at a time;
+//   * Gauss-Jordan: every thread owns a fixed 4-row chunk of one column and keeps it in registers over all pivot steps;
 //     rows are pivoted implicitly (no exchange, one un-permuting store at the end); the pivot of step k+1 is found by
 //     the owners of column k+1 with a shared-memory atomicMax on (magnitude bits | row) keys while they write step k;
 //     the two buffers ping-pong (one barrier per step); the reciprocal is a Newton-refined hardware seed;
 //   * the down-sweep records are pulled into shared memory by TMA bulk copies before the level loop starts, so the
 //     dependent mat-vec chain never waits for L2.
+// Measured latencies that shape this (scripts/micro/lat_bench.cu, B200): LDS 30, DFMA 8, bar.sync (128 thr) 20,
+// STS->bar->LDS 55, ATOMS.MAX+LDS 51, reciprocal 48 (IEEE division 72), 64-bit shuffle 28 cycles.
 #pragma once
 #include "tree_kernels.cuh"
 
@@ -33,6 +38,8 @@ PDPLQR_DEVINL double rcp_newton(double a) {
     return r;
 }
 
+constexpr int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
 template <int NX>
 struct LatSmem {
     using D = TreeDims<NX>;
@@ -47,25 +54,23 @@ struct LatSmem {
     static constexpr int WORK = 2 * AUG + NX;            // two Gauss-Jordan buffers (the idle one is the scratch of the
                                                          // later phases: [T1 | T2 | x_f | lv]) + pivot keys / row map
     static_assert(AUG >= 2 * D::N2 + 2 * NX, "phase scratch must fit in one Gauss-Jordan buffer");
-    // upper tree: one slot = [a | b | work]
-    static constexpr int o_WK = even_up(2 * D::SREC);   // the workspace is accessed with 16-byte vectors
+    // one slot per concurrent combine = [a | b | a' | b' | work]: the inputs of even and odd levels alternate between
+    // the two pairs, so that a combine can drop its result straight into the slot of the combine that consumes it
+    static constexpr int o_WK = even_up(4 * D::SREC);   // the workspace is accessed with 16-byte vectors
     static constexpr int SLOT = o_WK + even_up(WORK);
-    static constexpr int TOP_THREADS = 512;
-    static constexpr int TT_CAP = 256;                   // more threads than work items per phase do not help
+    static constexpr int TOP_THREADS = NX <= 12 ? 1024 : 512;
+    static constexpr int TT_CAP = 256;                   // threads per combine at most (measured: 256 beats 128 and 64
+                                                         // at nx = 12 although only ITEMS = 108 threads own elements)
     static constexpr int fit = (200 * 1024 / 8) / SLOT;
     static constexpr int by_threads = TOP_THREADS / MINTT;
     static constexpr int lim = fit < by_threads ? fit : by_threads;
-    static constexpr int TOP_SLOTS = lim >= 8 ? 8 : (lim >= 4 ? 4 : (lim >= 2 ? 2 : (lim >= 1 ? 1 : 0)));
-    static constexpr int TOP_NODES = 2 * TOP_SLOTS;      // widest level the one-launch upper tree accepts
+    // measured at nx = 12 (C2): blocks of 8 nodes (4 concurrent combines per SM) beat 16 and 4
+    static constexpr int TOP_SLOTS = lim >= 4 ? 4 : (lim >= 2 ? 2 : (lim >= 1 ? 1 : 0));
+    static constexpr int TOP_NODES = 2 * TOP_SLOTS;      // widest block of nodes one CTA reduces
     static constexpr size_t TOP_BYTES = (size_t)(TOP_SLOTS > 0 ? TOP_SLOTS : 1) * SLOT * 8;
-    // lower levels: [s0 | s1 | s2 | work], one group of UP_TT threads per CTA
-    static constexpr int UP_TT = ITEMS > 128 ? 256 : 128;
-    static constexpr int o_UPWK = even_up(3 * D::SREC);
-    static constexpr size_t UP_BYTES = (size_t)(o_UPWK + even_up(WORK)) * 8;
-    static constexpr bool UP_OK = UP_BYTES <= 220 * 1024;
-    // down-sweeps: the records of every pair of the upper tree (<= TOP_NODES - 1) + per-level vectors
+    // down-sweeps: the records of every pair of the block's sub-tree (<= TOP_NODES - 1) + per-level vectors
     static constexpr int DOWN_MAXREC = TOP_NODES > 1 ? TOP_NODES - 1 : 1;
-    static constexpr int DOWN_VEC = 2 * NX * (2 * (TOP_NODES > 0 ? TOP_NODES : 1)) + 4 * NX * 16;
+    static constexpr int DOWN_VEC = 2 * NX * (2 * (TOP_NODES > 0 ? TOP_NODES : 1)) + 4 * NX * (TOP_THREADS / 32);
     static constexpr size_t DOWN_BYTES = (size_t)(DOWN_MAXREC * D::DREC + DOWN_VEC) * 8;
     static constexpr bool DOWN_OK = TOP_NODES >= 2 && DOWN_BYTES <= 220 * 1024;
 };
@@ -248,7 +253,7 @@ PDPLQR_DEVINL void combine_lat(int t, int tt, int bar_id, const double* sa, cons
         out[D::SUM_f + r] = af;
     }
     rt_sync(tt, bar_id);
-    // ---- phase 5: p = p_a + F_a^T lv
+    // ---- phase 5: p = p_a + F_a^T lv   (then: `out` may be picked up by a bulk copy -> async-proxy fence)
     for (int r = t; r < NX; r += tt) {
         double ap0 = pa[r], ap1 = 0.0;
 #pragma unroll
@@ -259,89 +264,88 @@ PDPLQR_DEVINL void combine_lat(int t, int tt, int bar_id, const double* sa, cons
         if (NX & 1) ap0 = fma(Fa[NX - 1 + r * NX], lv[NX - 1], ap0);
         out[D::SUM_p + r] = ap0 + ap1;
     }
+    fence_proxy_async();
     rt_sync(tt, bar_id);
 }
 
-// ---------------------------------------------------------------- lower level: one CTA of TT threads per group
-template <int NX, int TT>
-__global__ void __launch_bounds__(TT) tree_up_lat_kernel(TreeParams p) {
-    using D = TreeDims<NX>;
-    using L = LatSmem<NX>;
-    constexpr int NPRE = (D::SREC + TT - 1) / TT;
-    extern __shared__ __align__(16) double smem[];
-    const int t = threadIdx.x;
-    const int b = blockIdx.x / p.groups, g = blockIdx.x % p.groups;
-    const int first = g * p.R, last = min(first + p.R, p.count) - 1;
-    double* sa = smem;
-    double* sb = smem + D::SREC;
-    double* sn = smem + 2 * D::SREC;
-    double* wk = smem + L::o_UPWK;
-    const double* in_b = p.sum_in + (size_t)b * p.count * D::SREC;
-    double* dd_b = p.dd + (size_t)b * p.count * D::DREC;
-    double pre[NPRE];
-    auto prefetch = [&](int node) {   // into registers: the L2 latency hides behind the running combine
-#pragma unroll
-        for (int q = 0; q < NPRE; ++q) {
-            const int e = t + q * TT;
-            if (e < D::SREC) pre[q] = in_b[(size_t)node * D::SREC + e];
-        }
-    };
-    if (last > first) prefetch(last - 1);
-    combine_lat_init<NX>(t, TT, wk);
-    for (int e = t; e < D::SREC; e += TT) sb[e] = in_b[(size_t)last * D::SREC + e];
-#pragma unroll 1
-    for (int i = last - 1; i >= first; --i) {
-#pragma unroll
-        for (int q = 0; q < NPRE; ++q) {
-            const int e = t + q * TT;
-            if (e < D::SREC) sa[e] = pre[q];
-        }
-        __syncthreads();
-        if (i > first) prefetch(i - 1);
-        combine_lat<NX>(t, TT, 1, sa, sb, wk, sn, dd_b + (size_t)i * D::DREC);
-        double* sw = sb; sb = sn; sn = sw;
-    }
-    __syncthreads();
-    if (p.sum_out) {
-        double* out = p.sum_out + ((size_t)b * p.groups + g) * D::SREC;
-        for (int e = t; e < D::SREC; e += TT) out[e] = sb[e];
-    }
-}
-
-// ---------------------------------------------------------------- upper levels: one CTA per problem, one launch
+// ---------------------------------------------------------------- binary sub-trees: one CTA per (problem, block of
+// `width` consecutive nodes of the launch's lowest level), all levels of the block inside one launch.  The launch of
+// the uppermost levels has one block per problem (is_root).  Level l of the launch holds count[l] nodes per problem,
+// count[l+1] = ceil(count[l] / 2); block g owns nodes [g (width >> l), (g+1) (width >> l)) of level l.
 template <int NX>
-__global__ void __launch_bounds__(LatSmem<NX>::TOP_THREADS) tree_top_up_lat_kernel(TreeTopParams p) {
+__global__ void __launch_bounds__(LatSmem<NX>::TOP_THREADS) tree_sub_up_lat_kernel(TreeTopParams p) {
     using D = TreeDims<NX>;
     using L = LatSmem<NX>;
     constexpr int THREADS = L::TOP_THREADS;
+    constexpr bool BULK_OUT = (D::SREC % 2 == 0);   // 16-byte granularity of cp.async.bulk
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
-    const int b = blockIdx.x;
+    const int b = blockIdx.x / p.ngroups, g0 = blockIdx.x % p.ngroups;
 #pragma unroll 1
-    for (int l = 0; l + 1 < p.nlevels; ++l) {   // level l (count[l] nodes) -> level l+1 (pairs)
-        const int cnt = p.count[l], groups = (cnt + 1) / 2;
+    for (int l = 0; l + 1 < p.nlevels; ++l) {   // level l -> level l+1 (pairs)
+        const int cnt = p.count[l], cnt_up = p.count[l + 1];
+        const int w = p.width >> l, n0 = g0 * w;
+        const int mine = min(w, cnt - n0);      // nodes of this block at this level (>= 1)
+        const int groups = (mine + 1) / 2;
         int ng = 1;
-        while (ng < groups) ng <<= 1;           // <= TOP_SLOTS (the plan caps count[0] at TOP_NODES)
+        while (ng < groups) ng <<= 1;           // <= TOP_SLOTS (width <= TOP_NODES)
         int tt = THREADS / ng;
-        if (tt > L::TT_CAP) tt = L::TT_CAP;     // a combine has at most ~3 NX^2 independent elements per phase
+        if (tt > p.tt_cap) tt = p.tt_cap;
         const int grp = tid / tt, t = tid % tt;
         if (grp < groups) {
-            const double* in_b = p.sum[l] + (size_t)b * cnt * D::SREC;
-            double* out = p.sum[l + 1] + ((size_t)b * groups + grp) * D::SREC;
+            const double* in_b = p.sum[l] + ((size_t)b * cnt + n0) * D::SREC;
+            double* out = p.sum[l + 1] + ((size_t)b * cnt_up + (n0 >> 1) + grp) * D::SREC;
+            double* dd_a = p.dd[l] + ((size_t)b * cnt + n0 + 2 * grp) * D::DREC;
             const int ia = 2 * grp, ib = 2 * grp + 1;
-            if (ib >= cnt) {                    // odd node out: passes through unchanged
-                for (int e = t; e < D::SREC; e += tt) out[e] = in_b[(size_t)ia * D::SREC + e];
+            double* ws = smem + (size_t)grp * L::SLOT;
+            if (p.affine_only) {                // members' p, f changed only: mat-vec work, through global memory
+                if (ib >= mine) {
+                    for (int r = t; r < NX; r += tt) {
+                        out[D::SUM_p + r] = in_b[(size_t)ia * D::SREC + D::SUM_p + r];
+                        out[D::SUM_f + r] = in_b[(size_t)ia * D::SREC + D::SUM_f + r];
+                    }
+                } else if (t < 32) {            // the first warp of the group (warp_combine_affine, tree_kernels.cuh)
+                    double* pb = ws;
+                    double* fb = ws + NX;
+                    for (int r = t; r < NX; r += 32) {
+                        pb[r] = in_b[(size_t)ib * D::SREC + D::SUM_p + r];
+                        fb[r] = in_b[(size_t)ib * D::SREC + D::SUM_f + r];
+                    }
+                    __syncwarp();
+                    warp_combine_affine<NX>(t, in_b + (size_t)ia * D::SREC, dd_a, pb, fb, ws + 2 * NX);
+                    for (int r = t; r < NX; r += 32) {
+                        out[D::SUM_p + r] = pb[r];
+                        out[D::SUM_f + r] = fb[r];
+                    }
+                }
             } else {
-                double* ws = smem + (size_t)grp * L::SLOT;
-                double* sa = ws;
-                double* sb = ws + D::SREC;
-                for (int e = t; e < D::SREC; e += tt) {
-                    sa[e] = in_b[(size_t)ia * D::SREC + e];
-                    sb[e] = in_b[(size_t)ib * D::SREC + e];
+                // inputs of this level: pair (l & 1) of the slot; the result goes to the other pair of the slot of the
+                // combine that consumes it at level l+1 (as its a if grp is even, its b if odd) and to global memory
+                double* sa = ws + (l & 1) * 2 * D::SREC;
+                double* sb = sa + D::SREC;
+                double* outs = smem + (size_t)(grp >> 1) * L::SLOT + ((l & 1) ^ 1) * 2 * D::SREC + (grp & 1) * D::SREC;
+                if (l == 0) {                   // the block's lowest level comes from global memory
+                    for (int e = t; e < D::SREC; e += tt) {
+                        sa[e] = in_b[(size_t)ia * D::SREC + e];
+                        if (ib < mine) sb[e] = in_b[(size_t)ib * D::SREC + e];
+                    }
                 }
                 combine_lat_init<NX>(t, tt, ws + L::o_WK);   // slots change owners between levels
                 rt_sync(tt, 1 + grp);
-                combine_lat<NX>(t, tt, 1 + grp, sa, sb, ws + L::o_WK, out, p.dd[l] + ((size_t)b * cnt + ia) * D::DREC);
+                if (ib >= mine) {               // odd node out: passes through unchanged
+                    for (int e = t; e < D::SREC; e += tt) outs[e] = sa[e];
+                    fence_proxy_async();
+                    rt_sync(tt, 1 + grp);
+                } else
+                    combine_lat<NX>(t, tt, 1 + grp, sa, sb, ws + L::o_WK, outs, dd_a);
+                if constexpr (BULK_OUT) {
+                    if (t == 0) {
+                        bulk_s2g(out, outs, D::SREC * 8);
+                        bulk_commit();
+                        bulk_wait_read<0>();    // before anyone overwrites `outs` (two levels on) or the CTA exits
+                    }
+                } else
+                    for (int e = t; e < D::SREC; e += tt) out[e] = outs[e];
             }
         }
         __threadfence_block();
@@ -349,8 +353,6 @@ __global__ void __launch_bounds__(LatSmem<NX>::TOP_THREADS) tree_top_up_lat_kern
     }
 }
 
-// one down-sweep step from a record in shared memory; x, le: entry state / exit costate of the pair (shared);
-// writes lam of the first member and x of the second (shared), pt: NX doubles of scratch
 template <int NX>
 PDPLQR_DEVINL void warp_down_step_smem(int lane, const double* rec, const double* x, const double* le, double* pt,
                                        double* lam_first, double* x_second) {
@@ -382,43 +384,45 @@ PDPLQR_DEVINL void warp_down_step_smem(int lane, const double* rec, const double
 }
 
 template <int NX>
-__global__ void __launch_bounds__(LatSmem<NX>::TOP_THREADS) tree_top_down_lat_kernel(TreeTopParams p) {
+__global__ void __launch_bounds__(LatSmem<NX>::TOP_THREADS) tree_sub_down_lat_kernel(TreeTopParams p) {
     using D = TreeDims<NX>;
     using L = LatSmem<NX>;
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar[TREE_TOP_MAX_LEVELS];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.x;
+    const int b = blockIdx.x / p.ngroups, g0 = blockIdx.x % p.ngroups;
     double* recs = smem;                                   // pair records, upper levels first
-    double* vec = smem + L::DOWN_MAXREC * D::DREC;         // per level: x[count][NX] then lam[count][NX]
+    double* vec = smem + L::DOWN_MAXREC * D::DREC;         // per level: x[width >> l][NX] then lam[width >> l][NX]
     double* scratch = vec + 2 * NX * 2 * L::TOP_NODES + warp * 4 * NX;
     const int top = p.nlevels - 1;
+    auto mine_at = [&](int l) { return min(p.width >> l, p.count[l] - g0 * (p.width >> l)); };
     if (tid == 0) {
         for (int l = 0; l < top; ++l) mbar_init(&bar[l], 1);
         mbar_fence_init();
         int off = 0;
         for (int l = top - 1; l >= 0; --l) {               // the order the sweep needs them in
-            const int cnt = p.count[l], pairs = cnt / 2;
+            const int cnt = p.count[l], n0 = g0 * (p.width >> l), pairs = mine_at(l) / 2;
             if (pairs > 0) mbar_expect_tx(&bar[l], (uint32_t)(pairs * D::DREC * 8));
             for (int g = 0; g < pairs; ++g) {
-                bulk_g2s(recs + (size_t)off * D::DREC, p.dd[l] + ((size_t)b * cnt + 2 * g) * D::DREC, D::DREC * 8, &bar[l]);
+                bulk_g2s(recs + (size_t)off * D::DREC, p.dd[l] + ((size_t)b * cnt + n0 + 2 * g) * D::DREC, D::DREC * 8, &bar[l]);
                 ++off;
             }
         }
     }
-    // vec offsets: level l starts after all upper levels
-    auto vec_off = [&](int l) {
+    auto vec_off = [&](int l) {                            // level l starts after all upper levels
         int o = 0;
-        for (int m = top; m > l; --m) o += p.count[m];
+        for (int m = top; m > l; --m) o += p.width >> m;
         return o * 2 * NX;
     };
-    if (warp == 1)
+    if (warp == 1) {   // the block's node of the launch's top level: the root boundary, or what the launch above left
+        const size_t at = ((size_t)b * p.count[top] + g0) * NX;
         for (int r = lane; r < NX; r += 32) {
-            vec[r] = p.x0[(size_t)b * NX + r];
-            vec[NX + r] = p.lam0 ? p.lam0[(size_t)b * NX + r] : 0.0;
+            vec[r] = p.is_root ? p.x0[(size_t)b * NX + r] : p.x[top][at + r];
+            vec[NX + r] = p.is_root ? (p.lam0 ? p.lam0[(size_t)b * NX + r] : 0.0) : p.lam[top][at + r];
         }
+    }
     __syncthreads();
-    if (top == 0 && warp == 1)   // a one-node upper tree: the root itself is what the lower levels read
+    if (top == 0 && warp == 1 && p.is_root)   // a one-node upper tree: the root itself is what the lower levels read
         for (int r = lane; r < NX; r += 32) {
             p.x[0][(size_t)b * NX + r] = vec[r];
             p.lam[0][(size_t)b * NX + r] = vec[NX + r];
@@ -426,15 +430,16 @@ __global__ void __launch_bounds__(LatSmem<NX>::TOP_THREADS) tree_top_down_lat_ke
     int rec_off = 0;
 #pragma unroll 1
     for (int l = top - 1; l >= 0; --l) {
-        const int cnt = p.count[l], groups = (cnt + 1) / 2, pairs = cnt / 2;
-        const int pcnt = p.count[l + 1];
+        const int cnt = p.count[l], w = p.width >> l, n0 = g0 * w;
+        const int mine = mine_at(l), groups = (mine + 1) / 2, pairs = mine / 2;
+        const int wup = p.width >> (l + 1);
         const double* xp = vec + vec_off(l + 1);
-        const double* lp = xp + pcnt * NX;
+        const double* lp = xp + wup * NX;
         double* xo = vec + vec_off(l);
-        double* lo = xo + cnt * NX;
+        double* lo = xo + w * NX;
         if (pairs > 0) mbar_wait(&bar[l], 0);
         if (warp < groups) {
-            const int g = warp, first = 2 * g, last = min(2 * g + 1, cnt - 1);
+            const int g = warp, first = 2 * g, last = min(2 * g + 1, mine - 1);
             for (int r = lane; r < NX; r += 32) {
                 xo[first * NX + r] = xp[g * NX + r];
                 lo[last * NX + r] = lp[g * NX + r];
@@ -443,9 +448,9 @@ __global__ void __launch_bounds__(LatSmem<NX>::TOP_THREADS) tree_top_down_lat_ke
             if (last > first)
                 warp_down_step_smem<NX>(lane, recs + (size_t)(rec_off + g) * D::DREC, xp + g * NX, lp + g * NX, scratch,
                                         lo + first * NX, xo + last * NX);
-            if (l == 0) {   // only the widest level is read by later launches
-                double* gx = p.x[0] + (size_t)b * cnt * NX;
-                double* gl = p.lam[0] + (size_t)b * cnt * NX;
+            if (l == 0) {   // only the launch's lowest level is read by later launches
+                double* gx = p.x[0] + ((size_t)b * cnt + n0) * NX;
+                double* gl = p.lam[0] + ((size_t)b * cnt + n0) * NX;
                 for (int r = lane; r < NX; r += 32) {
                     gx[first * NX + r] = xo[first * NX + r];
                     gl[last * NX + r] = lo[last * NX + r];
@@ -458,50 +463,6 @@ __global__ void __launch_bounds__(LatSmem<NX>::TOP_THREADS) tree_top_down_lat_ke
         }
         rec_off += pairs;
         __syncthreads();
-    }
-}
-
-// lower level down-sweep, one warp per group: the group's records arrive by TMA while the parent vectors are read
-template <int NX>
-__global__ void __launch_bounds__(32) tree_down_lat_kernel(TreeParams p) {
-    using D = TreeDims<NX>;
-    extern __shared__ __align__(16) double smem[];
-    __shared__ __align__(8) uint64_t bar;
-    const int lane = threadIdx.x;
-    const int b = blockIdx.x / p.groups, g = blockIdx.x % p.groups;
-    const int first = g * p.R, last = min(first + p.R, p.count) - 1;
-    const int nrec = last - first;
-    double* recs = smem;                            // (R-1) records
-    double* x = smem + (size_t)(p.R - 1) * D::DREC; // NX
-    double* le = x + NX;
-    double* pt = x + 2 * NX;
-    double* xn = x + 3 * NX;
-    const double* dd_b = p.dd + (size_t)b * p.count * D::DREC;
-    double* xo = p.x_node + (size_t)b * p.count * NX;
-    double* lo = p.lam_node + (size_t)b * p.count * NX;
-    if (lane == 0) {
-        mbar_init(&bar, 1);
-        mbar_fence_init();
-        if (nrec > 0) {
-            mbar_expect_tx(&bar, (uint32_t)(nrec * D::DREC * 8));
-            bulk_g2s(recs, dd_b + (size_t)first * D::DREC, (uint32_t)(nrec * D::DREC * 8), &bar);   // contiguous members
-        }
-    }
-    for (int r = lane; r < NX; r += 32) {
-        x[r] = p.x_parent[((size_t)b * p.groups + g) * NX + r];
-        le[r] = p.lam_parent ? p.lam_parent[((size_t)b * p.groups + g) * NX + r] : 0.0;
-        xo[(size_t)first * NX + r] = x[r];
-        lo[(size_t)last * NX + r] = le[r];
-    }
-    __syncwarp();
-    if (nrec > 0) mbar_wait(&bar, 0);
-    double* xc = x;
-    double* xs = xn;
-#pragma unroll 1
-    for (int i = first; i < last; ++i) {
-        warp_down_step_smem<NX>(lane, recs + (size_t)(i - first) * D::DREC, xc, le, pt, lo + (size_t)i * NX, xs);
-        for (int r = lane; r < NX; r += 32) xo[(size_t)(i + 1) * NX + r] = xs[r];
-        double* sw = xc; xc = xs; xs = sw;
     }
 }
 
