@@ -67,8 +67,11 @@ PDPLQR_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared:
 
 // ---------------------------------------------------------------- group GEMM with register tiles
 // C(i,j) = epi(i, j, sum_k A(i,k) * B(k,j))   for i < M, j < N.
-// Tiles of TM x TN outputs are dealt round-robin to the T threads of the group (tile index fastest along i, so
-// neighbouring threads read neighbouring rows of A: conflict-free for column-major A, broadcast for B).
+// Tiles of TM x TN outputs are dealt round-robin to the T threads of the group, tile index fastest along i.  The TM
+// rows of a tile are STRIDED (ti, ti + MT, ti + 2 MT, ...): lane l and lane l+1 then read and write adjacent rows, so
+// every warp-wide access to a column-major operand or result is one contiguous run (one shared-memory wavefront per
+// 128 bytes, no bank conflicts) and B is a broadcast.  Blocked rows (ti TM + r) cost 1.6-2.6x the wavefronts in the
+// stage kernels, which are shared-memory-bandwidth bound (profiles/r1_ncu_c5small_seg_backward_t64.txt).
 // LA(i,k), LB(k,j) are element loaders (any layout / transposition / scaling), EPI stores.
 template <int M, int N, int K, int TM, int TN, int T, class LA, class LB, class EPI>
 PDPLQR_DEVINL void group_mm(int tid, LA la, LB lb, EPI epi) {
@@ -79,7 +82,7 @@ PDPLQR_DEVINL void group_mm(int tid, LA la, LB lb, EPI epi) {
 #pragma unroll 1
     for (int t = tid; t < TILES; t += T) {
         const int ti = t % MT, tj = t / MT;
-        const int i0 = ti * TM, j0 = tj * TN;
+        const int j0 = tj * TN;
         double acc[TM][TN];
 #pragma unroll
         for (int r = 0; r < TM; ++r)
@@ -89,7 +92,7 @@ PDPLQR_DEVINL void group_mm(int tid, LA la, LB lb, EPI epi) {
         for (int k = 0; k < K; ++k) {
             double av[TM], bv[TN];
 #pragma unroll
-            for (int r = 0; r < TM; ++r) av[r] = la(FULL_M ? i0 + r : min(i0 + r, M - 1), k);
+            for (int r = 0; r < TM; ++r) av[r] = la(FULL_M ? ti + r * MT : min(ti + r * MT, M - 1), k);
 #pragma unroll
             for (int c = 0; c < TN; ++c) bv[c] = lb(k, FULL_N ? j0 + c : min(j0 + c, N - 1));
 #pragma unroll
@@ -101,7 +104,7 @@ PDPLQR_DEVINL void group_mm(int tid, LA la, LB lb, EPI epi) {
         for (int r = 0; r < TM; ++r)
 #pragma unroll
             for (int c = 0; c < TN; ++c)
-                if ((FULL_M || i0 + r < M) && (FULL_N || j0 + c < N)) epi(i0 + r, j0 + c, acc[r][c]);
+                if ((FULL_M || ti + r * MT < M) && (FULL_N || j0 + c < N)) epi(ti + r * MT, j0 + c, acc[r][c]);
     }
 }
 
@@ -115,7 +118,7 @@ PDPLQR_DEVINL void group_mm_rt(int tid, int K, LA la, LB lb, EPI epi) {
 #pragma unroll 1
     for (int t = tid; t < TILES; t += T) {
         const int ti = t % MT, tj = t / MT;
-        const int i0 = ti * TM, j0 = tj * TN;
+        const int j0 = tj * TN;
         double acc[TM][TN];
 #pragma unroll
         for (int r = 0; r < TM; ++r)
@@ -125,7 +128,7 @@ PDPLQR_DEVINL void group_mm_rt(int tid, int K, LA la, LB lb, EPI epi) {
         for (int k = 0; k < K; ++k) {
             double av[TM], bv[TN];
 #pragma unroll
-            for (int r = 0; r < TM; ++r) av[r] = la(FULL_M ? i0 + r : min(i0 + r, M - 1), k);
+            for (int r = 0; r < TM; ++r) av[r] = la(FULL_M ? ti + r * MT : min(ti + r * MT, M - 1), k);
 #pragma unroll
             for (int c = 0; c < TN; ++c) bv[c] = lb(k, FULL_N ? j0 + c : min(j0 + c, N - 1));
 #pragma unroll
@@ -137,7 +140,7 @@ PDPLQR_DEVINL void group_mm_rt(int tid, int K, LA la, LB lb, EPI epi) {
         for (int r = 0; r < TM; ++r)
 #pragma unroll
             for (int c = 0; c < TN; ++c)
-                if ((FULL_M || i0 + r < M) && (FULL_N || j0 + c < N)) epi(i0 + r, j0 + c, acc[r][c]);
+                if ((FULL_M || ti + r * MT < M) && (FULL_N || j0 + c < N)) epi(ti + r * MT, j0 + c, acc[r][c]);
     }
 }
 
@@ -153,7 +156,7 @@ PDPLQR_DEVINL void group_mm_multi(int tid, LA la, LB lb, EPI epi) {
     for (int t = tid; t < G * TILES; t += T) {
         const int g = t / TILES, tl = t - g * TILES;
         const int ti = tl % MT, tj = tl / MT;
-        const int i0 = ti * TM, j0 = tj * TN;
+        const int j0 = tj * TN;
         double acc[TM][TN];
 #pragma unroll
         for (int r = 0; r < TM; ++r)
@@ -163,7 +166,7 @@ PDPLQR_DEVINL void group_mm_multi(int tid, LA la, LB lb, EPI epi) {
         for (int k = 0; k < K; ++k) {
             double av[TM], bv[TN];
 #pragma unroll
-            for (int r = 0; r < TM; ++r) av[r] = la(g, FULL_M ? i0 + r : min(i0 + r, M - 1), k);
+            for (int r = 0; r < TM; ++r) av[r] = la(g, FULL_M ? ti + r * MT : min(ti + r * MT, M - 1), k);
 #pragma unroll
             for (int c = 0; c < TN; ++c) bv[c] = lb(g, k, FULL_N ? j0 + c : min(j0 + c, N - 1));
 #pragma unroll
@@ -175,7 +178,7 @@ PDPLQR_DEVINL void group_mm_multi(int tid, LA la, LB lb, EPI epi) {
         for (int r = 0; r < TM; ++r)
 #pragma unroll
             for (int c = 0; c < TN; ++c)
-                if ((FULL_M || i0 + r < M) && (FULL_N || j0 + c < N)) epi(g, i0 + r, j0 + c, acc[r][c]);
+                if ((FULL_M || ti + r * MT < M) && (FULL_N || j0 + c < N)) epi(g, ti + r * MT, j0 + c, acc[r][c]);
     }
 }
 
