@@ -65,6 +65,9 @@ PDPLQR_DEVINL void bulk_wait() {
 // order generic-proxy smem accesses before subsequent async-proxy (TMA) accesses of the same locations
 PDPLQR_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// smallest leading dimension >= n that is 4 (mod 8)  (see BwdSmem)
+constexpr int ld4mod8(int n) { return n + ((4 - n % 8) + 8) % 8; }
+
 // ---------------------------------------------------------------- group GEMM with register tiles
 // C(i,j) = epi(i, j, sum_k A(i,k) * B(k,j))   for i < M, j < N.
 // Tiles of TM x TN outputs are dealt round-robin to the T threads of the group, tile index fastest along i.  The TM
@@ -230,9 +233,69 @@ PDPLQR_DEVINL void dmma_tiles(int warp, int W, int lane, int K, LA la, LB lb, EP
         }
     }
 }
+// Register-blocked version: a warp owns a block of MB x NB output tiles and loads MB A-fragments + NB B-fragments per
+// k-step for MB*NB DMMAs (dmma_tiles: 2 loads per DMMA).  The stage kernels are bound by shared-memory wavefronts
+// (an LDS.64 with distinct lane addresses costs 2, scripts/micro/lds_bench.cu), so operand reuse in registers is what
+// pays.  Block shape: the cheapest of the candidates under a simple issue + load + latency cost with W warps.
+struct DmmaBlock { int mb, nb; };
+constexpr DmmaBlock pick_dmma_block(int G, int MT, int NT, int W) {
+    DmmaBlock best{1, 1};
+    long best_cost = 1L << 60;
+    for (int mb = 1; mb <= (MT < 4 ? MT : 4); ++mb)
+        for (int nb = 1; nb <= (NT < 4 ? NT : 4); ++nb) {
+            if (mb * nb > 9) continue;   // 2 accumulator registers (doubles) per tile and lane
+            const int blocks = G * ((MT + mb - 1) / mb) * ((NT + nb - 1) / nb);
+            const int rounds = (blocks + W - 1) / W;
+            const long cost = (long)rounds * (mb * nb * 16 + (mb + nb) * 10 + (mb * nb == 1 ? 26 : 8));
+            if (cost < best_cost) { best_cost = cost; best = DmmaBlock{mb, nb}; }
+        }
+    return best;
+}
+template <int G, int M, int N, int MB, int NB, class LA, class LB, class EPI>
+PDPLQR_DEVINL void dmma_blocks(int warp, int W, int lane, int K, LA la, LB lb, EPI epi) {
+    constexpr int MT = (M + 7) / 8, NT = (N + 7) / 8;
+    constexpr int MBT = (MT + MB - 1) / MB, NBT = (NT + NB - 1) / NB, BLOCKS = MBT * NBT;
+    const int r = lane >> 2, q = lane & 3;
+    const int KT = (K + 3) >> 2;
+#pragma unroll 1
+    for (int t = warp; t < G * BLOCKS; t += W) {
+        const int g = t / BLOCKS, l = t - g * BLOCKS;
+        const int i0 = (l % MBT) * (8 * MB), j0 = (l / MBT) * (8 * NB);
+        double c[MB][NB][2];
+#pragma unroll
+        for (int a = 0; a < MB; ++a)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) c[a][b][0] = c[a][b][1] = 0.0;
+#pragma unroll 2
+        for (int kt = 0; kt < KT; ++kt) {
+            const int k = kt * 4 + q;
+            const bool kin = k < K;
+            double af[MB], bf[NB];
+#pragma unroll
+            for (int a = 0; a < MB; ++a) af[a] = (kin && i0 + 8 * a + r < M) ? la(g, i0 + 8 * a + r, k) : 0.0;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) bf[b] = (kin && j0 + 8 * b + r < N) ? lb(g, k, j0 + 8 * b + r) : 0.0;
+#pragma unroll
+            for (int a = 0; a < MB; ++a)
+#pragma unroll
+                for (int b = 0; b < NB; ++b) dmma_m8n8k4(c[a][b][0], c[a][b][1], af[a], bf[b]);
+        }
+#pragma unroll
+        for (int a = 0; a < MB; ++a)
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+                const int i = i0 + 8 * a + r, j = j0 + 8 * b + 2 * q;
+                if (i < M) {
+                    if (j < N) epi(g, i, j, c[a][b][0]);
+                    if (j + 1 < N) epi(g, i, j + 1, c[a][b][1]);
+                }
+            }
+    }
+}
 template <int G, int M, int N, int T, class LA, class LB, class EPI>
 PDPLQR_DEVINL void group_mm_dmma_impl(int tid, int K, LA la, LB lb, EPI epi) {
-    dmma_tiles<G, M, N>(tid >> 5, T / 32, tid & 31, K, la, lb, epi);
+    constexpr DmmaBlock blk = pick_dmma_block(G, (M + 7) / 8, (N + 7) / 8, T / 32);
+    dmma_blocks<G, M, N, blk.mb, blk.nb>(tid >> 5, T / 32, tid & 31, K, la, lb, epi);
 }
 template <int M, int N, int K, int T, class LA, class LB, class EPI>
 PDPLQR_DEVINL void group_mm_dmma(int tid, LA la, LB lb, EPI epi) {
@@ -252,8 +315,8 @@ PDPLQR_DEVINL void group_mm_dmma_multi(int tid, LA la, LB lb, EPI epi) {
 }
 
 #ifndef PDPLQR_DMMA_MIN_MACS
-#define PDPLQR_DMMA_MIN_MACS 20000   // products smaller than this stay on the register-tile FMA path (measured:
-#endif                               // at nx=12/nu=4 the stage kernel is barrier/overhead-bound and DMMA is slower)
+#define PDPLQR_DMMA_MIN_MACS 500     // products smaller than this stay on the register-tile FMA path.  Measured (C5,
+#endif                               // nx12/nu4, same box): 20000 -> 4.22 ms, 3000 -> 3.90 ms, 500 and 1 -> 3.58 ms
 // dispatchers used by the kernels
 template <int M, int N, int K, int TM, int TN, int T, class LA, class LB, class EPI>
 PDPLQR_DEVINL void gmm(int tid, LA la, LB lb, EPI epi) {

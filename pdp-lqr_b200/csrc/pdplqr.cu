@@ -248,9 +248,10 @@ int backward_impl(Solver& h) {
     }
     const size_t bytes = BwdSmem<NX, NU>::bytes(h.ncmax, h.sel_mode);
     if constexpr (T == 32) {
-        // two warps per (problem, segment) share one shared-memory working set: twice the warps per SM hide more of the
-        // stage's latency (C5: 4.25 -> 4.09 ms).  Default for nx + nu >= 16; PDPLQR_SEG_T = 32 / 64 / 128 overrides.
-        const int seg_t = h.seg_t ? h.seg_t : ((NX + NU) >= 16 ? 64 : 32);
+        // One warp per (problem, segment) by default: with the products on register-blocked DMMA a single warp owns every
+        // output tile and reuses its operand fragments most (C5: 3.46 ms, against 3.58 ms with two warps sharing the
+        // working set).  PDPLQR_SEG_T = 32 / 64 / 128 overrides.
+        const int seg_t = h.seg_t ? h.seg_t : 32;
         if (!latency_mode && seg_t == 64) {
             int rc = h.ncmax > 0 ? launch_seg_bwd<NX, NU, 64, true>(h, p, bytes) : launch_seg_bwd<NX, NU, 64, false>(h, p, bytes);
             if (rc) return rc;
@@ -439,7 +440,7 @@ const Ops* find_ops(int nx, int nu) {
     return nullptr;
 }
 
-// flat (E, c, H, h) -> device stage records.  sym = 0: [[E c]^T | H | h] per (problem, stage) (segment kernels);
+// flat (E, c, H, h) -> device stage records.  sym = 0: [E | c | H | h] per (problem, stage) (segment kernels);
 // sym = 1: thread-per-problem path: [E | c | lower(H) packed by columns | h] with the records of the 32 problems of a
 // tile interleaved pair-wise (BatchDims::TR_*, tile_pos): one contiguous block per (tile, stage).  `nprob` is the
 // batch size, the tile count is ceil(nprob / 32) and lanes past the batch replicate the last problem.
@@ -470,10 +471,7 @@ __global__ void pack_model_kernel(const double* __restrict__ E, const double* __
         }
         const long long st = b * N + k;
         double v = 0.0;
-        if (e < oH && !sym) {      // segment records keep [E c] transposed: ET(j, kk) at j + kk*(s+1)
-            const int j = e % (s + 1), kk = e / (s + 1);
-            v = (j < s) ? E[st * oC + kk + j * nx] : c[st * nx + kk];
-        } else if (e < oC) v = E[st * oC + e];
+        if (e < oC) v = E[st * oC + e];
         else if (e < oH) v = c[st * nx + (e - oC)];
         else if (e < oh) {
             int q = e - oH;

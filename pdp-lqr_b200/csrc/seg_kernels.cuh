@@ -26,12 +26,12 @@ constexpr int even_up(int n) { return (n + 1) & ~1; }
 template <int NX, int NU>
 struct SegDims {
     static constexpr int S = NX + NU;
-    // model record (one stage): [ET ((S+1) x NX) | H (S x S) | h (S)], column-major, padded to 16 bytes, where
-    // ET(j, k) = [E c](k, j): E and c are stored TRANSPOSED so that the backward kernel's products read their operands
-    // straight from the TMA buffer (no per-stage transposition pass) and the affine / rollout kernels read contiguously
+    // model record (one stage): [E (NX x S) | c (NX) | H (S x S) | h (S)], column-major, padded to 16 bytes.  [E c] is
+    // an NX x (S+1) matrix with leading dimension NX: as a DMMA operand (k along the contiguous index) it is read in
+    // place from the TMA buffer without shared-memory bank conflicts for NX = 2, 4, 6 (mod 8) -- no transposed copy
     static constexpr int REC_E = 0;
-    static constexpr int LDE = S + 1;                 // leading dimension of ET; c is its row S
-    static constexpr int REC_H = NX * (S + 1);
+    static constexpr int REC_C = NX * S;
+    static constexpr int REC_H = REC_C + NX;
     static constexpr int REC_h = REC_H + S * S;
     static constexpr int REC = even_up(REC_h + S);
     static constexpr int REC_EC = even_up(NX * S + NX);  // prefix the rollout needs
@@ -108,11 +108,13 @@ template <int NX, int NU>
 struct BwdSmem {
     using D = SegDims<NX, NU>;
     static constexpr int S = D::S;
-    static constexpr int LDT = D::LDE;             // ET lives in the stage record itself
-    static constexpr int LDPF = odd_ld(2 * NX);    // PF: [P+; F+] stacked, (2NX) x NX
-    static constexpr int LDPE = odd_ld(2 * NX);    // PFE: [P+;F+] [E c], (2NX) x (S+1)
-    static constexpr int LDM = odd_ld(S);          // Ma: [M | g], S x (S+1)
-    static constexpr int LDY = odd_ld(D::NRHS);    // YT: NRHS x NU  (Y^T, Y = Luu^-1 [Qux Qu BtFt])
+    // Leading dimensions = 4 (mod 8): the DMMA fragment accesses of a column-major array are then free of bank
+    // conflicts both as an operand (lane -> row r = lane/4, k = lane%4: r + k ld) and as an accumulator
+    // (lane -> row r, columns 2 (lane%4) + {0,1}: r + 2 (lane%4) ld); measured with scripts/micro/lds_bench.cu rules
+    static constexpr int LDPF = ld4mod8(2 * NX);    // PF: [P+; F+] stacked, (2NX) x NX
+    static constexpr int LDPE = ld4mod8(2 * NX);    // PFE: [P+;F+] [E c], (2NX) x (S+1)
+    static constexpr int LDM = ld4mod8(S);          // Ma: [M | g], S x (S+1)
+    static constexpr int LDY = ld4mod8(D::NRHS);    // YT: NRHS x NU  (Y^T, Y = Luu^-1 [Qux Qu BtFt])
     static constexpr int o_rec = 0;                                 // REC (TMA destination, 16B aligned), single buffer:
                                                                     // the next record is fetched right after its last reader (S3)
     static constexpr int o_Z = o_rec + D::REC;                      // FREC
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         if (nck > 0) bulk_g2s(Dbuf + bufi * DSTRIDE, D_b + p.doff[kk], dbytes, &bar[bufi]);
     };
     if (tid == 0 && LEN > 0) issue_stage(N1 - 1, 0);
-    // The record holds ET(j,k') = [E c](k',j) ((S+1) x NX): both big products read it in place.
+    // The record holds [E c] (NX x (S+1), leading dimension NX): both big products read it in place.
 
     int bad = 0;
 #pragma unroll 1
@@ -265,7 +267,6 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         const int k = N1 - 1 - it;
         const int buf = 0;
         const double* R = rec;
-        const double* ET = rec;                  // [E c]^T of this stage, valid until the refill after S3
         mbar_wait(&bar[0], it & 1);              // requested after S3 of the previous stage (or in the prologue)
         const int nck = ncmax > 0 ? p.ncs[k] : 0;
         if (nck > 0) {  // g = z - y/rho ; keep rho and rho.*g   (lqr_solver_parallel.hpp:134-137, lqr_kernel.hpp:110)
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
             constexpr int MM = 2 * NX;
             constexpr Tile tl = pick_tile(MM, S + 1, T);
             auto la = [&](int i, int kk) { return PF[i + kk * L::LDPF]; };
-            auto lb = [&](int kk, int j) { return ET[j + kk * L::LDT]; };
+            auto lb = [&](int kk, int j) { return R[kk + j * NX]; };             // [E c](kk, j)
             auto epi = [&](int i, int j, double v) {
                 if (j == S && i < NX) { pc_s[i] = v; v += pn[i]; }
                 PFE[i + j * L::LDPE] = v;
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         // S3: [M | g] = [H + sigma I | h - sigma w_prev] + E^T * PE        (update_problem_data fused in)
         {
             constexpr Tile tl = pick_tile(S, S + 1, T);
-            auto la = [&](int i, int kk) { return ET[i + kk * L::LDT]; };
+            auto la = [&](int i, int kk) { return R[kk + i * NX]; };             // E^T(i, kk)
             auto lb = [&](int kk, int j) { return PFE[kk + j * L::LDPE]; };
             auto epi = [&](int i, int j, double v) {
                 double base;
@@ -637,7 +638,7 @@ __global__ void __launch_bounds__(T) seg_affine_kernel(SegParams p) {
                     for (int q = 0; q < nck; ++q) acc = fma(-Dk[q + i * nck], rg_s[q], acc);
                 }
 #pragma unroll 4
-                for (int q = 0; q < NX; ++q) acc = fma(R[i + q * D::LDE], tv[q], acc);
+                for (int q = 0; q < NX; ++q) acc = fma(R[q + i * NX], tv[q], acc);
                 gv[i] = acc;
             }
         }
@@ -762,11 +763,11 @@ __global__ void __launch_bounds__(T) seg_forward_kernel(SegParams p) {
         for (int r = 0; r < (NX + T - 1) / T; ++r) {
             const int i = tid + r * T;
             if (i < NX) {
-                double acc = R[S + i * D::LDE];
+                double acc = R[D::REC_C + i];
 #pragma unroll
-                for (int j = 0; j < NU; ++j) acc = fma(R[j + i * D::LDE], us[j], acc);
+                for (int j = 0; j < NU; ++j) acc = fma(R[i + j * NX], us[j], acc);
 #pragma unroll 4
-                for (int j = 0; j < NX; ++j) acc = fma(R[(NU + j) + i * D::LDE], xs[j], acc);
+                for (int j = 0; j < NX; ++j) acc = fma(R[i + (NU + j) * NX], xs[j], acc);
                 xn[r] = acc;
             }
         }

@@ -135,9 +135,9 @@ __global__ void __launch_bounds__(T) seg_backward_km_kernel(SegParams p) {
         bulk_g2s(rec, model_b + (size_t)kk * D::REC, D::REC * 8, &bar[0]);
     };
     if (tid == 0 && LEN > 0) issue_stage(N1 - 1);
-    auto transpose_stage = [&]() {   // record: ET(j, k') = [E c](k', j) with leading dimension S+1 -> padded to SP
+    auto transpose_stage = [&]() {   // ET(j, k') = [E c](k', j)
         for (int e = tid; e < NX * (S + 1); e += T) {
-            const int j = e % (S + 1), kk = e / (S + 1);
+            const int kk = e % NX, j = e / NX;
             ET[j + kk * SP] = rec[e];
         }
     };
