@@ -113,7 +113,8 @@ struct BwdSmem {
     // (lane -> row r, columns 2 (lane%4) + {0,1}: r + 2 (lane%4) ld); measured with scripts/micro/lds_bench.cu rules
     static constexpr int LDPF = ld4mod8(2 * NX);    // PF: [P+; F+] stacked, (2NX) x NX
     static constexpr int LDPE = ld4mod8(2 * NX);    // PFE: [P+;F+] [E c], (2NX) x (S+1)
-    static constexpr int LDM = ld4mod8(S);          // Ma: [M | g], S x (S+1)
+    static constexpr int LDM = S + ((2 - S % 4) + 4) % 4;   // Ma: [M | g], S x (S+1): only ever an accumulator tile
+                                                            // (r + 2 (lane%4) ld): 2 (mod 4) is conflict-free per half-warp
     static constexpr int LDY = ld4mod8(D::NRHS);    // YT: NRHS x NU  (Y^T, Y = Luu^-1 [Qux Qu BtFt])
     static constexpr int o_rec = 0;                                 // REC (TMA destination, 16B aligned), single buffer:
                                                                     // the next record is fetched right after its last reader (S3)
@@ -262,6 +263,19 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
     // The record holds [E c] (NX x (S+1), leading dimension NX): both big products read it in place.
 
     int bad = 0;
+    // w_prev of the stage is fetched one stage ahead into registers: a load consumed right away would stall the group
+    // for an L2 round trip at the top of every stage
+    constexpr int NW = (S + T - 1) / T;
+    double wreg[NW];
+    auto fetch_w = [&](int kk) {
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            const int i = tid + q * T;
+            wreg[q] = (ws_b && i < S) ? ws_b[(size_t)kk * S + i] : 0.0;
+        }
+    };
+    if (LEN > 0) fetch_w(N1 - 1);
+    constexpr bool Z_BULK = (D::FREC % 2 == 0) && ((NU * D::NRHS) % 2 == 0) && ((NU * (NX + 1)) % 2 == 0);
 #pragma unroll 1
     for (int it = 0; it < LEN; ++it) {
         const int k = N1 - 1 - it;
@@ -285,10 +299,10 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 }
             }
         }
-        if (tid < S) wp[tid] = ws_b ? ws_b[(size_t)k * S + tid] : 0.0;
-        if constexpr (S > T) {
-            for (int i = tid + T; i < S; i += T) wp[i] = ws_b ? ws_b[(size_t)k * S + i] : 0.0;
-        }
+#pragma unroll
+        for (int q = 0; q < NW; ++q)
+            if (tid + q * T < S) wp[tid + q * T] = wreg[q];
+        if (it + 1 < LEN) fetch_w(k - 1);
         // S2: PFE = [P+; F+] * [E c]  (+ p+ on the last column of the P rows)
         {
             constexpr int MM = 2 * NX;
@@ -415,7 +429,14 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 }
             }
         }
+        if constexpr (Z_BULK) fence_proxy_async();   // Z is picked up by a bulk copy below
         group_sync<T>();
+        if constexpr (Z_BULK) {   // factor record -> global, one TMA store; it drains while S6 runs
+            if (tid == 0) {
+                bulk_s2g(fac_b + (size_t)k * D::FREC, Z, (pdp ? NU * D::NRHS : NU * (NX + 1)) * 8);
+                bulk_commit();
+            }
+        }
 
         // S6: P = Qxx - Yx^T Yx, p = Qx - Yx^T yu  |  C += Yg^T Yg  |  [F f] = F+[A c] + (F+B)[K d] + [0 f+]
         {
@@ -445,10 +466,12 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 };
                 gmm<NX, NX + 1, NU, tl.tm, tl.tn, T>(tid, lfa, lfb, epf);
             }
-            // factor record -> global (coalesced)
-            double* fk = fac_b + (size_t)k * D::FREC;
-            const int nz = pdp ? NU * D::NRHS : NU * (NX + 1);
-            for (int e = tid; e < nz; e += T) fk[e] = Z[e];
+            if constexpr (!Z_BULK) {   // factor record -> global (coalesced)
+                double* fk = fac_b + (size_t)k * D::FREC;
+                const int nz = pdp ? NU * D::NRHS : NU * (NX + 1);
+                for (int e = tid; e < nz; e += T) fk[e] = Z[e];
+            } else if (tid == 0)
+                bulk_wait_read<0>();   // Z may be overwritten by the next stage
             if (aff_b) {  // what backward_without_factorization needs: Quu^-1, P+c, F+c, F+B
                 double* ak = aff_b + (size_t)k * D::AREC;
                 for (int e = tid; e < NU * NU; e += T) ak[D::AR_QI + e] = Qi[e];
