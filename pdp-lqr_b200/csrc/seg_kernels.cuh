@@ -33,6 +33,11 @@ struct SegDims {
     static constexpr int REC_C = NX * S;
     static constexpr int REC_H = REC_C + NX;
     static constexpr int REC_h = REC_H + S * S;
+    // H is only ever read as the initial value of a DMMA accumulator tile (lane -> row r, columns 2 (lane%4) + {0,1}).
+    // With a leading dimension S = 0 (mod 16) the 16 lanes of a half-warp would hit 4 banks 4 times each, so for those
+    // S the rows of column j are stored rotated by 4 (j / 2): element (i, j) at ((i + 4 (j/2)) mod S) + j S.
+    static constexpr bool H_ROT = (S % 16 == 0);
+    PDPLQR_DEVINL static int h_off(int i, int j) { return H_ROT ? ((i + 4 * (j >> 1)) % S) + j * S : i + j * S; }
     static constexpr int REC = even_up(REC_h + S);
     static constexpr int REC_EC = even_up(NX * S + NX);  // prefix the rollout needs
     // factor record (one stage): Z = [K (NU x NX) | d (NU) | Gt (NU x NX)], column-major
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
             auto lb = [&](int kk, int j) { return PFE[kk + j * L::LDPE]; };
             auto epi = [&](int i, int j, double v) {
                 double base;
-                if (j < S) base = R[D::REC_H + i + j * S] + ((i == j) ? sigma : 0.0);
+                if (j < S) base = R[D::REC_H + D::h_off(i, j)] + ((i == j) ? sigma : 0.0);
                 else base = R[D::REC_h + i] - sigma * wp[i];
                 if (sel && nck > 0) {   // selection-matrix fold-in (dg, dh were scatter-added at the top of the stage)
                     if (i == j) base += dg_s[i];

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(T) seg_backward_km_kernel(SegParams p) {
                     for (int r = 0; r < TS; ++r)
 #pragma unroll
                         for (int c = 0; c < TS; ++c)
-                            acc[r][c] = rec[D::REC_H + (i0 + r) + (j0 + c) * S] + ((i0 + r == j0 + c) ? sigma : 0.0);
+                            acc[r][c] = rec[D::REC_H + D::h_off(i0 + r, j0 + c)] + ((i0 + r == j0 + c) ? sigma : 0.0);
                     km_tile<TS, NX>(ET + i0, SP, PEt + j0, SP, acc);
 #pragma unroll
                     for (int c = 0; c < TS; ++c)
