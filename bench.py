@@ -67,8 +67,8 @@ def make_workload(name: str, rank: int):
         return prob, dict(num_segments=0), "C2: quadrotor LQR nx=12 nu=4 N=1024, single problem, segment-parallel (configs[1])"
     if name == "c5":
         prob = P.problems.quadrotor_ltv(1 << 20)
-        return prob, dict(num_segments=wave_aligned((1 << 20) // 64), load_balancing=2), \
-            "C5: quadrotor LQR nx=12 nu=4 N=2^20, single problem, ~64-stage segments in whole waves of 148x13 CTAs (configs[4])"
+        return prob, dict(num_segments=wave_aligned((1 << 20) // 180), load_balancing=2), \
+            "C5: quadrotor LQR nx=12 nu=4 N=2^20, single problem, ~180-stage segments in 3 whole waves of 148x13 CTAs (configs[4])"
     if name == "c5small":
         prob = P.problems.quadrotor_ltv(1 << 16)
         return prob, dict(num_segments=(1 << 16) // 64, load_balancing=False), \
@@ -80,7 +80,7 @@ def make_workload(name: str, rank: int):
 
 
 def wave_aligned(num_segments: int, wave: int = 148 * 13) -> int:
-    """Round a segment count down to whole waves of the stage kernel's resident CTAs (148 SMs x 13 CTAs of 64 threads at
+    """Round a segment count down to whole waves of the stage kernel's resident CTAs (148 SMs x 13 one-warp CTAs at
     nx12/nu4): a trailing partial wave costs a full wave of time (2048 segments = 1.06 waves ran as 2)."""
     if num_segments <= wave:
         return max(1, num_segments)

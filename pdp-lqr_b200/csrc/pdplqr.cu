@@ -12,7 +12,6 @@
 #include "admm_kernels.cuh"
 #include "batch_kernels.cuh"
 #include "seg_kernels.cuh"
-#include "seg_km_kernel.cuh"
 #include "tree_kernels.cuh"
 #include "tree_lat_kernels.cuh"
 
@@ -44,7 +43,6 @@ struct pdplqr_solver {
     int seg_mode = 0, seg_len0 = 0;   // closed-form partition handed to the kernels
     int lat_threads = 128;     // 0 disables the 128-thread latency mode of the segment backward kernel
     int seg_t = 0;             // PDPLQR_SEG_T: threads per (problem, segment) in throughput mode (0 = default 32)
-    int use_km = 1;            // specialised k-major stage kernel for nx, nu multiples of 4 (PDPLQR_USE_KM=0 disables)
     int tree_tt = 32;          // threads per tree combine (128 = experimental wide combine; measured slower)
     int tree_lat = 1;          // latency-mode tree kernels when a level has few groups (PDPLQR_TREE_LAT=0 disables)
     int tree_lat_max = 296;    // ... "few" = at most this many CTAs (PDPLQR_TREE_LAT_MAX)
@@ -223,29 +221,6 @@ int backward_impl(Solver& h) {
     // latency mode: with fewer (problem, segment) groups than SMs a whole 128-thread CTA works on each group
     constexpr int TL = (T < 128) ? 128 : T;
     const bool latency_mode = (T < 128) && h.lat_threads > 0 && (long long)h.batch * h.S <= 2 * 148;
-    if constexpr (KmSmem<NX, NU>::ELIGIBLE && T == 32) {
-        // quadrotor class (nx, nu multiples of 4), unconstrained, no affine cache: k-major tile kernel
-        // (measured: 3-10 % faster than the generic kernel in the 128-thread latency mode, slower in the one-warp
-        //  throughput mode where padded 4x4 tiles add as many FMAs as the overhead they remove -- DESIGN.md section 4;
-        //  use_km = 2 forces it for both)
-        if (h.use_km && h.ncmax == 0 && !h.keep_affine && (latency_mode || h.use_km == 2)) {
-            constexpr size_t kb = KmSmem<NX, NU>::BYTES;
-            if (latency_mode) {
-                auto kern = seg_backward_km_kernel<NX, NU, 128>;
-                int rc = set_smem(h, kern, kb);
-                if (rc) return rc;
-                kern<<<h.batch * h.S, 128, kb, h.stream>>>(p);
-            } else {
-                auto kern = seg_backward_km_kernel<NX, NU, 32>;
-                int rc = set_smem(h, kern, kb);
-                if (rc) return rc;
-                kern<<<h.batch * h.S, 32, kb, h.stream>>>(p);
-            }
-            h.launches++;
-            CU_TRY(&h, cudaGetLastError());
-            return PDPLQR_OK;
-        }
-    }
     const size_t bytes = BwdSmem<NX, NU>::bytes(h.ncmax, h.sel_mode);
     if constexpr (T == 32) {
         // One warp per (problem, segment) by default: with the products on register-blocked DMMA a single warp owns every
@@ -805,7 +780,6 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (const char* e = getenv("PDPLQR_TREE_LAT_MAX")) h->tree_lat_max = atoi(e);
     if (const char* e = getenv("PDPLQR_TREE_LAT_WIDTH")) h->lat_width = atoi(e);
     if (const char* e = getenv("PDPLQR_TREE_LAT_TT")) h->lat_tt_cap = atoi(e);
-    if (const char* e = getenv("PDPLQR_USE_KM")) h->use_km = atoi(e);
     if (const char* e = getenv("PDPLQR_SEG_T")) h->seg_t = atoi(e);
     if (const char* e = getenv("PDPLQR_SPARSE_D")) h->allow_sel = atoi(e);
     if (const char* e = getenv("PDPLQR_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(1, std::min(64, atoi(e)));

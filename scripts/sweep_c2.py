@@ -16,7 +16,7 @@ x0_dev = torch.from_numpy(prob.x0).to(dev)
 out_dev = torch.empty_like(ws_dev)
 stream = torch.cuda.current_stream()
 for S in [int(v) for v in os.environ.get("SWEEP_S", "16,32,64,128,256,512").split(",")]:
-    sol = P.LQRCudaSolver.from_problem(prob, num_segments=S, load_balancing=False)
+    sol = P.LQRCudaSolver.from_problem(prob, num_segments=S, load_balancing=int(os.environ.get("SWEEP_LB", "0")))
     sol.set_stream(stream.cuda_stream)
 
     def step():
