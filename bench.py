@@ -392,7 +392,10 @@ def main():
     if horizon_sharded:
         # one long problem, contiguous time slices per rank, ONE all_gather of a 3,648-byte summary per solve
         from pdplqr_b200.sharding import HorizonShardedSolver
-        hs = HorizonShardedSolver(prob, rank, world, num_segments=wave_aligned(kw["num_segments"] // world), device=local_rank)
+        # per rank: the single-GPU segment length, but never less than one full wave of (problem, segment) CTAs -- with a
+        # partial wave every SM runs fewer warps than it can hold and the sweep is a pure latency chain
+        hs = HorizonShardedSolver(prob, rank, world, num_segments=wave_aligned(max(kw["num_segments"] // world, 148 * 13)),
+                                  device=local_rank)
         hs.set_stream(stream.cuda_stream)
         sol = hs.sol
         full_N = prob.N
