@@ -43,7 +43,6 @@ struct pdplqr_solver {
     int seg_mode = 0, seg_len0 = 0;   // closed-form partition handed to the kernels
     int lat_threads = 128;     // 0 disables the 128-thread latency mode of the segment backward kernel
     int seg_t = 0;             // PDPLQR_SEG_T: threads per (problem, segment) in throughput mode (0 = default 32)
-    int tree_tt = 32;          // threads per tree combine (128 = experimental wide combine; measured slower)
     int tree_lat = 1;          // latency-mode tree kernels when a level has few groups (PDPLQR_TREE_LAT=0 disables)
     int tree_lat_max = 296;    // ... "few" = at most this many CTAs (PDPLQR_TREE_LAT_MAX)
     int lat_width = 0, lat_tt_cap = 0;   // PDPLQR_TREE_LAT_WIDTH / PDPLQR_TREE_LAT_TT: tuning overrides (0 = default)
@@ -283,17 +282,10 @@ int forward_impl(Solver& h, const double* d_x0, double* d_ws_out) {
 template <int NX>
 int tree_up_impl(Solver& h, const TreeParams& p) {
     constexpr size_t bytes = TreeSmem<NX>::BYTES;
-    if (h.tree_tt == 128 && (long long)p.batch * p.groups <= 2 * 148) {   // experimental: 128 threads per combine
-        auto kern = tree_up_kernel<NX, 128>;
-        int rc = set_smem(h, kern, bytes);
-        if (rc) return rc;
-        kern<<<p.batch * p.groups, 128, bytes, h.stream>>>(p);
-    } else {
-        auto kern = tree_up_kernel<NX, 32>;
-        int rc = set_smem(h, kern, bytes);
-        if (rc) return rc;
-        kern<<<p.batch * p.groups, 32, bytes, h.stream>>>(p);
-    }
+    auto kern = tree_up_kernel<NX, 32>;
+    int rc = set_smem(h, kern, bytes);
+    if (rc) return rc;
+    kern<<<p.batch * p.groups, 32, bytes, h.stream>>>(p);
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -334,17 +326,6 @@ template <int NX>
 int tree_top_up_impl(Solver& h, const TreeTopParams& p) {
     constexpr size_t bytes = TreeTopSmem<NX>::BYTES;
     constexpr int WARPS = TreeTopSmem<NX>::WARPS;
-    if constexpr (WARPS % 4 == 0) {
-        if (h.tree_tt == 128 && p.batch <= 2 * 148 && !p.affine_only) {   // experimental: 4 warps per combine
-            auto kern = tree_top_up_kernel<NX, 128>;
-            int rc = set_smem(h, kern, bytes);
-            if (rc) return rc;
-            kern<<<p.batch, WARPS * 32, bytes, h.stream>>>(p);
-            h.launches++;
-            CU_TRY(&h, cudaGetLastError());
-            return PDPLQR_OK;
-        }
-    }
     auto kern = tree_top_up_kernel<NX, 32>;
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
@@ -775,7 +756,6 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (const char* e = getenv("PDPLQR_BWD_VARIANT")) h->bwd_variant = atoi(e);
     if (const char* e = getenv("PDPLQR_FWD_VARIANT")) h->fwd_variant = atoi(e);
     if (const char* e = getenv("PDPLQR_LAT_THREADS")) h->lat_threads = atoi(e);
-    if (const char* e = getenv("PDPLQR_TREE_TT")) h->tree_tt = atoi(e);
     if (const char* e = getenv("PDPLQR_TREE_LAT")) h->tree_lat = atoi(e);
     if (const char* e = getenv("PDPLQR_TREE_LAT_MAX")) h->tree_lat_max = atoi(e);
     if (const char* e = getenv("PDPLQR_TREE_LAT_WIDTH")) h->lat_width = atoi(e);

@@ -120,47 +120,6 @@ PDPLQR_DEVINL void sub_sync(int bar_id) {
     else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TT) : "memory");
 }
 
-// Gauss-Jordan with partial pivoting for a TT-thread group (TT > 32): every thread finds the pivot redundantly, then
-// the (NX x remaining-columns) block is updated element-parallel: read phase, barrier, write phase, barrier.
-template <int NX, int NCOL, int LDA, int TT>
-PDPLQR_DEVINL void group_gauss_jordan(int tid, int bar_id, double* Aug) {
-    constexpr int MAXE = (NX * (NCOL - 1) + TT - 1) / TT;
-#pragma unroll 1
-    for (int k = 0; k < NX; ++k) {
-        double best = -1.0, pval = 1.0, akk = 0.0;
-        int piv = k;
-#pragma unroll
-        for (int i = 0; i < NX; ++i) {
-            const double c = Aug[i + k * LDA];
-            const double v = fabs(c);
-            if (i == k) akk = c;
-            if (i >= k && v > best) { best = v; piv = i; pval = c; }
-        }
-        const double pinv = 1.0 / pval;
-        const int nelem = NX * (NCOL - 1 - k);
-        double val[MAXE];
-#pragma unroll
-        for (int q = 0; q < MAXE; ++q) {
-            const int e = tid + q * TT;
-            if (e < nelem) {
-                const int i = e % NX, j = k + 1 + e / NX;
-                const double* cj = Aug + j * LDA;
-                const double t = cj[piv] * pinv;              // new row k
-                double mult = Aug[i + k * LDA], aij = cj[i];
-                if (i == piv) { mult = akk; aij = cj[k]; }    // row piv receives the old row k
-                val[q] = (i == k) ? t : fma(-mult, t, aij);
-            }
-        }
-        sub_sync<TT>(bar_id);
-#pragma unroll
-        for (int q = 0; q < MAXE; ++q) {
-            const int e = tid + q * TT;
-            if (e < nelem) Aug[(e % NX) + (k + 1 + e / NX) * LDA] = val[q];
-        }
-        sub_sync<TT>(bar_id);
-    }
-}
-
 template <int NX>
 struct CombSmem {   // per-warp workspace of one combine
     using D = TreeDims<NX>;
@@ -204,8 +163,8 @@ PDPLQR_DEVINL void group_combine(int lane, int bar_id, double* ws, double* out, 
         for (int r = lane; r < NX; r += TT) Aug[r + 3 * NX * LDA] = fa[r];
     }
     sub_sync<TT>(bar_id);
-    if constexpr (TT == 32) warp_gauss_jordan<NX, D::NCOL, LDA>(lane, Aug);
-    else group_gauss_jordan<NX, D::NCOL, LDA, TT>(lane, bar_id, Aug);
+    static_assert(TT == 32, "one warp per combine (the wide combines live in tree_lat_kernels.cuh)");
+    warp_gauss_jordan<NX, D::NCOL, LDA>(lane, Aug);
     const double* XF = Aug + NX * LDA;
     const double* XC = Aug + 2 * NX * LDA;
     const double* wf = Aug + 3 * NX * LDA;
