@@ -504,3 +504,34 @@ def test_equal_split_partition_mode(oracle):
     assert list(ln) == [21, 21, 21] + [20] * 7 and int(st[-1] + ln[-1]) == 203
     ws = sol.solve(p.zeros_ws(), p.x0, p.zeros_ws())
     assert rel_err(ws[0], oracle.OracleSolver(p).solve()) < TOL
+
+
+@pytest.mark.parametrize("seg_t", ["64", "128"])
+@pytest.mark.parametrize("nx,nu,nc", [(12, 4, 0), (12, 4, 8), (6, 3, 0)])
+def test_stage_kernel_group_sizes(oracle, nx, nu, nc, seg_t, monkeypatch):
+    """PDPLQR_SEG_T: two and four warps per (problem, segment) instead of the default single warp (throughput mode:
+    more groups than the latency-mode threshold), with and without the constraint fold-in."""
+    monkeypatch.setenv("PDPLQR_SEG_T", seg_t)
+    p = P.problems.random_lq(nx, nu, 24, batch=110, seed=5 + nc, nc=nc)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=3)
+    assert sol.num_segments * p.batch > 2 * 148
+    rng = np.random.default_rng(11)
+    wprev = rng.standard_normal((p.batch, p.ws_len))
+    picks = (0, 57, 109)
+    if nc:
+        _, ys, zs, rho, inv_rho = _admm_vectors(p, 4)
+        sol.update_problem_data(wprev, ys, zs, inv_rho, sigma=0.01)
+        sol.backward(rho)
+    else:
+        sol.update_problem_data(wprev, sigma=0.01)
+        sol.backward()
+    ws = sol.forward(p.x0, np.zeros_like(wprev))
+    for b in picks:
+        o = oracle.OracleSolver(p, b=b)
+        if nc:
+            o.update_problem_data(wprev[b], ys[b], zs[b], inv_rho[b], 0.01)
+            o.backward(rho[b])
+            ref = o.forward(p.x0[b], np.zeros(p.ws_len))
+        else:
+            ref = o.solve(ws_in=wprev[b], sigma=0.01)
+        assert rel_err(ws[b], ref) < TOL
