@@ -114,6 +114,37 @@ public:
         forward(x0, ws);
     }
 
+    // Additions for the conic outer iteration the reference only leaves hooks for (lqr_solver_parallel.hpp:33-37,
+    // lqr_model.hpp:21-24).  Every stage's constraint rows become one box cone [e_lb, e_ub] of the node.
+    void set_box_cones() {
+        std::vector<int> stage, row0, dim, type;
+        std::vector<scalar> lb((size_t)coff_[N_ + 1]), ub((size_t)coff_[N_ + 1]);
+        for (int k = 0; k <= N_; ++k) {
+            const Node& nd = model_.nodes[k];
+            if (nd.n_con == 0) continue;
+            stage.push_back(k); row0.push_back(0); dim.push_back(nd.n_con); type.push_back(PDPLQR_CONE_BOX);
+            for (int r = 0; r < nd.n_con; ++r) {
+                lb[(size_t)coff_[k] + r] = clamp_inf(nd.e_lb(r));
+                ub[(size_t)coff_[k] + r] = clamp_inf(nd.e_ub(r));
+            }
+        }
+        check(pdplqr_admm_set_cones(h_, (int)stage.size(), stage.data(), row0.data(), dim.data(), type.data(), lb.data(),
+                                    ub.data()));
+    }
+    // ADMM in OSQP form on the flat iterates (ws: N (nx+nu) + nx; zs, ys, rho: sum of ncs); returns the iteration count,
+    // residuals[0] = primal, [1] = dual.
+    int admm_solve(const VectorXs& x0, std::vector<scalar>& ws, std::vector<scalar>& zs, std::vector<scalar>& ys,
+                   const std::vector<scalar>& rho, scalar sigma, scalar alpha, int max_iter, scalar eps_abs,
+                   scalar eps_rel, int check_every, scalar residuals[2]) {
+        int iters = 0;
+        check(pdplqr_admm_solve(h_, x0.data(), ws.data(), zs.data(), ys.data(), rho.data(), sigma, alpha, max_iter,
+                                eps_abs, eps_rel, check_every, &iters, residuals));
+        return iters;
+    }
+    size_t ws_len() const { return (size_t)N_ * (nx_ + nu_) + nx_; }
+    size_t nc_total() const { return (size_t)coff_[N_ + 1]; }
+    const std::vector<long long>& constraint_offsets() const { return coff_; }
+
     // Accessors (additions).  K_k (nu x nx, column-major), d_k (nu): lqr_kernel_parallel.hpp:105-108.
     int num_segments() const { return pdplqr_num_segments(h_); }
     void gains(std::vector<scalar>& K, std::vector<scalar>& d) {
@@ -133,6 +164,7 @@ private:
     static void copy_n(const scalar* src, size_t n, scalar* dst) {
         for (size_t i = 0; i < n; ++i) dst[i] = src[i];
     }
+    static scalar clamp_inf(scalar v) { return v > 1e20 ? 1e20 : (v < -1e20 ? -1e20 : v); }
     void check(int rc) {
         if (rc != PDPLQR_OK) throw std::runtime_error(std::string("pdplqr: ") + pdplqr_last_error(h_));
     }
