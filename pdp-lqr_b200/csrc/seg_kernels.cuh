@@ -113,13 +113,15 @@ template <int NX, int NU>
 struct BwdSmem {
     using D = SegDims<NX, NU>;
     static constexpr int S = D::S;
-    // Leading dimensions = 4 (mod 8): the DMMA fragment accesses of a column-major array are then free of bank
-    // conflicts both as an operand (lane -> row r = lane/4, k = lane%4: r + k ld) and as an accumulator
-    // (lane -> row r, columns 2 (lane%4) + {0,1}: r + 2 (lane%4) ld); measured with scripts/micro/lds_bench.cu rules
+    // Leading dimensions.  Bank conflicts are counted per half-warp (16 lanes; scripts/micro/lds_bench.cu).  A DMMA
+    // OPERAND fragment of a column-major array (lane -> row r = lane/4, k = lane%4: address r + k ld, or k + r ld
+    // for the other orientation) is conflict-free for ld = 4 or 12 (mod 16) -- hence 4 (mod 8) for PF, PFE, YT.  An
+    // ACCUMULATOR fragment (lane -> row r, columns 2 (lane%4) + {0,1}: r + 2 (lane%4) ld) wants ld = 2 (mod 4): used
+    // for Ma, which is never an operand; the accumulator stores into PF / PFE keep a 2-way conflict (no plain ld serves
+    // both patterns; shifting every column pair by 4 elements does, but its index arithmetic cost what it saved).
     static constexpr int LDPF = ld4mod8(2 * NX);    // PF: [P+; F+] stacked, (2NX) x NX
     static constexpr int LDPE = ld4mod8(2 * NX);    // PFE: [P+;F+] [E c], (2NX) x (S+1)
-    static constexpr int LDM = S + ((2 - S % 4) + 4) % 4;   // Ma: [M | g], S x (S+1): only ever an accumulator tile
-                                                            // (r + 2 (lane%4) ld): 2 (mod 4) is conflict-free per half-warp
+    static constexpr int LDM = S + ((2 - S % 4) + 4) % 4;   // Ma: [M | g], S x (S+1)
     static constexpr int LDY = ld4mod8(D::NRHS);    // YT: NRHS x NU  (Y^T, Y = Luu^-1 [Qux Qu BtFt])
     static constexpr int o_rec = 0;                                 // REC (TMA destination, 16B aligned), single buffer:
                                                                     // the next record is fetched right after its last reader (S3)

@@ -19,9 +19,10 @@
 // group).  The group total becomes a node of the next level.
 // Down-sweep: given the group's entry state x and exit costate lam_e, left-to-right
 //        pt = p_b + F_b^T lam_e ;  x' = X_F x + w_f - X_C pt ;  lam' = P_b x' + pt .
-// Lower levels (many nodes) run one kernel launch per level, one warp per group; the upper levels (<= 32 nodes)
-// run inside ONE launch of a 16-warp CTA per problem (binary tree, __syncthreads between levels), because for a
-// single long-horizon problem the interface solve is pure latency.
+// These are the THROUGHPUT kernels (many problems: one warp per combine): lower levels (many nodes) run one kernel
+// launch per level, one warp per group of 4; the upper levels (<= 32 nodes) run inside ONE launch of a 16-warp CTA per
+// problem (binary tree, __syncthreads between levels).  With few problems the interface solve is pure latency and
+// tree_lat_kernels.cuh takes over (same records, wide element-parallel combines); the plan is made in pdplqr_create.
 #pragma once
 #include "common.cuh"
 #include "seg_kernels.cuh"
