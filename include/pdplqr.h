@@ -153,6 +153,17 @@ int pdplqr_get_partition(pdplqr_handle_t h, int* starts, int* lens);
 int pdplqr_get_gains(pdplqr_handle_t h, double* K, double* d, double* Gt);
 int pdplqr_get_interface(pdplqr_handle_t h, double* xhat, double* uhat);
 int pdplqr_get_summaries(pdplqr_handle_t h, double* P, double* p, double* F, double* f, double* C);
+/* Costates of the last solve: lam [batch][N][nx], lam[b][k-1] = lambda_k, the multiplier of
+ * x_k = A x_{k-1} + B u_{k-1} + c_{k-1} (k = 1..N) with L = cost + sum_k lambda_{k+1}^T (E_k w_k + c_k - x_{k+1}), for
+ * the ADMM-augmented data of the last update_problem_data / backward*.  This is the step the reference has written
+ * but commented out (lqr_kernel.hpp:205-211: lambda+ = Lxx+ (Lxx+^T x+) + p+; lqr_kernel_parallel.hpp:207-216 adds
+ * F+^T uhat); here it is recovered segment-parallel from the stage stationarity conditions, starting at the interface
+ * costates.  `ws` is the trajectory returned by the last forward; call after forward, before
+ * the next update_problem_data with different vectors (the device variant reads the ws / ys / zs / rho arrays of the
+ * last update through the pointers it was given).  Segment-path handles only: PDPLQR_ERR_UNSUPPORTED on the
+ * thread-per-problem path (batch of tiny systems with num_segments = 1). */
+int pdplqr_get_costates(pdplqr_handle_t h, const double* ws, double* lam);
+int pdplqr_get_costates_device(pdplqr_handle_t h, const double* ws, double* lam);
 /* Number of problems whose last factorising backward met a non-positive pivot; per-problem codes (0 = ok,
  * else 1 + stage index) are written to `status` ([batch], may be NULL). */
 int pdplqr_last_status(pdplqr_handle_t h, int* status);

@@ -157,6 +157,13 @@ public:
         uhat.resize((size_t)num_segments() * nx_);
         check(pdplqr_get_interface(h_, xhat.data(), uhat.data()));
     }
+    // Costates lambda_1 .. lambda_N of the last solve (lam[(k-1) nx + i]); the reference has this step commented out
+    // (lqr_kernel.hpp:205-211, lqr_kernel_parallel.hpp:207-216).  `ws` = what forward returned.
+    void costates(const std::vector<VectorXs>& ws, std::vector<scalar>& lam) {
+        flatten_ws(ws, out_flat_);
+        lam.resize((size_t)N_ * nx_);
+        check(pdplqr_get_costates(h_, out_flat_.data(), lam.data()));
+    }
     bool not_positive_definite() { return pdplqr_last_status(h_, nullptr) > 0; }
     pdplqr_handle_t handle() { return h_; }
 

@@ -48,6 +48,8 @@ SIGNATURES = {
     "pdplqr_get_gains": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
     "pdplqr_get_interface": (C.c_int, [C.c_void_p, _dp, _dp]),
     "pdplqr_get_summaries": (C.c_int, [C.c_void_p] + [_dp] * 5),
+    "pdplqr_get_costates": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "pdplqr_get_costates_device": (C.c_int, [C.c_void_p, _dp, _dp]),
     "pdplqr_last_status": (C.c_int, [C.c_void_p, _ip]),
     "pdplqr_last_error": (C.c_char_p, [C.c_void_p]),
     "pdplqr_launch_count": (C.c_longlong, [C.c_void_p]),

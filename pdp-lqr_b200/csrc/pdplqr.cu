@@ -14,6 +14,7 @@
 #include "seg_kernels.cuh"
 #include "tree_kernels.cuh"
 #include "tree_lat_kernels.cuh"
+#include "costate_kernels.cuh"
 
 using namespace pdplqr;
 
@@ -121,6 +122,7 @@ struct Ops {
     int (*tree_top_down)(Solver&, const TreeTopParams&);
     int (*tree_sub_up)(Solver&, const TreeTopParams&);
     int (*tree_sub_down)(Solver&, const TreeTopParams&);
+    int (*costates)(Solver&, const double* traj, double* lam);
 };
 
 int fail(Solver* h, int code, const std::string& msg) {
@@ -371,6 +373,23 @@ int tree_sub_down_impl(Solver& h, const TreeTopParams& p) {
         return fail(&h, PDPLQR_ERR_UNSUPPORTED, "latency-mode tree kernels are not built for this nx");
 }
 
+// costates of the last solve (costate_kernels.cuh); segment-path handles only
+template <int NX, int NU>
+int costates_impl(Solver& h, const double* traj, double* lam) {
+    CostateParams q{};
+    q.sp = seg_params(h);
+    q.traj = traj; q.lam = lam;
+    q.lam_root = (h.interior && h.have_root) ? h.d_root_lam : nullptr;
+    const size_t bytes = (size_t)(NX + (NX + NU) + std::max(h.ncmax, 1)) * sizeof(double);
+    auto kern = seg_costate_kernel<NX, NU>;
+    int rc = set_smem(h, kern, bytes);
+    if (rc) return rc;
+    kern<<<h.batch * h.S, 32, bytes, h.stream>>>(q);
+    h.launches++;
+    CU_TRY(&h, cudaGetLastError());
+    return PDPLQR_OK;
+}
+
 template <int NX, int NU, int T>
 constexpr Ops make_ops() {
     return Ops{NX, NU, T, SegDims<NX, NU>::REC, SegDims<NX, NU>::FREC, SegDims<NX, NU>::SREC, TreeDims<NX>::DREC,
@@ -379,7 +398,7 @@ constexpr Ops make_ops() {
                BatchDims<NX, NU>::ENABLED,
                &backward_impl<NX, NU, T>, &forward_impl<NX, NU, T>, &tree_up_impl<NX>, &tree_down_impl<NX>,
                &affine_impl<NX, NU>, &tree_up_affine_impl<NX>, &tree_top_up_impl<NX>, &tree_top_down_impl<NX>,
-               &tree_sub_up_impl<NX>, &tree_sub_down_impl<NX>};
+               &tree_sub_up_impl<NX>, &tree_sub_down_impl<NX>, &costates_impl<NX, NU>};
 }
 
 // Instantiated (nx, nu) pairs.  The BASELINE.json configs use (12,4), (4,1) and (30,10); the rest cover the
@@ -1208,6 +1227,35 @@ int pdplqr_get_summaries(pdplqr_handle_t h, double* P, double* p, double* F, dou
         if (f) std::memcpy(f + i * nx, r + 3 * n2 + nx, 8 * nx);
     }
     return PDPLQR_OK;
+}
+int pdplqr_get_costates_device(pdplqr_handle_t h, const double* ws, double* lam) {
+    if (!h || !ws || !lam) return fail(h, PDPLQR_ERR_INVALID, "get_costates: bad arguments");
+    cudaSetDevice(h->device);
+    if (h->is_coupler) return fail(h, PDPLQR_ERR_INVALID, "get_costates: a coupler handle has no stages");
+    if (h->thread_path)
+        return fail(h, PDPLQR_ERR_UNSUPPORTED,
+                    "get_costates: not available on the thread-per-problem path (create the handle with num_segments > 1)");
+    if (!h->factorized || h->backward_done)
+        return fail(h, PDPLQR_ERR_ORDER, "get_costates needs a completed backward + forward (interface costates)");
+    if (h->interior && !h->have_root)
+        return fail(h, PDPLQR_ERR_ORDER, "get_costates on an interior horizon shard needs its root boundary");
+    return h->ops->costates(*h, ws, lam);
+}
+int pdplqr_get_costates(pdplqr_handle_t h, const double* ws, double* lam) {
+    if (!h || !ws || !lam) return fail(h, PDPLQR_ERR_INVALID, "get_costates: bad arguments");
+    cudaSetDevice(h->device);
+    const size_t wsl = (size_t)h->N * h->s + h->nx, B = h->batch;
+    double *d_ws = nullptr, *d_lam = nullptr;
+    CU_TRY(h, cudaMalloc(&d_ws, B * wsl * 8));
+    if (cudaMalloc(&d_lam, B * h->N * h->nx * 8) != cudaSuccess) { cudaFree(d_ws); return fail(h, PDPLQR_ERR_CUDA, "cudaMalloc"); }
+    int rc = PDPLQR_OK;
+    if (cudaMemcpyAsync(d_ws, ws, B * wsl * 8, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = PDPLQR_ERR_CUDA;
+    if (!rc) rc = pdplqr_get_costates_device(h, d_ws, d_lam);
+    if (!rc && cudaMemcpyAsync(lam, d_lam, B * h->N * h->nx * 8, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) rc = PDPLQR_ERR_CUDA;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess && !rc) rc = PDPLQR_ERR_CUDA;
+    cudaFree(d_ws); cudaFree(d_lam);
+    if (rc == PDPLQR_ERR_CUDA && h->err.empty()) h->err = "get_costates: CUDA error";
+    return rc;
 }
 int pdplqr_last_status(pdplqr_handle_t h, int* status) {
     if (!h) return PDPLQR_ERR_INVALID;

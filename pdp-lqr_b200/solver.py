@@ -207,6 +207,16 @@ class LQRCudaSolver:
         self._check(self._lib.pdplqr_get_summaries(self._h, _hp(P), _hp(p), _hp(F), _hp(f), _hp(Cm)))
         return P, p, F, f, Cm
 
+    def costates(self, ws):
+        """lambda_1 .. lambda_N [batch, N, nx] of the last solve (`ws` = the trajectory forward returned); the step the
+        reference leaves commented out (lqr_kernel.hpp:205-211).  Segment-path handles only."""
+        lam = np.zeros((self.batch, self.N, self.nx))
+        self._check(self._lib.pdplqr_get_costates(self._h, _hp(np.ascontiguousarray(ws, dtype=np.float64)), _hp(lam)))
+        return lam
+
+    def costates_device(self, ws, lam):
+        self._check(self._lib.pdplqr_get_costates_device(self._h, _dptr(ws), _dptr(lam)))
+
     def last_status(self):
         st = np.zeros(self.batch, np.int32)
         bad = self._lib.pdplqr_last_status(self._h, st.ctypes.data_as(C.POINTER(C.c_int)))

@@ -29,7 +29,8 @@ def augmented_cost(prob, b, ws_prev, sigma, ys=None, zs=None, rho=None, inv_rho=
     return Hs, hs
 
 
-def kkt_solve(prob, b=0, ws_prev=None, sigma=1e-6, ys=None, zs=None, rho=None, inv_rho=None, x0=None):
+def kkt_solve(prob, b=0, ws_prev=None, sigma=1e-6, ys=None, zs=None, rho=None, inv_rho=None, x0=None,
+              return_costates=False):
     nx, nu, N, s = prob.nx, prob.nu, prob.N, prob.s
     ws_prev = np.zeros(prob.ws_len) if ws_prev is None else ws_prev
     x0 = prob.x0[b] if x0 is None else x0
@@ -56,4 +57,6 @@ def kkt_solve(prob, b=0, ws_prev=None, sigma=1e-6, ys=None, zs=None, rho=None, i
     K = sp.bmat([[Hb, Cm.T], [Cm, None]], format="csc")
     rhs = np.concatenate([-np.concatenate(hs), rhs_c])
     sol = spla.spsolve(K, rhs)
+    if return_costates:   # multiplier mu_{k+1} of x_{k+1} - E_k w_k = c_k; the costate convention of pdplqr.h is -mu
+        return sol[:nw], -sol[nw:nw + N * nx].reshape(N, nx)
     return sol[:nw]

@@ -322,15 +322,26 @@ def test_horizon_shards_on_one_gpu(oracle, G, S_local):
     coup.solve_device(torch.stack(sums).unsqueeze(0).contiguous(), x0, xhat, lam)
     coup._lib.pdplqr_synchronize(coup._h)
     full = np.zeros(p.ws_len)
+    costates = np.zeros((N, p.nx))
     for r, (start, count) in enumerate(sharding.horizon_slices(N, G)):
         out = torch.zeros(1, count * p.s + p.nx, dtype=torch.float64, device=dev)
         sols[r].set_root_boundary_device(xhat[:, r].contiguous(), lam[:, r].contiguous())
         sols[r].forward_device(x0, out)
+        lam_loc = torch.zeros(1, count, p.nx, dtype=torch.float64, device=dev)
+        sols[r].costates_device(out, lam_loc)          # local lambda_k = global lambda_{start + k}, k = 1..count
         sols[r].synchronize()
         o = out.cpu().numpy()[0]
         n = count * p.s + (p.nx if r == G - 1 else 0)
         full[start * p.s:start * p.s + n] = o[:n]
+        costates[start:start + count] = lam_loc.cpu().numpy()[0]
     assert rel_err(full, ref) < TOL
+    o_seq = oracle.OracleSolver(p)
+    o_seq.solve()
+    Pk, pk = o_seq.value()
+    for k in (1, N // G, N // G + 1, N // 2, N - 1, N):   # lambda_k = P_k x_k + p_k (lqr_kernel.hpp:205-211)
+        xk = ref[k * p.s + p.nu:(k + 1) * p.s] if k < N else ref[N * p.s:]
+        lk = Pk[k].reshape(p.nx, p.nx, order="F") @ xk + pk[k]
+        assert np.max(np.abs(costates[k - 1] - lk)) < 1e-8 * max(1.0, np.max(np.abs(lk)))
     xh_ref, _ = sharding.couple_numpy(torch.stack(sums).cpu().numpy(), p.x0[0])
     assert rel_err(xhat.cpu().numpy()[0], xh_ref) < TOL
 
@@ -535,3 +546,59 @@ def test_stage_kernel_group_sizes(oracle, nx, nu, nc, seg_t, monkeypatch):
         else:
             ref = o.solve(ws_in=wprev[b], sigma=0.01)
         assert rel_err(ws[b], ref) < TOL
+
+
+# ------------------------------------------------------------------------------------------------------------
+# costate recovery (commented out in the reference, lqr_kernel.hpp:205-211)
+@pytest.mark.parametrize("nx,nu,N,S", [(12, 4, 40, 1), (12, 4, 40, 4), (6, 3, 30, 3), (16, 4, 24, 2), (3, 2, 17, 5)])
+def test_costates_match_kkt_multipliers_and_value_function(oracle, nx, nu, N, S):
+    """lambda_k vs (i) the multipliers of an independent sparse KKT solve and (ii) the reference's own (commented)
+    formula lambda_k = P_k x_k + p_k with P_k = Lxx Lxx^T, p_k from the sequential oracle."""
+    from kkt_ref import kkt_solve
+    p = P.problems.random_lq(nx, nu, N, batch=2, seed=40 + nx)
+    rng = np.random.default_rng(2)
+    wprev = rng.standard_normal((p.batch, p.ws_len))
+    sol, ws = gpu_solve(p, S=S, ws_in=wprev, sigma=0.05)
+    if sol.num_segments == 1 and nx + nu <= 8:
+        pytest.skip("thread-per-problem path")
+    lam = sol.costates(ws)
+    for b in range(p.batch):
+        w_kkt, lam_kkt = kkt_solve(p, b, wprev[b], 0.05, return_costates=True)
+        assert rel_err(ws[b], w_kkt) < 1e-8
+        assert rel_err(lam[b], lam_kkt) < 1e-8
+        o = oracle.OracleSolver(p, b=b)
+        ref = o.solve(ws_in=wprev[b], sigma=0.05)
+        Pk, pk = o.value()
+        s = nx + nu
+        for k in (1, N // 2, N):
+            xk = ref[k * s + nu: k * s + s] if k < N else ref[N * s:]
+            lk = Pk[k].reshape(nx, nx, order="F") @ xk + pk[k]
+            assert np.max(np.abs(lam[b, k - 1] - lk)) < TOL * max(1.0, np.max(np.abs(lk)))
+
+
+@pytest.mark.parametrize("S", [1, 3])
+def test_costates_with_constraint_fold_in(oracle, S):
+    """Constrained stages (dense D, ragged counts incl. the terminal stage): the costates satisfy the KKT system of the
+    ADMM-augmented problem."""
+    from kkt_ref import kkt_solve
+    p = P.problems.random_lq(6, 3, 14, batch=2, seed=77, nc=5)
+    wprev, ys, zs, rho, inv_rho = _admm_vectors(p, 9)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=S)
+    sol.update_problem_data(wprev, ys, zs, inv_rho, sigma=1e-3)
+    sol.backward(rho)
+    ws = sol.forward(p.x0, np.zeros_like(wprev))
+    lam = sol.costates(ws)
+    for b in range(p.batch):
+        w_kkt, lam_kkt = kkt_solve(p, b, wprev[b], 1e-3, ys[b], zs[b], rho[b], inv_rho[b], return_costates=True)
+        assert rel_err(ws[b], w_kkt) < 1e-8 and rel_err(lam[b], lam_kkt) < 1e-8
+
+
+def test_costates_call_order_and_unsupported_path():
+    p = P.problems.random_lq(12, 4, 10, batch=1, seed=3)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=2)
+    with pytest.raises(P.PdplqrError):
+        sol.costates(p.zeros_ws())                      # nothing solved yet
+    q = P.problems.cartpole_batch(batch=40, N=16)
+    sol2, ws2 = gpu_solve(q)                            # thread-per-problem path
+    with pytest.raises(P.PdplqrError):
+        sol2.costates(ws2)
