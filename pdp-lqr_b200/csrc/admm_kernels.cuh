@@ -9,7 +9,9 @@
 //     z       = Proj_K(z^ + y / rho)                  K = product of boxes [e_lb, e_ub], second-order cones, balls
 //     y       = y + rho o (z^ - z)
 //     r_prim  = || z~ - z ||_inf ,    r_dual = || D^T (rho o (z - z_prev)) ||_inf
-// One warp per (problem, stage): lanes over constraint rows for the mat-vec, lanes over cones for the projections.
+// One warp per (problem, stage) item, lanes over constraint rows for the mat-vec and over cones for the projections;
+// the warps of a fixed-size grid loop over the items (a CTA per item made the kernel CTA-launch-rate bound: 2.9 ns per
+// 32-thread CTA, 3.1 ms per iteration at C4 against 0.6 ms of HBM time).
 // Parity is pinned against an independent numpy restatement of the same iteration kept with the test infrastructure
 // ("parity unpinned" by the reference by construction).
 #pragma once
@@ -50,31 +52,37 @@ PDPLQR_DEVINL void atomic_max_nonneg(unsigned long long* addr, double v) {
     atomicMax(addr, (unsigned long long)__double_as_longlong(v));
 }
 
-__global__ void __launch_bounds__(32) admm_update_kernel(AdmmParams p) {
+constexpr int ADMM_WARPS = 8;   // warps per CTA of admm_update_kernel
+
+__global__ void __launch_bounds__(ADMM_WARPS * 32) admm_update_kernel(AdmmParams p) {
     extern __shared__ __align__(16) double smem[];
-    const int lane = threadIdx.x;
-    const int k = blockIdx.x % (p.N + 1);
-    const int b = blockIdx.x / (p.N + 1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = p.nx + p.nu;
-    const int dim = (k < p.N) ? s : p.nx;
-    const int nc = p.ncs[k];
     const size_t ws_len = (size_t)p.N * s + p.nx;
-    const size_t wo = (size_t)b * ws_len + (size_t)k * s;
-    double* wt = smem;                 // w~ of this stage   (dim)
-    double* v = smem + s;              // z^ + y/rho         (ncmax)
+    double* wt = smem + (size_t)warp * (s + 3 * p.ncmax);   // w~ of this stage   (dim)
+    double* v = wt + s;                // z^ + y/rho         (ncmax)
     double* zt = v + p.ncmax;          // z~                 (ncmax)
     double* dz = zt + p.ncmax;         // rho o (z - z_prev) (ncmax)
+    double r_prim = 0.0, nrm = 0.0, r_dual = 0.0, nrm_d = 0.0;
+    const long long items = (long long)p.batch * (p.N + 1);
+#pragma unroll 1
+    for (long long item = (long long)blockIdx.x * ADMM_WARPS + warp; item < items; item += (long long)gridDim.x * ADMM_WARPS) {
+    const int k = (int)(item % (p.N + 1));
+    const int b = (int)(item / (p.N + 1));
+    const int dim = (k < p.N) ? s : p.nx;
+    const int nc = p.ncs[k];
+    const size_t wo = (size_t)b * ws_len + (size_t)k * s;
+    __syncwarp();                      // the previous item's readers of the scratch are done
     for (int i = lane; i < dim; i += 32) {
         const double a = p.w_tilde[wo + i];
         wt[i] = a;
         p.w[wo + i] = p.alpha * a + (1.0 - p.alpha) * p.w[wo + i];
     }
-    if (nc == 0) return;
+    if (nc == 0) continue;
     __syncwarp();
     const double* Dk = p.Dm + (size_t)b * p.d_total + p.doff[k];
     const size_t co = (size_t)b * p.nc_total + p.coff[k];
     const bool sel = p.sel_col != nullptr;
-    double r_prim = 0.0, nrm = 0.0;
     for (int r = lane; r < nc; r += 32) {
         double acc = 0.0;
         if (sel) {
@@ -88,9 +96,10 @@ __global__ void __launch_bounds__(32) admm_update_kernel(AdmmParams p) {
         v[r] = zh + p.y[co + r] / p.rho[co + r];
     }
     __syncwarp();
-    // projections: one lane per cone
-    for (int c = p.cone_first[k] + lane; c < p.cone_first[k + 1]; c += 32) {
-        const int r0 = p.cone_row[c], d = p.cone_dim[c], type = p.cone_type[c];
+    // projections.  Few cones per stage (the usual case: one box over all variables + a cone or two): the warp walks
+    // the cones together and clamps a box row-parallel (a lane per cone left 31 lanes idle for 40 serial clamps: 1,980
+    // warp-instructions per stage at C4).  Many cones per stage: one lane per cone.
+    auto project_serial = [&](int r0, int d, int type) {     // one lane, whole cone
         if (type == CONE_BOX) {
             for (int r = r0; r < r0 + d; ++r) v[r] = fmin(fmax(v[r], p.e_lb[co + r]), p.e_ub[co + r]);
         } else if (type == CONE_SOC) {
@@ -112,6 +121,18 @@ __global__ void __launch_bounds__(32) admm_update_kernel(AdmmParams p) {
             const double rad = p.e_ub[co + r0];
             if (nv > rad) { const double sc = rad / nv; for (int r = r0; r < r0 + d; ++r) v[r] *= sc; }
         }
+    };
+    const int c0 = p.cone_first[k], c1 = p.cone_first[k + 1];
+    if (c1 - c0 <= 8) {
+        for (int c = c0; c < c1; ++c) {                      // warp-uniform
+            const int r0 = p.cone_row[c], d = p.cone_dim[c], type = p.cone_type[c];
+            if (type == CONE_BOX) {
+                for (int r = r0 + lane; r < r0 + d; r += 32) v[r] = fmin(fmax(v[r], p.e_lb[co + r]), p.e_ub[co + r]);
+            } else if (lane == 0)
+                project_serial(r0, d, type);
+        }
+    } else {
+        for (int c = c0 + lane; c < c1; c += 32) project_serial(p.cone_row[c], p.cone_dim[c], p.cone_type[c]);
     }
     __syncwarp();
     for (int r = lane; r < nc; r += 32) {
@@ -125,9 +146,8 @@ __global__ void __launch_bounds__(32) admm_update_kernel(AdmmParams p) {
         r_prim = fmax(r_prim, fabs(zt[r] - znew));
         nrm = fmax(nrm, fmax(fabs(zt[r]), fabs(znew)));
     }
-    if (!p.compute_res) return;
+    if (!p.compute_res) continue;
     __syncwarp();
-    double r_dual = 0.0, nrm_d = 0.0;
     for (int j = lane; j < dim; j += 32) {
         double acc = 0.0, accy = 0.0;
         if (sel) {
@@ -147,6 +167,8 @@ __global__ void __launch_bounds__(32) admm_update_kernel(AdmmParams p) {
         r_dual = fmax(r_dual, fabs(acc));
         nrm_d = fmax(nrm_d, fabs(accy));
     }
+    }   // items
+    if (!p.compute_res) return;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         r_prim = fmax(r_prim, __shfl_xor_sync(0xffffffffu, r_prim, off));

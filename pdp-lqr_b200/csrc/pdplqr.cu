@@ -1360,7 +1360,13 @@ int pdplqr_admm_solve_device(pdplqr_handle_t h, const double* x0, double* w, dou
         ap.w_tilde = h->d_wtilde; ap.w = w; ap.z = z; ap.y = y; ap.rho = rho;
         ap.alpha = alpha; ap.res = h->d_res; ap.compute_res = check ? 1 : 0;
         const size_t smem = (size_t)(h->s + 3 * h->ncmax) * sizeof(double);
-        admm_update_kernel<<<h->batch * (h->N + 1), 32, smem, h->stream>>>(ap);
+        {   // persistent warps: a few CTAs per SM loop over the (problem, stage) items
+            const long long items = (long long)h->batch * (h->N + 1);
+            const int ctas = (int)std::min<long long>((items + ADMM_WARPS - 1) / ADMM_WARPS, 148LL * 8);
+            int rc2 = set_smem(*h, admm_update_kernel, smem * ADMM_WARPS);
+            if (rc2) return rc2;
+            admm_update_kernel<<<ctas, ADMM_WARPS * 32, smem * ADMM_WARPS, h->stream>>>(ap);
+        }
         h->launches++;
         CU_TRY(h, cudaGetLastError());
         if (check) {
