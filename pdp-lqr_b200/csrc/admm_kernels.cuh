@@ -52,9 +52,10 @@ PDPLQR_DEVINL void atomic_max_nonneg(unsigned long long* addr, double v) {
     atomicMax(addr, (unsigned long long)__double_as_longlong(v));
 }
 
-constexpr int ADMM_WARPS = 8;   // warps per CTA of admm_update_kernel
+constexpr int ADMM_WARPS = 8;   // warps per CTA of admm_update_kernel; 8 CTAs per SM (32 registers): the kernel is a chain of
+                                // dependent global loads per item, so resident warps are what hides the latency (C4 453 -> 422 ms)
 
-__global__ void __launch_bounds__(ADMM_WARPS * 32) admm_update_kernel(AdmmParams p) {
+__global__ void __launch_bounds__(ADMM_WARPS * 32, 8) admm_update_kernel(AdmmParams p) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = p.nx + p.nu;
