@@ -79,6 +79,16 @@ def make_workload(name: str, rank: int):
     raise SystemExit(f"unknown workload {name}")
 
 
+def c4_traffic(batch: int):
+    """Measured DRAM bytes per launch of the affine sweep (profiles/traffic.json, taken at batch 4096), scaled to `batch`:
+    well below the algorithmic figure because the sweep reads only [E|c], h and the cached affine terms."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None
+    t = json.load(open(path)).get("c4_affine_batch4096")
+    return None if t is None else t * batch / 4096.0
+
+
 def wave_aligned(num_segments: int, wave: int = 148 * 13) -> int:
     """Round a segment count down to whole waves of the stage kernel's resident CTAs (148 SMs x 13 one-warp CTAs at
     nx12/nu4): a trailing partial wave costs a full wave of time (2048 segments = 1.06 waves ran as 2)."""
@@ -327,7 +337,7 @@ def run_c4(args, rank, world, local_rank):
                 "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
                 "e2e": None, "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "seg_affine_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": aff_bytes * B * N,
+                             "frac": achieved / peak, "traffic": c4_traffic(B), "algorithmic_bytes_per_launch": aff_bytes * B * N,
                              "kernel_ms": ms_aff,
                              "factorizing_kernel": {"kernel": "seg_backward_kernel<30,10,128>", "ms": ms_fact,
                                                     "achieved": fact_bytes * B * N / (ms_fact * 1e-3) / 1e9,
