@@ -67,8 +67,8 @@ def make_workload(name: str, rank: int):
         return prob, dict(num_segments=0), "C2: quadrotor LQR nx=12 nu=4 N=1024, single problem, segment-parallel (configs[1])"
     if name == "c5":
         prob = P.problems.quadrotor_ltv(1 << 20)
-        return prob, dict(num_segments=wave_aligned((1 << 20) // 180), load_balancing=2), \
-            "C5: quadrotor LQR nx=12 nu=4 N=2^20, single problem, ~180-stage segments in 3 whole waves of 148x13 CTAs (configs[4])"
+        return prob, dict(num_segments=wave_aligned((1 << 20) // 250), load_balancing=2), \
+            "C5: quadrotor LQR nx=12 nu=4 N=2^20, single problem, ~250-stage segments in 2 whole waves of 148x14 CTAs (configs[4])"
     if name == "c5small":
         prob = P.problems.quadrotor_ltv(1 << 16)
         return prob, dict(num_segments=(1 << 16) // 64, load_balancing=False), \
@@ -89,8 +89,11 @@ def c4_traffic(batch: int):
     return None if t is None else t * batch / 4096.0
 
 
-def wave_aligned(num_segments: int, wave: int = 148 * 13) -> int:
-    """Round a segment count down to whole waves of the stage kernel's resident CTAs (148 SMs x 13 one-warp CTAs at
+WAVE = 148 * 14   # resident one-warp stage-kernel CTAs per GPU at nx12/nu4 (16 KB of shared memory each)
+
+
+def wave_aligned(num_segments: int, wave: int = WAVE) -> int:
+    """Round a segment count down to whole waves of the stage kernel's resident CTAs (148 SMs x 14 one-warp CTAs at
     nx12/nu4): a trailing partial wave costs a full wave of time (2048 segments = 1.06 waves ran as 2)."""
     if num_segments <= wave:
         return max(1, num_segments)
@@ -404,7 +407,7 @@ def main():
         from pdplqr_b200.sharding import HorizonShardedSolver
         # per rank: the single-GPU segment length, but never less than one full wave of (problem, segment) CTAs -- with a
         # partial wave every SM runs fewer warps than it can hold and the sweep is a pure latency chain
-        hs = HorizonShardedSolver(prob, rank, world, num_segments=wave_aligned(max(kw["num_segments"] // world, 148 * 13)),
+        hs = HorizonShardedSolver(prob, rank, world, num_segments=wave_aligned(max(kw["num_segments"] // world, WAVE)),
                                   device=local_rank)
         hs.set_stream(stream.cuda_stream)
         sol = hs.sol

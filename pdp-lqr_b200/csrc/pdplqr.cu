@@ -745,9 +745,9 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     const bool auto_seg = (S == 0);
     const bool equal_split = auto_seg || load_balancing == 2;   // GPU-style partition: equal lengths
     if (auto_seg) {
-        // GPU-appropriate default: one full wave of (problem, segment) groups (148 SMs x ~12 resident stage-kernel
+        // GPU-appropriate default: one full wave of (problem, segment) groups (148 SMs x ~14 resident stage-kernel
         // CTAs), segments >= 8 stages
-        const int target_groups = 148 * 12;
+        const int target_groups = 148 * 14;
         S = std::max(1, std::min(N / 8, (target_groups + batch - 1) / batch));
     }
     S = std::min(S, N);
