@@ -160,7 +160,9 @@ int pdplqr_get_summaries(pdplqr_handle_t h, double* P, double* p, double* F, dou
  * F+^T uhat); here it is recovered segment-parallel from the stage stationarity conditions, starting at the interface
  * costates.  `ws` is the trajectory returned by the last forward; call after forward, before
  * the next update_problem_data with different vectors (the device variant reads the ws / ys / zs / rho arrays of the
- * last update through the pointers it was given).  Segment-path handles only: PDPLQR_ERR_UNSUPPORTED on the
+ * last update through the pointers it was given; after pdplqr_admm_solve* those are the loop's final iterates, which
+ * have moved on by one relaxation / projection step from the ones the last LQ solve used).  Segment-path handles only:
+ * PDPLQR_ERR_UNSUPPORTED on the
  * thread-per-problem path (batch of tiny systems with num_segments = 1). */
 int pdplqr_get_costates(pdplqr_handle_t h, const double* ws, double* lam);
 int pdplqr_get_costates_device(pdplqr_handle_t h, const double* ws, double* lam);
