@@ -92,3 +92,18 @@ def test_two_rank_gloo_horizon_and_batch_sharding(oracle):
     for pr in procs:
         pr.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_bench_wave_alignment_helpers():
+    """bench.py rounds segment counts to whole waves of resident stage-kernel CTAs and scales measured traffic."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    W = bench.WAVE
+    assert bench.wave_aligned(5) == 5 and bench.wave_aligned(W) == W
+    assert bench.wave_aligned(W + 1) == W and bench.wave_aligned(3 * W - 1) == 2 * W
+    assert bench.wave_aligned((1 << 20) // 250) == 2 * W
+    t = bench.c4_traffic(4096)
+    assert t is None or abs(bench.c4_traffic(2048) - t / 2) < 1.0
