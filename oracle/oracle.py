@@ -48,6 +48,7 @@ def lib():
         L.oracle_get_partition.argtypes = [C.c_void_p, _ip, _ip]
         L.oracle_get_gains.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.oracle_get_value.argtypes = [C.c_void_p, _dp, _dp]
+        L.oracle_get_costates.argtypes = [C.c_void_p, _dp, _dp]
         L.oracle_get_summary.argtypes = [C.c_void_p, C.c_int] + [_dp] * 5
         L.oracle_get_interface.argtypes = [C.c_void_p, _dp, _dp]
         L.oracle_batch_pool_create.restype = C.c_void_p
@@ -146,6 +147,13 @@ class OracleSolver:
         pv = np.zeros((p.N + 1, p.nx))
         lib().oracle_get_value(self.h, _p(P), _p(pv))
         return P, pv
+
+    def costates(self, ws):
+        """lambda_1 .. lambda_N [N, nx] for the trajectory `ws` of the last solve (the reference's commented formula,
+        lqr_kernel.hpp:205-211 / lqr_kernel_parallel.hpp:207-216)."""
+        lam = np.zeros((self.p.N, self.p.nx))
+        lib().oracle_get_costates(self.h, _p(np.ascontiguousarray(ws, dtype=np.float64)), _p(lam))
+        return lam
 
     def summary(self, seg):
         n = self.p.nx

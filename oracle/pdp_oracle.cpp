@@ -703,6 +703,39 @@ void oracle_get_value(void* o, double* P, double* p) {
         std::memcpy(p + (size_t)k * nx, st.p(nx), sizeof(double) * nx);
     }
 }
+// Costates lambda_k (k = 1..N) of the last solve: the step the reference has written but commented out,
+// `lambda+ = Lxx+ (Lxx+^T x+) + p+` (lqr_kernel.hpp:205-211) and, inside non-last segments, `... + F+^T uhat`
+// (lqr_kernel_parallel.hpp:207-216).  `ws` is the trajectory forward returned; lam[(k-1) nx + i] = lambda_k(i).
+void oracle_get_costates(void* o, const double* ws, double* lam) {
+    auto* s = static_cast<Solver*>(o);
+    const int nx = s->dm.nx, nu = s->dm.nu, N = s->dm.N, sd = nx + nu;
+    std::vector<double> t(nx);
+    for (int k = 1; k <= N; ++k) {
+        int sid = 0;
+        oracle::Stage& st = s->stage_global(k, &sid);
+        const double* x = (k < N) ? ws + (size_t)k * sd + nu : ws + (size_t)N * sd;
+        double* out = lam + (size_t)(k - 1) * nx;
+        const double* Lxx = st.Lxx(nx);
+        for (int j = 0; j < nx; ++j) {           // t = Lxx^T x
+            double acc = 0.0;
+            for (int i = j; i < nx; ++i) acc += Lxx[i + (size_t)j * st.dim] * x[i];
+            t[j] = acc;
+        }
+        for (int i = 0; i < nx; ++i) {           // lambda = Lxx t + p
+            double acc = st.p(nx)[i];
+            for (int j = 0; j <= i; ++j) acc += Lxx[i + (size_t)j * st.dim] * t[j];
+            out[i] = acc;
+        }
+        if (s->parallel && sid < s->S - 1) {     // + F^T uhat of the owning segment
+            const double* uh = s->cond.w[sid].uhat.data();
+            for (int i = 0; i < nx; ++i) {
+                double acc = 0.0;
+                for (int j = 0; j < nx; ++j) acc += st.F[j + (size_t)i * nx] * uh[j];
+                out[i] += acc;
+            }
+        }
+    }
+}
 // Segment summaries as sent to the condensed solver (lqr_solver_parallel.hpp:180-187), read from the
 // segment workspaces (the condensed solver modifies its own copies in place).
 void oracle_get_summary(void* o, int seg_id, double* P, double* p, double* F, double* f, double* C) {

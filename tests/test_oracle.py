@@ -131,3 +131,25 @@ def test_augmented_cost_helper():
     Hs, hs = augmented_cost(q, 0, np.ones(q.ws_len), 0.5)
     assert Hs[0].shape == (5, 5) and Hs[-1].shape == (3, 3)
     assert np.allclose(hs[0], q.h[0, 0] - 0.5)
+
+
+@pytest.mark.parametrize("S,condensed", [(2, "LU"), (4, "CHOLESKY"), (5, "LU")])
+def test_oracle_costates_sequential_parallel_and_kkt(oracle, S, condensed):
+    """Costates by the reference's commented formula (lqr_kernel.hpp:205-211, lqr_kernel_parallel.hpp:207-216):
+    sequential == multipliers of the exact KKT system; segment-parallel (+ F^T uhat inside non-last segments) ==
+    sequential."""
+    from kkt_ref import kkt_solve
+    p = P.problems.random_lq(6, 3, 25, batch=1, seed=91)
+    rng = np.random.default_rng(4)
+    wprev = rng.standard_normal(p.ws_len)
+    seq = oracle.OracleSolver(p)
+    ws = seq.solve(ws_in=wprev, sigma=0.02)
+    lam = seq.costates(ws)
+    w_kkt, lam_kkt = kkt_solve(p, 0, wprev, 0.02, return_costates=True)
+    assert np.max(np.abs(ws - w_kkt)) < 1e-10
+    assert np.max(np.abs(lam - lam_kkt)) < 1e-9 * max(1.0, np.max(np.abs(lam_kkt)))
+    par = oracle.OracleSolver(p, parallel=True, num_segments=S, load_balancing=False,
+                              condensed=getattr(oracle, condensed))
+    wp = par.solve(ws_in=wprev, sigma=0.02)
+    assert np.max(np.abs(wp - ws)) < 1e-10
+    assert np.max(np.abs(par.costates(wp) - lam)) < 1e-9 * max(1.0, np.max(np.abs(lam)))

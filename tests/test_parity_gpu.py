@@ -568,12 +568,8 @@ def test_costates_match_kkt_multipliers_and_value_function(oracle, nx, nu, N, S)
         assert rel_err(lam[b], lam_kkt) < 1e-8
         o = oracle.OracleSolver(p, b=b)
         ref = o.solve(ws_in=wprev[b], sigma=0.05)
-        Pk, pk = o.value()
-        s = nx + nu
-        for k in (1, N // 2, N):
-            xk = ref[k * s + nu: k * s + s] if k < N else ref[N * s:]
-            lk = Pk[k].reshape(nx, nx, order="F") @ xk + pk[k]
-            assert np.max(np.abs(lam[b, k - 1] - lk)) < TOL * max(1.0, np.max(np.abs(lk)))
+        lam_ref = o.costates(ref)                      # lambda_k = Lxx (Lxx^T x_k) + p_k, all k
+        assert np.max(np.abs(lam[b] - lam_ref)) < TOL * max(1.0, np.max(np.abs(lam_ref)))
 
 
 @pytest.mark.parametrize("S", [1, 3])
