@@ -1,20 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- LQ solves/sec of the B200-native PDP-LQR hot path (BASELINE.json metric), one JSON line.
+"""bench.py -- LQ solves/sec of the B200-native PDP-LQR hot path (BASELINE.json metric), ONE JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c5|c1] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--legs c2,c5,c4] [--workload c3|c2|c5|c4|c1]
+                    [--impl reference]
 
 A "step" is one pass of the hot path over one batch of synthetic problems:
     update_problem_data + backward (factorising) + forward          (lqr_solver_parallel.hpp:115-238)
-Default workload = BASELINE.json configs[2] ("c3"): 65,536 independent cart-pole LQ problems, nx=4 nu=1 N=128,
-per GPU -- the configuration the headline metric "LQ solves/sec (batched)" is quoted on and the one that shards
-across 1/2/4/8 GPUs (independent problems, no data-path collective; weak scaling: 65,536 problems per rank).
-`value`   : whole-job solves/s with model + iterates already resident in HBM (CUDA events on the launch stream).
-`e2e`     : the same metric through the host-buffer C-ABI call pdplqr_solve() -- H2D of the iterate ws / x0 from
-            pinned host memory and D2H of the solution inside the timed region (model resident, uploaded once by
-            pdplqr_set_model like the reference's constructor builds its workspaces once).
-`roofline`: dominant kernel (backward sweep) against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
-`cpu_baseline` / `--impl reference`: the CPU oracle port (the reference needs Eigen3, absent from this image) on
-            the box's host cores, bounded sample of the same workload.
+Headline (`value`, `e2e`, `roofline`, `cpu_baseline`): BASELINE.json configs[2] ("c3"): 65,536 independent cart-pole LQ
+problems, nx=4 nu=1 N=128, per GPU -- the configuration the metric "LQ solves/sec (batched)" is quoted on and the one
+that shards across 1/2/4/8 GPUs without a collective (weak scaling: 65,536 problems per rank).
+`configs` block: the other BASELINE.json configurations measured in the SAME run, each with its own ms_per_step,
+roofline (HBM and FP64-pipe fractions), cpu_baseline, e2e and `parity_rel_err` (max relative error of THIS run's
+output against the CPU oracle):
+    c2  quadrotor nx12/nu4 N=1024, one problem, segment-parallel: per-solve latency, and latency vs N
+    c5  quadrotor N=2^20: at N GPUs > 1 the horizon is split into per-rank time slices with ONE NCCL all_gather of a
+        3,648-byte summary per solve (strong scaling) + a per-phase breakdown and `parity_vs_1gpu`
+    c4  conic (box + SOC) LQ MPC nx30/nu10 N=256, batch 4096 per GPU, full ADMM outer iterations
+`value`   : whole-job solves/s with model + iterates resident in HBM (CUDA events on the launch stream, max over ranks).
+`e2e`     : the same metric through the host-buffer C-ABI call pdplqr_solve() -- H2D of the iterate ws / x0 from pinned
+            host memory and D2H of the solution inside the timed region (model resident, uploaded once by
+            pdplqr_set_model like the reference's constructor builds its workspaces once); `link_frac` relates it to the
+            host link bandwidth measured in the same run (all ranks copying at once).
+`cpu_baseline` / `--impl reference`: the CPU oracle port on the box's host cores (the reference itself needs Eigen3,
+            absent from this image; the shim-backed build of the reference's own headers, oracle/_ref, is timed beside it).
 """
 from __future__ import annotations
 
@@ -26,6 +34,7 @@ import subprocess
 import sys
 import tempfile
 import time
+import traceback
 
 import numpy as np
 
@@ -41,6 +50,10 @@ def emit(line: dict) -> None:
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
 def host_cores() -> int:
     """Cores this process may use (torchrun sets OMP_NUM_THREADS=1, which must not throttle the CPU baseline)."""
     try:
@@ -51,42 +64,70 @@ def host_cores() -> int:
 
 METRIC = "lq_solves_per_sec"
 UNIT = "solves/s"
+SIGMA = 1e-6
+# FP64 peak of this pool's B200s, measured with scripts/micro/dmma_bench.cu (profiles/r1_dmma_microbench.txt):
+# 36.8 TFLOP/s on the FP64 tensor pipe (mma.sync.m8n8k4.f64 = SASS DMMA), 31.9 TFLOP/s on the DFMA pipe.
+FP64_PEAK_TFLOPS = 36.8
+FP64_PEAK_SOURCE = "profiles/r1_dmma_microbench.txt (DMMA, measured on this pool; DFMA pipe 31.9)"
+C3_BATCH, C3_N = 65536, 128
+C5_N = 1 << 20
+C4_BATCH, C4_N, C4_ITERS = 4096, 256, 50
+LATENCY_NS = (100, 256, 1024, 4096, 16384)
 
 
-# --------------------------------------------------------------------------------------------- workloads
-def make_workload(name: str, rank: int):
-    import pdplqr_b200 as P
-    if name == "c3":
-        prob = P.problems.cartpole_batch(batch=65536, N=128, seed=1234 + 7919 * rank)
-        return prob, dict(num_segments=1), "C3: 65536 x cart-pole LQR nx=4 nu=1 N=128 per GPU (BASELINE.json configs[2])"
-    if name == "c3small":
-        prob = P.problems.cartpole_batch(batch=4096, N=128, seed=1234 + 7919 * rank)
-        return prob, dict(num_segments=1), "C3-small: 4096 x cart-pole LQR nx=4 nu=1 N=128 per GPU (debug size)"
-    if name == "c2":
-        prob = P.problems.quadrotor_ltv(1024)
-        return prob, dict(num_segments=0), "C2: quadrotor LQR nx=12 nu=4 N=1024, single problem, segment-parallel (configs[1])"
-    if name == "c5":
-        prob = P.problems.quadrotor_ltv(1 << 20)
-        return prob, dict(num_segments=wave_aligned((1 << 20) // 250), load_balancing=2), \
-            "C5: quadrotor LQR nx=12 nu=4 N=2^20, single problem, ~250-stage segments in 2 whole waves of 148x14 CTAs (configs[4])"
-    if name == "c5small":
-        prob = P.problems.quadrotor_ltv(1 << 16)
-        return prob, dict(num_segments=(1 << 16) // 64, load_balancing=False), \
-            "C5-small: quadrotor LQR nx=12 nu=4 N=2^16 (debug size)"
-    if name == "c1":
-        prob = P.problems.quadrotor_example()
-        return prob, dict(num_segments=4), "C1: examples/lqr_example.cpp as shipped (configs[0])"
-    raise SystemExit(f"unknown workload {name}")
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path)).get("hbm_gbs", 6650.0)), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    return 6650.0, "fallback 6650 GB/s (B200_PROFILING.md)"
 
 
-def c4_traffic(batch: int):
-    """Measured DRAM bytes per launch of the affine sweep (profiles/traffic.json, taken at batch 4096), scaled to `batch`:
-    well below the algorithmic figure because the sweep reads only [E|c], h and the cached affine terms."""
+def measured_traffic(key):
+    """DRAM bytes per launch from an `ncu --set full` capture (profiles/traffic.json) -- a recorded constant of an
+    earlier capture of the same kernel and workload, NOT measured in this run."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(path):
         return None
-    t = json.load(open(path)).get("c4_affine_batch4096")
-    return None if t is None else t * batch / 4096.0
+    return json.load(open(path)).get(key)
+
+
+# --------------------------------------------------------------------------------------------- byte / flop models
+def stage_bytes(nx, nu, pdp: bool, sym_h: bool = False):
+    """algorithmic bytes per stage (nc = 0), LTV storage, carrying P,p,F,f,C on chip.
+    Returns (backward, forward); their sum is the survey's B_stage (760 B nx4/nu1 sequential, 7424 B nx12/nu4 PDP).
+    sym_h: count only the lower triangle of H (what the thread-per-problem record actually holds)."""
+    s = nx + nu
+    nH = s * (s + 1) // 2 if sym_h else s * s
+    model = nx * s + nx + nH + s
+    fac = s * nu + nu + (nu * nx if pdp else 0)
+    return 8 * (model + fac), 8 * (fac + nx * s + nx + s)
+
+
+def stage_flops(nx, nu, nc=0, pdp=False):
+    """flops per stage as the reference executes them (dense): (factorising backward, forward)."""
+    s = nx + nu
+    f_seq = 2 * s * nx * nx + 2 * s * s * nx + s ** 3 / 3 + 4 * nx * nx + 2 * s * nx + nu * nu + 2 * nx * nu
+    f_par = 2 * nx * nu * nu + 6 * nx * nx * nu + 2 * nx ** 3 + 2 * nx * nu + 2 * nx * nx + 2 * nu * nu
+    f_con = nc * s + 2 * s * s * nc + nc + 2 * s * nc
+    f_fwd = 2 * nx * nu + nu * nu + 2 * nx * s + (2 * nu * nx if pdp else 0)
+    return f_seq + (f_par if pdp else 0) + (f_con if nc else 0), f_fwd
+
+
+def roofline(kernel, bytes_per_launch, flops_per_launch, ms, traffic_key=None, extra=None):
+    peak, src = peaks()
+    gbs = bytes_per_launch / (ms * 1e-3) / 1e9
+    tfs = flops_per_launch / (ms * 1e-3) / 1e12
+    bound = "hbm" if gbs / peak >= tfs / FP64_PEAK_TFLOPS else "fp64"
+    out = {"bound": bound, "kernel": kernel, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+           "peak_source": src, "algorithmic_bytes_per_launch": int(bytes_per_launch), "kernel_ms": ms,
+           "fp64": {"achieved": tfs, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tfs / FP64_PEAK_TFLOPS,
+                    "peak_source": FP64_PEAK_SOURCE, "algorithmic_flops_per_launch": int(flops_per_launch)},
+           "traffic": measured_traffic(traffic_key) if traffic_key else None,
+           "traffic_source": ("profiles/traffic.json['%s'] (recorded ncu --set full capture, not measured in this run)" % traffic_key)
+           if traffic_key and measured_traffic(traffic_key) else None}
+    if extra:
+        out.update(extra)
+    return out
 
 
 WAVE = 148 * 14   # resident one-warp stage-kernel CTAs per GPU at nx12/nu4 (16 KB of shared memory each)
@@ -100,16 +141,45 @@ def wave_aligned(num_segments: int, wave: int = WAVE) -> int:
     return (num_segments // wave) * wave
 
 
-def algorithmic_bytes_per_stage(nx, nu, pdp: bool):
-    """doubles per stage, LTV storage, carrying P,p,F,f,C on chip (nc = 0).
-    Returns (backward_bytes, forward_bytes); their sum is the survey's B_stage (760 B for nx4/nu1 sequential,
-    7424 B for nx12/nu4 PDP)."""
-    s = nx + nu
-    model = nx * s + nx + s * s + s
-    fac = s * nu + nu + (nu * nx if pdp else 0)
-    bwd = 8 * (model + fac)
-    fwd = 8 * (fac + nx * s + nx + s)
-    return bwd, fwd
+def c4_traffic(batch: int):
+    t = measured_traffic("c4_affine_batch4096")
+    return None if t is None else t * batch / 4096.0
+
+
+def c5_segments(world: int = 1) -> int:
+    """Segments per rank for the 2^20-stage problem: ~250-stage segments in whole waves, never less than one full wave."""
+    per_rank = wave_aligned(C5_N // 250)
+    return wave_aligned(max(per_rank // world, WAVE))
+
+
+def workload_config(name: str, world: int) -> dict:
+    """Deterministic description of a workload (identical in the GPU arm and in `--impl reference`)."""
+    if name == "c3":
+        return {"workload": "C3: 65536 x cart-pole LQR nx=4 nu=1 N=128 per GPU (BASELINE.json configs[2])",
+                "problems_per_gpu": C3_BATCH, "nx": 4, "nu": 1, "N": C3_N, "num_segments": 1, "sigma": SIGMA,
+                "l2": "inputs larger than L2 (model records 2.95 GB per GPU)",
+                "sharding": "independent problems per rank, no data-path collective"}
+    if name == "c2":
+        return {"workload": "C2: quadrotor LQR nx=12 nu=4 N=1024, single problem, segment-parallel (configs[1])",
+                "problems_per_gpu": 1, "nx": 12, "nu": 4, "N": 1024, "sigma": SIGMA,
+                "l2": "latency-bound: the whole problem (7.6 MB) is L2-resident by construction",
+                "sharding": "replicas only (one problem per GPU)"}
+    if name == "c5":
+        return {"workload": "C5: quadrotor LQR nx=12 nu=4 N=2^20, single problem (configs[4])",
+                "problems_per_gpu": 1, "nx": 12, "nu": 4, "N": C5_N, "sigma": SIGMA,
+                "l2": "inputs larger than L2 (model records 3.99 GB)",
+                "sharding": "1 GPU: whole horizon" if world == 1 else
+                "horizon: contiguous time slices per rank, one all_gather of a 3648-byte slice summary per solve"}
+    if name == "c4":
+        return {"workload": "C4: conic (box + SOC) LQ MPC nx=30 nu=10 N=%d, batch %d per GPU, %d fixed ADMM outer iterations per solve (configs[3])" % (C4_N, C4_BATCH, C4_ITERS),
+                "problems_per_gpu": C4_BATCH, "nx": 30, "nu": 10, "N": C4_N, "nc": 44, "admm_iterations": C4_ITERS,
+                "sigma": SIGMA, "l2": "inputs larger than L2",
+                "sharding": "independent problems per rank, no data-path collective"}
+    if name == "c1":
+        return {"workload": "C1: examples/lqr_example.cpp as shipped (configs[0])", "problems_per_gpu": 1, "nx": 12,
+                "nu": 4, "N": 100, "num_segments": 4, "sigma": SIGMA, "l2": "latency-bound (0.74 MB)",
+                "sharding": "replicas only"}
+    raise SystemExit(f"unknown workload {name}")
 
 
 # --------------------------------------------------------------------------------------------- helpers
@@ -163,37 +233,146 @@ class ClockSampler:
         return out
 
 
-def cpu_baseline(prob, seconds=6.0, max_problems=16384):
-    """Time the CPU oracle port (OpenMP over problems, sequential Riccati each -- or the PDP solver for a single
-    long problem) on a bounded sample of the workload.  Returns (solves_per_s, cores, sample_description)."""
-    from oracle import oracle as O
-    cores = host_cores()
-    if prob.batch > 1:
-        nb = min(prob.batch, max_problems)
-        sub = prob.select(slice(0, nb))
-        pool = O.OracleBatch(sub)
-        ws_in = sub.zeros_ws()
-        out = np.empty_like(ws_in)
-        pool.solve(ws_in=ws_in, ws_out=out, nthreads=cores)  # warm-up
-        best, reps, t_end = 1e30, 0, time.perf_counter() + seconds
-        while reps < 2 or time.perf_counter() < t_end:
+class Ctx:
+    """Per-process run context (one process per GPU)."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.torch, self.dist = torch, dist
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.current_stream()
+        self.windows = []
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values):
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
+
+    def time_loop(self, fn, steps, warmup):
+        """W untimed + K timed calls of fn() bracketed by barrier + synchronize; CUDA events on the launch stream;
+        returns ms per step as the MAX over ranks."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        t0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            fn()
+        e1.record(self.stream)
+        self.barrier()
+        self.windows.append((t0, time.time()))
+        return self.max_over_ranks([e0.elapsed_time(e1) / steps])[0]
+
+    def time_wall(self, fn, steps, warmup=1):
+        """Same bracket, host wall clock (end-to-end calls that synchronise themselves)."""
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        t0w = time.time()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        self.torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / steps
+        self.windows.append((t0w, time.time()))
+        self.barrier()
+        return self.max_over_ranks([dt * 1e3])[0]
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+def link_bandwidth(ctx, nbytes=256 << 20):
+    """Pinned host <-> device copy bandwidth of this box measured in this run, every rank copying at the same time
+    (the ranks share the host link): GB/s per rank for H2D alone, D2H alone, and both directions at once."""
+    torch = ctx.torch
+    n = nbytes // 8
+    hin = torch.empty(n, dtype=torch.float64).pin_memory()
+    hout = torch.empty(n, dtype=torch.float64).pin_memory()
+    din, dout = torch.empty(n, dtype=torch.float64, device=ctx.dev), torch.zeros(n, dtype=torch.float64, device=ctx.dev)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    res = {}
+    for name in ("h2d", "d2h", "duplex"):
+        for rep in range(2):   # first repetition warms the path up
+            ctx.barrier()
             t0 = time.perf_counter()
-            pool.solve(ws_in=ws_in, ws_out=out, nthreads=cores)
-            best = min(best, time.perf_counter() - t0)
-            reps += 1
-        return nb / best, cores, f"first {nb} of {prob.batch} problems, full solve, best of {reps} reps, {cores} OpenMP threads"
-    S = max(1, min(8, cores))
-    n_stages = min(prob.N, 1 << 17)
-    sub = prob if n_stages == prob.N else None
-    if sub is None:
-        import pdplqr_b200 as P
-        sub = P.problems.quadrotor_ltv(n_stages)
+            if name in ("h2d", "duplex"):
+                with torch.cuda.stream(s1):
+                    din.copy_(hin, non_blocking=True)
+            if name in ("d2h", "duplex"):
+                with torch.cuda.stream(s2):
+                    hout.copy_(dout, non_blocking=True)
+            s1.synchronize(); s2.synchronize()
+            dt = time.perf_counter() - t0
+        dt = ctx.max_over_ranks([dt])[0]
+        res[name] = nbytes / dt / 1e9           # per direction
+    return res
+
+
+def e2e_block(ctx, value, ms, h2d, d2h, link, extra=None):
+    out = {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms,
+           "model": "resident (uploaded once by pdplqr_set_model)"}
+    if link:
+        ideal_ms = max(h2d / link["duplex"], d2h / link["duplex"]) / 1e6   # both directions overlap (two copy engines)
+        out.update(link_gbs_per_rank=link, link_ideal_ms=ideal_ms, link_frac=ideal_ms / ms if ms > 0 else None,
+                   link_note="pinned-copy GB/s per rank measured in this run with all %d rank(s) copying at once; "
+                             "link_frac = (bytes / duplex rate) / e2e time" % ctx.world)
+    if extra:
+        out.update(extra)
+    return out
+
+
+# --------------------------------------------------------------------------------------------- CPU legs (oracle port)
+def cpu_batch(prob, seconds=6.0, max_problems=None, threads=None):
+    """CPU oracle port, OpenMP over problems, sequential Riccati each.  Returns (solves/s, cores, sample text)."""
+    from oracle import oracle as O
+    cores = threads or host_cores()
+    nb = prob.batch if max_problems is None else min(prob.batch, max_problems)
+    sub = prob if nb == prob.batch else prob.select(slice(0, nb))
+    pool = O.OracleBatch(sub)
+    ws_in = sub.zeros_ws()
+    out = np.empty_like(ws_in)
+    pool.solve(ws_in=ws_in, ws_out=out, nthreads=cores)  # warm-up
+    best, reps, t_end = 1e30, 0, time.perf_counter() + seconds
+    while reps < 2 or time.perf_counter() < t_end:
+        t0 = time.perf_counter()
+        pool.solve(ws_in=ws_in, ws_out=out, nthreads=cores)
+        best = min(best, time.perf_counter() - t0)
+        reps += 1
+    what = "all %d problems" % nb if nb == prob.batch else "first %d of %d problems" % (nb, prob.batch)
+    return nb / best, cores, f"{what}, full solve, best of {reps} reps, {cores} OpenMP threads"
+
+
+def cpu_single(prob, seconds=4.0, max_stages=1 << 17):
+    """CPU oracle port, the reference's PDP solver (S segments on S threads) on one long problem."""
+    from oracle import oracle as O
+    import pdplqr_b200 as P
+    S = max(1, min(8, host_cores()))
+    n_stages = min(prob.N, max_stages)
+    sub = prob if n_stages == prob.N else P.problems.quadrotor_ltv(n_stages)
     o = O.OracleSolver(sub, parallel=S > 1, num_segments=S, load_balancing=True, condensed=O.CHOLESKY, nthreads=S)
-    ws_in = np.zeros(sub.ws_len)
-    out = np.zeros(sub.ws_len)
+    ws_in, out = np.zeros(sub.ws_len), np.zeros(sub.ws_len)
 
     def one():
-        o.update_problem_data(ws_in, sigma=1e-6)
+        o.update_problem_data(ws_in, sigma=SIGMA)
         o.backward()
         o.forward(sub.x0[0], out)
     one()
@@ -209,54 +388,368 @@ def cpu_baseline(prob, seconds=6.0, max_problems=16384):
                                      + f", best of {reps} reps")
 
 
+def cpu_reference_build(prob, seconds=5.0, max_problems=256):
+    """The reference's OWN solver class (lqr::LQRSolver compiled from /root/reference's headers against the Eigen-API
+    shim: oracle/_ref/libpdpref.so) on a sample of the batch, one problem per thread at a time."""
+    from oracle import reflib
+    if not reflib.available():
+        return None
+    from concurrent.futures import ThreadPoolExecutor
+    cores = host_cores()
+    nb = min(prob.batch, max_problems)
+    sols = [reflib.ReferenceSolver(prob, b=b) for b in range(nb)]
+    ws_in = np.zeros(prob.ws_len)
+
+    def one(b):
+        sols[b].update_problem_data(ws_in, sigma=SIGMA)
+        sols[b].backward()
+        sols[b].forward(prob.x0[b])
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(one, range(nb)))
+        best, reps, t_end = 1e30, 0, time.perf_counter() + seconds
+        while reps < 2 or time.perf_counter() < t_end:
+            t0 = time.perf_counter()
+            list(ex.map(one, range(nb)))
+            best = min(best, time.perf_counter() - t0)
+            reps += 1
+    return {"value": nb / best, "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"lqr::LQRSolver (reference headers + Eigen-API shim, oracle/_ref) on the first {nb} problems, "
+                      f"{cores} host threads (ctypes thread pool), best of {reps} reps"}
+
+
 def run_reference_arm(args, rank, world):
+    """`--impl reference`: the reference's CPU implementation of the path on the host cores, all threads, on the main
+    arm's config.  Rank 0 alone runs and prints; the other ranks exit 0 without work."""
     if rank != 0:
         return
-    prob, _, desc = make_workload(args.workload, 0)
+    import pdplqr_b200 as P
+    name = args.workload if args.workload != "all" else "c3"
+    cfg = workload_config(name, world)
+    if name == "c3":
+        prob = P.problems.cartpole_batch(batch=C3_BATCH, N=C3_N, seed=1234)
+        runner = lambda sec: cpu_batch(prob, seconds=sec, max_problems=None)   # every one of the 65,536 problems
+    elif name in ("c2", "c1"):
+        prob = P.problems.quadrotor_ltv(1024) if name == "c2" else P.problems.quadrotor_example()
+        runner = lambda sec: cpu_single(prob, seconds=sec)
+    elif name == "c5":
+        prob = P.problems.quadrotor_ltv(C5_N)
+        runner = lambda sec: cpu_single(prob, seconds=sec, max_stages=C5_N)
+    else:
+        raise SystemExit("--impl reference supports c3, c2, c1, c5")
     times = []
-    val, cores, sample = None, None, None
-    per_step = min(1.0, 120.0 / max(1, args.warmup + args.steps))   # whole arm bounded to ~2 minutes of CPU timing
+    cores = sample = None
+    per_step = min(2.0, 150.0 / max(1, args.warmup + args.steps))   # whole arm bounded to a few minutes of CPU timing
     for i in range(args.warmup + args.steps):
-        v, cores, sample = cpu_baseline(prob, seconds=per_step, max_problems=8192)
+        v, cores, sample = runner(per_step)
         if i >= args.warmup:
             times.append(v)
     val = statistics.median(times)
-    solves_per_step = prob.batch
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * solves_per_step / val, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "cpu_only": True},
+            "warmup": args.warmup, "ms_per_step": 1e3 * prob.batch / val, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-            "note": "reference needs Eigen3 (absent): timed the CPU oracle port of the same algorithm"}
+            "note": "the reference needs Eigen3 (absent from this image): `value` times the CPU oracle port of the same "
+                    "algorithm (allocation-free, the faster of the two CPU builds, i.e. the conservative baseline); "
+                    "`reference_build` times the reference's own headers compiled against the Eigen-API shim"}
+    if name == "c3":
+        try:
+            line["reference_build"] = cpu_reference_build(prob)
+        except Exception as e:   # the labelled second number must not take the arm down
+            line["reference_build"] = {"error": repr(e)}
     emit(line)
 
 
+# --------------------------------------------------------------------------------------------- C3 (headline)
+def run_c3(ctx, steps, warmup, want_cpu=True, batch=C3_BATCH):
+    import pdplqr_b200 as P
+    torch = ctx.torch
+    t_gen = time.time()
+    prob = P.problems.cartpole_batch(batch=batch, N=C3_N, seed=1234 + 7919 * ctx.rank)
+    log("c3: problem generated in %.1f s" % (time.time() - t_gen))
+    sol = P.LQRCudaSolver.from_problem(prob, device=ctx.local_rank, num_segments=1)
+    sol.set_stream(ctx.stream.cuda_stream)
+    B, N, nx, nu, s = prob.batch, prob.N, prob.nx, prob.nu, prob.s
+    rng = np.random.default_rng(17 + ctx.rank)
+    ws_host = torch.from_numpy(0.01 * rng.standard_normal((B, prob.ws_len))).pin_memory()
+    x0_host = torch.from_numpy(np.ascontiguousarray(prob.x0)).pin_memory()
+    out_host = torch.empty_like(ws_host).pin_memory()
+    ws_dev, x0_dev = ws_host.to(ctx.dev), x0_host.to(ctx.dev)
+    out_dev = torch.empty_like(ws_dev)
 
-# --------------------------------------------------------------------------------------------- config 4 (conic ADMM)
-def run_c4(args, rank, world, local_rank):
+    def step_device():
+        sol.update_problem_data_device(ws_dev, sigma=SIGMA)
+        sol.backward_device()
+        sol.forward_device(x0_dev, out_dev)
+
+    l0 = None
+
+    def counted():
+        nonlocal l0
+        if l0 is None:
+            l0 = sol.launch_count()
+        step_device()
+    for _ in range(warmup):
+        step_device()
+    ms_step = ctx.time_loop(counted, steps, 0)
+    launches = sol.launch_count() - l0
+    bad, _ = sol.last_status()
+
+    def bwd_only():
+        sol.update_problem_data_device(ws_dev, sigma=SIGMA)
+        sol.backward_device()
+    ms_bwd = ctx.time_loop(bwd_only, max(5, steps), 1)
+    sol.forward_device(x0_dev, out_dev)   # leave the handle consistent (one forward per backward)
+    torch.cuda.synchronize()
+
+    # end to end through the host-buffer C ABI (pinned host memory; H2D + kernels + D2H inside the timed region)
+    ws_np, x0_np, out_np = ws_host.numpy(), x0_host.numpy(), out_host.numpy()
+    link = link_bandwidth(ctx)
+    ms_e2e = ctx.time_wall(lambda: sol.solve(ws_np, x0_np, out_np, sigma=SIGMA), max(3, min(steps, 10)))
+    got = out_dev.cpu().numpy()
+    same = bool(np.array_equal(out_np, got))
+
+    # parity of THIS run against the CPU oracle on a sample of problems: first tile, last tile (padded lanes), random
+    parity = None
+    if ctx.rank == 0:
+        from oracle import oracle as O
+        pick = np.unique(np.concatenate([np.arange(64), np.arange(B - 64, B),
+                                         np.random.default_rng(5).integers(0, B, 128)]))
+        sub = prob.select(pick)
+        ref, _ = O.OracleBatch(sub).solve(ws_in=np.ascontiguousarray(ws_np[pick]), sigma=SIGMA)
+        parity = rel_err(got[pick], ref)
+    bwd_b, fwd_b = stage_bytes(nx, nu, False)
+    bwd_sym, _ = stage_bytes(nx, nu, False, sym_h=True)
+    ffl, wfl = stage_flops(nx, nu)
+    res = {"ms_per_step": ms_step, "value": ctx.world * B * 1e3 / ms_step, "launches": int(launches), "bad": int(bad),
+           "e2e": e2e_block(ctx, ctx.world * B / (ms_e2e * 1e-3), ms_e2e, ws_host.numel() * 8 + x0_host.numel() * 8,
+                            out_host.numel() * 8, link, {"matches_device_path": same}),
+           "roofline": roofline("batch_backward_kernel", bwd_b * B * N, ffl * B * N, ms_bwd, "c3",
+                                {"launches_per_backward": 1,
+                                 "frac_symmetric_h": bwd_sym * B * N / (ms_bwd * 1e-3) / 1e9 / peaks()[0],
+                                 "bytes_note": "frac counts the survey's record (full H, 54 doubles); the device record "
+                                               "holds the lower triangle (44): frac_symmetric_h is the traffic-true figure",
+                                 "step_hbm_frac": (bwd_b + fwd_b) * B * N / (ms_step * 1e-3) / 1e9 / peaks()[0]}),
+           "parity_rel_err": parity, "parity_sample": "256 problems of this run (first tile, last tile, 128 random) vs the CPU oracle"}
+    if want_cpu and ctx.world == 1 and ctx.rank == 0:
+        v, cores, sample = cpu_batch(prob, seconds=4.0, max_problems=None)
+        res["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    del sol, ws_dev, out_dev
+    torch.cuda.empty_cache()
+    return res
+
+
+# --------------------------------------------------------------------------------------------- C2 (latency)
+def run_single(ctx, prob, num_segments, steps, warmup, load_balancing=True):
+    """One long problem on one GPU: returns (solver, ms per device-resident step, output array, ws / x0 tensors)."""
+    import pdplqr_b200 as P
+    torch = ctx.torch
+    sol = P.LQRCudaSolver.from_problem(prob, device=ctx.local_rank, num_segments=num_segments, load_balancing=load_balancing)
+    sol.set_stream(ctx.stream.cuda_stream)
+    rng = np.random.default_rng(17)
+    ws_host = torch.from_numpy(0.01 * rng.standard_normal((1, prob.ws_len))).pin_memory()
+    x0_host = torch.from_numpy(np.ascontiguousarray(prob.x0)).pin_memory()
+    ws_dev, x0_dev = ws_host.to(ctx.dev), x0_host.to(ctx.dev)
+    out_dev = torch.empty_like(ws_dev)
+
+    def step():
+        sol.update_problem_data_device(ws_dev, sigma=SIGMA)
+        sol.backward_device()
+        sol.forward_device(x0_dev, out_dev)
+    ms = ctx.time_loop(step, steps, warmup)
+    return sol, ms, out_dev, ws_host, x0_host, step
+
+
+def leg_c2(ctx, steps):
+    import pdplqr_b200 as P
+    from oracle import oracle as O
+    torch = ctx.torch
+    out = dict(workload_config("c2", ctx.world))
+    prob = P.problems.quadrotor_ltv(1024)
+    sol, ms, out_dev, ws_host, x0_host, step = run_single(ctx, prob, 0, max(steps, 50), 5)
+    l0 = sol.launch_count(); step(); launches = sol.launch_count() - l0
+    torch.cuda.synchronize()
+    out_np = np.empty((1, prob.ws_len))
+    ms_e2e = ctx.time_wall(lambda: sol.solve(ws_host.numpy(), x0_host.numpy(), out_np, sigma=SIGMA), 20, 3)
+    bwd_b, fwd_b = stage_bytes(12, 4, True)
+    ffl, wfl = stage_flops(12, 4, pdp=True)
+    out.update(num_segments=sol.num_segments, ms_per_step=ms, latency_us=ms * 1e3, value=ctx.world * 1e3 / ms, unit=UNIT,
+               gpu_launches=int(launches),
+               roofline=roofline("whole step (latency-bound by construction: small fraction expected)", (bwd_b + fwd_b) * 1024,
+                                 (ffl + wfl) * 1024, ms),
+               e2e=e2e_block(ctx, ctx.world / (ms_e2e * 1e-3), ms_e2e, (prob.ws_len + 12) * 8, prob.ws_len * 8, None))
+    if ctx.rank == 0:
+        ref = O.OracleSolver(prob, parallel=False).solve(ws_in=ws_host.numpy()[0].copy(), sigma=SIGMA)
+        out["parity_rel_err"] = rel_err(out_dev.cpu().numpy()[0], ref)
+    del sol
+    # the metric's "per-solve latency vs N": library-chosen segmentation, device-resident step
+    lat = {}
+    for n in LATENCY_NS:
+        pn = P.problems.quadrotor_ltv(n) if n != 100 else P.problems.quadrotor_example()
+        sn, msn, on, wh, _, _ = run_single(ctx, pn, 0, 30, 5)
+        entry = {"us": msn * 1e3, "num_segments": sn.num_segments}
+        if ctx.rank == 0:
+            refn = O.OracleSolver(pn, parallel=False).solve(ws_in=wh.numpy()[0].copy(), sigma=SIGMA)
+            entry["parity_rel_err"] = rel_err(on.cpu().numpy()[0], refn)
+        lat[str(n)] = entry
+        del sn
+    out["latency_vs_N_us"] = lat
+    if ctx.world == 1 and not ctx.args.no_cpu_baseline:
+        v, cores, sample = cpu_single(prob, seconds=2.0)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                               "latency_us": 1e6 / v}
+    return out
+
+
+# --------------------------------------------------------------------------------------------- C5 (long horizon)
+def leg_c5(ctx, steps):
+    """N = 2^20.  1 GPU: whole horizon on one handle.  N > 1 GPUs: contiguous time slices per rank, ONE all_gather of a
+    3,648-byte summary per solve (HorizonShardedSolver); strong scaling: `value` = solves/s of the ONE problem."""
+    import pdplqr_b200 as P
+    from pdplqr_b200 import sharding
+    torch, dist = ctx.torch, ctx.dist
+    world, rank = ctx.world, ctx.rank
+    out = dict(workload_config("c5", world))
+    steps = max(3, min(steps, 10))
+    nseg = c5_segments(world)
+    rng = np.random.default_rng(17)
+    ws_full_host = None
+    t0 = time.time()
+    if world == 1:
+        prob = P.problems.quadrotor_ltv(C5_N)
+        log("c5: problem generated in %.1f s" % (time.time() - t0))
+        sol, ms, out_dev, ws_host, x0_host, step = run_single(ctx, prob, nseg, steps, 3, load_balancing=2)
+        ws_full_host = ws_host.numpy()
+        l0 = sol.launch_count(); step(); launches = sol.launch_count() - l0
+
+        def bwd_only():
+            sol.update_problem_data_device(ws_dev1, sigma=SIGMA)
+            sol.backward_device()
+        ws_dev1 = ws_host.to(ctx.dev)
+        x0_dev1 = x0_host.to(ctx.dev)
+        ms_bwd = ctx.time_loop(bwd_only, 5, 1)
+        sol.forward_device(x0_dev1, out_dev)
+        torch.cuda.synchronize()
+        out_np = np.empty((1, prob.ws_len))
+        link = link_bandwidth(ctx, 128 << 20)
+        ms_e2e = ctx.time_wall(lambda: sol.solve(ws_host.numpy(), x0_host.numpy(), out_np, sigma=SIGMA), 3, 1)
+        local_N, h2d, d2h = C5_N, (prob.ws_len + 12) * 8, prob.ws_len * 8
+        got_full = out_dev.cpu().numpy()[0]
+        out["num_segments"] = sol.num_segments
+    else:
+        start, count = sharding.horizon_slices(C5_N, world)[rank]
+        local = P.problems.quadrotor_ltv(C5_N, start=start, count=count)
+        log("c5: slice [%d, %d) generated in %.1f s" % (start, start + count, time.time() - t0))
+        hs = sharding.HorizonShardedSolver(None, rank, world, num_segments=nseg, device=ctx.local_rank, local=local)
+        hs.set_stream(ctx.stream.cuda_stream)
+        sol = hs.sol
+        # the iterate w_prev of the full problem, seeded so that every rank can cut its own slice
+        ws_full_host = 0.01 * rng.standard_normal((1, C5_N * 16 + 12))
+        lo = start * 16
+        hi = lo + count * 16 + 12          # the slice's last entry is x at its exit stage
+        ws_host = torch.from_numpy(np.ascontiguousarray(ws_full_host[:, lo:hi])).pin_memory()
+        ws_dev = ws_host.to(ctx.dev)
+        out_dev = torch.empty_like(ws_dev)
+        out_host = torch.empty_like(ws_host).pin_memory()
+
+        def step():
+            hs.solve_device(ws_dev, SIGMA, out_dev)
+        ms = ctx.time_loop(step, steps, 3)
+        l0 = sol.launch_count(); step(); launches = sol.launch_count() - l0
+
+        def bwd_only():
+            sol.update_problem_data_device(ws_dev, sigma=SIGMA)
+            sol.backward_device()
+        ms_bwd = ctx.time_loop(bwd_only, 5, 1)
+        step()
+        torch.cuda.synchronize()
+        # per-phase breakdown (CUDA events between the phases of a few instrumented solves; median, max over ranks)
+        per = {k: [] for k in hs.PHASES}
+        for _ in range(5):
+            ev = []
+            ctx.barrier()
+            hs.solve_device(ws_dev, SIGMA, out_dev, events=ev)
+            torch.cuda.synchronize()
+            for i, k in enumerate(hs.PHASES):
+                per[k].append(ev[i].elapsed_time(ev[i + 1]) * 1e3)
+        med = ctx.max_over_ranks([statistics.median(per[k]) for k in hs.PHASES])
+        out["phase_us"] = dict(zip(hs.PHASES, med))
+        out["phase_us"]["note"] = ("max over ranks of the per-rank median; all_gather includes waiting for the slowest rank's "
+                                   "local sweep; local_sweep_and_tree = stage sweep + local interface tree up-sweep")
+        out["limiting_phase"] = max(hs.PHASES, key=lambda k: out["phase_us"][k])
+        link = link_bandwidth(ctx, 128 << 20)
+
+        def step_e2e():   # host slice in, sharded solve, host slice out (pinned buffers)
+            ws_dev.copy_(ws_host, non_blocking=True)
+            hs.solve_device(ws_dev, SIGMA, out_dev)
+            out_host.copy_(out_dev, non_blocking=True)
+            torch.cuda.synchronize()
+        ms_e2e = ctx.time_wall(step_e2e, 3, 1)
+        local_N, h2d, d2h = count, ws_host.numel() * 8, out_host.numel() * 8
+        # gather the slices on rank 0 for the parity checks
+        parts = [torch.empty(sharding.horizon_slices(C5_N, world)[r][1] * 16 + 12, dtype=torch.float64, device=ctx.dev)
+                 for r in range(world)] if rank == 0 else None
+        dist.gather(out_dev[0], parts, dst=0)
+        got_full = None
+        if rank == 0:
+            got_full = np.empty(C5_N * 16 + 12)
+            for r in range(world):
+                s0, cnt = sharding.horizon_slices(C5_N, world)[r]
+                pr = parts[r].cpu().numpy()
+                got_full[s0 * 16:(s0 + cnt) * 16] = pr[:cnt * 16]
+                if r == world - 1:
+                    got_full[-12:] = pr[-12:]
+        out["num_segments"] = sol.num_segments * world
+        out["segments_per_rank"] = sol.num_segments
+    bwd_b, fwd_b = stage_bytes(12, 4, True)
+    ffl, wfl = stage_flops(12, 4, pdp=True)
+    out.update(ms_per_step=ms, value=1e3 / ms, unit=UNIT, scaling="strong" if world > 1 else "n/a (1 GPU)",
+               gpu_launches=int(launches),
+               roofline=roofline("seg_backward_kernel<12,4,32> (+ local interface tree up-sweep)", bwd_b * local_N,
+                                 ffl * local_N, ms_bwd, "c5" if world == 1 else None,
+                                 {"step_hbm_frac": (bwd_b + fwd_b) * C5_N / world / (ms * 1e-3) / 1e9 / peaks()[0],
+                                  "per_rank": world > 1}),
+               e2e=e2e_block(ctx, 1.0 / (ms_e2e * 1e-3), ms_e2e, h2d, d2h, link))
+    del sol
+    torch.cuda.empty_cache()
+    if rank == 0:   # parity of this run: sequential CPU oracle over the whole horizon (and the 1-GPU solve when sharded)
+        from oracle import oracle as O
+        t0 = time.time()
+        full = P.problems.quadrotor_ltv(C5_N) if world > 1 else prob
+        ref = O.OracleSolver(full, parallel=False).solve(ws_in=np.ascontiguousarray(ws_full_host[0]), sigma=SIGMA)
+        out["parity_rel_err"] = rel_err(got_full, ref)
+        out["parity_sample"] = "all 2^20 stages vs the sequential CPU oracle (%.0f s)" % (time.time() - t0)
+        if world > 1:
+            s1 = P.LQRCudaSolver.from_problem(full, device=ctx.local_rank, num_segments=c5_segments(1), load_balancing=2)
+            one = np.empty((1, full.ws_len))
+            s1.solve(np.ascontiguousarray(ws_full_host), full.x0, one, sigma=SIGMA)
+            out["parity_vs_1gpu"] = rel_err(got_full, one[0])
+            del s1
+        if world == 1 and not ctx.args.no_cpu_baseline:
+            v, cores, sample = cpu_single(full, seconds=3.0)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    return out
+
+
+# --------------------------------------------------------------------------------------------- C4 (conic ADMM)
+def leg_c4(ctx, steps):
     """BASELINE.json configs[3]: conic-constrained (box + SOC) LQ MPC nx=30 nu=10 N=256, batch 4096 per GPU, full outer
     iterations.  A step = one ADMM solve with a FIXED number of outer iterations (1 factorising + ITERS-1 affine-only
-    LQ solves, projections, residuals), all device-resident.  The outer iteration is not in the reference (hooks only)."""
-    import torch
-    import torch.distributed as dist
+    LQ solves, projections, residuals), device-resident.  The outer iteration is not in the reference (hooks only)."""
     import pdplqr_b200 as P
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B = int(os.environ.get("C4_BATCH", "4096"))
-    N = int(os.environ.get("C4_N", "256"))
-    ITERS = int(os.environ.get("C4_ITERS", "50"))
+    torch = ctx.torch
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    B = int(os.environ.get("C4_BATCH", str(C4_BATCH)))
+    N = int(os.environ.get("C4_N", str(C4_N)))
+    ITERS = int(os.environ.get("C4_ITERS", str(C4_ITERS)))
+    out = dict(workload_config("c4", world))
     base = 64 if B % 64 == 0 else B
-    sampler = ClockSampler(local_rank)
     hp = P.problems.random_conic_batch(batch=base, N=N, seed=99 + rank)
     rep = B // base
     nx, nu, s = hp.nx, hp.nu, hp.s
-    sol = P.LQRCudaSolver(nx, nu, N, batch=B, num_segments=1, ncs=hp.ncs, device=local_rank)
-    stream = torch.cuda.current_stream()
-    sol.set_stream(stream.cuda_stream)
+    sol = P.LQRCudaSolver(nx, nu, N, batch=B, num_segments=1, ncs=hp.ncs, device=ctx.local_rank)
+    sol.set_stream(ctx.stream.cuda_stream)
 
     def up(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -275,290 +768,163 @@ def run_c4(args, rank, world, local_rank):
     w = torch.zeros(B, hp.ws_len, dtype=torch.float64, device=dev)
     z = torch.zeros(B, nct, dtype=torch.float64, device=dev)
     y = torch.zeros(B, nct, dtype=torch.float64, device=dev)
+    last = {}
 
     def step():
         w.zero_(); z.zero_(); y.zero_()
-        return sol.admm_solve_device(x0, w, z, y, rho, inv_rho, sigma=1e-6, alpha=1.6, max_iter=ITERS, eps_abs=0.0,
-                                     eps_rel=0.0, check_every=ITERS)
-    steps = max(1, min(args.steps, int(os.environ.get("C4_STEPS", "3"))))
-    for _ in range(min(args.warmup, 1)):
-        step()
+        last["it"], last["res"] = sol.admm_solve_device(x0, w, z, y, rho, inv_rho, sigma=SIGMA, alpha=1.6, max_iter=ITERS,
+                                                        eps_abs=0.0, eps_rel=0.0, check_every=ITERS)
+    steps = max(1, min(steps, int(os.environ.get("C4_STEPS", "2"))))
+    step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t_w0 = time.time()
     l0 = sol.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(steps):
-        it, res = step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms_step = e0.elapsed_time(e1) / steps
-    launches = sol.launch_count() - l0
-    windows = [(t_w0, time.time())]
-    # affine-only iteration alone (the common ADMM iteration): CUDA events around update + backward_without_factorization
-    ka = 10
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a0.record(stream)
-    for _ in range(ka):
-        sol.update_problem_data_device(w, y, z, inv_rho, sigma=1e-6)
+    ms_step = ctx.time_loop(step, steps, 0)
+    launches = (sol.launch_count() - l0) // steps
+    w_gpu = w[:base].cpu().numpy()
+
+    def aff():
+        sol.update_problem_data_device(w, y, z, inv_rho, sigma=SIGMA)
         sol.backward_without_factorization_device(rho)
-    a1.record(stream)
+    ms_aff = ctx.time_loop(aff, 10, 1)
+
+    def fact():
+        sol.update_problem_data_device(w, y, z, inv_rho, sigma=SIGMA)
+        sol.backward_device(rho)
+    ms_fact = ctx.time_loop(fact, 2, 1)
+    sol.forward_device(x0, torch.empty_like(w))
     torch.cuda.synchronize()
-    ms_aff = a0.elapsed_time(a1) / ka
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(stream)
-    sol.update_problem_data_device(w, y, z, inv_rho, sigma=1e-6)
-    sol.backward_device(rho)
-    f1.record(stream)
-    torch.cuda.synchronize()
-    ms_fact = f0.elapsed_time(f1)
-    clocks = sampler.summary(windows)
-    t = torch.tensor([ms_step, ms_aff, ms_fact], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, ms_aff, ms_fact = (float(v) for v in t.cpu())
+    nc = int(hp.ncs[1])
+    # traffic-true algorithmic bytes (selection-matrix constraints: the dense D, nc*s doubles per stage, is never read):
+    # affine sweep reads [E|c], h, [K|d], [Quu^-1|P+c], w_prev, rho/z/y/inv_rho + (column, value) of every row, writes d
+    aff_bytes = 8 * (nx * s + nx + s + nu * (nx + 1) + nu * nu + nx + s + 5.5 * nc + nu)
+    # factorising sweep: model record + ADMM vectors in, factor record + affine cache out (no dense D either)
+    fact_bytes = 8 * (nx * s + nx + s * s + s + s + 5.5 * nc + nu * (nx + 1) + nu * nu + nx)
+    fact_flops, _ = stage_flops(nx, nu, nc=0, pdp=False)     # the selection fold-in is O(nc): not counted
+    aff_flops = 2 * nx * s + 2 * nu * nu + 2 * nu * nx + 4 * nc + 2 * s
+    out.update(ms_per_step=ms_step, value=world * B * 1e3 / ms_step, unit=UNIT, steps=steps, gpu_launches=int(launches),
+               problem_iterations_per_sec=world * B * ITERS * 1e3 / ms_step,
+               ms_factorizing_backward=ms_fact, ms_affine_backward=ms_aff,
+               final_residuals=[float(last["res"][0]), float(last["res"][1])],
+               roofline=roofline("seg_affine_kernel<30,10,128> (the common ADMM iteration)", aff_bytes * B * N,
+                                 aff_flops * B * N, ms_aff, None,
+                                 {"traffic": c4_traffic(B),
+                                  "traffic_source": "profiles/traffic.json['c4_affine_batch4096'] scaled to the batch (recorded ncu capture)",
+                                  "bytes_note": "selection-matrix constraints: no dense D traffic counted (the survey's 55,488 B/stage model does)",
+                                  "factorizing_kernel": roofline("seg_backward_kernel<30,10,128,CON>", fact_bytes * B * N,
+                                                                 fact_flops * B * N, ms_fact)}))
+    # e2e: host iterates in / out through pdplqr_admm_solve (pinned), a bounded sub-batch would change the workload:
+    # the whole batch is solved once
+    link = link_bandwidth(ctx, 128 << 20)
+    hw = torch.zeros(B, hp.ws_len, dtype=torch.float64).pin_memory()
+    hz = torch.zeros(B, nct, dtype=torch.float64).pin_memory()
+    hy = torch.zeros(B, nct, dtype=torch.float64).pin_memory()
+    hrho = torch.full((B, nct), 0.1, dtype=torch.float64).pin_memory()
+    hx0 = x0.cpu().pin_memory()
+
+    def step_e2e():
+        hw.zero_(); hz.zero_(); hy.zero_()
+        sol.admm_solve(hx0.numpy(), hw.numpy(), hz.numpy(), hy.numpy(), hrho.numpy(), sigma=SIGMA, alpha=1.6,
+                       max_iter=ITERS, eps_abs=0.0, eps_rel=0.0, check_every=ITERS)
+    ms_e2e = ctx.time_wall(step_e2e, 1, 1)
+    h2d = (hw.numel() + hz.numel() + hy.numel() + 2 * hrho.numel() + hx0.numel()) * 8
+    d2h = (hw.numel() + hz.numel() + hy.numel()) * 8
+    out["e2e"] = e2e_block(ctx, world * B / (ms_e2e * 1e-3), ms_e2e, h2d, d2h, link)
     if rank == 0:
-        nc = int(hp.ncs[1])
-        aff_bytes = 8 * (nx * s + s + nu * nx + nu * nu + 2 * nx + nc * s + 3 * nc + s)
-        fact_bytes = 55488
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = aff_bytes * B * N / (ms_aff * 1e-3) / 1e9
-        line = {"metric": METRIC, "value": world * B * 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": steps,
-                "warmup": min(args.warmup, 1), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "C4: conic (box + SOC) LQ MPC nx=30 nu=10 N=%d, batch %d per GPU, %d fixed ADMM outer iterations per solve (configs[3])" % (N, B, ITERS),
-                           "problems_per_gpu": B, "nx": nx, "nu": nu, "N": N, "nc": nc, "admm_iterations": ITERS,
-                           "problem_iterations_per_sec": world * B * ITERS * 1e3 / ms_step,
-                           "ms_factorizing_backward": ms_fact, "ms_affine_backward": ms_aff,
-                           "final_residuals": [float(res[0]), float(res[1])],
-                           "l2": "inputs larger than L2", "sharding": "independent problems per rank, no data-path collective"},
-                "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
-                "e2e": None, "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "seg_affine_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": c4_traffic(B), "algorithmic_bytes_per_launch": aff_bytes * B * N,
-                             "kernel_ms": ms_aff,
-                             "factorizing_kernel": {"kernel": "seg_backward_kernel<30,10,128>", "ms": ms_fact,
-                                                    "achieved": fact_bytes * B * N / (ms_fact * 1e-3) / 1e9,
-                                                    "frac": fact_bytes * B * N / (ms_fact * 1e-3) / 1e9 / peak}}}
-        if not args.no_cpu_baseline and world == 1:
+        from oracle import admm_ref
+        t0 = time.time()
+        errs = []
+        for b in range(2):   # two problems of this run, all ITERS outer iterations, numpy restatement + CPU oracle
+            wr, zr, yr, rp, rd = admm_ref.admm(hp, b, np.full(nct, 0.1), sigma=SIGMA, alpha=1.6, iters=ITERS)
+            errs.append(rel_err(w_gpu[b], wr))
+        out["parity_rel_err"] = max(errs)
+        out["parity_sample"] = ("2 problems x %d outer iterations vs oracle/admm_ref.py (%.0f s); the outer iteration is "
+                                "not in the reference: parity unpinned by construction" % (ITERS, time.time() - t0))
+        if world == 1 and not ctx.args.no_cpu_baseline:
             from oracle import oracle as O
             nb = min(base, 2 * host_cores())
             sub = hp.select(slice(0, nb))
             pool = O.OracleBatch(sub)
-            rng = np.random.default_rng(0)
-            ys_, zs_ = rng.standard_normal((nb, nct)), rng.standard_normal((nb, nct))
+            rngc = np.random.default_rng(0)
+            ys_, zs_ = rngc.standard_normal((nb, nct)), rngc.standard_normal((nb, nct))
             rh = np.full((nb, nct), 0.1)
             nt = host_cores()
             t0 = time.perf_counter(); pool.solve(ys=ys_, zs=zs_, rho=rh, inv_rho=1.0 / rh, factorize=True, nthreads=nt); tf = time.perf_counter() - t0
             t0 = time.perf_counter(); pool.solve(ys=ys_, zs=zs_, rho=rh, inv_rho=1.0 / rh, factorize=False, nthreads=nt); tn = time.perf_counter() - t0
-            v = nb / (tf + (ITERS - 1) * tn)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": host_cores(), "kind": "port",
-                                    "sample": "%d problems: 1 factorising + 1 affine-only LQ solve timed, extrapolated to %d iterations (projections not counted)" % (nb, ITERS)}
-        emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+            out["cpu_baseline"] = {"value": nb / (tf + (ITERS - 1) * tn), "unit": UNIT, "cores": nt, "kind": "port",
+                                   "sample": "%d problems: 1 factorising + 1 affine-only LQ solve timed, extrapolated to %d iterations (projections not counted)" % (nb, ITERS)}
+    del sol
+    torch.cuda.empty_cache()
+    return out
+
+
+LEGS = {"c2": leg_c2, "c5": leg_c5, "c4": leg_c4}
+
 
 # --------------------------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--workload", default="c3", help="headline workload (c3), or one of c2 / c5 / c4 alone")
+    ap.add_argument("--legs", default=os.environ.get("BENCH_LEGS", "c2,c5,c4"),
+                    help="extra configurations measured into the `configs` block of the c3 line ('' for none)")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
         return
 
     import torch
-    import torch.distributed as dist
-    import pdplqr_b200 as P
-
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    if args.workload == "c4":
-        run_c4(args, rank, world, local_rank)
-        return
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    sampler = ClockSampler(local_rank)
-    windows = []
-    horizon_sharded = args.workload in ("c5", "c5small") and world > 1
-    prob, kw, desc = make_workload(args.workload, 0 if horizon_sharded else rank)
-    stream = torch.cuda.current_stream()
-    if horizon_sharded:
-        # one long problem, contiguous time slices per rank, ONE all_gather of a 3,648-byte summary per solve
-        from pdplqr_b200.sharding import HorizonShardedSolver
-        # per rank: the single-GPU segment length, but never less than one full wave of (problem, segment) CTAs -- with a
-        # partial wave every SM runs fewer warps than it can hold and the sweep is a pure latency chain
-        hs = HorizonShardedSolver(prob, rank, world, num_segments=wave_aligned(max(kw["num_segments"] // world, WAVE)),
-                                  device=local_rank)
-        hs.set_stream(stream.cuda_stream)
-        sol = hs.sol
-        full_N = prob.N
-        prob = hs.local
-        prob.x0 = hs.x0.cpu().numpy()
+    ctx = Ctx(args)
+    sampler = ClockSampler(ctx.local_rank)
+    t_start = time.time()
+    if args.workload in LEGS:        # one configuration alone, as the line's own value
+        leg = LEGS[args.workload](ctx, args.steps)
+        main_res = None
     else:
-        sol = P.LQRCudaSolver.from_problem(prob, device=local_rank, **kw)
-        sol.set_stream(stream.cuda_stream)
-        full_N = prob.N
-    pdp = sol.num_segments > 1 or horizon_sharded
-    B, N, nx, nu, s = prob.batch, prob.N, prob.nx, prob.nu, prob.s
-
-    # device-resident iterates (ADMM would update ws between solves; here a fixed seeded iterate)
-    rng = np.random.default_rng(17 + rank)
-    ws_host = torch.from_numpy(0.01 * rng.standard_normal((B, prob.ws_len))).pin_memory()
-    x0_host = torch.from_numpy(np.ascontiguousarray(prob.x0)).pin_memory()
-    out_host = torch.empty_like(ws_host).pin_memory()
-    ws_dev = ws_host.to(dev)
-    x0_dev = x0_host.to(dev)
-    out_dev = torch.empty_like(ws_dev)
-    sigma = 1e-6
-
-    def step_device():
-        if horizon_sharded:
-            hs.solve_device(ws_dev, sigma, out_dev)
-            return
-        sol.update_problem_data_device(ws_dev, sigma=sigma)
-        sol.backward_device()
-        sol.forward_device(x0_dev, out_dev)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    t_w0 = time.time()
-    l0 = sol.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    ev1.record(stream)
-    barrier()
-    launches = sol.launch_count() - l0
-    ms_total = ev0.elapsed_time(ev1)
-    windows.append((t_w0, time.time()))
-    bad, _ = sol.last_status()
-
-    # dominant kernel alone (backward sweep): CUDA events around back-to-back launches on the same stream
-    kb = max(5, args.steps)
-    t_w0 = time.time()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l_b0 = sol.launch_count()
-    e0.record(stream)
-    for _ in range(kb):
-        sol.update_problem_data_device(ws_dev, sigma=sigma)
-        sol.backward_device()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    bwd_launches = (sol.launch_count() - l_b0) // kb
-    ms_bwd = e0.elapsed_time(e1) / kb
-    windows.append((t_w0, time.time()))
-    # leave the handle in a consistent state (one forward per backward)
-    if horizon_sharded:
-        hs.solve_device(ws_dev, sigma, out_dev)
-    else:
-        sol.forward_device(x0_dev, out_dev)
-    torch.cuda.synchronize()
-
-    # end-to-end through the host-buffer C ABI (pinned host memory; H2D + kernels + D2H inside the timed region)
-    ws_np, x0_np, out_np = ws_host.numpy(), x0_host.numpy(), out_host.numpy()
-    e2e_steps = max(3, min(args.steps, 10))
-
-    def step_e2e():
-        if horizon_sharded:   # host slice in, sharded solve, host slice out (pinned buffers)
-            ws_dev.copy_(ws_host, non_blocking=True)
-            hs.solve_device(ws_dev, sigma, out_dev)
-            out_host.copy_(out_dev, non_blocking=True)
-            torch.cuda.synchronize()
+        main_res = run_c3(ctx, args.steps, args.warmup, want_cpu=not args.no_cpu_baseline,
+                          batch=int(os.environ.get("C3_BATCH", str(C3_BATCH))))
+        c3_windows = list(ctx.windows)
+        legs = {}
+        for name in [x for x in args.legs.split(",") if x]:
+            t0 = time.time()
+            try:
+                legs[name] = LEGS[name](ctx, args.steps)
+            except Exception as e:   # an auxiliary configuration must not take the headline down
+                traceback.print_exc()
+                legs[name] = {"error": repr(e)}
+            legs[name]["leg_wall_s"] = time.time() - t0
+            log("leg %s done in %.1f s" % (name, time.time() - t0))
+            ctx.torch.cuda.empty_cache()
+    clocks = sampler.summary(ctx.windows if main_res is None else c3_windows)
+    if ctx.rank == 0:
+        if main_res is None:
+            line = {"metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True,
+                    "scaling": leg.get("scaling", "weak"), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": workload_config(args.workload, ctx.world), "clocks": clocks, "e2e": leg.get("e2e"),
+                    "gpu_launches": leg.get("gpu_launches"), "roofline": leg.get("roofline"),
+                    "cpu_baseline": leg.get("cpu_baseline"), "detail": leg}
         else:
-            sol.solve(ws_np, x0_np, out_np, sigma=sigma)
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    torch.cuda.synchronize()
-    t_e2e = (time.perf_counter() - t0) / e2e_steps
-    windows.append((time.time() - t_e2e * e2e_steps, time.time()))
-    clocks = sampler.summary(windows)
-    same = bool(np.array_equal(out_np, out_dev.cpu().numpy()))
-
-    t = torch.tensor([ms_total, t_e2e * 1e3, ms_bwd], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_bwd = (float(v) for v in t.cpu())
-
-    if rank == 0:
-        ms_step = ms_total / args.steps
-        solves_per_step = B if horizon_sharded else world * B   # a sharded long horizon is ONE solve across all ranks
-        value = solves_per_step * 1e3 / ms_step
-        bwd_b, fwd_b = algorithmic_bytes_per_stage(nx, nu, pdp)
-        peaks = {}
-        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(pk_path):
-            peaks = json.load(open(pk_path))
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = bwd_b * B * N / (ms_bwd * 1e-3) / 1e9
-        traffic = None
-        tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tr_path):
-            traffic = json.load(open(tr_path)).get(args.workload)
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if horizon_sharded else "weak",
-            "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": desc, "problems_per_gpu": B, "nx": nx, "nu": nu, "N": N,
-                       "num_segments": sol.num_segments, "sigma": sigma,
-                       "l2": "inputs larger than L2 (model records %.2f GB per GPU)" % (B * N * sol.record_doubles()[0] * 8 / 1e9),
-                       "sharding": ("horizon: contiguous time slices per rank, one all_gather of a %d-byte slice summary per solve"
-                                    % (sol.summary_doubles() * 8)) if horizon_sharded else
-                                   "independent problems per rank, no data-path collective",
-                       "full_horizon": full_N},
-            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"],
-                       "samples": clocks["samples"]},
-            "e2e": {"value": solves_per_step / (ms_e2e * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(ws_host.numel() * 8 + x0_host.numel() * 8),
-                    "d2h_bytes_per_step": int(out_host.numel() * 8), "ms_per_step": ms_e2e,
-                    "model": "resident (uploaded once by pdplqr_set_model)", "matches_device_path": same},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "batch_backward_kernel" if sol.num_segments == 1 and nx + nu <= 8 else "seg_backward_kernel",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                         "traffic": traffic, "algorithmic_bytes_per_launch": bwd_b * B * N,
-                         "kernel_ms": ms_bwd, "launches_per_backward": int(bwd_launches),
-                         "step_hbm_frac": (bwd_b + fwd_b) * B * N / (ms_step * 1e-3) / 1e9 / peak},
-            "non_pd_problems": int(bad),
-        }
-        if not args.no_cpu_baseline and world == 1:
-            v, cores, sample = cpu_baseline(prob)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            line = {"metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": workload_config("c3", ctx.world), "clocks": clocks, "e2e": main_res["e2e"],
+                    "gpu_launches": main_res["launches"], "roofline": main_res["roofline"],
+                    "parity_rel_err": main_res["parity_rel_err"], "parity_sample": main_res["parity_sample"],
+                    "non_pd_problems": main_res["bad"], "configs": legs, "bench_wall_s": time.time() - t_start}
+            if "cpu_baseline" in main_res:
+                line["cpu_baseline"] = main_res["cpu_baseline"]
         emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

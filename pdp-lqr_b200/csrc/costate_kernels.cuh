@@ -14,6 +14,7 @@
 // L = cost + sum_k lambda_{k+1}^T (E_k w_k + c_k - x_{k+1});  output lam[b][k-1] = lambda_k, k = 1..N.
 // One warp per (problem, segment); not a hot path (plain loads, no staging).
 #pragma once
+#include "batch_kernels.cuh"
 #include "seg_kernels.cuh"
 
 namespace pdplqr {
@@ -111,6 +112,62 @@ __global__ void __launch_bounds__(32) seg_costate_kernel(CostateParams q) {
             }
         }
         __syncwarp();
+    }
+}
+
+// Thread-per-problem version (batches of tiny systems, one segment, no constraints: batch_kernels.cuh): the same
+// recursion with the whole state of a problem in one thread's registers; the stage records are read straight from the
+// tile-interleaved blocks (adjacent lanes read adjacent 16-byte pairs: coalesced).  Not a hot path.
+template <int NX, int NU>
+__global__ void __launch_bounds__(128) batch_costate_kernel(CostateParams q) {
+    using B = BatchDims<NX, NU>;
+    constexpr int S = NX + NU;
+    const SegParams& p = q.sp;
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.batch) return;
+    const size_t tile = (size_t)(b >> 5);
+    const int lane = (int)(b & 31);
+    const size_t ws_len = (size_t)p.N * S + NX;
+    const double* tr = q.traj + (size_t)b * ws_len;
+    const double* wprev = p.ws_prev ? p.ws_prev + (size_t)b * ws_len : nullptr;
+    const double* model_t = p.model + tile * p.N * (B::TREC * 32);
+    double* lam_b = q.lam + (size_t)b * p.N * NX;
+    double ln[NX];
+    {   // lambda_N = (H_N + sigma I) x_N + h_N - sigma w_prev_N
+        const double* xN = tr + (size_t)p.N * S;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            double acc = p.hN[(size_t)b * NX + i] + p.sigma * (xN[i] - (wprev ? wprev[(size_t)p.N * S + i] : 0.0));
+#pragma unroll
+            for (int j = 0; j < NX; ++j) acc = fma(p.HN[(size_t)b * NX * NX + i + j * NX], xN[j], acc);
+            ln[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) lam_b[(size_t)(p.N - 1) * NX + i] = ln[i];
+    }
+#pragma unroll 1
+    for (int k = p.N - 1; k >= 1; --k) {
+        const double* blk = model_t + (size_t)k * (B::TREC * 32);
+        auto ld = [&](int e) { return blk[tile_pos(e, lane)]; };
+        double w[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) w[j] = tr[(size_t)k * S + j];
+        double out[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            const int row = NU + i;
+            double acc = ld(B::TR_h + row) + p.sigma * (w[row] - (wprev ? wprev[(size_t)k * S + row] : 0.0));
+#pragma unroll
+            for (int j = 0; j < S; ++j) acc = fma(ld(B::TR_H + (row >= j ? B::hl(row, j) : B::hl(j, row))), w[j], acc);
+#pragma unroll
+            for (int j = 0; j < NX; ++j) acc = fma(ld(B::TR_E + j + row * NX), ln[j], acc);   // A^T lambda+
+            out[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            ln[i] = out[i];
+            lam_b[(size_t)(k - 1) * NX + i] = out[i];
+        }
     }
 }
 

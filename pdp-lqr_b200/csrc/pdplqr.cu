@@ -14,6 +14,8 @@ PDPLQR_INST_LIST(PDPLQR_DECL_OPS)
 
 namespace {
 
+thread_local std::string g_create_error;   // why the last pdplqr_create on this thread failed (pdplqr_last_error(NULL))
+
 // registry of the instantiated (nx, nu) pairs (inst_list.h; one translation unit each)
 const Ops* find_ops(int nx, int nu) {
 #define PDPLQR_FIND_OPS(a, b, t) \
@@ -22,6 +24,19 @@ const Ops* find_ops(int nx, int nu) {
 #undef PDPLQR_FIND_OPS
     return nullptr;
 }
+// cheapest instantiated pair with NX >= nx and NU >= nu (cost ~ the (nx + nu)^3 stage flops)
+const Ops* find_padded_ops(int nx, int nu) {
+    const Ops* best = nullptr;
+    long best_cost = 0;
+#define PDPLQR_PAD_OPS(a, b, t)                                                    \
+    if (a >= nx && b >= nu) {                                                      \
+        const long cost = (long)(a + b) * (a + b) * (a + b);                       \
+        if (!best || cost < best_cost) { best = pdplqr_ops_##a##_##b(); best_cost = cost; } \
+    }
+    PDPLQR_INST_LIST(PDPLQR_PAD_OPS)
+#undef PDPLQR_PAD_OPS
+    return best;
+}
 
 // flat (E, c, H, h) -> device stage records.  sym = 0: [E | c | H | h] per (problem, stage) (segment kernels);
 // sym = 1: thread-per-problem path: [E | c | lower(H) packed by columns | h] with the records of the 32 problems of a
@@ -29,7 +44,11 @@ const Ops* find_ops(int nx, int nu) {
 // batch size, the tile count is ceil(nprob / 32) and lanes past the batch replicate the last problem.
 __global__ void pack_model_kernel(const double* __restrict__ E, const double* __restrict__ c,
                                   const double* __restrict__ H, const double* __restrict__ hv, double* __restrict__ rec,
-                                  long long nprob, int N, int nx, int s, int REC, int sym) {
+                                  long long nprob, int N, int nx, int s, int REC, int sym, int nxu, int nuu) {
+    // kernel dimensions (nx, s) vs the caller's (nxu, nuu): index i of w = [u; x] maps to the caller's index umap(i), or
+    // -1 for a padded input / state (identity cost, zero dynamics -- see pdplqr_solver::padded)
+    const int nu = s - nx, su = nxu + nuu;
+    auto umap = [&](int i) { return i < nu ? (i < nuu ? i : -1) : (i - nu < nxu ? nuu + (i - nu) : -1); };
     const int nH = sym ? s * (s + 1) / 2 : s * s;
     const int oC = nx * s, oH = oC + nx, oh = oH + nH, oend = oh + s;
     const long long npad = sym ? ((nprob + 31) / 32) * 32 : nprob;
@@ -54,9 +73,12 @@ __global__ void pack_model_kernel(const double* __restrict__ E, const double* __
         }
         const long long st = b * N + k;
         double v = 0.0;
-        if (e < oC) v = E[st * oC + e];
-        else if (e < oH) v = c[st * nx + (e - oC)];
-        else if (e < oh) {
+        if (e < oC) {
+            const int i = e % nx, ju = umap(e / nx);
+            if (i < nxu && ju >= 0) v = E[st * (long long)(nxu * su) + i + ju * nxu];
+        } else if (e < oH) {
+            if (e - oC < nxu) v = c[st * nxu + (e - oC)];
+        } else if (e < oh) {
             int q = e - oH;
             if (sym) {  // q -> (i, j), i >= j, columns packed one after the other
                 int j = 0;
@@ -66,21 +88,98 @@ __global__ void pack_model_kernel(const double* __restrict__ E, const double* __
                 const int di = q % s, j = q / s;
                 q = (((di - 4 * (j >> 1)) % s + s) % s) + j * s;
             }
-            v = H[st * (long long)(s * s) + q];
-        } else if (e < oend) v = hv[st * s + (e - oh)];
+            const int iu = umap(q % s), ju = umap(q / s);
+            if (iu >= 0 && ju >= 0) v = H[st * (long long)(su * su) + iu + ju * su];
+            else v = (q % s == q / s) ? 1.0 : 0.0;
+        } else if (e < oend) {
+            const int iu = umap(e - oh);
+            if (iu >= 0) v = hv[st * su + iu];
+        }
         rec[idx] = v;
     }
 }
 
-// flat D (reference layout, stage chunks back to back) -> device copy with every stage chunk padded to 16 bytes
+// flat D (reference layout, stage chunks back to back, nc_k x dim_user column-major) -> device copy in kernel dimensions
+// (zero columns for padded inputs / states) with every stage chunk padded to 16 bytes
 __global__ void pad_D_kernel(const double* __restrict__ src, double* __restrict__ dst, const long long* __restrict__ soff,
-                             const long long* __restrict__ doff, long long s_total, long long d_total, int nstages) {
-    const int b = blockIdx.y, k = blockIdx.x;
-    if (k >= nstages) return;
-    const long long n = soff[k + 1] - soff[k], nd = doff[k + 1] - doff[k];
+                             const long long* __restrict__ doff, const int* __restrict__ ncs, long long s_total,
+                             long long d_total, int nstages, int nx, int nu, int nxu, int nuu) {
+    const int b = blockIdx.x / nstages, k = blockIdx.x % nstages;   // 1-D grid: grid.y is capped at 65535
+    const long long nd = doff[k + 1] - doff[k];
+    const int nc = ncs[k];
+    const bool term = (k == nstages - 1);                            // terminal stage: columns are states only
     const double* s = src + (long long)b * s_total + soff[k];
     double* d = dst + (long long)b * d_total + doff[k];
-    for (long long e = threadIdx.x; e < nd; e += blockDim.x) d[e] = e < n ? s[e] : 0.0;
+    const int dim = term ? nx : nx + nu;
+    for (long long e = threadIdx.x; e < nd; e += blockDim.x) {
+        double v = 0.0;
+        if (nc > 0 && e < (long long)nc * dim) {
+            const int r = (int)(e % nc), j = (int)(e / nc);
+            int ju;
+            if (term) ju = j < nxu ? j : -1;
+            else ju = j < nu ? (j < nuu ? j : -1) : (j - nu < nxu ? nuu + (j - nu) : -1);
+            if (ju >= 0) v = s[r + (long long)ju * nc];
+        }
+        d[e] = v;
+    }
+}
+
+// layout conversion of trajectories [batch][N (nu + nx) + nx] between caller and kernel dimensions (either direction:
+// components the source does not have are zero, components the destination does not have are dropped)
+__global__ void repack_ws_kernel(const double* __restrict__ src, double* __restrict__ dst, long long batch, int N,
+                                 int nx_s, int nu_s, int nx_d, int nu_d) {
+    const int s_s = nx_s + nu_s, s_d = nx_d + nu_d;
+    const long long wl_s = (long long)N * s_s + nx_s, wl_d = (long long)N * s_d + nx_d, total = batch * wl_d;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / wl_d, r = idx - b * wl_d;
+        const long long k = r / s_d < N ? r / s_d : N;
+        const int i = (int)(r - k * s_d);
+        int is;
+        if (k == N) is = i < nx_s ? i : -1;
+        else is = i < nu_d ? (i < nu_s ? i : -1) : (i - nu_d < nx_s ? nu_s + (i - nu_d) : -1);
+        dst[idx] = is >= 0 ? src[b * wl_s + k * s_s + is] : 0.0;
+    }
+}
+// same for arrays of vectors / square blocks: [items][n_s (x n_s)] -> [items][n_d (x n_d)], `fill` on the padded diagonal
+__global__ void repack_vec_kernel(const double* __restrict__ src, double* __restrict__ dst, long long items, int n_s,
+                                  int n_d, int square, double fill) {
+    const long long per_d = square ? (long long)n_d * n_d : n_d, per_s = square ? (long long)n_s * n_s : n_s;
+    const long long total = items * per_d;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long it = idx / per_d;
+        const int e = (int)(idx - it * per_d);
+        const int i = square ? e % n_d : e, j = square ? e / n_d : 0;
+        double v = (square && i == j) ? fill : 0.0;
+        if (i < n_s && j < (square ? n_s : 1)) v = src[it * per_s + i + (long long)j * n_s];
+        dst[idx] = v;
+    }
+}
+
+// factor records -> gains in the caller's layout for problems [b0, b0 + nb): K [nb][N][nuu x nxu], d [nb][N][nuu],
+// Gt [nb][N][nuu x nxu] (zero in the last segment, which ends at the terminal cost, and on the thread-per-problem path)
+__global__ void unpack_gains_kernel(const double* __restrict__ fac, double* __restrict__ K, double* __restrict__ d,
+                                    double* __restrict__ Gt, int b0, int nb, int N, int nx, int nu, int nxu, int nuu,
+                                    int FREC, int tiled, int last_start) {
+    const int nK = nuu * nxu, per = 2 * nK + nuu;
+    const long long total = (long long)nb * N * per;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long st = idx / per;
+        const int e = (int)(idx - st * per);
+        const long long bl = st / N, b = b0 + bl;
+        const int k = (int)(st - bl * N);
+        int which, q;                               // 0: K, 1: d, 2: Gt ; q = index inside the caller's block
+        if (e < nK) { which = 0; q = e; } else if (e < nK + nuu) { which = 1; q = e - nK; } else { which = 2; q = e - nK - nuu; }
+        const int i = which == 1 ? q : q % nuu, j = which == 1 ? 0 : q / nuu;
+        const int src = which == 0 ? i + j * nu : (which == 1 ? nu * nx + i : nu * (nx + 1) + i + j * nu);
+        double v = 0.0;
+        if (which == 2 && (tiled || k >= last_start)) v = 0.0;
+        else if (tiled) v = fac[((b / 32) * N + k) * (long long)FREC * 32 + (src & ~1) * 32 + (b % 32) * 2 + (src & 1)];
+        else v = fac[(b * N + k) * (long long)FREC + src];
+        (which == 0 ? K + st * nK : (which == 1 ? d + st * nuu : Gt + st * nK))[q] = v;
+    }
 }
 
 // one block per (stage, problem): for every constraint row find its non-zeros; rows with at most one non-zero are
@@ -89,7 +188,7 @@ __global__ void detect_selection_kernel(const double* __restrict__ D, const long
                                         const long long* __restrict__ coff, const int* __restrict__ ncs, long long d_total,
                                         long long nc_total, int N, int nx, int s, int* __restrict__ col,
                                         double* __restrict__ val, int* flag) {
-    const int k = blockIdx.x, b = blockIdx.y;
+    const int k = blockIdx.x % (N + 1), b = blockIdx.x / (N + 1);   // 1-D grid: grid.y is capped at 65535
     const int nc = ncs[k], dim = (k < N) ? s : nx;
     const double* Dk = D + (long long)b * d_total + doff[k];
     for (int r = threadIdx.x; r < nc; r += blockDim.x) {
@@ -114,34 +213,61 @@ int dev_alloc(Solver& h, Tp** p, size_t count) {
     return PDPLQR_OK;
 }
 
+// grid for an element-wise helper kernel
+inline int ew_blocks(long long total) { return (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, 148LL * 32)); }
+
+// caller-layout trajectory -> kernel layout (or back): only used by padded handles
+int repack_ws(Solver& h, const double* src, double* dst, bool to_kernel) {
+    const long long total = (long long)h.batch * ((long long)h.N * (to_kernel ? h.s : h.su) + (to_kernel ? h.nx : h.nxu));
+    if (to_kernel) repack_ws_kernel<<<ew_blocks(total), 256, 0, h.stream>>>(src, dst, h.batch, h.N, h.nxu, h.nuu, h.nx, h.nu);
+    else repack_ws_kernel<<<ew_blocks(total), 256, 0, h.stream>>>(src, dst, h.batch, h.N, h.nx, h.nu, h.nxu, h.nuu);
+    h.launches++;
+    CU_TRY(&h, cudaGetLastError());
+    return PDPLQR_OK;
+}
+// [items][n_src (x n_src)] -> [items][n_dst (x n_dst)]
+int repack_vec(Solver& h, const double* src, double* dst, long long items, int n_src, int n_dst, bool square = false,
+               double fill = 0.0) {
+    const long long total = items * (square ? (long long)n_dst * n_dst : n_dst);
+    repack_vec_kernel<<<ew_blocks(total), 256, 0, h.stream>>>(src, dst, items, n_src, n_dst, square ? 1 : 0, fill);
+    h.launches++;
+    CU_TRY(&h, cudaGetLastError());
+    return PDPLQR_OK;
+}
+
 int set_model_common(Solver& h, const double* E, const double* c, const double* H, const double* hv,
                      const double* HN, const double* hN, const double* Dflat, bool on_device) {
     if (h.nc_total > 0 && !Dflat) return fail(&h, PDPLQR_ERR_INVALID, "set_model: D is required when ncs has non-zero entries");
-    const size_t nst = (size_t)h.batch * h.N;
-    const size_t nE = nst * h.nx * h.s, nc = nst * h.nx, nH = nst * h.s * h.s, nh = nst * h.s;
-    const double *dE = E, *dc = c, *dH = H, *dh = hv;
+    const size_t nst = (size_t)h.batch * h.N, B = h.batch;
+    const size_t nE = nst * h.nxu * h.su, nc = nst * h.nxu, nH = nst * h.su * h.su, nh = nst * h.su;   // caller's layout
+    const size_t nHN = B * h.nxu * h.nxu, nhN = B * h.nxu;
+    const double *dE = E, *dc = c, *dH = H, *dh = hv, *dHN = HN, *dhN = hN;
     double* stage = nullptr;
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (!on_device) {
-        CU_TRY(&h, cudaMalloc((void**)&stage, (nE + nc + nH + nh) * sizeof(double)));
+        CU_TRY(&h, cudaMalloc((void**)&stage, (nE + nc + nH + nh + nHN + nhN) * sizeof(double)));
         cudaError_t e1 = cudaMemcpyAsync(stage, E, nE * 8, kind, h.stream);
         cudaError_t e2 = cudaMemcpyAsync(stage + nE, c, nc * 8, kind, h.stream);
         cudaError_t e3 = cudaMemcpyAsync(stage + nE + nc, H, nH * 8, kind, h.stream);
         cudaError_t e4 = cudaMemcpyAsync(stage + nE + nc + nH, hv, nh * 8, kind, h.stream);
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
-            cudaFree(stage);
-            return fail(&h, PDPLQR_ERR_CUDA, "model upload failed");
-        }
+        cudaError_t e5 = cudaMemcpyAsync(stage + nE + nc + nH + nh, HN, nHN * 8, kind, h.stream);
+        cudaError_t e6 = cudaMemcpyAsync(stage + nE + nc + nH + nh + nHN, hN, nhN * 8, kind, h.stream);
+        for (cudaError_t e : {e1, e2, e3, e4, e5, e6})
+            if (e != cudaSuccess) {
+                cudaFree(stage);
+                return fail(&h, PDPLQR_ERR_CUDA, std::string("set_model: model upload failed: ") + cudaGetErrorString(e));
+            }
         dE = stage; dc = stage + nE; dH = stage + nE + nc; dh = stage + nE + nc + nH;
+        dHN = dh + nh; dhN = dHN + nHN;
     }
     const long long total = (long long)(h.thread_path ? ((h.batch + 31) / 32) * 32 : h.batch) * h.N * h.mrec;
-    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
-    pack_model_kernel<<<blocks, 256, 0, h.stream>>>(dE, dc, dH, dh, h.d_model, (long long)h.batch, h.N, h.nx, h.s, h.mrec,
-                                                    h.thread_path ? 1 : 0);
+    pack_model_kernel<<<ew_blocks(total), 256, 0, h.stream>>>(dE, dc, dH, dh, h.d_model, (long long)h.batch, h.N, h.nx, h.s,
+                                                              h.mrec, h.thread_path ? 1 : 0, h.nxu, h.nuu);
     h.launches++;
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h.d_HN, HN, (size_t)h.batch * h.nx * h.nx * 8, kind, h.stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h.d_hN, hN, (size_t)h.batch * h.nx * 8, kind, h.stream);
+    // terminal cost; padded states get a unit diagonal (they are zero, the value function stays positive definite)
+    if (e == cudaSuccess && repack_vec(h, dHN, h.d_HN, (long long)B, h.nxu, h.nx, true, 1.0)) e = cudaErrorUnknown;
+    if (e == cudaSuccess && repack_vec(h, dhN, h.d_hN, (long long)B, h.nxu, h.nx)) e = cudaErrorUnknown;
     double* dstage = nullptr;
     if (e == cudaSuccess && h.nc_total > 0) {
         const double* dsrc = Dflat;
@@ -150,18 +276,19 @@ int set_model_common(Solver& h, const double* E, const double* c, const double* 
             if (e == cudaSuccess) e = cudaMemcpyAsync(dstage, Dflat, (size_t)h.batch * h.d_total_host * 8, kind, h.stream);
             dsrc = dstage;
         }
+        const unsigned grid = (unsigned)((h.N + 1) * (long long)h.batch);   // 1-D: grid.y is capped at 65535
         if (e == cudaSuccess) {
-            pad_D_kernel<<<dim3(h.N + 1, h.batch), 128, 0, h.stream>>>(dsrc, h.d_D, h.d_doff_host, h.d_doff, h.d_total_host,
-                                                                     h.d_total_dev, h.N + 1);
+            pad_D_kernel<<<grid, 128, 0, h.stream>>>(dsrc, h.d_D, h.d_doff_host, h.d_doff, h.d_ncs, h.d_total_host,
+                                                     h.d_total_dev, h.N + 1, h.nx, h.nu, h.nxu, h.nuu);
             h.launches++;
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) {   // structure detection: selection-matrix constraints need no dense D in the kernels
             e = cudaMemsetAsync(h.d_sel_flag, 0, sizeof(int), h.stream);
-            detect_selection_kernel<<<dim3(h.N + 1, h.batch), 64, 0, h.stream>>>(h.d_D, h.d_doff, h.d_coff, h.d_ncs, h.d_total_dev,
-                                                                                h.nc_total, h.N, h.nx, h.s, h.d_sel_col, h.d_sel_val,
-                                                                                h.d_sel_flag);
+            detect_selection_kernel<<<grid, 64, 0, h.stream>>>(h.d_D, h.d_doff, h.d_coff, h.d_ncs, h.d_total_dev, h.nc_total, h.N,
+                                                               h.nx, h.s, h.d_sel_col, h.d_sel_val, h.d_sel_flag);
             h.launches++;
+            if (e == cudaSuccess) e = cudaGetLastError();
             int flag = 1;
             if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, h.d_sel_flag, sizeof(int), cudaMemcpyDeviceToHost, h.stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(h.stream);
@@ -294,8 +421,12 @@ int run_tree_down(Solver& h, const double* d_x0, const double* d_lam0) {
 
 int run_forward(Solver& h, const double* d_x0, double* d_ws_out) {
     if (!h.backward_done) return fail(&h, PDPLQR_ERR_ORDER, "forward before backward (one forward per backward)");
-    if (h.interior && !h.have_root)
-        return fail(&h, PDPLQR_ERR_ORDER, "forward on an interior horizon shard needs pdplqr_set_root_boundary_device first");
+    if (h.interior && !h.root_fresh)
+        return fail(&h, PDPLQR_ERR_ORDER, "forward on an interior horizon shard needs a fresh pdplqr_set_root_boundary_device");
+    // a root boundary is consumed by the forward that follows it: a handle reused without refreshing the boundary
+    // rolls out from the caller's x0 again (have_root = "the last forward used the root boundary", read by the costates)
+    h.have_root = h.root_fresh;
+    h.root_fresh = false;
     if (h.have_root) d_x0 = h.d_root_x;
     if (h.S > 1) {
         int rc = run_tree_down(h, d_x0, h.have_root ? h.d_root_lam : nullptr);
@@ -305,6 +436,16 @@ int run_forward(Solver& h, const double* d_x0, double* d_ws_out) {
     if (rc) return rc;
     h.backward_done = false;
     return PDPLQR_OK;
+}
+
+// forward with caller-layout device arrays (x0 [batch][nxu], ws_out [batch][N su + nxu])
+int run_forward_user(Solver& h, const double* d_x0, double* d_ws_out) {
+    if (!h.padded) return run_forward(h, d_x0, d_ws_out);
+    int rc = repack_vec(h, d_x0, h.d_x0p, h.batch, h.nxu, h.nx);
+    if (rc) return rc;
+    rc = run_forward(h, h.d_x0p, h.d_wsp_out);
+    if (rc) return rc;
+    return repack_ws(h, h.d_wsp_out, d_ws_out, false);
 }
 
 }  // namespace
@@ -321,14 +462,24 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (nx < 1 || nu < 1 || N < 1 || batch < 1 || num_segments < 0) return PDPLQR_ERR_INVALID;  // lqr_model.hpp:75-77
     if (condensed_type != PDPLQR_CONDENSED_LU && condensed_type != PDPLQR_CONDENSED_CHOLESKY)
         return PDPLQR_ERR_INVALID;  // lqr_solver_parallel.hpp:98-99
+    const int nxu = nx, nuu = nu;
     const Ops* ops = find_ops(nx, nu);
-    if (!ops) return PDPLQR_ERR_UNSUPPORTED;
+    if (!ops) {   // not an instantiated pair: embed in the cheapest one that contains it (the reference takes any n, m:
+                  // lqr_model.hpp:66-89)
+        ops = find_padded_ops(nx, nu);
+        if (!ops) {
+            g_create_error = "pdplqr_create: (nx, nu) exceeds the largest instantiated kernel size (csrc/inst_list.h)";
+            return PDPLQR_ERR_UNSUPPORTED;
+        }
+        nx = ops->nx; nu = ops->nu;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) return PDPLQR_ERR_CUDA;
     if (cudaSetDevice(device) != cudaSuccess) return PDPLQR_ERR_CUDA;
 
     Solver* h = new Solver();
     h->nx = nx; h->nu = nu; h->N = N; h->batch = batch; h->s = nx + nu; h->device = device;
+    h->nxu = nxu; h->nuu = nuu; h->su = nxu + nuu; h->padded = (nxu != nx || nuu != nu);
     h->load_balancing = load_balancing == 1; h->condensed_type = condensed_type; h->ops = ops;
     h->ncs.assign(N + 1, 0);
     if (ncs) h->ncs.assign(ncs, ncs + N + 1);
@@ -338,9 +489,9 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     }
     h->coff.assign(N + 2, 0); h->doff_host.assign(N + 2, 0); h->doff_dev.assign(N + 2, 0);
     for (int k = 0; k <= N; ++k) {
-        const long long dim = (k < N) ? nx + nu : nx;
+        const long long dim = (k < N) ? nx + nu : nx, dim_user = (k < N) ? nxu + nuu : nxu;
         h->coff[k + 1] = h->coff[k] + h->ncs[k];
-        h->doff_host[k + 1] = h->doff_host[k] + h->ncs[k] * dim;
+        h->doff_host[k + 1] = h->doff_host[k] + h->ncs[k] * dim_user;
         h->doff_dev[k + 1] = h->doff_dev[k] + ((h->ncs[k] * dim + 1) & ~1LL);
         h->ncmax = std::max(h->ncmax, h->ncs[k]);
     }
@@ -391,8 +542,20 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (const char* e = getenv("PDPLQR_SPARSE_D")) h->allow_sel = atoi(e);
     if (const char* e = getenv("PDPLQR_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(1, std::min(64, atoi(e)));
 
-    auto bail = [&](int rc) { std::string e = h->err; pdplqr_destroy(h); (void)e; return rc; };
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PDPLQR_ERR_CUDA);
+    auto bail = [&](int rc) {   // keep the error text: the handle does not survive
+        g_create_error = h->err.empty() ? std::string("pdplqr_create: ") + cudaGetErrorString(cudaGetLastError()) : h->err;
+        pdplqr_destroy(h);
+        return rc;
+    };
+#define CREATE_TRY(expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            h->err = std::string("pdplqr_create: " #expr ": ") + cudaGetErrorString(_e);              \
+            return bail(PDPLQR_ERR_CUDA);                                                             \
+        }                                                                                             \
+    } while (0)
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
     const size_t B = batch, ws_len = (size_t)N * h->s + nx;
     int rc = 0;
@@ -410,6 +573,11 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     rc |= dev_alloc(*h, &h->d_seg_start, S);
     rc |= dev_alloc(*h, &h->d_seg_len, S);
     rc |= dev_alloc(*h, &h->d_status, B);
+    if (h->padded) {
+        rc |= dev_alloc(*h, &h->d_wsp_in, ws_len * B);
+        rc |= dev_alloc(*h, &h->d_wsp_out, ws_len * B);
+        rc |= dev_alloc(*h, &h->d_x0p, B * nx);
+    }
     if (h->nc_total > 0) {
         rc |= dev_alloc(*h, &h->d_ncs, N + 1);
         rc |= dev_alloc(*h, &h->d_coff, N + 2);
@@ -425,18 +593,20 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
         rc |= dev_alloc(*h, &h->d_sel_flag, 1);
     }
     if (h->keep_affine) rc |= dev_alloc(*h, &h->d_aff, B * N * ops->AREC);
-    if (rc) return bail(PDPLQR_ERR_CUDA);
+    if (rc) return bail(PDPLQR_ERR_CUDA);   // (dev_alloc left the CUDA error text in h->err)
     if (h->nc_total > 0) {
-        cudaMemcpy(h->d_ncs, h->ncs.data(), sizeof(int) * (N + 1), cudaMemcpyHostToDevice);
-        cudaMemcpy(h->d_coff, h->coff.data(), sizeof(long long) * (N + 2), cudaMemcpyHostToDevice);
-        cudaMemcpy(h->d_doff, h->doff_dev.data(), sizeof(long long) * (N + 2), cudaMemcpyHostToDevice);
-        cudaMemcpy(h->d_doff_host, h->doff_host.data(), sizeof(long long) * (N + 2), cudaMemcpyHostToDevice);
+        CREATE_TRY(cudaMemcpy(h->d_ncs, h->ncs.data(), sizeof(int) * (N + 1), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(h->d_coff, h->coff.data(), sizeof(long long) * (N + 2), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(h->d_doff, h->doff_dev.data(), sizeof(long long) * (N + 2), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(h->d_doff_host, h->doff_host.data(), sizeof(long long) * (N + 2), cudaMemcpyHostToDevice));
     }
-    cudaMemcpy(h->d_seg_start, h->seg_start.data(), sizeof(int) * S, cudaMemcpyHostToDevice);
-    cudaMemcpy(h->d_seg_len, h->seg_len.data(), sizeof(int) * S, cudaMemcpyHostToDevice);
-    cudaMemset(h->d_fac, 0, Bpad * N * ops->FREC * sizeof(double));
-    cudaMemset(h->d_uhat, 0, B * S * nx * sizeof(double));
-    cudaMemset(h->d_status, 0, B * sizeof(int));
+    CREATE_TRY(cudaMemcpy(h->d_seg_start, h->seg_start.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemcpy(h->d_seg_len, h->seg_len.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+    CREATE_TRY(cudaMemset(h->d_fac, 0, Bpad * N * ops->FREC * sizeof(double)));
+    CREATE_TRY(cudaMemset(h->d_uhat, 0, B * S * nx * sizeof(double)));
+    CREATE_TRY(cudaMemset(h->d_status, 0, B * sizeof(int)));
+    // the thread-per-problem kernels write only P, p of the summary: F, C, f of a one-segment terminal slice are zero
+    CREATE_TRY(cudaMemset(h->d_sum, 0, B * S * ops->SREC * sizeof(double)));
 
     // ---- interface tree plan: lower levels (one launch each, fan-in 4) until <= 32 nodes, then binary levels
     //      that all run inside one launch (tree_top_*_kernel); the last level is the root (1 node)
@@ -486,7 +656,8 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
         }
         if (rc) return bail(PDPLQR_ERR_CUDA);
     }
-    if (cudaDeviceSynchronize() != cudaSuccess) return bail(PDPLQR_ERR_CUDA);
+    CREATE_TRY(cudaDeviceSynchronize());
+#undef CREATE_TRY
     *out = h;
     return PDPLQR_OK;
 }
@@ -532,6 +703,12 @@ int pdplqr_update_problem_data_device(pdplqr_handle_t h, const double* ws, const
     if (!h) return PDPLQR_ERR_INVALID;
     if (h->nc_total > 0 && (!ys || !zs || !inv_rho))
         return fail(h, PDPLQR_ERR_INVALID, "update_problem_data: ys, zs, inv_rho are required when the problem has constraints");
+    if (h->padded && ws) {   // caller layout -> kernel layout (copied now: the caller's array may change afterwards)
+        cudaSetDevice(h->device);
+        int rc = repack_ws(*h, ws, h->d_wsp_in, true);
+        if (rc) return rc;
+        ws = h->d_wsp_in;
+    }
     h->cur_ws = ws;
     h->cur_ys = ys; h->cur_zs = zs; h->cur_inv_rho = inv_rho;
     h->sigma = sigma;
@@ -542,7 +719,7 @@ int pdplqr_update_problem_data(pdplqr_handle_t h, const double* ws, const double
                                const double* inv_rho, double sigma) {
     if (!h) return PDPLQR_ERR_INVALID;
     cudaSetDevice(h->device);
-    const size_t ws_len = (size_t)h->N * h->s + h->nx;
+    const size_t ws_len = (size_t)h->N * h->su + h->nxu;   // caller's layout
     if (ws) CU_TRY(h, cudaMemcpyAsync(h->d_ws_in, ws, ws_len * h->batch * 8, cudaMemcpyHostToDevice, h->stream));
     if (h->nc_total > 0) {
         if (!ys || !zs || !inv_rho)
@@ -605,7 +782,10 @@ int pdplqr_set_option(pdplqr_handle_t h, int option, int value) {
         return PDPLQR_OK;
     }
     if (option == PDPLQR_OPT_INTERIOR_SHARD) {
+        if (!value && h->interior && h->model_set)
+            return fail(h, PDPLQR_ERR_ORDER, "PDPLQR_OPT_INTERIOR_SHARD cannot be switched off after set_model (create a new handle)");
         h->interior = value != 0;
+        h->have_root = h->root_fresh = false;
         if (h->interior) {
             if (h->thread_path) {   // the thread-per-problem records are packed differently: re-plan before set_model
                 if (h->model_set) return fail(h, PDPLQR_ERR_ORDER, "set PDPLQR_OPT_INTERIOR_SHARD before set_model");
@@ -646,10 +826,12 @@ int pdplqr_set_root_boundary_device(pdplqr_handle_t h, const double* xhat, const
         if (dev_alloc(*h, &h->d_root_lam, (size_t)h->batch * h->nx)) return PDPLQR_ERR_CUDA;
     }
     const size_t nb = (size_t)h->batch * h->nx * 8;
-    CU_TRY(h, cudaMemcpyAsync(h->d_root_x, xhat, nb, cudaMemcpyDeviceToDevice, h->stream));
-    if (lam) CU_TRY(h, cudaMemcpyAsync(h->d_root_lam, lam, nb, cudaMemcpyDeviceToDevice, h->stream));
+    int rc = repack_vec(*h, xhat, h->d_root_x, h->batch, h->nxu, h->nx);   // (a plain copy when nothing is padded)
+    if (rc) return rc;
+    if (lam) rc = repack_vec(*h, lam, h->d_root_lam, h->batch, h->nxu, h->nx);
     else CU_TRY(h, cudaMemsetAsync(h->d_root_lam, 0, nb, h->stream));
-    h->have_root = true;
+    if (rc) return rc;
+    h->root_fresh = true;
     return PDPLQR_OK;
 }
 
@@ -672,35 +854,41 @@ int pdplqr_coupler_solve_device(pdplqr_handle_t c, const double* summaries, cons
         return fail(c, PDPLQR_ERR_INVALID, "coupler_solve: bad arguments");
     cudaSetDevice(c->device);
     const int G = c->S;
-    const size_t nb = (size_t)c->batch * G * c->nx * 8;
+    const long long items = (long long)c->batch * G;
     if (G == 1) {
-        CU_TRY(c, cudaMemcpyAsync(xhat, x0, (size_t)c->batch * c->nx * 8, cudaMemcpyDeviceToDevice, c->stream));
-        CU_TRY(c, cudaMemsetAsync(lam, 0, nb, c->stream));
+        CU_TRY(c, cudaMemcpyAsync(xhat, x0, (size_t)c->batch * c->nxu * 8, cudaMemcpyDeviceToDevice, c->stream));
+        CU_TRY(c, cudaMemsetAsync(lam, 0, (size_t)items * c->nxu * 8, c->stream));
         return PDPLQR_OK;
     }
-    // summaries are laid out [batch][G][SREC] exactly like the level-0 array of the tree
-    CU_TRY(c, cudaMemcpyAsync(c->d_sum, summaries, (size_t)c->batch * G * c->ops->SREC * 8, cudaMemcpyDeviceToDevice,
-                              c->stream));
-    int rc = run_tree_up(*c, false);
+    // summaries are laid out [batch][G][SREC] exactly like the level-0 array of the tree (kernel dimensions: for a padded
+    // (nx, nu) they are opaque records, produced by pdplqr_get_root_summary_device of handles with the same (nx, nu))
+    CU_TRY(c, cudaMemcpyAsync(c->d_sum, summaries, (size_t)items * c->ops->SREC * 8, cudaMemcpyDeviceToDevice, c->stream));
+    int rc = PDPLQR_OK;
+    if (c->padded) {
+        rc = repack_vec(*c, x0, c->d_x0p, c->batch, c->nxu, c->nx);
+        if (rc) return rc;
+        x0 = c->d_x0p;
+    }
+    rc = run_tree_up(*c, false);
     if (rc) return rc;
     rc = run_tree_down(*c, x0, nullptr);
     if (rc) return rc;
-    CU_TRY(c, cudaMemcpyAsync(xhat, c->d_xhat, nb, cudaMemcpyDeviceToDevice, c->stream));
-    CU_TRY(c, cudaMemcpyAsync(lam, c->d_uhat, nb, cudaMemcpyDeviceToDevice, c->stream));
-    return PDPLQR_OK;
+    rc = repack_vec(*c, c->d_xhat, xhat, items, c->nx, c->nxu);
+    if (rc) return rc;
+    return repack_vec(*c, c->d_uhat, lam, items, c->nx, c->nxu);
 }
 
 int pdplqr_forward_device(pdplqr_handle_t h, const double* x0, double* ws_out) {
     if (!h || !x0 || !ws_out) return fail(h, PDPLQR_ERR_INVALID, "forward: null pointer");
     cudaSetDevice(h->device);
-    return run_forward(*h, x0, ws_out);
+    return run_forward_user(*h, x0, ws_out);
 }
 int pdplqr_forward(pdplqr_handle_t h, const double* x0, double* ws_out) {
     if (!h || !x0 || !ws_out) return fail(h, PDPLQR_ERR_INVALID, "forward: null pointer");
     cudaSetDevice(h->device);
-    const size_t ws_len = (size_t)h->N * h->s + h->nx;
-    CU_TRY(h, cudaMemcpyAsync(h->d_x0, x0, (size_t)h->batch * h->nx * 8, cudaMemcpyHostToDevice, h->stream));
-    int rc = run_forward(*h, h->d_x0, h->d_ws_out);
+    const size_t ws_len = (size_t)h->N * h->su + h->nxu;   // caller's layout
+    CU_TRY(h, cudaMemcpyAsync(h->d_x0, x0, (size_t)h->batch * h->nxu * 8, cudaMemcpyHostToDevice, h->stream));
+    int rc = run_forward_user(*h, h->d_x0, h->d_ws_out);
     if (rc) return rc;
     CU_TRY(h, cudaMemcpyAsync(ws_out, h->d_ws_out, ws_len * h->batch * 8, cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(h, cudaStreamSynchronize(h->stream));
@@ -755,7 +943,7 @@ static int solve_pipelined(Solver& h, const double* ws_in, double sigma, const d
 
 int pdplqr_solve(pdplqr_handle_t h, const double* ws_in, const double* ys, const double* zs, const double* rho,
                  const double* inv_rho, double sigma, const double* x0, double* ws_out) {
-    if (h && x0 && ws_out && h->thread_path && h->model_set && h->pipeline_chunks > 1 && h->batch >= 4096 && !h->have_root) {
+    if (h && x0 && ws_out && h->thread_path && h->model_set && h->pipeline_chunks > 1 && h->batch >= 4096 && !h->root_fresh && !h->padded) {
         cudaSetDevice(h->device);
         return solve_pipelined(*h, ws_in, sigma, x0, ws_out);
     }
@@ -783,87 +971,122 @@ int pdplqr_get_partition(pdplqr_handle_t h, int* starts, int* lens) {
 int pdplqr_get_gains(pdplqr_handle_t h, double* K, double* d, double* Gt) {
     if (!h) return PDPLQR_ERR_INVALID;
     cudaSetDevice(h->device);
-    const int nx = h->nx, nu = h->nu, FREC = h->frec;
-    const size_t nst = (size_t)h->batch * h->N;
-    const size_t bpad = h->thread_path ? ((size_t)(h->batch + 31) / 32) * 32 : (size_t)h->batch;
-    std::vector<double> host(bpad * h->N * FREC);
-    CU_TRY(h, cudaStreamSynchronize(h->stream));
-    CU_TRY(h, cudaMemcpy(host.data(), h->d_fac, host.size() * 8, cudaMemcpyDeviceToHost));
-    std::vector<double> rec(FREC);
-    for (size_t st = 0; st < nst; ++st) {
-        const double* z = host.data() + st * FREC;
-        if (h->thread_path) {   // tile-interleaved factor records (batch_kernels.cuh, tile_pos)
-            const size_t b = st / h->N, kk = st % h->N, tile = b / 32, lane = b % 32;
-            const double* blk = host.data() + (tile * h->N + kk) * (size_t)FREC * 32;
-            for (int e = 0; e < FREC; ++e) rec[e] = blk[(size_t)(e & ~1) * 32 + lane * 2 + (e & 1)];
-            z = rec.data();
-        }
-        const int k = (int)(st % h->N);
-        const bool in_last = !h->interior && k >= h->seg_start[h->S - 1];
-        if (K) std::memcpy(K + st * nu * nx, z, sizeof(double) * nu * nx);
-        if (d) std::memcpy(d + st * nu, z + nu * nx, sizeof(double) * nu);
-        if (Gt) {
-            if (in_last || (h->S == 1 && !h->interior)) std::memset(Gt + st * nu * nx, 0, sizeof(double) * nu * nx);
-            else std::memcpy(Gt + st * nu * nx, z + nu * (nx + 1), sizeof(double) * nu * nx);
-        }
+    // the factor records are unpacked on the device into the caller's layout, a bounded chunk of problems at a time
+    // (this accessor used to copy the whole factor array to the host)
+    const int nxu = h->nxu, nuu = h->nuu;
+    const size_t per_prob = (size_t)h->N * (2 * (size_t)nuu * nxu + nuu);
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>(h->batch, (64u << 20) / (per_prob * 8 + 1) + 1));
+    double* scratch = nullptr;
+    CU_TRY(h, cudaMalloc(&scratch, chunk * per_prob * 8));
+    int rc = PDPLQR_OK;
+    for (int b0 = 0; b0 < h->batch && rc == PDPLQR_OK; b0 += chunk) {
+        const int nb = std::min(chunk, h->batch - b0);
+        const size_t nst = (size_t)nb * h->N;
+        double *dK = scratch, *dd = dK + nst * nuu * nxu, *dG = dd + nst * nuu;
+        const long long total = (long long)nst * (2 * nuu * nxu + nuu);
+        unpack_gains_kernel<<<ew_blocks(total), 256, 0, h->stream>>>(h->d_fac, dK, dd, dG, b0, nb, h->N, h->nx, h->nu, nxu, nuu,
+                                                                     h->frec, h->thread_path ? 1 : 0,
+                                                                     h->interior ? h->N : h->seg_start[h->S - 1]);
+        h->launches++;
+        cudaError_t e = cudaGetLastError();
+        const size_t o = (size_t)b0 * h->N;
+        if (e == cudaSuccess && K) e = cudaMemcpyAsync(K + o * nuu * nxu, dK, nst * nuu * nxu * 8, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && d) e = cudaMemcpyAsync(d + o * nuu, dd, nst * nuu * 8, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess && Gt) e = cudaMemcpyAsync(Gt + o * nuu * nxu, dG, nst * nuu * nxu * 8, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(h, PDPLQR_ERR_CUDA, std::string("get_gains: ") + cudaGetErrorString(e));
     }
-    return PDPLQR_OK;
+    cudaFree(scratch);
+    return rc;
 }
 int pdplqr_get_interface(pdplqr_handle_t h, double* xhat, double* uhat) {
     if (!h) return PDPLQR_ERR_INVALID;
     cudaSetDevice(h->device);
     CU_TRY(h, cudaStreamSynchronize(h->stream));
-    const size_t n = (size_t)h->batch * h->S * h->nx;
-    if (xhat) CU_TRY(h, cudaMemcpy(xhat, h->d_xhat, n * 8, cudaMemcpyDeviceToHost));
-    if (uhat) CU_TRY(h, cudaMemcpy(uhat, h->d_uhat, n * 8, cudaMemcpyDeviceToHost));
+    const size_t cnt = (size_t)h->batch * h->S;
+    std::vector<double> host(cnt * h->nx);
+    for (int which = 0; which < 2; ++which) {
+        double* dst = which ? uhat : xhat;
+        if (!dst) continue;
+        CU_TRY(h, cudaMemcpy(host.data(), which ? h->d_uhat : h->d_xhat, host.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < cnt; ++i) std::memcpy(dst + i * h->nxu, host.data() + i * h->nx, 8 * h->nxu);
+    }
     return PDPLQR_OK;
 }
 int pdplqr_get_summaries(pdplqr_handle_t h, double* P, double* p, double* F, double* f, double* C) {
     if (!h) return PDPLQR_ERR_INVALID;
     cudaSetDevice(h->device);
     CU_TRY(h, cudaStreamSynchronize(h->stream));
-    const int nx = h->nx, n2 = nx * nx, SREC = h->ops->SREC;
+    const int nx = h->nx, n2 = nx * nx, SREC = h->ops->SREC, nxu = h->nxu;
     const size_t cnt = (size_t)h->batch * h->S;
     std::vector<double> host(cnt * SREC);
     CU_TRY(h, cudaMemcpy(host.data(), h->d_sum, host.size() * 8, cudaMemcpyDeviceToHost));
+    auto block = [&](double* dst, const double* src) {   // leading nxu x nxu block of an nx x nx column-major matrix
+        for (int j = 0; j < nxu; ++j) std::memcpy(dst + (size_t)j * nxu, src + (size_t)j * nx, 8 * nxu);
+    };
     for (size_t i = 0; i < cnt; ++i) {
         const double* r = host.data() + i * SREC;
-        if (P) std::memcpy(P + i * n2, r, 8 * n2);
-        if (F) std::memcpy(F + i * n2, r + n2, 8 * n2);
-        if (C) std::memcpy(C + i * n2, r + 2 * n2, 8 * n2);
-        if (p) std::memcpy(p + i * nx, r + 3 * n2, 8 * nx);
-        if (f) std::memcpy(f + i * nx, r + 3 * n2 + nx, 8 * nx);
+        if (P) block(P + i * nxu * nxu, r);
+        if (F) block(F + i * nxu * nxu, r + n2);
+        if (C) block(C + i * nxu * nxu, r + 2 * n2);
+        if (p) std::memcpy(p + i * nxu, r + 3 * n2, 8 * nxu);
+        if (f) std::memcpy(f + i * nxu, r + 3 * n2 + nx, 8 * nxu);
     }
+    return PDPLQR_OK;
+}
+// costates with kernel-layout device arrays (traj [batch][N s + nx], lam [batch][N][nx])
+static int costates_raw(pdplqr_handle_t h, const double* traj, double* lam) {
+    if (h->is_coupler) return fail(h, PDPLQR_ERR_INVALID, "get_costates: a coupler handle has no stages");
+    if (!h->factorized || h->backward_done)
+        return fail(h, PDPLQR_ERR_ORDER, "get_costates needs a completed backward + forward (interface costates)");
+    if (h->interior && !h->have_root)
+        return fail(h, PDPLQR_ERR_ORDER, "get_costates on an interior horizon shard needs its root boundary");
+    return h->ops->costates(*h, traj, lam);
+}
+static int costate_scratch(pdplqr_handle_t h) {   // allocated once, on first use
+    if (h->d_cost_ws) return PDPLQR_OK;
+    const size_t wsl = (size_t)h->N * h->s + h->nx, B = h->batch;
+    if (dev_alloc(*h, &h->d_cost_ws, B * wsl)) return PDPLQR_ERR_CUDA;
+    if (dev_alloc(*h, &h->d_cost_lam, B * h->N * h->nx)) return PDPLQR_ERR_CUDA;
     return PDPLQR_OK;
 }
 int pdplqr_get_costates_device(pdplqr_handle_t h, const double* ws, double* lam) {
     if (!h || !ws || !lam) return fail(h, PDPLQR_ERR_INVALID, "get_costates: bad arguments");
     cudaSetDevice(h->device);
-    if (h->is_coupler) return fail(h, PDPLQR_ERR_INVALID, "get_costates: a coupler handle has no stages");
-    if (h->thread_path)
-        return fail(h, PDPLQR_ERR_UNSUPPORTED,
-                    "get_costates: not available on the thread-per-problem path (create the handle with num_segments > 1)");
-    if (!h->factorized || h->backward_done)
-        return fail(h, PDPLQR_ERR_ORDER, "get_costates needs a completed backward + forward (interface costates)");
-    if (h->interior && !h->have_root)
-        return fail(h, PDPLQR_ERR_ORDER, "get_costates on an interior horizon shard needs its root boundary");
-    return h->ops->costates(*h, ws, lam);
+    if (!h->padded) return costates_raw(h, ws, lam);
+    int rc = costate_scratch(h);
+    if (rc) return rc;
+    rc = repack_ws(*h, ws, h->d_cost_ws, true);
+    if (rc) return rc;
+    rc = costates_raw(h, h->d_cost_ws, h->d_cost_lam);
+    if (rc) return rc;
+    return repack_vec(*h, h->d_cost_lam, lam, (long long)h->batch * h->N, h->nx, h->nxu);
 }
 int pdplqr_get_costates(pdplqr_handle_t h, const double* ws, double* lam) {
     if (!h || !ws || !lam) return fail(h, PDPLQR_ERR_INVALID, "get_costates: bad arguments");
     cudaSetDevice(h->device);
-    const size_t wsl = (size_t)h->N * h->s + h->nx, B = h->batch;
-    double *d_ws = nullptr, *d_lam = nullptr;
-    CU_TRY(h, cudaMalloc(&d_ws, B * wsl * 8));
-    if (cudaMalloc(&d_lam, B * h->N * h->nx * 8) != cudaSuccess) { cudaFree(d_ws); return fail(h, PDPLQR_ERR_CUDA, "cudaMalloc"); }
-    int rc = PDPLQR_OK;
-    if (cudaMemcpyAsync(d_ws, ws, B * wsl * 8, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) rc = PDPLQR_ERR_CUDA;
-    if (!rc) rc = pdplqr_get_costates_device(h, d_ws, d_lam);
-    if (!rc && cudaMemcpyAsync(lam, d_lam, B * h->N * h->nx * 8, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) rc = PDPLQR_ERR_CUDA;
-    if (cudaStreamSynchronize(h->stream) != cudaSuccess && !rc) rc = PDPLQR_ERR_CUDA;
-    cudaFree(d_ws); cudaFree(d_lam);
-    if (rc == PDPLQR_ERR_CUDA && h->err.empty()) h->err = "get_costates: CUDA error";
-    return rc;
+    const size_t wsl_user = (size_t)h->N * h->su + h->nxu, B = h->batch;
+    int rc = costate_scratch(h);
+    if (rc) return rc;
+    // d_ws_out holds nothing the costate kernel reads (w_prev lives in d_ws_in / d_wsp_in): use it for the upload
+    CU_TRY(h, cudaMemcpyAsync(h->d_ws_out, ws, B * wsl_user * 8, cudaMemcpyHostToDevice, h->stream));
+    const double* traj = h->d_ws_out;
+    if (h->padded) {
+        rc = repack_ws(*h, h->d_ws_out, h->d_cost_ws, true);
+        if (rc) return rc;
+        traj = h->d_cost_ws;
+    }
+    rc = costates_raw(h, traj, h->d_cost_lam);
+    if (rc) return rc;
+    const double* src = h->d_cost_lam;
+    if (h->padded) {   // crop into the (now free) trajectory scratch
+        rc = repack_vec(*h, h->d_cost_lam, h->d_cost_ws, (long long)B * h->N, h->nx, h->nxu);
+        if (rc) return rc;
+        src = h->d_cost_ws;
+    }
+    CU_TRY(h, cudaMemcpyAsync(lam, src, B * h->N * h->nxu * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    return PDPLQR_OK;
 }
 int pdplqr_last_status(pdplqr_handle_t h, int* status) {
     if (!h) return PDPLQR_ERR_INVALID;
@@ -878,7 +1101,8 @@ int pdplqr_last_status(pdplqr_handle_t h, int* status) {
     }
     return bad;
 }
-const char* pdplqr_last_error(pdplqr_handle_t h) { return h ? h->err.c_str() : "null handle"; }
+// h == NULL: the reason the last pdplqr_create / pdplqr_coupler_create on this thread failed
+const char* pdplqr_last_error(pdplqr_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 long long pdplqr_launch_count(pdplqr_handle_t h) { return h ? h->launches : 0; }
 int pdplqr_record_doubles(pdplqr_handle_t h, int* model_rec, int* factor_rec) {
     if (!h) return PDPLQR_ERR_INVALID;
@@ -892,6 +1116,7 @@ int pdplqr_admm_set_cones(pdplqr_handle_t h, int ncones, const int* stage, const
                           const int* type, const double* e_lb, const double* e_ub) {
     if (!h || h->nc_total == 0) return fail(h, PDPLQR_ERR_INVALID, "admm_set_cones: the problem has no constraints");
     if (ncones < 1 || !stage || !row0 || !dim || !type || !e_lb || !e_ub) return fail(h, PDPLQR_ERR_INVALID, "admm_set_cones: bad arguments");
+    if (h->padded) return fail(h, PDPLQR_ERR_UNSUPPORTED, "admm: (nx, nu) is not an instantiated pair (TODO: padded handles)");
     cudaSetDevice(h->device);
     // cones must be given stage by stage (non-decreasing), tile the rows of every stage exactly once
     std::vector<int> first(h->N + 2, 0);

@@ -33,7 +33,16 @@ using pdplqr_host::Ops;
 using pdplqr_host::TreeLevel;
 
 struct pdplqr_solver {
-    int nx = 0, nu = 0, N = 0, batch = 0, S = 1, s = 0, device = 0;
+    int nx = 0, nu = 0, N = 0, batch = 0, S = 1, s = 0, device = 0;   // nx, nu, s: KERNEL dimensions (an instantiated pair)
+    // Caller's dimensions.  When (nxu, nuu) is not an instantiated pair the problem is embedded in the cheapest pair that
+    // contains it (padded states: A = 0, B = 0, c = 0, Q = I, x0 = 0; padded inputs: R = I, zero columns of B and D), so
+    // the padded components stay exactly zero and the caller's components are unchanged; every array that crosses the
+    // C ABI is converted between the two layouts by the repack kernels (pdplqr.cu).
+    int nxu = 0, nuu = 0, su = 0;
+    bool padded = false;
+    double *d_wsp_in = nullptr, *d_wsp_out = nullptr, *d_x0p = nullptr;   // kernel-layout staging (padded handles only)
+    double *d_cost_ws = nullptr, *d_cost_lam = nullptr;                   // scratch of the host costate accessor (lazy)
+    bool root_fresh = false;       // a root boundary was set since the last forward (consumed by forward)
     bool load_balancing = true;
     int condensed_type = 1;
     std::vector<int> ncs, seg_start, seg_len;
@@ -382,6 +391,14 @@ int costates_impl(Solver& h, const double* traj, double* lam) {
     q.sp = seg_params(h);
     q.traj = traj; q.lam = lam;
     q.lam_root = (h.interior && h.have_root) ? h.d_root_lam : nullptr;
+    if constexpr (BatchDims<NX, NU>::ENABLED) {
+        if (h.thread_path) {
+            batch_costate_kernel<NX, NU><<<(h.batch + 127) / 128, 128, 0, h.stream>>>(q);
+            h.launches++;
+            CU_TRY(&h, cudaGetLastError());
+            return PDPLQR_OK;
+        }
+    }
     const size_t bytes = (size_t)(NX + (NX + NU) + std::max(h.ncmax, 1)) * sizeof(double);
     auto kern = seg_costate_kernel<NX, NU>;
     int rc = set_smem(h, kern, bytes);

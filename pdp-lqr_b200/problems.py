@@ -157,28 +157,48 @@ def quadrotor_example(N: int = 100, constrained: bool = False) -> Problem:
     return p
 
 
-def quadrotor_ltv(N: int, seed: int = 20251018, x0_seed: int = 7) -> Problem:
+LTV_CHUNK = 1 << 16   # stages per independently seeded chunk of quadrotor_ltv
+
+
+def quadrotor_ltv(N: int, seed: int = 20251018, x0_seed: int = 7, start: int = 0, count: int | None = None) -> Problem:
     """Configs 2 / 5: quadrotor replicated to N stages, stored per stage (LTV layout) with a seeded
-    perturbation so that stages are distinct:  A_k = A + 1e-3 U(-1,1) o |A|, c_k = 1e-3 N(0,1)."""
+    perturbation so that stages are distinct:  A_k = A + 1e-3 U(-1,1) o |A|, c_k = 1e-3 N(0,1).
+    The perturbations are drawn per chunk of LTV_CHUNK stages (chunk j: seed + j), so that a rank of a horizon-sharded
+    run can generate ITS time slice [start, start + count) of the N-stage problem without building the rest
+    (returned as an N = count problem with the attributes `start` and `x0_global`; terminal cost only on the last)."""
     nx, nu = 12, 4
     s = nx + nu
-    rng = np.random.default_rng(seed)
+    count = N - start if count is None else count
+    assert 0 <= start and count >= 1 and start + count <= N
     Q = np.diag(_QUAD_QDIAG)
     R = np.diag(_QUAD_RDIAG)
     q = -_QUAD_XREF @ Q
     Hk = np.zeros((s, s)); Hk[:nu, :nu] = R; Hk[nu:, nu:] = Q
     hk = np.concatenate([np.zeros(nu), q])
     # E_k column-major: columns 0..nu-1 = B, nu.. = A
-    Ecm = np.empty((N, s, nx))           # [k, col, row]  == column-major (nx x s)
+    Ecm = np.empty((count, s, nx))           # [k, col, row]  == column-major (nx x s)
     Ecm[:, :nu, :] = _QUAD_B.T[None]
-    Ak = _QUAD_A[None] + 1e-3 * rng.uniform(-1, 1, (N, nx, nx)) * np.abs(_QUAD_A)[None]
-    Ecm[:, nu:, :] = np.transpose(Ak, (0, 2, 1))
-    E = Ecm.reshape(1, N, nx * s)
-    c = (1e-3 * rng.standard_normal((N, nx)))[None]
-    H = np.broadcast_to(_cm(Hk), (1, N, s * s)).copy()
-    h = np.broadcast_to(hk, (1, N, s)).copy()
+    c = np.empty((count, nx))
+    absA = np.abs(_QUAD_A)
+    for j in range(start // LTV_CHUNK, (start + count - 1) // LTV_CHUNK + 1):
+        k0, k1 = j * LTV_CHUNK, min((j + 1) * LTV_CHUNK, N)
+        rng = np.random.default_rng(seed + j)
+        Ak = _QUAD_A[None] + 1e-3 * rng.uniform(-1, 1, (k1 - k0, nx, nx)) * absA[None]
+        ck = 1e-3 * rng.standard_normal((k1 - k0, nx))
+        lo, hi = max(k0, start), min(k1, start + count)
+        Ecm[lo - start:hi - start, nu:, :] = np.transpose(Ak[lo - k0:hi - k0], (0, 2, 1))
+        c[lo - start:hi - start] = ck[lo - k0:hi - k0]
+    E = Ecm.reshape(1, count, nx * s)
+    H = np.broadcast_to(_cm(Hk), (1, count, s * s)).copy()
+    h = np.broadcast_to(hk, (1, count, s)).copy()
     x0 = 0.1 * np.random.default_rng(x0_seed).standard_normal((1, nx))
-    return Problem(nx, nu, N, 1, E, c, H, h, _cm(Q)[None], q[None].copy(), x0, name=f"quadrotor-LTV-N{N}")
+    whole = start == 0 and count == N
+    is_last = start + count == N
+    p = Problem(nx, nu, count, 1, E, c[None], H, h, _cm(Q)[None] if is_last else np.zeros((1, nx * nx)),
+                q[None].copy() if is_last else np.zeros((1, nx)), x0 if whole else np.zeros((1, nx)),
+                name=f"quadrotor-LTV-N{N}" + ("" if whole else f"[{start}:{start + count}]"))
+    p.start, p.x0_global = start, x0
+    return p
 
 
 def cartpole_batch(batch: int = 65536, N: int = 128, seed: int = 1234) -> Problem:

@@ -34,17 +34,35 @@ def horizon_slices(N: int, world: int):
 
 
 def slice_problem(prob, start: int, count: int, is_last: bool):
-    """Time slice [start, start+count) of a single long-horizon Problem as its own Problem (constraints not sliced)."""
+    """Time slice [start, start+count) of a long-horizon Problem as its own Problem.  Constraint rows travel with their
+    stages; the slice's "terminal" stage count is the next slice's first stage, so an interior slice has no terminal rows
+    (and no terminal cost: its handle runs with PDPLQR_OPT_INTERIOR_SHARD)."""
     from .problems import Problem
-    assert prob.ncs is None, "horizon slicing of constrained problems is not implemented"
     sl = slice(start, start + count)
     nx = prob.nx
     HN = prob.HN if is_last else np.zeros_like(prob.HN)
     hN = prob.hN if is_last else np.zeros_like(prob.hN)
-    return Problem(prob.nx, prob.nu, count, prob.batch, np.ascontiguousarray(prob.E[:, sl]),
-                   np.ascontiguousarray(prob.c[:, sl]), np.ascontiguousarray(prob.H[:, sl]),
-                   np.ascontiguousarray(prob.h[:, sl]), HN, hN, np.zeros((prob.batch, nx)),
-                   name=f"{prob.name}[{start}:{start + count}]")
+    out = Problem(prob.nx, prob.nu, count, prob.batch, np.ascontiguousarray(prob.E[:, sl]),
+                  np.ascontiguousarray(prob.c[:, sl]), np.ascontiguousarray(prob.H[:, sl]),
+                  np.ascontiguousarray(prob.h[:, sl]), HN, hN, np.zeros((prob.batch, nx)),
+                  name=f"{prob.name}[{start}:{start + count}]")
+    if prob.ncs is not None:
+        coff, doff = prob.coff(), prob.doff()
+        ncs = np.zeros(count + 1, np.int32)
+        ncs[:count] = prob.ncs[start:start + count]
+        last_stage = start + count            # == prob.N for the last slice: its terminal rows belong to it
+        if is_last:
+            ncs[count] = prob.ncs[prob.N]
+        c0, c1 = int(coff[start]), int(coff[last_stage + 1] if is_last else coff[last_stage])
+        d0, d1 = int(doff[start]), int(doff[last_stage + 1] if is_last else doff[last_stage])
+        out.ncs = ncs
+        out.D = np.ascontiguousarray(prob.D[:, d0:d1])
+        out.e_lb = None if prob.e_lb is None else np.ascontiguousarray(prob.e_lb[:, c0:c1])
+        out.e_ub = None if prob.e_ub is None else np.ascontiguousarray(prob.e_ub[:, c0:c1])
+        out.cones = [(k - start, r0, d, t) for (k, r0, d, t) in prob.cones
+                     if start <= k < last_stage or (is_last and k == prob.N)]
+        out.con_slice = (c0, c1)              # where this slice's ys / zs / rho live in the full vectors
+    return out
 
 
 def couple_numpy(summaries, x0):
@@ -74,15 +92,20 @@ def couple_numpy(summaries, x0):
     return xhat, lam
 
 
-def all_gather_rows(local_row, world: int, group=None):
-    """all_gather of one fixed-size row per rank -> [world, len] tensor (NCCL for CUDA tensors, gloo for CPU)."""
+def all_gather_rows(local_row, world: int, group=None, out=None):
+    """all_gather of one fixed-size row per rank -> [world, len] tensor (NCCL for CUDA tensors, gloo for CPU).  `out`
+    (persistent, contiguous) avoids a per-call allocation; on NCCL one all_gather_into_tensor, no list of views."""
     import torch
     import torch.distributed as dist
-    out = torch.empty((world,) + tuple(local_row.shape), dtype=local_row.dtype, device=local_row.device)
+    if out is None:
+        out = torch.empty((world,) + tuple(local_row.shape), dtype=local_row.dtype, device=local_row.device)
     if world == 1:
-        out[0] = local_row
+        out[0].copy_(local_row)
         return out
-    dist.all_gather([out[r] for r in range(world)], local_row.contiguous(), group=group)
+    if local_row.is_cuda:
+        dist.all_gather_into_tensor(out, local_row, group=group)
+    else:
+        dist.all_gather([out[r] for r in range(world)], local_row.contiguous(), group=group)
     return out
 
 
@@ -90,40 +113,65 @@ class HorizonShardedSolver:
     """One long-horizon problem split into per-rank time slices (BASELINE.json config 5).
 
     solve_device(ws_prev_local, sigma, ws_out_local): update_problem_data + backward on the local slice, one
-    all_gather of the slice summary, redundant interface solve, forward on the local slice."""
+    all_gather of the slice summary, redundant interface solve, forward on the local slice.
 
-    def __init__(self, prob, rank: int, world: int, num_segments: int = 0, device: int = 0):
+    Stream discipline: the slice handle, the coupler, the collective and every torch op run on ONE stream -- torch's
+    current stream of `device` at construction (or the one given to set_stream) -- so their order is the program order.
+    All buffers that cross the phases are persistent members (nothing is handed back to torch's caching allocator while
+    work that reads it is still queued)."""
+
+    PHASES = ("local_sweep_and_tree", "all_gather", "coupler", "rollout")
+
+    def __init__(self, prob, rank: int, world: int, num_segments: int = 0, device: int = 0, local=None):
         import torch
         from .solver import Coupler, LQRCudaSolver
         from . import capi
         self.rank, self.world = rank, world
-        start, count = horizon_slices(prob.N, world)[rank]
+        start, count = horizon_slices(prob.N, world)[rank] if local is None else (local.start, local.N)
         self.start, self.count = start, count
         self.is_last = rank == world - 1
-        self.local = slice_problem(prob, start, count, self.is_last)
+        self.local = slice_problem(prob, start, count, self.is_last) if local is None else local
         self.dev = torch.device("cuda", device)
-        self.sol = LQRCudaSolver(prob.nx, prob.nu, count, batch=1, num_segments=num_segments, load_balancing=2,
-                                 device=device)
+        nx, nu = self.local.nx, self.local.nu
+        self.sol = LQRCudaSolver(nx, nu, count, batch=1, num_segments=num_segments, load_balancing=2,
+                                 ncs=self.local.ncs, device=device)
         if not self.is_last:
             self.sol.set_option(capi.OPT_INTERIOR_SHARD, 1)
         self.sol.set_model(self.local)
-        self.coupler = Coupler(prob.nx, prob.nu, world, batch=1, device=device)
-        self.nx = prob.nx
+        self.coupler = Coupler(nx, nu, world, batch=1, device=device)
+        self.nx = nx
         self.srec = self.sol.summary_doubles()
-        self.my_sum = torch.empty(1, self.srec, dtype=torch.float64, device=self.dev)
-        self.xhat = torch.empty(1, world, prob.nx, dtype=torch.float64, device=self.dev)
-        self.lam = torch.empty(1, world, prob.nx, dtype=torch.float64, device=self.dev)
-        self.x0 = torch.from_numpy(np.ascontiguousarray(prob.x0)).to(self.dev)
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self.my_sum = torch.empty(1, self.srec, **f64)
+        self.allsum = torch.empty(world, self.srec, **f64)          # == [batch = 1][world][srec] for the coupler
+        self.xhat = torch.empty(1, world, nx, **f64)
+        self.lam = torch.empty(1, world, nx, **f64)
+        self.x0 = torch.from_numpy(np.ascontiguousarray(prob.x0 if local is None else local.x0_global)).to(self.dev)
+        self.set_stream(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def set_stream(self, ptr: int):
+        """`ptr` must be the stream torch treats as current when solve_device runs (the collective is issued there)."""
         self.sol.set_stream(ptr)
         self.coupler.set_stream(ptr)
 
-    def solve_device(self, ws_prev, sigma, ws_out):
-        self.sol.update_problem_data_device(ws_prev, sigma=sigma)
-        self.sol.backward_device()
+    def solve_device(self, ws_prev, sigma, ws_out, ys=None, zs=None, rho=None, inv_rho=None, events=None):
+        """`events` (optional list) receives one torch.cuda.Event after every phase (PHASES) -- bench.py's breakdown."""
+        import torch
+
+        def mark():
+            if events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                events.append(e)
+        mark()
+        self.sol.update_problem_data_device(ws_prev, ys, zs, inv_rho, sigma=sigma)
+        self.sol.backward_device(rho)
         self.sol.root_summary_device(self.my_sum)
-        allsum = all_gather_rows(self.my_sum[0], self.world)            # [world, srec]  (the only collective)
-        self.coupler.solve_device(allsum.unsqueeze(0).contiguous(), self.x0, self.xhat, self.lam)
-        self.sol.set_root_boundary_device(self.xhat[:, self.rank].contiguous(), self.lam[:, self.rank].contiguous())
+        mark()
+        all_gather_rows(self.my_sum[0], self.world, out=self.allsum)       # the only collective
+        mark()
+        self.coupler.solve_device(self.allsum, self.x0, self.xhat, self.lam)
+        self.sol.set_root_boundary_device(self.xhat[0, self.rank], self.lam[0, self.rank])
+        mark()
         self.sol.forward_device(self.x0, ws_out)
+        mark()

@@ -56,7 +56,10 @@ def kkt_solve(prob, b=0, ws_prev=None, sigma=1e-6, ys=None, zs=None, rho=None, i
     Hb = sp.block_diag([sp.csc_matrix(Hk) for Hk in Hs], format="csc")
     K = sp.bmat([[Hb, Cm.T], [Cm, None]], format="csc")
     rhs = np.concatenate([-np.concatenate(hs), rhs_c])
-    sol = spla.spsolve(K, rhs)
+    lu = spla.splu(K)
+    sol = lu.solve(rhs)
+    for _ in range(2):   # iterative refinement: the 1e-9 parity checks must not be limited by the sparse LU itself
+        sol = sol + lu.solve(rhs - K @ sol)
     if return_costates:   # multiplier mu_{k+1} of x_{k+1} - E_k w_k = c_k; the costate convention of pdplqr.h is -mu
         return sol[:nw], -sol[nw:nw + N * nx].reshape(N, nx)
     return sol[:nw]

@@ -496,8 +496,9 @@ def test_invalid_arguments_are_rejected():
     with pytest.raises(P.PdplqrError) as e:
         P.LQRCudaSolver(12, 4, 0)                      # N >= 1  (lqr_model.hpp:75-77)
     assert e.value.code == P.capi.ERR_INVALID
+    P.LQRCudaSolver(5, 5, 10).close()                  # not an instantiated pair: padded to one (lqr_model.hpp:66-89)
     with pytest.raises(P.PdplqrError) as e:
-        P.LQRCudaSolver(5, 5, 10)                      # (nx, nu) not instantiated
+        P.LQRCudaSolver(64, 5, 10)                     # beyond the largest instantiated kernel size
     assert e.value.code == P.capi.ERR_UNSUPPORTED
     with pytest.raises(P.PdplqrError):
         P.LQRCudaSolver(12, 4, 10, solver_type=7)      # unknown condensed solver type (lqr_solver_parallel.hpp:98-99)
@@ -550,7 +551,8 @@ def test_stage_kernel_group_sizes(oracle, nx, nu, nc, seg_t, monkeypatch):
 
 # ------------------------------------------------------------------------------------------------------------
 # costate recovery (commented out in the reference, lqr_kernel.hpp:205-211)
-@pytest.mark.parametrize("nx,nu,N,S", [(12, 4, 40, 1), (12, 4, 40, 4), (6, 3, 30, 3), (16, 4, 24, 2), (3, 2, 17, 5)])
+@pytest.mark.parametrize("nx,nu,N,S", [(12, 4, 40, 1), (12, 4, 40, 4), (6, 3, 30, 3), (16, 4, 24, 2), (3, 2, 17, 5),
+                                       (4, 1, 33, 1), (3, 2, 20, 1), (5, 2, 21, 1), (7, 3, 19, 3)])
 def test_costates_match_kkt_multipliers_and_value_function(oracle, nx, nu, N, S):
     """lambda_k vs (i) the multipliers of an independent sparse KKT solve and (ii) the reference's own (commented)
     formula lambda_k = P_k x_k + p_k with P_k = Lxx Lxx^T, p_k from the sequential oracle."""
@@ -559,13 +561,11 @@ def test_costates_match_kkt_multipliers_and_value_function(oracle, nx, nu, N, S)
     rng = np.random.default_rng(2)
     wprev = rng.standard_normal((p.batch, p.ws_len))
     sol, ws = gpu_solve(p, S=S, ws_in=wprev, sigma=0.05)
-    if sol.num_segments == 1 and nx + nu <= 8:
-        pytest.skip("thread-per-problem path")
     lam = sol.costates(ws)
     for b in range(p.batch):
         w_kkt, lam_kkt = kkt_solve(p, b, wprev[b], 0.05, return_costates=True)
-        assert rel_err(ws[b], w_kkt) < 1e-8
-        assert rel_err(lam[b], lam_kkt) < 1e-8
+        assert rel_err(ws[b], w_kkt) < TOL
+        assert rel_err(lam[b], lam_kkt) < TOL
         o = oracle.OracleSolver(p, b=b)
         ref = o.solve(ws_in=wprev[b], sigma=0.05)
         lam_ref = o.costates(ref)                      # lambda_k = Lxx (Lxx^T x_k) + p_k, all k
@@ -586,15 +586,20 @@ def test_costates_with_constraint_fold_in(oracle, S):
     lam = sol.costates(ws)
     for b in range(p.batch):
         w_kkt, lam_kkt = kkt_solve(p, b, wprev[b], 1e-3, ys[b], zs[b], rho[b], inv_rho[b], return_costates=True)
-        assert rel_err(ws[b], w_kkt) < 1e-8 and rel_err(lam[b], lam_kkt) < 1e-8
+        assert rel_err(ws[b], w_kkt) < TOL and rel_err(lam[b], lam_kkt) < TOL
 
 
-def test_costates_call_order_and_unsupported_path():
+def test_costates_call_order_and_thread_path(oracle):
     p = P.problems.random_lq(12, 4, 10, batch=1, seed=3)
     sol = P.LQRCudaSolver.from_problem(p, num_segments=2)
     with pytest.raises(P.PdplqrError):
         sol.costates(p.zeros_ws())                      # nothing solved yet
-    q = P.problems.cartpole_batch(batch=40, N=16)
-    sol2, ws2 = gpu_solve(q)                            # thread-per-problem path
-    with pytest.raises(P.PdplqrError):
-        sol2.costates(ws2)
+    q = P.problems.cartpole_batch(batch=40, N=16)       # thread-per-problem path (ragged last tile: 40 = 32 + 8)
+    sol2, ws2 = gpu_solve(q)
+    lam = sol2.costates(ws2)
+    for b in (0, 31, 32, 39):
+        o = oracle.OracleSolver(q, b=b)
+        ref = o.solve()
+        assert rel_err(ws2[b], ref) < TOL
+        lam_ref = o.costates(ref)
+        assert np.max(np.abs(lam[b] - lam_ref)) < TOL * max(1.0, np.max(np.abs(lam_ref)))

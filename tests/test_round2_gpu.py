@@ -1,0 +1,329 @@
+"""Round-2 GPU parity tests (through the C ABI): parity at BENCHMARK size and shape, arbitrary (nx, nu) by padding,
+the real multi-process NCCL horizon-sharded path, constrained horizon shards, ADMM at the C4 dimensions.
+Tolerance: 1e-9 relative (BASELINE.json north_star)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import pdplqr_b200 as P
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+# ---------------------------------------------------------------------------------- benchmark size and shape
+@pytest.mark.parametrize("logN", [17, 20])
+def test_long_horizon_at_benchmark_segmentation(oracle, logN):
+    """C5 shape: nx12/nu4, N = 2^17 and the benchmarked 2^20, the bench's wave-aligned equal segmentation
+    (load_balancing = 2; 4,144 segments and a 13-level interface tree at 2^20) against the SEQUENTIAL oracle over the
+    whole horizon -- checks that 1e-9 survives the tree depth and the interface conditioning."""
+    bench = _bench()
+    N = 1 << logN
+    p = P.problems.quadrotor_ltv(N)
+    S = bench.wave_aligned(N // 250) if logN == 20 else bench.wave_aligned(N // 64)
+    rng = np.random.default_rng(17)
+    wprev = 0.01 * rng.standard_normal((1, p.ws_len))
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=S, load_balancing=2)
+    assert sol.num_segments == S
+    ws = sol.solve(wprev, p.x0, np.empty_like(wprev), sigma=1e-6)
+    assert sol.last_status()[0] == 0
+    ref = oracle.OracleSolver(p, parallel=False).solve(ws_in=wprev[0].copy(), sigma=1e-6)
+    assert rel_err(ws[0], ref) < TOL
+    # per-stage check as well (a max-norm over 16 M numbers would hide a locally wrong stage with small entries)
+    e = np.abs(ws[0, :N * 16] - ref[:N * 16]).reshape(N, 16).max(axis=1)
+    scale = np.maximum(np.abs(ref[:N * 16]).reshape(N, 16).max(axis=1), 1e-3)
+    assert float(np.max(e / scale)) < 1e-7
+    del sol
+
+
+def test_c3_at_benchmark_batch(oracle):
+    """C3 at the benchmarked 65,536 x (nx4, nu1, N128): sampled problems incl. the first and the last tile of 32, and
+    the pipelined host-buffer call the bench's e2e number goes through."""
+    B = 65536
+    q = P.problems.cartpole_batch(batch=B, N=128, seed=1234)
+    rng = np.random.default_rng(17)
+    wprev = 0.01 * rng.standard_normal((B, q.ws_len))
+    sol = P.LQRCudaSolver.from_problem(q)
+    ws = sol.solve(wprev, q.x0, np.empty_like(wprev), sigma=1e-6)
+    assert sol.last_status()[0] == 0
+    pick = np.unique(np.concatenate([np.arange(40), np.arange(B - 40, B), rng.integers(0, B, 120)]))
+    sub = q.select(pick)
+    ref, bad = oracle.OracleBatch(sub).solve(ws_in=np.ascontiguousarray(wprev[pick]), sigma=1e-6)
+    assert bad == 0
+    for i, b in enumerate(pick):
+        assert rel_err(ws[b], ref[i]) < TOL, b
+
+
+# ---------------------------------------------------------------------------------- arbitrary (nx, nu)
+@pytest.mark.parametrize("nx,nu,N,S,batch", [(5, 5, 30, 1, 3), (5, 5, 30, 4, 2), (7, 2, 25, 3, 2), (13, 3, 40, 5, 1),
+                                             (20, 6, 24, 2, 2), (3, 1, 20, 1, 70), (1, 1, 9, 1, 5), (9, 9, 12, 2, 1)])
+def test_arbitrary_dimensions_by_padding(oracle, nx, nu, N, S, batch):
+    """(nx, nu) pairs that are not instantiated run on the cheapest instantiated pair that contains them (zero /
+    identity padding): states, controls, gains, interface values and costates equal the oracle's on the
+    caller's dimensions (the reference takes any n, m at run time, lqr_model.hpp:66-89)."""
+    p = P.problems.random_lq(nx, nu, N, batch=batch, seed=7 * nx + nu)
+    rng = np.random.default_rng(3)
+    wprev = rng.standard_normal((batch, p.ws_len))
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=S, load_balancing=False)
+    sol.update_problem_data(wprev, sigma=0.02)
+    sol.backward()
+    ws = sol.forward(p.x0, np.zeros_like(wprev))
+    K, d, Gt = sol.gains()
+    lam = sol.costates(ws)
+    for b in range(min(batch, 3)):
+        o = oracle.OracleSolver(p, b=b, parallel=S > 1, num_segments=S, load_balancing=False, condensed=oracle.LU)
+        ref = o.solve(ws_in=wprev[b], sigma=0.02)
+        assert rel_err(ws[b], ref) < TOL
+        Ko, do, Gto = o.gains()
+        assert rel_err(K[b], Ko) < TOL and rel_err(d[b], do) < TOL
+        if S > 1:
+            assert rel_err(Gt[b], Gto) < TOL
+            xh, uh = sol.interface()
+            xo, uo = o.interface()
+            assert rel_err(xh[b], xo) < TOL
+        seq = oracle.OracleSolver(p, b=b)
+        sref = seq.solve(ws_in=wprev[b], sigma=0.02)
+        lam_ref = seq.costates(sref)
+        assert np.max(np.abs(lam[b] - lam_ref)) < TOL * max(1.0, np.max(np.abs(lam_ref)))
+
+
+@pytest.mark.parametrize("nx,nu,nc,S", [(5, 3, 4, 1), (7, 2, 6, 3), (13, 3, 9, 2)])
+def test_arbitrary_dimensions_with_constraints_and_no_refactor(oracle, nx, nu, nc, S):
+    """Padded sizes through the constraint fold-in (dense D with zero columns for the padded variables) and the
+    backward_without_factorization protocol."""
+    p = P.problems.random_lq(nx, nu, 14, batch=2, seed=50 + nx, nc=nc)
+    rng = np.random.default_rng(4)
+    nct = p.nc_total
+    rho = rng.uniform(0.5, 2.0, (p.batch, nct))
+    inv_rho = np.ascontiguousarray(1.0 / rho)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=S, load_balancing=False)
+    os_ = [oracle.OracleSolver(p, b=b) for b in range(p.batch)]
+    for it in range(3):
+        wprev = rng.standard_normal((p.batch, p.ws_len))
+        ys, zs = rng.standard_normal((p.batch, nct)), rng.standard_normal((p.batch, nct))
+        sol.update_problem_data(wprev, ys, zs, inv_rho, sigma=1e-3)
+        if it == 0:
+            sol.backward(rho)
+        else:
+            sol.backward_without_factorization(rho)
+        ws = sol.forward(p.x0, np.zeros_like(wprev))
+        for b in range(p.batch):
+            os_[b].update_problem_data(wprev[b], ys[b], zs[b], inv_rho[b], 1e-3)
+            if it == 0:
+                os_[b].backward(rho[b])
+            else:
+                os_[b].backward_without_factorization(rho[b])
+            assert rel_err(ws[b], os_[b].forward(p.x0[b], np.zeros(p.ws_len))) < TOL
+
+
+def test_device_pointer_api_with_padded_dimensions(oracle):
+    import torch
+    p = P.problems.random_lq(5, 2, 33, batch=4, seed=9)
+    dev = torch.device("cuda", 0)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=3)
+    wprev = torch.from_numpy(np.random.default_rng(1).standard_normal((4, p.ws_len))).to(dev)
+    out = torch.empty_like(wprev)
+    x0 = torch.from_numpy(p.x0).to(dev)
+    sol.update_problem_data_device(wprev, sigma=0.1)
+    sol.backward_device()
+    sol.forward_device(x0, out)
+    sol.synchronize()
+    got, wp = out.cpu().numpy(), wprev.cpu().numpy()
+    for b in range(4):
+        assert rel_err(got[b], oracle.OracleSolver(p, b=b).solve(ws_in=wp[b], sigma=0.1)) < TOL
+
+
+# ---------------------------------------------------------------------------------- horizon shards
+def _sharded_emulation(p, G, S_local, wprev, sigma, ys=None, zs=None, rho=None, inv_rho=None):
+    """G handles own G time slices on ONE GPU (interior shards + the terminal one); same calls as
+    sharding.HorizonShardedSolver with the all_gather replaced by a torch.stack."""
+    import torch
+    from pdplqr_b200 import sharding
+    from pdplqr_b200.solver import Coupler
+    dev = torch.device("cuda", 0)
+    N = p.N
+    x0 = torch.from_numpy(p.x0).to(dev)
+    sols, sums, locs = [], [], []
+    slices = sharding.horizon_slices(N, G)
+    for r, (start, count) in enumerate(slices):
+        last = r == G - 1
+        loc = sharding.slice_problem(p, start, count, last)
+        s = P.LQRCudaSolver(p.nx, p.nu, count, num_segments=S_local, load_balancing=False, ncs=loc.ncs)
+        if not last:
+            s.set_option(P.capi.OPT_INTERIOR_SHARD, 1)
+        s.set_model(loc)
+        lo = start * p.s
+        wp = np.ascontiguousarray(wprev[:, lo:lo + count * p.s + p.nx])
+        kw = {}
+        if loc.ncs is not None:
+            c0, c1 = loc.con_slice
+            kw = dict(ys=np.ascontiguousarray(ys[:, c0:c1]), zs=np.ascontiguousarray(zs[:, c0:c1]),
+                      inv_rho_vecs=np.ascontiguousarray(inv_rho[:, c0:c1]))
+        s.update_problem_data(wp, sigma=sigma, **kw)
+        s.backward(None if loc.ncs is None else np.ascontiguousarray(rho[:, loc.con_slice[0]:loc.con_slice[1]]))
+        sm = torch.empty(1, s.summary_doubles(), dtype=torch.float64, device=dev)
+        s.root_summary_device(sm)
+        s.synchronize()
+        sols.append(s); sums.append(sm[0]); locs.append(loc)
+    coup = Coupler(p.nx, p.nu, G)
+    xhat = torch.empty(1, G, p.nx, dtype=torch.float64, device=dev)
+    lam = torch.empty(1, G, p.nx, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    coup.solve_device(torch.stack(sums).unsqueeze(0).contiguous(), x0, xhat, lam)
+    coup._lib.pdplqr_synchronize(coup._h)
+    full = np.zeros(p.ws_len)
+    for r, (start, count) in enumerate(slices):
+        out = torch.zeros(1, count * p.s + p.nx, dtype=torch.float64, device=dev)
+        sols[r].set_root_boundary_device(xhat[0, r], lam[0, r])
+        sols[r].forward_device(x0, out)
+        sols[r].synchronize()
+        o = out.cpu().numpy()[0]
+        n = count * p.s + (p.nx if r == G - 1 else 0)
+        full[start * p.s:start * p.s + n] = o[:n]
+    return full, sols
+
+
+@pytest.mark.parametrize("nx,nu,nc,G,S_local", [(12, 4, 8, 3, 2), (6, 3, 5, 4, 1), (7, 2, 4, 2, 3)])
+def test_horizon_shards_with_constraints(oracle, nx, nu, nc, G, S_local):
+    """Constrained problems split into time slices (the constraint rows travel with their stages; an interior slice has
+    no terminal rows) -- incl. a padded (nx, nu)."""
+    p = P.problems.random_lq(nx, nu, 36, batch=1, seed=21 + nx, nc=nc)
+    rng = np.random.default_rng(6)
+    nct = p.nc_total
+    wprev = rng.standard_normal((1, p.ws_len))
+    ys, zs = rng.standard_normal((1, nct)), rng.standard_normal((1, nct))
+    rho = rng.uniform(0.5, 2.0, (1, nct))
+    inv_rho = np.ascontiguousarray(1.0 / rho)
+    full, _ = _sharded_emulation(p, G, S_local, wprev, 1e-3, ys, zs, rho, inv_rho)
+    o = oracle.OracleSolver(p)
+    o.update_problem_data(wprev[0], ys[0], zs[0], inv_rho[0], 1e-3)
+    o.backward(rho[0])
+    assert rel_err(full, o.forward(p.x0[0], np.zeros(p.ws_len))) < TOL
+
+
+def test_root_boundary_is_consumed_by_forward(oracle):
+    """A root boundary set for one solve must not leak into the next: a terminal-slice handle reused as an ordinary
+    solver rolls out from the caller's x0 again; an interior shard refuses to roll out without a fresh boundary."""
+    import torch
+    p = P.problems.quadrotor_ltv(64)
+    dev = torch.device("cuda", 0)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=4)
+    ref = oracle.OracleSolver(p).solve()
+    x0 = torch.from_numpy(p.x0).to(dev)
+    out = torch.zeros(1, p.ws_len, dtype=torch.float64, device=dev)
+    other = torch.ones(1, p.nx, dtype=torch.float64, device=dev)
+    sol.update_problem_data_device(None, sigma=1e-6); sol.backward_device()
+    sol.set_root_boundary_device(other, None)
+    sol.forward_device(x0, out); sol.synchronize()
+    assert rel_err(out.cpu().numpy()[0], ref) > 1e-3          # rolled out from the boundary state, not from x0
+    sol.update_problem_data_device(None, sigma=1e-6); sol.backward_device()
+    sol.forward_device(x0, out); sol.synchronize()
+    assert rel_err(out.cpu().numpy()[0], ref) < TOL           # boundary consumed: the caller's x0 again
+    shard = P.LQRCudaSolver(p.nx, p.nu, 64, num_segments=2)
+    shard.set_option(P.capi.OPT_INTERIOR_SHARD, 1)
+    shard.set_model(p)
+    shard.update_problem_data_device(None, sigma=1e-6); shard.backward_device()
+    with pytest.raises(P.PdplqrError) as e:
+        shard.forward_device(x0, out)
+    assert e.value.code == P.capi.ERR_ORDER
+
+
+# ---------------------------------------------------------------------------------- real multi-process NCCL path
+def _nccl_worker(rank, world, port, q, N, nseg):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    try:
+        import torch
+        import torch.distributed as dist
+        import pdplqr_b200 as P2
+        from pdplqr_b200 import sharding as sh
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        start, count = sh.horizon_slices(N, world)[rank]
+        local = P2.problems.quadrotor_ltv(N, start=start, count=count)       # every rank builds ONLY its slice
+        side = torch.cuda.Stream()                                           # a non-default stream: order must still hold
+        with torch.cuda.stream(side):
+            hs = sh.HorizonShardedSolver(None, rank, world, num_segments=nseg, device=rank, local=local)
+            wfull = 0.01 * np.random.default_rng(17).standard_normal((1, N * 16 + 12))
+            ws = torch.from_numpy(np.ascontiguousarray(wfull[:, start * 16:(start + count) * 16 + 12])).to(dev)
+            out = torch.zeros_like(ws)
+            for _ in range(3):                                               # repeated solves back to back, no host syncs
+                hs.solve_device(ws, 1e-6, out)
+        torch.cuda.synchronize()
+        q.put((rank, start, count, out.cpu().numpy()[0]))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:  # report instead of hanging the parent
+        import traceback
+        q.put((rank, -1, -1, traceback.format_exc() + repr(e)))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_horizon_sharded_solver_nccl_multiprocess(oracle, world):
+    """sharding.HorizonShardedSolver.solve_device as bench.py runs it: one process per GPU, NCCL all_gather of the slice
+    summaries, every rank generating only its own time slice -- against the sequential oracle over the whole horizon."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    N, nseg = 1 << 14, 64
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, 29700 + world, q, N, nseg)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=120)
+    p = P.problems.quadrotor_ltv(N)
+    wfull = 0.01 * np.random.default_rng(17).standard_normal((1, N * 16 + 12))
+    ref = oracle.OracleSolver(p).solve(ws_in=wfull[0].copy(), sigma=1e-6)
+    full = np.zeros(p.ws_len)
+    for rank, start, count, o in res:
+        assert start >= 0, o
+        n = count * 16 + (12 if rank == world - 1 else 0)
+        full[start * 16:start * 16 + n] = o[:n]
+    assert rel_err(full, ref) < TOL
+
+
+# ---------------------------------------------------------------------------------- ADMM at the C4 dimensions
+def test_admm_box_and_soc_at_c4_dimensions(oracle):
+    """The conic outer iteration with box + second-order-cone rows at the C4 dimensions (nx30, nu10, nc = 44 per
+    interior stage) against oracle/admm_ref.py (NOT in the reference: parity unpinned by construction)."""
+    from oracle import admm_ref
+    p = P.problems.random_conic_batch(batch=3, N=12, seed=5)
+    assert (p.nx, p.nu, int(p.ncs[1])) == (30, 10, 44) and any(c[3] == 1 for c in p.cones)
+    lb = np.where(np.isfinite(p.e_lb), p.e_lb, -1e20)
+    ub = np.where(np.isfinite(p.e_ub), p.e_ub, 1e20)
+    rho = np.full((p.batch, p.nc_total), 0.1)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=1)
+    sol.admm_set_cones(p.cones, lb, ub)
+    ws, zs, ys = p.zeros_ws(), np.zeros((p.batch, p.nc_total)), np.zeros((p.batch, p.nc_total))
+    iters, res = sol.admm_solve(p.x0, ws, zs, ys, rho, sigma=1e-6, alpha=1.6, max_iter=25, eps_abs=0.0, eps_rel=0.0,
+                                check_every=25)
+    assert iters == 25
+    p.e_lb, p.e_ub = lb, ub
+    for b in range(p.batch):
+        w, z, y, r_prim, r_dual = admm_ref.admm(p, b, rho[b], sigma=1e-6, alpha=1.6, iters=25)
+        assert rel_err(ws[b], w) < TOL and rel_err(zs[b], z) < TOL
+        assert np.max(np.abs(ys[b] - y)) < TOL * max(1.0, np.max(np.abs(y)))
+    # the SOC rows really are inside their cones after the projection
+    coff = p.coff()
+    for (k, r0, d, typ) in p.cones:
+        if typ == 1:
+            v = zs[0, coff[k] + r0:coff[k] + r0 + d]
+            assert np.linalg.norm(v[1:]) <= v[0] + 1e-12
