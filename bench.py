@@ -570,7 +570,7 @@ def leg_c2(ctx, steps):
     sol, ms, out_dev, ws_host, x0_host, step = run_single(ctx, prob, 0, max(steps, 50), 5)
     l0 = sol.launch_count(); step(); launches = sol.launch_count() - l0
     torch.cuda.synchronize()
-    out_np = np.empty((1, prob.ws_len))
+    out_np = torch.empty(1, prob.ws_len, dtype=torch.float64).pin_memory().numpy()
     ms_e2e = ctx.time_wall(lambda: sol.solve(ws_host.numpy(), x0_host.numpy(), out_np, sigma=SIGMA), 20, 3)
     bwd_b, fwd_b = stage_bytes(12, 4, True)
     ffl, wfl = stage_flops(12, 4, pdp=True)
@@ -631,7 +631,8 @@ def leg_c5(ctx, steps):
         ms_bwd = ctx.time_loop(bwd_only, 5, 1)
         sol.forward_device(x0_dev1, out_dev)
         torch.cuda.synchronize()
-        out_np = np.empty((1, prob.ws_len))
+        out_pin = torch.empty(1, prob.ws_len, dtype=torch.float64).pin_memory()
+        out_np = out_pin.numpy()
         link = link_bandwidth(ctx, 128 << 20)
         ms_e2e = ctx.time_wall(lambda: sol.solve(ws_host.numpy(), x0_host.numpy(), out_np, sigma=SIGMA), 3, 1)
         local_N, h2d, d2h = C5_N, (prob.ws_len + 12) * 8, prob.ws_len * 8

@@ -10,7 +10,9 @@
 //     (the reference re-reads `const LQRModel&` on every call, lqr_solver_parallel.hpp:52);
 //   * errors are exceptions (std::runtime_error) carrying the C-ABI message; a non-positive-definite stage, which
 //     the reference never detects (lqr_kernel.hpp:89,126), is available through not_positive_definite();
-//   * additions: solve(), gains / interface accessors.
+//   * additions: solve(), gains / interface accessors;
+//   * the constructor takes the reference's own enum lqr::CondensedSystemSolverType: replacing LQRParallelSolver by
+//     LQRCudaSolver is a change of the class name and one #include.
 // With Eigen3 installed this header uses the reference's own clqr/lqr_model.hpp types; without it (this image)
 // it uses the API-compatible stand-ins of pdplqr/mini_model.hpp.
 #pragma once
@@ -20,18 +22,26 @@
 
 #include "../pdplqr.h"
 #if defined(PDPLQR_USE_EIGEN) || __has_include(<Eigen/Dense>)
+// the reference's own types: Node / LQRModel (lqr_model.hpp:8-89), scalar / VectorXs (typedefs.hpp:8-21) and the
+// enum lqr::CondensedSystemSolverType, which lives next to LQRParallelSolver (lqr_solver_parallel.hpp:14-17)
+#include "clqr/lqr/lqr_solver_parallel.hpp"
 #include "clqr/lqr_model.hpp"
 #include "clqr/typedefs.hpp"
+#define PDPLQR_REFERENCE_TYPES 1
 #else
 #include "mini_model.hpp"
 #endif
 
 namespace lqr {
 
-#ifndef PDPLQR_HAVE_CONDENSED_ENUM
-#define PDPLQR_HAVE_CONDENSED_ENUM
-enum class CondensedSystemSolverTypeCuda { LU = PDPLQR_CONDENSED_LU, CHOLESKY = PDPLQR_CONDENSED_CHOLESKY };
+#ifndef PDPLQR_REFERENCE_TYPES
+// stand-in with the reference's name and values (lqr_solver_parallel.hpp:14-17): LU = 0, CHOLESKY = 1
+enum class CondensedSystemSolverType { LU = PDPLQR_CONDENSED_LU, CHOLESKY = PDPLQR_CONDENSED_CHOLESKY };
 #endif
+static_assert(static_cast<int>(CondensedSystemSolverType::LU) == PDPLQR_CONDENSED_LU &&
+                  static_cast<int>(CondensedSystemSolverType::CHOLESKY) == PDPLQR_CONDENSED_CHOLESKY,
+              "enum values must match the C ABI");
+using CondensedSystemSolverTypeCuda = CondensedSystemSolverType;   // round-1 name, kept for source compatibility
 
 class LQRCudaSolver {
 public:
