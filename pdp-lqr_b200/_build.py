@@ -13,11 +13,13 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libpdplqr.so")
+# PDPLQR_VARIANT=name + PDPLQR_CFLAGS="-D..." build an instrumented copy (libpdplqr_<name>.so) next to the product library
+VARIANT = os.environ.get("PDPLQR_VARIANT", "")
+OBJ = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "libpdplqr" + ("_" + VARIANT if VARIANT else "") + ".so")
 NVCC = os.environ.get("PDPLQR_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
-         "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
+         "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC", "-diag-suppress", "177"] + os.environ.get("PDPLQR_CFLAGS", "").split()
 
 
 def sources():

@@ -65,6 +65,18 @@ PDPLQR_DEVINL void bulk_wait() {
 // order generic-proxy smem accesses before subsequent async-proxy (TMA) accesses of the same locations
 PDPLQR_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// 1/a to within an ulp or two: hardware seed (2^-23) + two Newton steps (~48 cycles against ~72 for an IEEE division
+// and ~130 for rsqrt, scripts/micro/lat_bench.cu); a must be a normal, non-zero number (a pivot)
+PDPLQR_DEVINL double rcp_newton(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 // smallest leading dimension >= n that is 4 (mod 8)  (see BwdSmem)
 constexpr int ld4mod8(int n) { return n + ((4 - n % 8) + 8) % 8; }
 

@@ -14,7 +14,11 @@
 //   * the affine terms ride along as an extra column:  [M | g] = [H~ | h~] + E^T (P+ [E c] + [0 p+]);
 //   * F+ [B A c] is formed up front (off the critical path): F = F+A + (F+B) K, f = F+c + (F+B) d + f+;
 //   * what is stored per stage is Z = [K | d | Gt] with K = -Quu^-1 Qux, d = -Quu^-1 Qu, Gt = Luu^-T G
-//     (G as in lqr_kernel_parallel.hpp:127-128), so the rollout is u = K x + d + Gt uhat with no solves.
+//     (G as in lqr_kernel_parallel.hpp:127-128), so the rollout is u = K x + d + Gt uhat with no solves;
+//   * Quu is factorised as L D L^T (no square roots: a Newton-refined reciprocal per pivot, the pivot signs are the
+//     Cholesky's) and the value-function updates use Z directly:  P = Qxx + Qxu K,  p = Qx + Qxu d,
+//     C += (F+B)(-Gt)  [= G^T G],  so no Y = Luu^-1 [...] is formed or stored.  Round-2 clock64() breakdown: the
+//     Cholesky + substitution phase was 1,700-1,900 of the 4,000 (latency mode) / 6,700 (throughput mode) cycles of a stage.
 #pragma once
 #include "common.cuh"
 
@@ -122,19 +126,17 @@ struct BwdSmem {
     static constexpr int LDPF = ld4mod8(2 * NX);    // PF: [P+; F+] stacked, (2NX) x NX
     static constexpr int LDPE = ld4mod8(2 * NX);    // PFE: [P+;F+] [E c], (2NX) x (S+1)
     static constexpr int LDM = S + ((2 - S % 4) + 4) % 4;   // Ma: [M | g], S x (S+1)
-    static constexpr int LDY = ld4mod8(D::NRHS);    // YT: NRHS x NU  (Y^T, Y = Luu^-1 [Qux Qu BtFt])
     static constexpr int o_rec = 0;                                 // REC (TMA destination, 16B aligned), single buffer:
                                                                     // the next record is fetched right after its last reader (S3)
     static constexpr int o_Z = o_rec + D::REC;                      // FREC
     static constexpr int o_PF = o_Z + D::FREC;
     static constexpr int o_PFE = o_PF + LDPF * NX;
     static constexpr int o_Ma = o_PFE + LDPE * (S + 1);
-    static constexpr int o_YT = o_Ma + LDM * (S + 1);
     // C (NX x NX) accumulates over the whole segment.  For small NX it lives in the DMMA accumulator registers of the
     // group's first warp (2 x 2 tiles, 8 doubles per lane) instead of a shared-memory array that is read and written
     // every stage: fewer wavefronts and 1.1 KB less per group (14 instead of 13 CTAs/SM at nx12/nu4).
     static constexpr bool C_REGS = (NX <= 16) && ((long long)NX * NX * NU >= PDPLQR_DMMA_MIN_MACS);
-    static constexpr int o_Cn = o_YT + LDY * NU;
+    static constexpr int o_Cn = o_Ma + LDM * (S + 1);
     static constexpr int o_pn = o_Cn + (C_REGS ? 0 : NX * NX);
     static constexpr int o_fn = o_pn + NX;
     static constexpr int o_dinv = o_fn + NX;
@@ -156,6 +158,20 @@ struct BwdSmem {
 // ------------------------------------------------------------------------------------------------
 // Backward: segment-local Riccati sweep (+ sensitivities F, f, C for non-last segments).
 // CON = false compiles every constraint path out (unconstrained problems pay nothing for them).
+// -DPDPLQR_PHASE_CLOCKS: thread 0 of two CTAs accumulates clock64() per phase of the stage loop and prints cycles per
+// stage at the end (instrumented builds only: PDPLQR_VARIANT=prof PDPLQR_CFLAGS=-DPDPLQR_PHASE_CLOCKS, scripts/prof_phases.py)
+#ifdef PDPLQR_PHASE_CLOCKS
+#define PHASE_DECL long long ph_acc[12] = {0}, ph_t = 0; const bool ph_on = (threadIdx.x == 0) && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2);
+#define PHASE_START() do { if (ph_on) ph_t = clock64(); } while (0)
+#define PHASE(i) do { if (ph_on) { const long long t_ = clock64(); ph_acc[i] += t_ - ph_t; ph_t = t_; } } while (0)
+#define PHASE_PRINT(name, n) do { if (ph_on && (n) > 0) printf("%s blk %d T %d stages %d | cycles/stage: wait %lld fold %lld S2 %lld sync %lld S3 %lld sync+issue %lld chol %lld solve %lld sync+bulk %lld S6 %lld tail %lld | total %lld\n", name, (int)blockIdx.x, (int)blockDim.x, (int)(n), ph_acc[0]/(n), ph_acc[1]/(n), ph_acc[2]/(n), ph_acc[3]/(n), ph_acc[4]/(n), ph_acc[5]/(n), ph_acc[6]/(n), ph_acc[7]/(n), ph_acc[8]/(n), ph_acc[9]/(n), ph_acc[10]/(n), (ph_acc[0]+ph_acc[1]+ph_acc[2]+ph_acc[3]+ph_acc[4]+ph_acc[5]+ph_acc[6]+ph_acc[7]+ph_acc[8]+ph_acc[9]+ph_acc[10])/(n)); } while (0)
+#else
+#define PHASE_DECL
+#define PHASE_START() do {} while (0)
+#define PHASE(i) do {} while (0)
+#define PHASE_PRINT(name, n) do {} while (0)
+#endif
+
 template <int NX, int NU, int T, bool CON>
 __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
     using D = SegDims<NX, NU>;
@@ -174,7 +190,6 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
     double* PF = smem + L::o_PF;
     double* PFE = smem + L::o_PFE;
     double* Ma = smem + L::o_Ma;
-    double* YT = smem + L::o_YT;
     double* Cn = smem + L::o_Cn;
     double* pn = smem + L::o_pn;
     double* fn = smem + L::o_fn;
@@ -293,12 +308,15 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
     };
     if (LEN > 0) fetch_w(N1 - 1);
     constexpr bool Z_BULK = (D::FREC % 2 == 0) && ((NU * D::NRHS) % 2 == 0) && ((NU * (NX + 1)) % 2 == 0);
+    PHASE_DECL
+    PHASE_START();
 #pragma unroll 1
     for (int it = 0; it < LEN; ++it) {
         const int k = N1 - 1 - it;
         const int buf = 0;
         const double* R = rec;
         mbar_wait(&bar[0], it & 1);              // requested after S3 of the previous stage (or in the prologue)
+        PHASE(0);
         const int nck = ncmax > 0 ? p.ncs[k] : 0;
         if (nck > 0) {  // g = z - y/rho ; keep rho and rho.*g   (lqr_solver_parallel.hpp:134-137, lqr_kernel.hpp:110)
             const size_t co = cbase + p.coff[k];
@@ -320,6 +338,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         for (int q = 0; q < NW; ++q)
             if (tid + q * T < S) wp[tid + q * T] = wreg[q];
         if (it + 1 < LEN) fetch_w(k - 1);
+        PHASE(1);
         // S2: PFE = [P+; F+] * [E c]  (+ p+ on the last column of the P rows)
         {
             constexpr int MM = 2 * NX;
@@ -336,7 +355,9 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 gmm<NX, S + 1, NX, t2.tm, t2.tn, T>(tid, la, lb, epi);
             }
         }
+        PHASE(2);
         group_sync<T>();
+        PHASE(3);
 
         // S3: [M | g] = [H + sigma I | h - sigma w_prev] + E^T * PE        (update_problem_data fused in)
         {
@@ -362,6 +383,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 gmm_rt<S, S + 1, tl.tm, tl.tn, T>(tid, nck, lda, ldb, epd);
             }
         }
+        PHASE(4);
         group_sync<T>();
         if (tid == 0 && it + 1 < LEN) {  // the record (H, h) and D had their last readers in S3: fetch stage k-1 into
             fence_proxy_async();         // the same buffer; it lands while S4-S6 run and is waited for at the top of the next stage
@@ -370,32 +392,42 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         if (sel && nck > 0)
             for (int i = tid; i < 2 * S; i += T) dg_s[i] = 0.0;   // ready for the next stage's scatter-add
 
-        // S4: Luu = chol(Quu).  Small NU: every solving thread factorises its own register copy (no barriers);
-        //     larger NU: cooperative in-place factorisation of the leading block of Ma.
-        constexpr bool REG_CHOL = NU <= 8;
-        double Lr[REG_CHOL ? NU : 1][REG_CHOL ? NU : 1];
-        double dr[REG_CHOL ? NU : 1];
+        PHASE(5);
+        // S4: Quu = L D L^T (unit lower L).  NU <= 12: every solving thread factorises its own register copy (no
+        //     barriers, no square roots); larger NU: cooperative Cholesky of the leading block of Ma in place.
+        constexpr bool REG_CHOL = NU <= 12;
+        double Lr[REG_CHOL ? NU : 1][REG_CHOL ? NU : 1];   // Lr[i][j], i > j: L(i,j)  (registers up to NU = 8; at NU = 10
+                                                            // the compiler keeps the array in L1-cached local memory)
+        double dr[REG_CHOL ? NU : 1];                       // 1 / D(c)
         const int n1 = NX + 1, n2 = pdp ? NX : 0, n3 = aff_b ? NU : 0;
         if constexpr (REG_CHOL) {
             if (tid < n1 + n2 + n3) {
+                double dd[NU];                              // D(q)
 #pragma unroll
                 for (int j = 0; j < NU; ++j)
 #pragma unroll
-                    for (int i = j; i < NU; ++i) Lr[i][j] = Ma[i + j * L::LDM];
+                    for (int i = j + 1; i < NU; ++i) Lr[i][j] = Ma[i + j * L::LDM];
 #pragma unroll
                 for (int c = 0; c < NU; ++c) {
-                    double a = Lr[c][c];
+                    double vc[NU];                          // vc[q] = L(c,q) D(q): row c of L D (off the pivot chain for q < c-1)
 #pragma unroll
-                    for (int q = 0; q < c; ++q) a = fma(-Lr[c][q], Lr[c][q], a);
-                    if (!(a > 0.0)) { if (!bad) bad = k + 1; a = fabs(a) + 1e-300; }
-                    const double r = rsqrt(a);
+                    for (int q = 0; q < c; ++q) vc[q] = Lr[c][q] * dd[q];
+                    double a = Ma[c + c * L::LDM];
+#pragma unroll
+                    for (int q = 0; q < c; ++q) a = fma(-Lr[c][q], vc[q], a);
+                    double r = rcp_newton(a);              // the pivot test stays off the dependent chain
+                    if (!(a > 0.0)) {                      // (rare) keep the sweep finite, report through the status word
+                        if (!bad) bad = k + 1;
+                        a = fabs(a) + 1e-300;
+                        r = rcp_newton(a);
+                    }
                     dr[c] = r;
-                    Lr[c][c] = a * r;
+                    dd[c] = a;
 #pragma unroll
                     for (int i = c + 1; i < NU; ++i) {
                         double v = Lr[i][c];
 #pragma unroll
-                        for (int q = 0; q < c; ++q) v = fma(-Lr[i][q], Lr[c][q], v);
+                        for (int q = 0; q < c; ++q) v = fma(-Lr[i][q], vc[q], v);
                         Lr[i][c] = v * r;
                     }
                 }
@@ -404,38 +436,56 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
             const int info = group_chol<NU, T>(tid, Ma, L::LDM, dinv);
             if (info && !bad) bad = k + 1;
         }
-        auto Lel = [&](int i, int j) { if constexpr (REG_CHOL) return Lr[i][j]; else return Ma[i + j * L::LDM]; };
-        auto Dinv = [&](int m) { if constexpr (REG_CHOL) return dr[m]; else return dinv[m]; };
-
-        // S5: one right-hand side per thread: y = Luu^-1 r, z = -Luu^-T y;  r in [Qux | Qu | (F+B)^T]
+        PHASE(6);
+        // S5: one right-hand side per thread: z = -Quu^-1 r,  r in [Qux | Qu | (F+B)^T]  (unit vectors -> Quu^-1)
         {
             for (int q = tid; q < n1 + n2 + n3; q += T) {
                 const int c = (q < n1 + n2) ? q : D::NRHS + (q - n1 - n2);   // >= NRHS: unit vectors -> Quu^-1
+                // branch-free gather of the right-hand side (a per-element if / else chain here compiled into 4 x 4 divergent
+                // paths with their shared-memory latencies exposed one after the other: ~500 of the stage's cycles)
+                const double* src;
+                int stride;
+                if (c < NX) { src = Ma + (NU + c); stride = L::LDM; }                                // Qux(m,c) = Qxu(c,m)
+                else if (c == NX) { src = Ma + S * L::LDM; stride = 1; }                             // Qu(m)
+                else if (c < D::NRHS) { src = PFE + (NX + (c - NX - 1)); stride = L::LDPE; }         // (F+ B)(c', m)
+                else { src = Ma; stride = 0; }                                                       // unit vector (below)
                 double y[NU];
 #pragma unroll
                 for (int m = 0; m < NU; ++m) {
-                    double r;
-                    if (c < NX) r = Ma[(NU + c) + m * L::LDM];               // Qux(m,c) = Qxu(c,m)
-                    else if (c == NX) r = Ma[m + S * L::LDM];                // Qu(m)
-                    else if (c < D::NRHS) r = PFE[(NX + (c - NX - 1)) + m * L::LDPE];   // (F+ B)(c', m)
-                    else r = (m == c - D::NRHS) ? 1.0 : 0.0;
-                    y[m] = r;
-                }
-#pragma unroll
-                for (int m = 0; m < NU; ++m) {
-                    double v = y[m];
-#pragma unroll
-                    for (int q = 0; q < m; ++q) v = fma(-Lel(m, q), y[q], v);
-                    y[m] = v * Dinv(m);
-                    if (c < D::NRHS) YT[c + m * L::LDY] = y[m];
+                    const double r = src[m * stride];
+                    y[m] = (c < D::NRHS) ? r : ((m == c - D::NRHS) ? 1.0 : 0.0);
                 }
                 double z[NU];
+                if constexpr (REG_CHOL) {      // L D L^T: forward (unit lower), scale, backward
 #pragma unroll
-                for (int m = NU - 1; m >= 0; --m) {
-                    double v = y[m];
+                    for (int m = 1; m < NU; ++m) {
+                        double v = y[m];
 #pragma unroll
-                    for (int q = m + 1; q < NU; ++q) v = fma(-Lel(q, m), z[q], v);
-                    z[m] = v * Dinv(m);
+                        for (int qq = 0; qq < m; ++qq) v = fma(-Lr[m][qq], y[qq], v);
+                        y[m] = v;
+                    }
+#pragma unroll
+                    for (int m = NU - 1; m >= 0; --m) {
+                        double v = y[m] * dr[m];
+#pragma unroll
+                        for (int qq = m + 1; qq < NU; ++qq) v = fma(-Lr[qq][m], z[qq], v);
+                        z[m] = v;
+                    }
+                } else {                       // Cholesky factor in Ma, reciprocal diagonal in dinv
+#pragma unroll
+                    for (int m = 0; m < NU; ++m) {
+                        double v = y[m];
+#pragma unroll
+                        for (int qq = 0; qq < m; ++qq) v = fma(-Ma[m + qq * L::LDM], y[qq], v);
+                        y[m] = v * dinv[m];
+                    }
+#pragma unroll
+                    for (int m = NU - 1; m >= 0; --m) {
+                        double v = y[m];
+#pragma unroll
+                        for (int qq = m + 1; qq < NU; ++qq) v = fma(-Ma[qq + m * L::LDM], z[qq], v);
+                        z[m] = v * dinv[m];
+                    }
                 }
                 if (c < D::NRHS) {
 #pragma unroll
@@ -446,6 +496,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 }
             }
         }
+        PHASE(7);
         if constexpr (Z_BULK) fence_proxy_async();   // Z is picked up by a bulk copy below
         group_sync<T>();
         if constexpr (Z_BULK) {   // factor record -> global, one TMA store; it drains while S6 runs
@@ -455,41 +506,48 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
             }
         }
 
-        // S6: P = Qxx - Yx^T Yx, p = Qx - Yx^T yu  |  C += Yg^T Yg  |  [F f] = F+[A c] + (F+B)[K d] + [0 f+]
+        PHASE(8);
+        // S6: P = Qxx + Qxu K, p = Qx + Qxu d  |  C += (F+B)(-Gt)  |  [F f] = F+[A c] + (F+B)[K d] + [0 f+]
         {
             constexpr Tile tl = pick_tile(NX, NX + 1, T);
-            auto la = [&](int i, int m) { return YT[i + m * L::LDY]; };
-            auto lb = [&](int m, int j) { return YT[j + m * L::LDY]; };
+            auto la = [&](int i, int m) { return Ma[(NU + i) + m * L::LDM]; };      // Qxu(i,m)
+            auto lb = [&](int m, int j) { return Z[m + j * NU]; };                   // [K d](m,j)
             auto epi = [&](int i, int j, double v) {
-                if (j < NX) {
-                    const int r = max(i, j), c = min(i, j);
-                    PF[i + j * L::LDPF] = Ma[(NU + r) + (NU + c) * L::LDM] - v;
+                if (j < NX) {   // the lower triangle is computed, the upper one mirrored: P stays exactly symmetric
+                    if (i >= j) {
+                        const double pv = Ma[(NU + i) + (NU + j) * L::LDM] + v;
+                        PF[i + j * L::LDPF] = pv;
+                        PF[j + i * L::LDPF] = pv;
+                    }
                 } else {
-                    pn[i] = Ma[(NU + i) + S * L::LDM] - v;
+                    pn[i] = Ma[(NU + i) + S * L::LDM] + v;
                 }
             };
             gmm<NX, NX + 1, NU, tl.tm, tl.tn, T>(tid, la, lb, epi);
             if (pdp) {
                 if constexpr (L::C_REGS) {
-                    if (tid < 32) {   // C += Yg^T Yg: the A and B fragments of a symmetric rank-NU update are the same values
+                    if (tid < 32) {   // C += (F+B)(-Gt), accumulated in the tensor-core accumulator registers of warp 0
                         const int fr = tid >> 2, fq = tid & 3;
 #pragma unroll
                         for (int kt = 0; kt < (NU + 3) / 4; ++kt) {
                             const int m = kt * 4 + fq;
-                            double fg[CT];
+                            double fa[CT], fb[CT];
+#pragma unroll
+                            for (int a = 0; a < CT; ++a) {
+                                const bool in = m < NU && 8 * a + fr < NX;
+                                fa[a] = in ? PFE[(NX + 8 * a + fr) + m * L::LDPE] : 0.0;            // (F+B)(i, m)
+                                fb[a] = in ? -Z[m + (NX + 1 + 8 * a + fr) * NU] : 0.0;              // -Gt(m, j)
+                            }
 #pragma unroll
                             for (int a = 0; a < CT; ++a)
-                                fg[a] = (m < NU && 8 * a + fr < NX) ? YT[(NX + 1 + 8 * a + fr) + m * L::LDY] : 0.0;
 #pragma unroll
-                            for (int a = 0; a < CT; ++a)
-#pragma unroll
-                                for (int c = 0; c < CT; ++c) dmma_m8n8k4(creg[a][c][0], creg[a][c][1], fg[a], fg[c]);
+                                for (int c = 0; c < CT; ++c) dmma_m8n8k4(creg[a][c][0], creg[a][c][1], fa[a], fb[c]);
                         }
                     }
                 } else {
                     constexpr Tile tc = pick_tile(NX, NX, T);
-                    auto lga = [&](int i, int m) { return YT[(NX + 1 + i) + m * L::LDY]; };
-                    auto lgb = [&](int m, int j) { return YT[(NX + 1 + j) + m * L::LDY]; };
+                    auto lga = [&](int i, int m) { return PFE[(NX + i) + m * L::LDPE]; };
+                    auto lgb = [&](int m, int j) { return -Z[m + (NX + 1 + j) * NU]; };
                     auto epc = [&](int i, int j, double v) { Cn[i + j * NX] += v; };
                     gmm<NX, NX, NU, tc.tm, tc.tn, T>(tid, lga, lgb, epc);
                 }
@@ -518,8 +576,11 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                     for (int e = tid; e < NX * NU; e += T) ak[D::AR_FB + e] = PFE[(NX + e % NX) + (e / NX) * L::LDPE];
             }
         }
+        PHASE(9);
         group_sync<T>();
+        PHASE(10);
     }
+    PHASE_PRINT("seg_backward", LEN);
 
     // segment summary (lqr_solver_parallel.hpp:180-187): P, F, C, p, f at the segment entry
     double* sm = p.sum + ((size_t)b * p.S + seg) * D::SREC;

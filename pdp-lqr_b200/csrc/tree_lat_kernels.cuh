@@ -27,17 +27,6 @@ PDPLQR_DEVINL void rt_sync(int tt, int bar_id) {
     else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(tt) : "memory");
 }
 
-// 1/a to within an ulp or two: hardware seed (2^-23) + two Newton steps; a is a Gauss-Jordan pivot (normal, non-zero)
-PDPLQR_DEVINL double rcp_newton(double a) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
-    double e = fma(-a, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-a, r, 1.0);
-    r = fma(r, e, r);
-    return r;
-}
-
 constexpr int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 template <int NX>
