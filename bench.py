@@ -130,12 +130,22 @@ def roofline(kernel, bytes_per_launch, flops_per_launch, ms, traffic_key=None, e
     return out
 
 
-WAVE = 148 * 14   # resident one-warp stage-kernel CTAs per GPU at nx12/nu4 (16 KB of shared memory each)
+WAVE = 148 * 14   # fallback when no GPU is visible (the round-1 stage kernel: 14 one-warp CTAs per SM at nx12/nu4)
+
+
+def stage_wave() -> int:
+    """(problem, segment) groups the GPU keeps resident in the nx12/nu4 stage sweep (pdplqr_wave_size: SMs x CTAs per SM
+    from the occupancy calculator)."""
+    try:
+        import pdplqr_b200 as P
+        return P.wave_size(12, 4)
+    except Exception:
+        return WAVE
 
 
 def wave_aligned(num_segments: int, wave: int = WAVE) -> int:
-    """Round a segment count down to whole waves of the stage kernel's resident CTAs (148 SMs x 14 one-warp CTAs at
-    nx12/nu4): a trailing partial wave costs a full wave of time (2048 segments = 1.06 waves ran as 2)."""
+    """Round a segment count down to whole waves of the stage kernel's resident CTAs: a trailing partial wave costs a
+    full wave of time (2048 segments = 1.06 waves ran as 2)."""
     if num_segments <= wave:
         return max(1, num_segments)
     return (num_segments // wave) * wave
@@ -147,9 +157,11 @@ def c4_traffic(batch: int):
 
 
 def c5_segments(world: int = 1) -> int:
-    """Segments per rank for the 2^20-stage problem: ~250-stage segments in whole waves, never less than one full wave."""
-    per_rank = wave_aligned(C5_N // 250)
-    return wave_aligned(max(per_rank // world, WAVE))
+    """Segments per rank for the 2^20-stage problem: whole waves of the stage kernel, ~200-stage segments at 1 GPU, never
+    less than one full wave per rank."""
+    wave = stage_wave()
+    per_rank = wave_aligned(max(C5_N // 200, wave), wave)
+    return wave_aligned(max(per_rank // world, wave), wave)
 
 
 def workload_config(name: str, world: int) -> dict:

@@ -174,6 +174,10 @@ const char* pdplqr_last_error(pdplqr_handle_t h);
 long long pdplqr_launch_count(pdplqr_handle_t h);
 /* Bytes of one device model record / factor record (DESIGN.md data layout), for roofline bookkeeping. */
 int pdplqr_record_doubles(pdplqr_handle_t h, int* model_rec, int* factor_rec);
+/* (problem, segment) groups one GPU keeps resident in the throughput-mode stage sweep (SMs x resident CTAs per SM of the
+ * stage kernel for this (nx, nu), from the CUDA occupancy calculator): a segment count that is a whole multiple of it
+ * avoids a trailing partial wave.  num_segments = 0 in pdplqr_create uses it. */
+int pdplqr_wave_size(int nx, int nu, int device);
 int pdplqr_version(void);
 
 #ifdef __cplusplus

@@ -6,6 +6,6 @@ mpc.py (receding-horizon driver over the conic ADMM solve).
 The directory is named `pdp-lqr_b200`; import it as `pdplqr_b200` (shim module at the repo root)."""
 from . import capi, mpc, problems  # noqa: F401
 from ._build import build  # noqa: F401
-from .solver import CHOLESKY, LU, LQRCudaSolver, PdplqrError  # noqa: F401
+from .solver import CHOLESKY, LU, LQRCudaSolver, PdplqrError, wave_size  # noqa: F401
 
-__all__ = ["capi", "mpc", "problems", "build", "LQRCudaSolver", "PdplqrError", "LU", "CHOLESKY"]
+__all__ = ["capi", "mpc", "problems", "build", "LQRCudaSolver", "PdplqrError", "LU", "CHOLESKY", "wave_size"]

@@ -54,6 +54,7 @@ SIGNATURES = {
     "pdplqr_last_error": (C.c_char_p, [C.c_void_p]),
     "pdplqr_launch_count": (C.c_longlong, [C.c_void_p]),
     "pdplqr_record_doubles": (C.c_int, [C.c_void_p, _ip, _ip]),
+    "pdplqr_wave_size": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "pdplqr_version": (C.c_int, []),
 }
 

@@ -77,6 +77,32 @@ PDPLQR_DEVINL double rcp_newton(double a) {
     return r;
 }
 
+// ---------------------------------------------------------------- stage-record index permutations (seg_warp_kernel.cuh)
+// For the sizes the register-resident warp kernel supports, the stage record keeps [E c], H, h in the order that
+// kernel wants them (the record layout is ours -- pack_model_kernel writes it, every reader goes through these):
+//   * w-indices x FIRST, then u  ([A B c] instead of [B A c]; H, h likewise): Qxx and F+A then sit at the tile origin
+//     of the tensor-core accumulators and become the next P / F without any data movement;
+//   * the NX rows of [E c] in "accumulator order": position 4 s + q holds the row that lane q of a quad owns in
+//     contraction step s when an accumulator fragment (columns 2q, 2q+1 of an 8-wide tile) is fed back as an operand
+//     (rows 0,2,4,6 | 1,3,5,7 of every full group of 8; rows 0,2,1,3 of a trailing group of 4).
+// Both are the identity for every other size.
+#define PDPLQR_HD __host__ __device__ __forceinline__
+PDPLQR_HD constexpr bool warp_layout(int nx, int nu) { return nx % 4 == 0 && nx <= 16 && nu <= 8 && nx + nu + 1 <= 24; }
+PDPLQR_HD constexpr int erow_pos(int i, int nx, bool on) {       // storage position of row i
+    if (!on) return i;
+    const int b = i / 8, j = i % 8;
+    if (nx - 8 * b == 4) return 8 * b + (((j & 1) << 1) | (j >> 1));
+    return 8 * b + 4 * (j & 1) + (j >> 1);
+}
+PDPLQR_HD constexpr int erow_inv(int p, int nx, bool on) {       // row stored at position p
+    if (!on) return p;
+    const int b = p / 8, j = p % 8;
+    if (nx - 8 * b == 4) return 8 * b + (((j & 1) << 1) | (j >> 1));   // (0,2,1,3) is its own inverse
+    return 8 * b + 2 * (j & 3) + (j >> 2);
+}
+PDPLQR_HD constexpr int widx_pos(int i, int nx, int nu, bool on) { return on ? (i < nu ? nx + i : i - nu) : i; }
+PDPLQR_HD constexpr int widx_inv(int p, int nx, int nu, bool on) { return on ? (p < nx ? nu + p : p - nx) : p; }
+
 // smallest leading dimension >= n that is 4 (mod 8)  (see BwdSmem)
 constexpr int ld4mod8(int n) { return n + ((4 - n % 8) + 8) % 8; }
 
@@ -204,7 +230,8 @@ PDPLQR_DEVINL void group_mm_multi(int tid, LA la, LB lb, EPI epi) {
 // segment kernels need.  Fragment layout: A(row) lane l -> A[l/4][l%4]; B(col) lane l -> B[l%4][l/4];
 // C lane l -> C[l/4][2(l%4) + {0,1}].  Out-of-range rows / columns / k of the padded 8x8x4 tiles are fed zeros.
 PDPLQR_DEVINL void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+    // (not volatile: a pure function of its operands -- the compiler may interleave it with shuffle / FMA chains)
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }

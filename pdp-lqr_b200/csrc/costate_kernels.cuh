@@ -95,9 +95,9 @@ __global__ void __launch_bounds__(32) seg_costate_kernel(CostateParams q) {
             const int i = lane + 32 * t;
             if (i < NX) {
                 const int row = NU + i;
-                double acc = R[D::REC_h + row] + p.sigma * (w[row] - (wprev ? wprev[(size_t)k * S + row] : 0.0));
-                for (int j = 0; j < S; ++j) acc = fma(R[D::REC_H + D::h_off(row, j)], w[j], acc);      // [H w]_x
-                for (int j = 0; j < NX; ++j) acc = fma(R[j + (size_t)row * NX], ln[j], acc);           // A^T lambda+
+                double acc = R[D::h_at(row)] + p.sigma * (w[row] - (wprev ? wprev[(size_t)k * S + row] : 0.0));
+                for (int j = 0; j < S; ++j) acc = fma(R[D::H_at(row, j)], w[j], acc);      // [H w]_x
+                for (int j = 0; j < NX; ++j) acc = fma(R[D::er(j) + D::wi(row) * NX], ln[j], acc);           // A^T lambda+
                 for (int r = 0; r < nck; ++r) acc = fma(Dk[r + (size_t)row * nck], qr[r], acc);        // [D^T q]_x
                 out[t] = acc;
             }

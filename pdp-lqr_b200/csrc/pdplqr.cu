@@ -49,6 +49,9 @@ __global__ void pack_model_kernel(const double* __restrict__ E, const double* __
     // -1 for a padded input / state (identity cost, zero dynamics -- see pdplqr_solver::padded)
     const int nu = s - nx, su = nxu + nuu;
     auto umap = [&](int i) { return i < nu ? (i < nuu ? i : -1) : (i - nu < nxu ? nuu + (i - nu) : -1); };
+    // record order (common.cuh): row positions of [E c] and positions of the w-indices; identity on the thread path and
+    // for the sizes without the warp kernel's layout
+    const bool lay = !sym && warp_layout(nx, nu);
     const int nH = sym ? s * (s + 1) / 2 : s * s;
     const int oC = nx * s, oH = oC + nx, oh = oH + nH, oend = oh + s;
     const long long npad = sym ? ((nprob + 31) / 32) * 32 : nprob;
@@ -74,10 +77,11 @@ __global__ void pack_model_kernel(const double* __restrict__ E, const double* __
         const long long st = b * N + k;
         double v = 0.0;
         if (e < oC) {
-            const int i = e % nx, ju = umap(e / nx);
+            const int i = erow_inv(e % nx, nx, lay), ju = umap(widx_inv(e / nx, nx, nu, lay));
             if (i < nxu && ju >= 0) v = E[st * (long long)(nxu * su) + i + ju * nxu];
         } else if (e < oH) {
-            if (e - oC < nxu) v = c[st * nxu + (e - oC)];
+            const int i = erow_inv(e - oC, nx, lay);
+            if (i < nxu) v = c[st * nxu + i];
         } else if (e < oh) {
             int q = e - oH;
             if (sym) {  // q -> (i, j), i >= j, columns packed one after the other
@@ -88,11 +92,11 @@ __global__ void pack_model_kernel(const double* __restrict__ E, const double* __
                 const int di = q % s, j = q / s;
                 q = (((di - 4 * (j >> 1)) % s + s) % s) + j * s;
             }
-            const int iu = umap(q % s), ju = umap(q / s);
+            const int iu = umap(widx_inv(q % s, nx, nu, lay)), ju = umap(widx_inv(q / s, nx, nu, lay));
             if (iu >= 0 && ju >= 0) v = H[st * (long long)(su * su) + iu + ju * su];
             else v = (q % s == q / s) ? 1.0 : 0.0;
         } else if (e < oend) {
-            const int iu = umap(e - oh);
+            const int iu = umap(widx_inv(e - oh, nx, nu, lay));
             if (iu >= 0) v = hv[st * su + iu];
         }
         rec[idx] = v;
@@ -453,7 +457,21 @@ int run_forward_user(Solver& h, const double* d_x0, double* d_ws_out) {
 // =====================================================================================================
 extern "C" {
 
-int pdplqr_version(void) { return 100; }
+int pdplqr_version(void) { return 200; }
+
+// (problem, segment) groups one GPU keeps resident in the throughput-mode stage sweep = SMs x CTAs per SM of that kernel
+// (occupancy calculator).  Segment counts that are whole multiples of it avoid a trailing partial wave.
+int pdplqr_wave_size(int nx, int nu, int device) {
+    const Ops* ops = find_ops(nx, nu);
+    if (!ops) ops = find_padded_ops(nx, nu);
+    if (!ops) return PDPLQR_ERR_UNSUPPORTED;
+    int sms = 0;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess)
+        return PDPLQR_ERR_CUDA;
+    const int per_sm = ops->wave(0, false);
+    return per_sm > 0 ? sms * per_sm : PDPLQR_ERR_CUDA;
+}
 
 int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, int batch, int num_segments,
                   int load_balancing, int condensed_type, int device) {
@@ -504,9 +522,9 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     const bool auto_seg = (S == 0);
     const bool equal_split = auto_seg || load_balancing == 2;   // GPU-style partition: equal lengths
     if (auto_seg) {
-        // GPU-appropriate default: one full wave of (problem, segment) groups (148 SMs x ~14 resident stage-kernel
-        // CTAs), segments >= 8 stages
-        const int target_groups = 148 * 14;
+        // GPU-appropriate default: one full wave of (problem, segment) groups (SMs x resident stage-kernel CTAs per SM,
+        // from the occupancy calculator), segments >= 8 stages
+        const int target_groups = std::max(1, pdplqr_wave_size(nx, nu, device));
         S = std::max(1, std::min(N / 8, (target_groups + batch - 1) / batch));
     }
     S = std::min(S, N);
@@ -539,6 +557,7 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (const char* e = getenv("PDPLQR_TREE_LAT_WIDTH")) h->lat_width = atoi(e);
     if (const char* e = getenv("PDPLQR_TREE_LAT_TT")) h->lat_tt_cap = atoi(e);
     if (const char* e = getenv("PDPLQR_SEG_T")) h->seg_t = atoi(e);
+    if (const char* e = getenv("PDPLQR_WARP_KERNEL")) h->warp_kernel = atoi(e);
     if (const char* e = getenv("PDPLQR_SPARSE_D")) h->allow_sel = atoi(e);
     if (const char* e = getenv("PDPLQR_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(1, std::min(64, atoi(e)));
 

@@ -42,6 +42,15 @@ struct SegDims {
     // S the rows of column j are stored rotated by 4 (j / 2): element (i, j) at ((i + 4 (j/2)) mod S) + j S.
     static constexpr bool H_ROT = (S % 16 == 0);
     PDPLQR_DEVINL static int h_off(int i, int j) { return H_ROT ? ((i + 4 * (j >> 1)) % S) + j * S : i + j * S; }
+    // record order of the rows of [E c] and of the w-indices (common.cuh): identity unless the warp kernel's layout is on.
+    // Everywhere below i, j are the reference's indices (w = [u; x], lqr_model.hpp:12-19); er / wi give the position.
+    static constexpr bool WLAY = warp_layout(NX, NU);
+    PDPLQR_DEVINL static constexpr int er(int i) { return erow_pos(i, NX, WLAY); }           // position of row i of [E c]
+    PDPLQR_DEVINL static constexpr int eri(int p) { return erow_inv(p, NX, WLAY); }          // row at position p
+    PDPLQR_DEVINL static constexpr int wi(int i) { return widx_pos(i, NX, NU, WLAY); }       // position of w-index i
+    PDPLQR_DEVINL static constexpr int wic(int j) { return j < S ? widx_pos(j, NX, NU, WLAY) : j; }   // ... of column j of [E c]
+    PDPLQR_DEVINL static int H_at(int i, int j) { return REC_H + h_off(wi(i), wi(j)); }      // H(i,j) inside the record
+    PDPLQR_DEVINL static constexpr int h_at(int i) { return REC_h + wi(i); }
     static constexpr int REC = even_up(REC_h + S);
     static constexpr int REC_EC = even_up(NX * S + NX);  // prefix the rollout needs
     // factor record (one stage): Z = [K (NU x NX) | d (NU) | Gt (NU x NX)], column-major
@@ -343,8 +352,9 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         {
             constexpr int MM = 2 * NX;
             constexpr Tile tl = pick_tile(MM, S + 1, T);
-            auto la = [&](int i, int kk) { return PF[i + kk * L::LDPF]; };
-            auto lb = [&](int kk, int j) { return R[kk + j * NX]; };             // [E c](kk, j)
+            // (kk is the storage position of a row of [E c]: the contraction runs in the record's row order)
+            auto la = [&](int i, int kk) { return PF[i + D::eri(kk) * L::LDPF]; };
+            auto lb = [&](int kk, int j) { return R[kk + D::wic(j) * NX]; };     // [E c](row at kk, j)
             auto epi = [&](int i, int j, double v) {
                 if (j == S && i < NX) { pc_s[i] = v; v += pn[i]; }
                 PFE[i + j * L::LDPE] = v;
@@ -362,12 +372,12 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         // S3: [M | g] = [H + sigma I | h - sigma w_prev] + E^T * PE        (update_problem_data fused in)
         {
             constexpr Tile tl = pick_tile(S, S + 1, T);
-            auto la = [&](int i, int kk) { return R[kk + i * NX]; };             // E^T(i, kk)
-            auto lb = [&](int kk, int j) { return PFE[kk + j * L::LDPE]; };
+            auto la = [&](int i, int kk) { return R[kk + D::wi(i) * NX]; };      // E^T(i, row at kk)
+            auto lb = [&](int kk, int j) { return PFE[D::eri(kk) + j * L::LDPE]; };
             auto epi = [&](int i, int j, double v) {
                 double base;
-                if (j < S) base = R[D::REC_H + D::h_off(i, j)] + ((i == j) ? sigma : 0.0);
-                else base = R[D::REC_h + i] - sigma * wp[i];
+                if (j < S) base = R[D::H_at(i, j)] + ((i == j) ? sigma : 0.0);
+                else base = R[D::h_at(i)] - sigma * wp[i];
                 if (sel && nck > 0) {   // selection-matrix fold-in (dg, dh were scatter-added at the top of the stage)
                     if (i == j) base += dg_s[i];
                     else if (j == S) base -= dh_s[i];
@@ -761,7 +771,7 @@ __global__ void __launch_bounds__(T) seg_affine_kernel(SegParams p) {
         for (int r = 0; r < (S + T - 1) / T; ++r) {
             const int i = tid + r * T;
             if (i < S) {
-                double acc = hrec[i] - sigma * wpv[r];
+                double acc = hrec[D::wi(i)] - sigma * wpv[r];
                 if (nck > 0 && sel) {
                     acc -= dh_s[i];
                     dh_s[i] = 0.0;          // ready for the next stage's scatter-add (same thread, next use after a sync)
@@ -770,7 +780,7 @@ __global__ void __launch_bounds__(T) seg_affine_kernel(SegParams p) {
                     for (int q = 0; q < nck; ++q) acc = fma(-Dk[q + i * nck], rg_s[q], acc);
                 }
 #pragma unroll 4
-                for (int q = 0; q < NX; ++q) acc = fma(R[q + i * NX], tv[q], acc);
+                for (int q = 0; q < NX; ++q) acc = fma(R[q + D::wi(i) * NX], tv[D::eri(q)], acc);
                 gv[i] = acc;
             }
         }
@@ -895,11 +905,11 @@ __global__ void __launch_bounds__(T) seg_forward_kernel(SegParams p) {
         for (int r = 0; r < (NX + T - 1) / T; ++r) {
             const int i = tid + r * T;
             if (i < NX) {
-                double acc = R[D::REC_C + i];
+                double acc = R[D::REC_C + D::er(i)];
 #pragma unroll
-                for (int j = 0; j < NU; ++j) acc = fma(R[i + j * NX], us[j], acc);
+                for (int j = 0; j < NU; ++j) acc = fma(R[D::er(i) + D::wi(j) * NX], us[j], acc);
 #pragma unroll 4
-                for (int j = 0; j < NX; ++j) acc = fma(R[i + (NU + j) * NX], xs[j], acc);
+                for (int j = 0; j < NX; ++j) acc = fma(R[D::er(i) + D::wi(NU + j) * NX], xs[j], acc);
                 xn[r] = acc;
             }
         }

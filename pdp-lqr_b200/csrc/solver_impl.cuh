@@ -12,6 +12,7 @@
 
 #include "batch_kernels.cuh"
 #include "seg_kernels.cuh"
+#include "seg_warp_kernel.cuh"
 #include "tree_kernels.cuh"
 #include "tree_lat_kernels.cuh"
 #include "costate_kernels.cuh"
@@ -55,6 +56,7 @@ struct pdplqr_solver {
     int seg_mode = 0, seg_len0 = 0;   // closed-form partition handed to the kernels
     int lat_threads = 128;     // 0 disables the 128-thread latency mode of the segment backward kernel
     int seg_t = 0;             // PDPLQR_SEG_T: threads per (problem, segment) in throughput mode (0 = default 32)
+    int warp_kernel = 1;       // PDPLQR_WARP_KERNEL: register-resident warp kernel (0 off, 1 throughput mode, 2 always)
     int tree_lat = 1;          // latency-mode tree kernels when a level has few groups (PDPLQR_TREE_LAT=0 disables)
     int tree_lat_max = 296;    // ... "few" = at most this many CTAs (PDPLQR_TREE_LAT_MAX)
     int lat_width = 0, lat_tt_cap = 0;   // PDPLQR_TREE_LAT_WIDTH / PDPLQR_TREE_LAT_TT: tuning overrides (0 = default)
@@ -134,6 +136,7 @@ struct Ops {
     int (*tree_sub_up)(Solver&, const TreeTopParams&);
     int (*tree_sub_down)(Solver&, const TreeTopParams&);
     int (*costates)(Solver&, const double* traj, double* lam);
+    int (*wave)(int ncmax, bool sel);   // resident (problem, segment) CTAs per SM of the throughput-mode stage kernel
 };
 
 inline int fail(Solver* h, int code, const std::string& msg) {
@@ -233,6 +236,20 @@ int backward_impl(Solver& h) {
     // latency mode: with fewer (problem, segment) groups than SMs a whole 128-thread CTA works on each group
     constexpr int TL = (T < 128) ? 128 : T;
     const bool latency_mode = (T < 128) && h.lat_threads > 0 && (long long)h.batch * h.S <= 2 * 148;
+    if constexpr (SegDims<NX, NU>::WLAY) {
+        // register-resident warp kernel (seg_warp_kernel.cuh): unconstrained stages, no affine cache.
+        // PDPLQR_WARP_KERNEL = 0: off, 1 (default): throughput mode, 2: latency mode as well
+        if (h.ncmax == 0 && !h.keep_affine && h.seg_t == 0 && (h.warp_kernel >= 2 || (h.warp_kernel == 1 && !latency_mode))) {
+            auto kern = seg_backward_warp_kernel<NX, NU>;
+            constexpr size_t wbytes = WarpSmem<NX, NU>::BYTES;
+            int rc = set_smem(h, kern, wbytes);
+            if (rc) return rc;
+            kern<<<h.batch * h.S, 32, wbytes, h.stream>>>(p);
+            h.launches++;
+            CU_TRY(&h, cudaGetLastError());
+            return PDPLQR_OK;
+        }
+    }
     const size_t bytes = BwdSmem<NX, NU>::bytes(h.ncmax, h.sel_mode);
     if constexpr (T == 32) {
         // One warp per (problem, segment) by default: with the products on register-blocked DMMA a single warp owns every
@@ -409,6 +426,33 @@ int costates_impl(Solver& h, const double* traj, double* lam) {
     return PDPLQR_OK;
 }
 
+// resident CTAs per SM of the stage kernel a throughput-mode backward would launch (unconstrained: the warp kernel where
+// its layout is on, else seg_backward_kernel with T threads)
+template <int NX, int NU, int T>
+int wave_impl(int ncmax, bool sel) {
+    int n = 0;
+    if constexpr (SegDims<NX, NU>::WLAY) {
+        if (ncmax == 0) {
+            auto kern = seg_backward_warp_kernel<NX, NU>;
+            constexpr size_t wbytes = WarpSmem<NX, NU>::BYTES;
+            if (wbytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wbytes);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 32, wbytes) != cudaSuccess) n = 0;
+            return n;
+        }
+    }
+    const size_t bytes = BwdSmem<NX, NU>::bytes(ncmax, sel);
+    if (ncmax > 0) {
+        auto kern = seg_backward_kernel<NX, NU, T, true>;
+        if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, T, bytes) != cudaSuccess) n = 0;
+    } else {
+        auto kern = seg_backward_kernel<NX, NU, T, false>;
+        if (bytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, T, bytes) != cudaSuccess) n = 0;
+    }
+    return n;
+}
+
 template <int NX, int NU, int T>
 constexpr Ops make_ops() {
     return Ops{NX, NU, T, SegDims<NX, NU>::REC, SegDims<NX, NU>::FREC, SegDims<NX, NU>::SREC, TreeDims<NX>::DREC,
@@ -417,7 +461,7 @@ constexpr Ops make_ops() {
                BatchDims<NX, NU>::ENABLED,
                &backward_impl<NX, NU, T>, &forward_impl<NX, NU, T>, &tree_up_impl<NX>, &tree_down_impl<NX>,
                &affine_impl<NX, NU>, &tree_up_affine_impl<NX>, &tree_top_up_impl<NX>, &tree_top_down_impl<NX>,
-               &tree_sub_up_impl<NX>, &tree_sub_down_impl<NX>, &costates_impl<NX, NU>};
+               &tree_sub_up_impl<NX>, &tree_sub_down_impl<NX>, &costates_impl<NX, NU>, &wave_impl<NX, NU, T>};
 }
 
 }  // namespace pdplqr_host

@@ -45,6 +45,14 @@ def _dptr(t):
     return t.data_ptr()
 
 
+def wave_size(nx: int, nu: int, device: int = 0) -> int:
+    """(problem, segment) groups one GPU keeps resident in the throughput-mode stage sweep (pdplqr_wave_size)."""
+    n = capi.load().pdplqr_wave_size(nx, nu, device)
+    if n <= 0:
+        raise PdplqrError(n, "pdplqr_wave_size failed (no CUDA device, or (nx, nu) too large)")
+    return n
+
+
 class LQRCudaSolver:
     def __init__(self, nx, nu, N, batch=1, num_segments=1, load_balancing=True, solver_type=CHOLESKY, ncs=None,
                  device=0):

@@ -27,12 +27,12 @@ def _bench():
 @pytest.mark.parametrize("logN", [17, 20])
 def test_long_horizon_at_benchmark_segmentation(oracle, logN):
     """C5 shape: nx12/nu4, N = 2^17 and the benchmarked 2^20, the bench's wave-aligned equal segmentation
-    (load_balancing = 2; 4,144 segments and a 13-level interface tree at 2^20) against the SEQUENTIAL oracle over the
+    (load_balancing = 2; whole waves of ~200-stage segments and a 13-level interface tree at 2^20) against the SEQUENTIAL oracle over the
     whole horizon -- checks that 1e-9 survives the tree depth and the interface conditioning."""
     bench = _bench()
     N = 1 << logN
     p = P.problems.quadrotor_ltv(N)
-    S = bench.wave_aligned(N // 250) if logN == 20 else bench.wave_aligned(N // 64)
+    S = bench.c5_segments(1) if logN == 20 else bench.wave_aligned(N // 64, bench.stage_wave())
     rng = np.random.default_rng(17)
     wprev = 0.01 * rng.standard_normal((1, p.ws_len))
     sol = P.LQRCudaSolver.from_problem(p, num_segments=S, load_balancing=2)
