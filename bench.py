@@ -259,7 +259,9 @@ class Ctx:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
-            dist.init_process_group("nccl", device_id=self.dev)
+            import datetime
+            # a rank that fails inside an auxiliary leg must not leave the others waiting for the default 10 minutes
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=240))
         self.stream = torch.cuda.current_stream()
         self.windows = []
 
@@ -725,6 +727,10 @@ def leg_c5(ctx, steps):
                                   "per_rank": world > 1}),
                e2e=e2e_block(ctx, 1.0 / (ms_e2e * 1e-3), ms_e2e, h2d, d2h, link))
     del sol
+    if world > 1:
+        del hs, step, bwd_only, step_e2e
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
     if rank == 0:   # parity of this run: sequential CPU oracle over the whole horizon (and the 1-GPU solve when sharded)
         from oracle import oracle as O
@@ -905,6 +911,31 @@ def main():
                           batch=int(os.environ.get("C3_BATCH", str(C3_BATCH))))
         c3_windows = list(ctx.windows)
         legs = {}
+        c3_clocks = sampler.summary(c3_windows)
+
+        def headline(extra):
+            line = {"metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": workload_config("c3", ctx.world), "clocks": c3_clocks, "e2e": main_res["e2e"],
+                    "gpu_launches": main_res["launches"], "roofline": main_res["roofline"],
+                    "parity_rel_err": main_res["parity_rel_err"], "parity_sample": main_res["parity_sample"],
+                    "non_pd_problems": main_res["bad"], "configs": legs, "bench_wall_s": time.time() - t_start}
+            if "cpu_baseline" in main_res:
+                line["cpu_baseline"] = main_res["cpu_baseline"]
+            line.update(extra)
+            return line
+        # safety net: if the auxiliary legs hang (e.g. a desynchronised collective after a failure on one rank), rank 0
+        # still prints the headline measured above and the process exits instead of waiting for the NCCL watchdog
+        import threading
+        done = threading.Event()
+
+        def watchdog():
+            if not done.wait(float(os.environ.get("BENCH_LEGS_BUDGET_S", "420"))):
+                if ctx.rank == 0:
+                    emit(headline({"configs_error": "auxiliary legs exceeded their time budget; headline only"}))
+                os._exit(0)
+        threading.Thread(target=watchdog, daemon=True).start()
         for name in [x for x in args.legs.split(",") if x]:
             t0 = time.time()
             try:
@@ -912,10 +943,16 @@ def main():
             except Exception as e:   # an auxiliary configuration must not take the headline down
                 traceback.print_exc()
                 legs[name] = {"error": repr(e)}
+                import gc
+                e = None
+                gc.collect()
             legs[name]["leg_wall_s"] = time.time() - t0
             log("leg %s done in %.1f s" % (name, time.time() - t0))
             ctx.torch.cuda.empty_cache()
-    clocks = sampler.summary(ctx.windows if main_res is None else c3_windows)
+    if main_res is None:
+        clocks = sampler.summary(ctx.windows)
+    else:
+        done.set()
     if ctx.rank == 0:
         if main_res is None:
             line = {"metric": METRIC, "value": leg["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps,
@@ -925,15 +962,7 @@ def main():
                     "gpu_launches": leg.get("gpu_launches"), "roofline": leg.get("roofline"),
                     "cpu_baseline": leg.get("cpu_baseline"), "detail": leg}
         else:
-            line = {"metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps,
-                    "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
-                    "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                    "config": workload_config("c3", ctx.world), "clocks": clocks, "e2e": main_res["e2e"],
-                    "gpu_launches": main_res["launches"], "roofline": main_res["roofline"],
-                    "parity_rel_err": main_res["parity_rel_err"], "parity_sample": main_res["parity_sample"],
-                    "non_pd_problems": main_res["bad"], "configs": legs, "bench_wall_s": time.time() - t_start}
-            if "cpu_baseline" in main_res:
-                line["cpu_baseline"] = main_res["cpu_baseline"]
+            line = headline({})
         emit(line)
     if ctx.world > 1:
         ctx.dist.barrier()

@@ -578,7 +578,9 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     h->own_stream = true;
     const size_t B = batch, ws_len = (size_t)N * h->s + nx;
     int rc = 0;
-    const size_t Bpad = ((B + 31) / 32) * 32;   // thread-path tiles of 32 problems
+    // thread-per-problem handles keep whole tiles of 32 problems; everything else exactly `batch` records (allocating the
+    // padded count for every handle cost 32 x the model memory of a single long problem: 128 GB at N = 2^20)
+    const size_t Bpad = h->thread_path ? ((B + 31) / 32) * 32 : B;
     rc |= dev_alloc(*h, &h->d_model, Bpad * N * ops->REC);
     rc |= dev_alloc(*h, &h->d_HN, B * nx * nx);
     rc |= dev_alloc(*h, &h->d_hN, B * nx);

@@ -65,9 +65,11 @@ class LQRCudaSolver:
         rc = self._lib.pdplqr_create(C.byref(h), nx, nu, N, ncs_ptr, batch, num_segments, int(load_balancing),  # 2 = equal split
                                      solver_type, device)
         if rc != capi.OK:
+            why = self._lib.pdplqr_last_error(None).decode()   # text of the failed create (no handle survives it)
             raise PdplqrError(rc, {capi.ERR_INVALID: "invalid dimensions / arguments",
-                                   capi.ERR_UNSUPPORTED: f"(nx={nx}, nu={nu}) or constraint set not supported by this build",
-                                   capi.ERR_CUDA: "no usable CUDA device (there is no CPU fallback)"}.get(rc, "create failed"))
+                                   capi.ERR_UNSUPPORTED: f"(nx={nx}, nu={nu}) exceeds the largest instantiated kernel size",
+                                   capi.ERR_CUDA: "CUDA failure or no usable CUDA device (there is no CPU fallback)"}.get(rc, "create failed")
+                              + (f": {why}" if why else ""))
         self._h = h
         self.num_segments = self._lib.pdplqr_num_segments(h)
         self.nc_total = 0 if ncs is None else int(np.sum(ncs))
