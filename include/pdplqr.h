@@ -135,11 +135,23 @@ int pdplqr_admm_set_cones(pdplqr_handle_t h, int ncones, const int* stage, const
 int pdplqr_admm_solve(pdplqr_handle_t h, const double* x0, double* ws, double* zs, double* ys, const double* rho,
                       double sigma, double alpha, int max_iter, double eps_abs, double eps_rel, int check_every,
                       int* iters_out, double* residuals_out);
-/* Same loop on device arrays (w, z, y in/out; inv_rho = 1/rho supplied by the caller); no host copies except the
- * residual read every `check_every` iterations. */
+/* Same loop on device arrays (w, z, y in/out; inv_rho = 1/rho supplied by the caller).  The whole outer iteration is ONE
+ * CUDA graph launch: a factorising iteration followed by a WHILE conditional node whose body is an affine-only
+ * iteration (update_problem_data + backward_without_factorization + forward + projections); the convergence test runs on
+ * the device every `check_every` iterations and the host reads one 120-byte control block when the graph has finished.
+ * residuals_out[1] is the stationarity residual || H w~ + h + D^T y + (dynamics multipliers) ||_inf (admm_kernels.cuh). */
 int pdplqr_admm_solve_device(pdplqr_handle_t h, const double* x0, double* w, double* z, double* y, const double* rho,
                              const double* inv_rho, double sigma, double alpha, int max_iter, double eps_abs,
                              double eps_rel, int check_every, int* iters_out, double* residuals_out);
+
+/* use_graph = 0: issue the iterations from a host loop instead (debugging; also PDPLQR_ADMM_GRAPH=0).  adaptive_rho = 1:
+ * on a check iteration rho is rescaled by sqrt((r_prim / n_prim) / (r_dual / n_dual)) when that factor leaves
+ * [1 / rho_tau, rho_tau] (OSQP's rule; the hooks are rho_vecs / inv_rho_vecs of lqr_solver_parallel.hpp:33-40), at most
+ * max_rho_updates times per solve; the next iteration re-factorises (one more graph launch per rescale).  The caller's
+ * rho arrays are not modified.  Defaults: graph on, adaptation off, rho_tau 5, 10 updates. */
+int pdplqr_admm_configure(pdplqr_handle_t h, int use_graph, int adaptive_rho, double rho_tau, int max_rho_updates);
+/* Graph launches so far and rho rescales of the last solve (bench / tests). */
+int pdplqr_admm_stats(pdplqr_handle_t h, int* graph_launches, int* rho_updates);
 
 /* Accessors (additions; the reference keeps these in a private workspace, lqr_solver_parallel.hpp:55-60).
  * All outputs are host arrays; any pointer may be NULL to skip it.

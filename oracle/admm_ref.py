@@ -50,20 +50,28 @@ def admm(prob, b, rho, sigma=1e-6, alpha=1.6, iters=20, ws=None, zs=None, ys=Non
         else:
             sol.backward_without_factorization(rho)
         wt = sol.forward(prob.x0[b], np.zeros(prob.ws_len))
+        w_old = w
         w = alpha * wt + (1.0 - alpha) * w
         r_prim = r_dual = 0.0
         for k in range(N + 1):
             nc = int(prob.ncs[k])
-            if nc == 0:
-                continue
             dim = s if k < N else nx
+            # rows that are stationarity conditions: all of them, except those of x_0 (data, not a variable)
+            rows = slice(0, nu) if k == 0 else slice(0, dim)
+            wd = (wt - w_old)[k * s:k * s + dim]
+            if nc == 0:
+                r_dual = max(r_dual, float(np.max(np.abs(sigma * wd[rows]))) if wd[rows].size else 0.0)
+                continue
             Dk = prob.D[b, doff[k]:doff[k + 1]].reshape(nc, dim, order="F")
             sl = slice(coff[k], coff[k + 1])
             zt = Dk @ wt[k * s:k * s + dim]
             zh = alpha * zt + (1.0 - alpha) * z[sl]
             znew = project(zh + y[sl] / rho[sl], cones_by_stage[k], prob.e_lb[b, sl], prob.e_ub[b, sl])
             y[sl] = y[sl] + rho[sl] * (zh - znew)
-            r_dual = max(r_dual, np.max(np.abs(Dk.T @ (rho[sl] * (znew - z[sl])))))
+            # stationarity residual H w~ + h + D^T y + (dynamics multipliers) of the conic problem: the LQ solve makes the
+            # augmented stationarity exact, so it equals  -(sigma (w~ - w_prev) + D^T rho ((1-alpha)(z~ - z_prev) + (z - z_prev)))
+            rd = sigma * wd + Dk.T @ (rho[sl] * ((1.0 - alpha) * (zt - z[sl]) + (znew - z[sl])))
+            r_dual = max(r_dual, float(np.max(np.abs(rd[rows]))))
             r_prim = max(r_prim, np.max(np.abs(zt - znew)))
             z[sl] = znew
     return w, z, y, r_prim, r_dual

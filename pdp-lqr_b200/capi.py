@@ -43,6 +43,8 @@ SIGNATURES = {
                                     C.c_double, C.c_int, _ip, _dp]),
     "pdplqr_admm_solve_device": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int,
                                            C.c_double, C.c_double, C.c_int, _ip, _dp]),
+    "pdplqr_admm_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int]),
+    "pdplqr_admm_stats": (C.c_int, [C.c_void_p, _ip, _ip]),
     "pdplqr_num_segments": (C.c_int, [C.c_void_p]),
     "pdplqr_get_partition": (C.c_int, [C.c_void_p, _ip, _ip]),
     "pdplqr_get_gains": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),

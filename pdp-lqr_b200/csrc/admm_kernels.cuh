@@ -8,7 +8,14 @@
 //     w       = alpha w~ + (1 - alpha) w_prev ,      z^ = alpha z~ + (1 - alpha) z_prev
 //     z       = Proj_K(z^ + y / rho)                  K = product of boxes [e_lb, e_ub], second-order cones, balls
 //     y       = y + rho o (z^ - z)
-//     r_prim  = || z~ - z ||_inf ,    r_dual = || D^T (rho o (z - z_prev)) ||_inf
+//     r_prim  = || z~ - z ||_inf
+//     r_dual  = || H w~ + h + D^T y + (dynamics multipliers) ||_inf , the stationarity residual of the conic problem at
+//               (w~, y, lambda).  The LQ solve makes the AUGMENTED stationarity exact, so by subtraction
+//               r_dual = || sigma (w~ - w_prev) + D^T (rho o ((1 - alpha)(z~ - z_prev) + (z - z_prev))) ||_inf
+//               -- all stage-local quantities, no second pass over H (tests check it against the definition evaluated with
+//               the costates of pdplqr_get_costates / the KKT multipliers)
+//     rho adaptation (OSQP rule, optional): on a check iteration rho *= sqrt((r_prim / n_prim) / (r_dual / n_dual)) when that
+//               factor leaves [1/tau, tau]; the next iteration then re-factorises
 // One warp per (problem, stage) item, lanes over constraint rows for the mat-vec and over cones for the projections;
 // the warps of a fixed-size grid loop over the items (a CTA per item made the kernel CTA-launch-rate bound: 2.9 ns per
 // 32-thread CTA, 3.1 ms per iteration at C4 against 0.6 ms of HBM time).
@@ -42,10 +49,30 @@ struct AdmmParams {
     double* z;                 // [batch][nc_total] in: z_prev, out: z
     double* y;                 // [batch][nc_total] in/out
     const double* rho;         // [batch][nc_total]
-    double alpha;
-    int compute_res;           // 0: skip the residual norms (only read on check iterations)
-    unsigned long long* res;   // [4] bit patterns of non-negative doubles: r_prim, r_dual, max|z~|,|z| , max|D^T y|
+    double alpha, sigma;
+    struct AdmmCtl* ctl;       // device-resident loop state: decides whether this iteration computes the residual norms
 };
+
+// Loop state of one conic solve, resident on the device: the whole outer iteration runs as ONE CUDA graph launch (a
+// factorising iteration followed by a WHILE conditional node whose body is an affine-only iteration); admm_ctl_kernel
+// ends every iteration, tests convergence on check iterations and sets the WHILE condition.
+struct AdmmCtl {
+    int iter;                  // iterations completed
+    int max_iter, check_every;
+    int converged;             // set on a check iteration
+    int rho_update;            // the loop stopped because rho should be rescaled by rho_scale (host relaunches)
+    int adaptive, n_rho_updates, max_rho_updates;
+    int cont;                  // last WHILE condition (read by the host-loop fallback)
+    int pad_;
+    double eps_abs, eps_rel, rho_tau, rho_scale;
+    double res[4];             // residuals of the last check iteration: r_prim, r_dual, n_prim, n_dual
+    unsigned long long acc[4]; // running maxima of the current check iteration (bit patterns of non-negative doubles)
+};
+
+PDPLQR_DEVINL bool admm_is_check(const AdmmCtl* c) {
+    const int it = c->iter + 1;
+    return (it % c->check_every == 0) || it >= c->max_iter;
+}
 
 PDPLQR_DEVINL void atomic_max_nonneg(unsigned long long* addr, double v) {
     // non-negative IEEE doubles order like their bit patterns
@@ -55,7 +82,12 @@ PDPLQR_DEVINL void atomic_max_nonneg(unsigned long long* addr, double v) {
 constexpr int ADMM_WARPS = 8;   // warps per CTA of admm_update_kernel; 8 CTAs per SM (32 registers): the kernel is a chain of
                                 // dependent global loads per item, so resident warps are what hides the latency (C4 453 -> 422 ms)
 
+// ORDINARY iterations (no residual norms).  Enqueued every iteration next to admm_update_res_kernel; exactly one of the two
+// does the work, decided on the device from the loop state, so the iteration can sit in a CUDA graph unchanged.  Kept
+// separate (not a template flag on one body): with the residual code in the same kernel the hot loop went from 1.3 to
+// 2.5 ms per iteration at C4.
 __global__ void __launch_bounds__(ADMM_WARPS * 32, 8) admm_update_kernel(AdmmParams p) {
+    if (admm_is_check(p.ctl)) return;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s = p.nx + p.nu;
@@ -147,7 +179,7 @@ __global__ void __launch_bounds__(ADMM_WARPS * 32, 8) admm_update_kernel(AdmmPar
         r_prim = fmax(r_prim, fabs(zt[r] - znew));
         nrm = fmax(nrm, fmax(fabs(zt[r]), fabs(znew)));
     }
-    if (!p.compute_res) continue;
+    if (!false) continue;
     __syncwarp();
     for (int j = lane; j < dim; j += 32) {
         double acc = 0.0, accy = 0.0;
@@ -169,7 +201,7 @@ __global__ void __launch_bounds__(ADMM_WARPS * 32, 8) admm_update_kernel(AdmmPar
         nrm_d = fmax(nrm_d, fabs(accy));
     }
     }   // items
-    if (!p.compute_res) return;
+    if (!false) return;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         r_prim = fmax(r_prim, __shfl_xor_sync(0xffffffffu, r_prim, off));
@@ -178,10 +210,197 @@ __global__ void __launch_bounds__(ADMM_WARPS * 32, 8) admm_update_kernel(AdmmPar
         nrm_d = fmax(nrm_d, __shfl_xor_sync(0xffffffffu, nrm_d, off));
     }
     if (lane == 0) {
-        atomic_max_nonneg(&p.res[0], r_prim);
-        atomic_max_nonneg(&p.res[1], r_dual);
-        atomic_max_nonneg(&p.res[2], nrm);
-        atomic_max_nonneg(&p.res[3], nrm_d);
+        atomic_max_nonneg(&p.ctl->acc[0], r_prim);
+        atomic_max_nonneg(&p.ctl->acc[1], r_dual);
+        atomic_max_nonneg(&p.ctl->acc[2], nrm);
+        atomic_max_nonneg(&p.ctl->acc[3], nrm_d);
+    }
+}
+
+
+// CHECK iterations: the same update plus the residual norms (r_prim, r_dual and their scales) into the loop state.
+__global__ void __launch_bounds__(ADMM_WARPS * 32, 4) admm_update_res_kernel(AdmmParams p) {
+    constexpr bool RES = true;
+    if (!admm_is_check(p.ctl)) return;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = p.nx + p.nu;
+    const size_t ws_len = (size_t)p.N * s + p.nx;
+    double* wt = smem + (size_t)warp * (2 * s + 3 * p.ncmax);   // w~ of this stage   (dim)
+    double* wd = wt + s;               // w~ - w_prev        (dim)
+    double* v = wd + s;                // z^ + y/rho         (ncmax)
+    double* zt = v + p.ncmax;          // z~                 (ncmax)
+    double* dz = zt + p.ncmax;         // rho o ((1 - alpha)(z~ - z_prev) + (z - z_prev))   (ncmax)
+    constexpr bool compute_res = RES;
+    double r_prim = 0.0, nrm = 0.0, r_dual = 0.0, nrm_d = 0.0;
+    const long long items = (long long)p.batch * (p.N + 1);
+#pragma unroll 1
+    for (long long item = (long long)blockIdx.x * ADMM_WARPS + warp; item < items; item += (long long)gridDim.x * ADMM_WARPS) {
+    const int k = (int)(item % (p.N + 1));
+    const int b = (int)(item / (p.N + 1));
+    const int dim = (k < p.N) ? s : p.nx;
+    const int nc = p.ncs[k];
+    const size_t wo = (size_t)b * ws_len + (size_t)k * s;
+    __syncwarp();                      // the previous item's readers of the scratch are done
+    for (int i = lane; i < dim; i += 32) {
+        const double a = p.w_tilde[wo + i], wold = p.w[wo + i];
+        wt[i] = a;
+        if constexpr (RES) wd[i] = a - wold;
+        p.w[wo + i] = p.alpha * a + (1.0 - p.alpha) * wold;
+    }
+    if (nc == 0) {   // unconstrained stage: only the sigma term of the dual residual
+        if (compute_res) {
+            __syncwarp();
+            for (int j = lane; j < dim; j += 32)
+                if (k > 0 || j < p.nu) r_dual = fmax(r_dual, fabs(p.sigma * wd[j]));   // (x_0 is data, not a variable)
+        }
+        continue;
+    }
+    __syncwarp();
+    const double* Dk = p.Dm + (size_t)b * p.d_total + p.doff[k];
+    const size_t co = (size_t)b * p.nc_total + p.coff[k];
+    const bool sel = p.sel_col != nullptr;
+    for (int r = lane; r < nc; r += 32) {
+        double acc = 0.0;
+        if (sel) {
+            const int cj = p.sel_col[co + r];
+            if (cj >= 0) acc = p.sel_val[co + r] * wt[cj];
+        } else {
+            for (int j = 0; j < dim; ++j) acc = fma(Dk[r + (size_t)j * nc], wt[j], acc);
+        }
+        zt[r] = acc;
+        const double zh = p.alpha * acc + (1.0 - p.alpha) * p.z[co + r];
+        v[r] = zh + p.y[co + r] / p.rho[co + r];
+    }
+    __syncwarp();
+    // projections.  Few cones per stage (the usual case: one box over all variables + a cone or two): the warp walks
+    // the cones together and clamps a box row-parallel (a lane per cone left 31 lanes idle for 40 serial clamps: 1,980
+    // warp-instructions per stage at C4).  Many cones per stage: one lane per cone.
+    auto project_serial = [&](int r0, int d, int type) {     // one lane, whole cone
+        if (type == CONE_BOX) {
+            for (int r = r0; r < r0 + d; ++r) v[r] = fmin(fmax(v[r], p.e_lb[co + r]), p.e_ub[co + r]);
+        } else if (type == CONE_SOC) {
+            double nv = 0.0;
+            for (int r = r0 + 1; r < r0 + d; ++r) nv = fma(v[r], v[r], nv);
+            nv = sqrt(nv);
+            const double t = v[r0];
+            if (nv <= t) { /* inside */ }
+            else if (nv <= -t) { for (int r = r0; r < r0 + d; ++r) v[r] = 0.0; }
+            else {
+                const double a = 0.5 * (t + nv), sc = a / nv;
+                v[r0] = a;
+                for (int r = r0 + 1; r < r0 + d; ++r) v[r] *= sc;
+            }
+        } else {  // ball of radius e_ub[first row]
+            double nv = 0.0;
+            for (int r = r0; r < r0 + d; ++r) nv = fma(v[r], v[r], nv);
+            nv = sqrt(nv);
+            const double rad = p.e_ub[co + r0];
+            if (nv > rad) { const double sc = rad / nv; for (int r = r0; r < r0 + d; ++r) v[r] *= sc; }
+        }
+    };
+    const int c0 = p.cone_first[k], c1 = p.cone_first[k + 1];
+    if (c1 - c0 <= 8) {
+        for (int c = c0; c < c1; ++c) {                      // warp-uniform
+            const int r0 = p.cone_row[c], d = p.cone_dim[c], type = p.cone_type[c];
+            if (type == CONE_BOX) {
+                for (int r = r0 + lane; r < r0 + d; r += 32) v[r] = fmin(fmax(v[r], p.e_lb[co + r]), p.e_ub[co + r]);
+            } else if (lane == 0)
+                project_serial(r0, d, type);
+        }
+    } else {
+        for (int c = c0 + lane; c < c1; c += 32) project_serial(p.cone_row[c], p.cone_dim[c], p.cone_type[c]);
+    }
+    __syncwarp();
+    for (int r = lane; r < nc; r += 32) {
+        const double zold = p.z[co + r], znew = v[r], rr = p.rho[co + r];
+        const double zh = p.alpha * zt[r] + (1.0 - p.alpha) * zold;
+        const double ynew = p.y[co + r] + rr * (zh - znew);
+        p.z[co + r] = znew;
+        p.y[co + r] = ynew;
+        if constexpr (RES) {
+            dz[r] = rr * ((1.0 - p.alpha) * (zt[r] - zold) + (znew - zold));
+            v[r] = ynew;                   // reuse: y for the D^T y norm
+            r_prim = fmax(r_prim, fabs(zt[r] - znew));
+            nrm = fmax(nrm, fmax(fabs(zt[r]), fabs(znew)));
+        }
+    }
+    if (!compute_res) continue;
+    __syncwarp();
+    for (int j = lane; j < dim; j += 32) {
+        double acc = p.sigma * wd[j], accy = 0.0;
+        if (sel) {
+            for (int r = 0; r < nc; ++r)
+                if (p.sel_col[co + r] == j) {
+                    const double dv = p.sel_val[co + r];
+                    acc = fma(dv, dz[r], acc);
+                    accy = fma(dv, v[r], accy);
+                }
+        } else {
+            for (int r = 0; r < nc; ++r) {
+                const double dv = Dk[r + (size_t)j * nc];
+                acc = fma(dv, dz[r], acc);
+                accy = fma(dv, v[r], accy);
+            }
+        }
+        if (k > 0 || j < p.nu) {   // the rows of x_0 are not stationarity conditions (x_0 is data)
+            r_dual = fmax(r_dual, fabs(acc));
+            nrm_d = fmax(nrm_d, fabs(accy));
+        }
+    }
+    }   // items
+    if (!compute_res) return;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        r_prim = fmax(r_prim, __shfl_xor_sync(0xffffffffu, r_prim, off));
+        r_dual = fmax(r_dual, __shfl_xor_sync(0xffffffffu, r_dual, off));
+        nrm = fmax(nrm, __shfl_xor_sync(0xffffffffu, nrm, off));
+        nrm_d = fmax(nrm_d, __shfl_xor_sync(0xffffffffu, nrm_d, off));
+    }
+    if (lane == 0) {
+        atomic_max_nonneg(&p.ctl->acc[0], r_prim);
+        atomic_max_nonneg(&p.ctl->acc[1], r_dual);
+        atomic_max_nonneg(&p.ctl->acc[2], nrm);
+        atomic_max_nonneg(&p.ctl->acc[3], nrm_d);
+    }
+}
+
+// Ends an iteration (one thread): counts it, on a check iteration moves the residual maxima out, tests convergence
+// (eps_abs + eps_rel * norm, OSQP form), decides on a rho rescale, and sets the WHILE condition of the graph.
+__global__ void admm_ctl_kernel(AdmmCtl* c, cudaGraphConditionalHandle handle, int use_handle) {
+    const bool check = admm_is_check(c);
+    const int it = c->iter + 1;
+    int cont = it < c->max_iter ? 1 : 0;
+    if (check) {
+        double r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r[i] = __longlong_as_double((long long)c->acc[i]);
+            c->res[i] = r[i];
+            c->acc[i] = 0ull;
+        }
+        const bool conv = r[0] <= c->eps_abs + c->eps_rel * r[2] && r[1] <= c->eps_abs + c->eps_rel * r[3];
+        c->converged = conv ? 1 : 0;
+        if (conv) cont = 0;
+        if (!conv && cont && c->adaptive && c->n_rho_updates < c->max_rho_updates) {
+            const double sc = sqrt((r[0] / fmax(r[2], 1e-30)) / fmax(r[1] / fmax(r[3], 1e-30), 1e-30));
+            if (sc > c->rho_tau || sc < 1.0 / c->rho_tau) {
+                c->rho_scale = fmin(fmax(sc, 1e-3), 1e3);
+                c->rho_update = 1;
+                cont = 0;   // the host rescales rho and relaunches: the graph starts with a factorising iteration
+            }
+        }
+    }
+    c->iter = it;
+    c->cont = cont;
+    if (use_handle) cudaGraphSetConditional(handle, (unsigned)cont);
+}
+
+__global__ void admm_rho_scale_kernel(double* __restrict__ rho, double* __restrict__ inv_rho, long long n, double scale) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double r = fmin(fmax(rho[i] * scale, 1e-6), 1e6);
+        rho[i] = r;
+        inv_rho[i] = 1.0 / r;
     }
 }
 

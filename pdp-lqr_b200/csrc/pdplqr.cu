@@ -305,6 +305,7 @@ int set_model_common(Solver& h, const double* E, const double* c, const double* 
     if (e != cudaSuccess) return fail(&h, PDPLQR_ERR_CUDA, std::string("set_model: ") + cudaGetErrorString(e));
     h.model_set = true;
     h.factorized = false;
+    if (h.admm_exec) { cudaGraphExecDestroy(h.admm_exec); h.admm_exec = nullptr; }   // sel_mode etc. are baked into the graph
     return PDPLQR_OK;
 }
 
@@ -558,6 +559,7 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (const char* e = getenv("PDPLQR_TREE_LAT_TT")) h->lat_tt_cap = atoi(e);
     if (const char* e = getenv("PDPLQR_SEG_T")) h->seg_t = atoi(e);
     if (const char* e = getenv("PDPLQR_WARP_KERNEL")) h->warp_kernel = atoi(e);
+    if (const char* e = getenv("PDPLQR_ADMM_GRAPH")) h->admm_use_graph = atoi(e);
     if (const char* e = getenv("PDPLQR_SPARSE_D")) h->allow_sel = atoi(e);
     if (const char* e = getenv("PDPLQR_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(1, std::min(64, atoi(e)));
 
@@ -687,6 +689,8 @@ int pdplqr_destroy(pdplqr_handle_t h) {
     if (!h) return PDPLQR_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->admm_exec) cudaGraphExecDestroy(h->admm_exec);
+    if (h->admm_graph) cudaGraphDestroy(h->admm_graph);
     for (void* p : h->owned) cudaFree(p);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -703,6 +707,7 @@ int pdplqr_set_stream(pdplqr_handle_t h, void* cuda_stream) {
     if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     h->stream = static_cast<cudaStream_t>(cuda_stream);
     h->own_stream = false;
+    if (h->admm_exec) { cudaGraphExecDestroy(h->admm_exec); h->admm_exec = nullptr; }   // captured for the old stream
     return PDPLQR_OK;
 }
 
@@ -1132,12 +1137,11 @@ int pdplqr_record_doubles(pdplqr_handle_t h, int* model_rec, int* factor_rec) {
     return PDPLQR_OK;
 }
 
-// ---- conic ADMM outer iteration (addition; NOT in the reference -- SURVEY.md section 8 row a11) -----------------
+// ---- conic ADMM outer iteration (addition; NOT in the reference -- SURVEY.md section 8 rows a11 / f1) -----------------
 int pdplqr_admm_set_cones(pdplqr_handle_t h, int ncones, const int* stage, const int* row0, const int* dim,
                           const int* type, const double* e_lb, const double* e_ub) {
     if (!h || h->nc_total == 0) return fail(h, PDPLQR_ERR_INVALID, "admm_set_cones: the problem has no constraints");
     if (ncones < 1 || !stage || !row0 || !dim || !type || !e_lb || !e_ub) return fail(h, PDPLQR_ERR_INVALID, "admm_set_cones: bad arguments");
-    if (h->padded) return fail(h, PDPLQR_ERR_UNSUPPORTED, "admm: (nx, nu) is not an instantiated pair (TODO: padded handles)");
     cudaSetDevice(h->device);
     // cones must be given stage by stage (non-decreasing), tile the rows of every stage exactly once
     std::vector<int> first(h->N + 2, 0);
@@ -1152,7 +1156,7 @@ int pdplqr_admm_set_cones(pdplqr_handle_t h, int ncones, const int* stage, const
         if (covered[k] != h->ncs[k]) return fail(h, PDPLQR_ERR_INVALID, "admm_set_cones: rows of a stage not covered");
         if (first[k + 1] < first[k]) first[k + 1] = first[k];
     }
-    const size_t B = h->batch, nct = (size_t)h->nc_total, wsl = (size_t)h->N * h->s + h->nx;
+    const size_t B = h->batch, nct = (size_t)h->nc_total, wsl = (size_t)h->N * h->s + h->nx;   // (kernel layout: >= caller's)
     int rc = 0;
     if (!h->d_cone_first) {
         rc |= dev_alloc(*h, &h->d_cone_first, h->N + 2);
@@ -1164,7 +1168,12 @@ int pdplqr_admm_set_cones(pdplqr_handle_t h, int ncones, const int* stage, const
         rc |= dev_alloc(*h, &h->d_y, B * nct);
         rc |= dev_alloc(*h, &h->d_rho_admm, B * nct);
         rc |= dev_alloc(*h, &h->d_invrho_admm, B * nct);
-        rc |= dev_alloc(*h, &h->d_res, 4);
+        rc |= dev_alloc(*h, &h->d_rho_work, B * nct);
+        rc |= dev_alloc(*h, &h->d_invrho_work, B * nct);
+        if (h->padded) rc |= dev_alloc(*h, &h->d_wk, B * wsl);
+        AdmmCtl* ctl = nullptr;
+        rc |= dev_alloc(*h, &ctl, 1);
+        h->d_ctl = ctl;
     }
     rc |= dev_alloc(*h, &h->d_cone_type, ncones);
     rc |= dev_alloc(*h, &h->d_cone_row, ncones);
@@ -1178,11 +1187,143 @@ int pdplqr_admm_set_cones(pdplqr_handle_t h, int ncones, const int* stage, const
     CU_TRY(h, cudaMemcpy(h->d_elb, e_lb, B * nct * 8, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(h->d_eub, e_ub, B * nct * 8, cudaMemcpyHostToDevice));
     h->cones_set = true;
+    if (h->admm_exec) { cudaGraphExecDestroy(h->admm_exec); h->admm_exec = nullptr; }   // the cone tables are baked in
+    if (h->admm_graph) { cudaGraphDestroy(h->admm_graph); h->admm_graph = nullptr; }
     return PDPLQR_OK;
 }
 
-// device-resident loop: w, z, y (in/out), rho, inv_rho, x0 are device arrays; no host copies except the 4-double
-// residual read every `check_every` iterations
+int pdplqr_admm_configure(pdplqr_handle_t h, int use_graph, int adaptive_rho, double rho_tau, int max_rho_updates) {
+    if (!h || rho_tau <= 1.0 || max_rho_updates < 0) return fail(h, PDPLQR_ERR_INVALID, "admm_configure: bad arguments");
+    h->admm_use_graph = use_graph ? 1 : 0;
+    h->admm_adaptive = adaptive_rho ? 1 : 0;
+    h->admm_rho_tau = rho_tau;
+    h->admm_max_rho_updates = max_rho_updates;
+    return PDPLQR_OK;
+}
+int pdplqr_admm_stats(pdplqr_handle_t h, int* graph_launches, int* rho_updates) {
+    if (!h) return PDPLQR_ERR_INVALID;
+    if (graph_launches) *graph_launches = h->admm_graph_launches;
+    if (rho_updates) *rho_updates = h->admm_rho_updates_last;
+    return PDPLQR_OK;
+}
+
+namespace {
+
+struct AdmmRun {   // kernel-layout device pointers of one conic solve
+    const double* x0;
+    double *w, *z, *y;
+    double sigma, alpha;
+};
+
+// one outer iteration, enqueued on the handle's stream (captured into the graph, or issued directly by the fallback)
+int admm_iteration(Solver& h, const AdmmRun& r, bool factorize, cudaGraphConditionalHandle handle, int use_handle) {
+    h.cur_ws = r.w; h.cur_ys = r.y; h.cur_zs = r.z; h.cur_inv_rho = h.d_invrho_work; h.cur_rho = h.d_rho_work;
+    h.sigma = r.sigma;
+    h.updated = true;                                              // update_problem_data   lqr_solver_parallel.hpp:115-140
+    int rc = factorize ? run_backward(h) : run_backward_nofact(h);  // backward[_without_factorization]   :142-154
+    if (rc) return rc;
+    rc = run_forward(h, r.x0, h.d_wtilde);                         // forward   :213-238
+    if (rc) return rc;
+    AdmmParams ap{};
+    ap.nx = h.nx; ap.nu = h.nu; ap.N = h.N; ap.batch = h.batch; ap.ncmax = h.ncmax;
+    ap.ncs = h.d_ncs; ap.coff = h.d_coff; ap.doff = h.d_doff; ap.Dm = h.d_D;
+    ap.d_total = h.d_total_dev; ap.nc_total = h.nc_total;
+    ap.sel_col = h.sel_mode ? h.d_sel_col : nullptr; ap.sel_val = h.sel_mode ? h.d_sel_val : nullptr;
+    ap.cone_first = h.d_cone_first; ap.cone_type = h.d_cone_type; ap.cone_row = h.d_cone_row; ap.cone_dim = h.d_cone_dim;
+    ap.e_lb = h.d_elb; ap.e_ub = h.d_eub;
+    ap.w_tilde = h.d_wtilde; ap.w = r.w; ap.z = r.z; ap.y = r.y; ap.rho = h.d_rho_work;
+    ap.alpha = r.alpha; ap.sigma = r.sigma; ap.ctl = static_cast<AdmmCtl*>(h.d_ctl);
+    const size_t smem = (size_t)(h.s + 3 * h.ncmax) * sizeof(double) * ADMM_WARPS;            // ordinary iterations
+    const size_t smem_res = (size_t)(2 * h.s + 3 * h.ncmax) * sizeof(double) * ADMM_WARPS;    // check iterations
+    // persistent warps: a few CTAs per SM loop over the (problem, stage) items
+    const long long items = (long long)h.batch * (h.N + 1);
+    const int ctas = (int)std::min<long long>((items + ADMM_WARPS - 1) / ADMM_WARPS, 148LL * 8);
+    rc = set_smem(h, admm_update_kernel, smem);
+    if (rc) return rc;
+    rc = set_smem(h, admm_update_res_kernel, smem_res);
+    if (rc) return rc;
+    // both kernels are enqueued; the one whose turn it is not returns at once (decided on the device)
+    admm_update_kernel<<<ctas, ADMM_WARPS * 32, smem, h.stream>>>(ap);
+    admm_update_res_kernel<<<ctas, ADMM_WARPS * 32, smem_res, h.stream>>>(ap);
+    h.launches += 2;
+    CU_TRY(&h, cudaGetLastError());
+    admm_ctl_kernel<<<1, 1, 0, h.stream>>>(static_cast<AdmmCtl*>(h.d_ctl), handle, use_handle);
+    h.launches++;
+    CU_TRY(&h, cudaGetLastError());
+    return PDPLQR_OK;
+}
+
+// Builds the graph of one conic solve:  [factorising iteration] -> WHILE (condition set by admm_ctl_kernel) { affine-only
+// iteration }.  Returns PDPLQR_OK with h.admm_exec set, or an error (the caller falls back to the host loop).
+int admm_build_graph(Solver& h, const AdmmRun& r) {
+    if (h.admm_exec) { cudaGraphExecDestroy(h.admm_exec); h.admm_exec = nullptr; }
+    if (h.admm_graph) { cudaGraphDestroy(h.admm_graph); h.admm_graph = nullptr; }
+    const bool was_factorized = h.factorized;
+    const long long l0 = h.launches;   // the capture counts kernels without running them: per-iteration counts are kept
+    cudaGraph_t g = nullptr;
+    CU_TRY(&h, cudaGraphCreate(&g, 0));
+    cudaGraphConditionalHandle handle;
+    cudaError_t e = cudaGraphConditionalHandleCreate(&handle, g, 0, cudaGraphCondAssignDefault);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(&h, PDPLQR_ERR_CUDA, std::string("conditional handle: ") + cudaGetErrorString(e)); }
+    int rc = PDPLQR_OK;
+    e = cudaStreamBeginCaptureToGraph(h.stream, g, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed);
+    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(&h, PDPLQR_ERR_CUDA, std::string("begin capture: ") + cudaGetErrorString(e)); }
+    rc = admm_iteration(h, r, true, handle, 1);
+    h.admm_fact_kernels = (int)(h.launches - l0);
+    cudaGraph_t body = nullptr;
+    if (rc == PDPLQR_OK) {   // WHILE node after everything captured so far; later captured work would depend on it
+        cudaStreamCaptureStatus st;
+        unsigned long long id;
+        cudaGraph_t cg;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t nd = 0;
+        e = cudaStreamGetCaptureInfo_v2(h.stream, &st, &id, &cg, &deps, &nd);
+        cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+        cp.conditional.handle = handle;
+        cp.conditional.type = cudaGraphCondTypeWhile;
+        cp.conditional.size = 1;
+        cudaGraphNode_t node;
+        if (e == cudaSuccess) e = cudaGraphAddNode(&node, g, deps, nd, &cp);
+        if (e == cudaSuccess) e = cudaStreamUpdateCaptureDependencies(h.stream, &node, 1, cudaStreamSetCaptureDependencies);
+        if (e == cudaSuccess) body = cp.conditional.phGraph_out[0];
+        else rc = fail(&h, PDPLQR_ERR_CUDA, std::string("conditional node: ") + cudaGetErrorString(e));
+    }
+    cudaGraph_t ended = nullptr;
+    e = cudaStreamEndCapture(h.stream, &ended);
+    if (rc == PDPLQR_OK && e != cudaSuccess) rc = fail(&h, PDPLQR_ERR_CUDA, std::string("end capture: ") + cudaGetErrorString(e));
+    if (rc == PDPLQR_OK) {
+        e = cudaStreamBeginCaptureToGraph(h.stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed);
+        if (e != cudaSuccess) rc = fail(&h, PDPLQR_ERR_CUDA, std::string("begin body capture: ") + cudaGetErrorString(e));
+        else {
+            const long long l1 = h.launches;
+            rc = admm_iteration(h, r, false, handle, 1);
+            h.admm_aff_kernels = (int)(h.launches - l1);
+            e = cudaStreamEndCapture(h.stream, &ended);
+            if (rc == PDPLQR_OK && e != cudaSuccess) rc = fail(&h, PDPLQR_ERR_CUDA, std::string("end body capture: ") + cudaGetErrorString(e));
+        }
+    }
+    if (rc == PDPLQR_OK) {
+        e = cudaGraphInstantiate(&h.admm_exec, g, 0);
+        if (e != cudaSuccess) rc = fail(&h, PDPLQR_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+    }
+    // nothing ran during the capture: restore the host-side protocol state
+    h.launches = l0;
+    h.factorized = was_factorized; h.backward_done = false; h.updated = false;
+    if (rc != PDPLQR_OK) {
+        cudaGetLastError();
+        cudaGraphDestroy(g);
+        h.admm_exec = nullptr;
+        return rc;
+    }
+    h.admm_graph = g;
+    h.admm_key = {r.x0, r.w, r.z, r.y, r.sigma, r.alpha, h.stream};
+    return PDPLQR_OK;
+}
+
+}  // namespace
+
+// device-resident loop: w, z, y (in/out), rho, inv_rho, x0 are device arrays.  One CUDA graph launch per conic solve
+// (plus one per rho rescale when the adaptation is on); the only host reads are the 120-byte control block at the end.
 int pdplqr_admm_solve_device(pdplqr_handle_t h, const double* x0, double* w, double* z, double* y, const double* rho,
                              const double* inv_rho, double sigma, double alpha, int max_iter, double eps_abs,
                              double eps_rel, int check_every, int* iters_out, double* residuals_out) {
@@ -1192,47 +1333,82 @@ int pdplqr_admm_solve_device(pdplqr_handle_t h, const double* x0, double* w, dou
     if (!h->model_set) return fail(h, PDPLQR_ERR_ORDER, "admm_solve before set_model");
     cudaSetDevice(h->device);
     if (check_every < 1) check_every = 1;
-    int it = 0, rc = 0;
-    double res[4] = {0, 0, 0, 0};
-    bool converged = false;
-    for (it = 0; it < max_iter && !converged; ++it) {
-        rc = pdplqr_update_problem_data_device(h, w, y, z, inv_rho, sigma);
+    const size_t nb = (size_t)h->batch * h->nc_total * 8;
+    // rho and 1/rho are copied: the adaptation rescales the library's copies, the caller's arrays stay as given
+    CU_TRY(h, cudaMemcpyAsync(h->d_rho_work, rho, nb, cudaMemcpyDeviceToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_invrho_work, inv_rho, nb, cudaMemcpyDeviceToDevice, h->stream));
+    AdmmRun r{x0, w, z, y, sigma, alpha};
+    int rc = PDPLQR_OK;
+    if (h->padded) {   // iterate and initial state in kernel layout for the whole loop
+        rc = repack_ws(*h, w, h->d_wk, true);
         if (rc) return rc;
-        rc = (it == 0) ? pdplqr_backward_device(h, rho) : pdplqr_backward_without_factorization_device(h, rho);
+        rc = repack_vec(*h, x0, h->d_x0p, h->batch, h->nxu, h->nx);
         if (rc) return rc;
-        rc = run_forward(*h, x0, h->d_wtilde);
-        if (rc) return rc;
-        const bool check = ((it + 1) % check_every == 0) || (it + 1 == max_iter);
-        if (check) CU_TRY(h, cudaMemsetAsync(h->d_res, 0, 4 * sizeof(unsigned long long), h->stream));
-        AdmmParams ap{};
-        ap.nx = h->nx; ap.nu = h->nu; ap.N = h->N; ap.batch = h->batch; ap.ncmax = h->ncmax;
-        ap.ncs = h->d_ncs; ap.coff = h->d_coff; ap.doff = h->d_doff; ap.Dm = h->d_D;
-        ap.d_total = h->d_total_dev; ap.nc_total = h->nc_total;
-        ap.sel_col = h->sel_mode ? h->d_sel_col : nullptr; ap.sel_val = h->sel_mode ? h->d_sel_val : nullptr;
-        ap.cone_first = h->d_cone_first; ap.cone_type = h->d_cone_type; ap.cone_row = h->d_cone_row; ap.cone_dim = h->d_cone_dim;
-        ap.e_lb = h->d_elb; ap.e_ub = h->d_eub;
-        ap.w_tilde = h->d_wtilde; ap.w = w; ap.z = z; ap.y = y; ap.rho = rho;
-        ap.alpha = alpha; ap.res = h->d_res; ap.compute_res = check ? 1 : 0;
-        const size_t smem = (size_t)(h->s + 3 * h->ncmax) * sizeof(double);
-        {   // persistent warps: a few CTAs per SM loop over the (problem, stage) items
-            const long long items = (long long)h->batch * (h->N + 1);
-            const int ctas = (int)std::min<long long>((items + ADMM_WARPS - 1) / ADMM_WARPS, 148LL * 8);
-            int rc2 = set_smem(*h, admm_update_kernel, smem * ADMM_WARPS);
-            if (rc2) return rc2;
-            admm_update_kernel<<<ctas, ADMM_WARPS * 32, smem * ADMM_WARPS, h->stream>>>(ap);
+        r.w = h->d_wk; r.x0 = h->d_x0p;
+    }
+    AdmmCtl ctl{};
+    ctl.max_iter = max_iter; ctl.check_every = check_every;
+    ctl.adaptive = h->admm_adaptive; ctl.max_rho_updates = h->admm_max_rho_updates;
+    ctl.eps_abs = eps_abs; ctl.eps_rel = eps_rel; ctl.rho_tau = h->admm_rho_tau; ctl.rho_scale = 1.0;
+    AdmmCtl* d_ctl = static_cast<AdmmCtl*>(h->d_ctl);
+    CU_TRY(h, cudaMemcpyAsync(d_ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, h->stream));
+    bool use_graph = h->admm_use_graph != 0;
+    if (use_graph) {
+        const auto& k = h->admm_key;
+        const bool same = h->admm_exec && k.x0 == r.x0 && k.w == r.w && k.z == r.z && k.y == r.y && k.sigma == sigma &&
+                          k.alpha == alpha && k.stream == h->stream;
+        if (!same && admm_build_graph(*h, r) != PDPLQR_OK) use_graph = false;   // (reason kept in last_error)
+    }
+    h->admm_rho_updates_last = 0;
+    for (;;) {
+        if (use_graph) {
+            const int it0 = ctl.iter;
+            CU_TRY(h, cudaGraphLaunch(h->admm_exec, h->stream));
+            h->admm_graph_launches++;
+            CU_TRY(h, cudaMemcpyAsync(&ctl, d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(h, cudaStreamSynchronize(h->stream));
+            // kernels that ran inside this launch: one factorising iteration, then affine-only ones
+            h->launches += h->admm_fact_kernels + (long long)std::max(0, ctl.iter - it0 - 1) * h->admm_aff_kernels;
+        } else {   // host loop (PDPLQR_ADMM_GRAPH=0 / pdplqr_admm_configure, or graph capture unavailable)
+            bool first = true;
+            do {
+                rc = admm_iteration(*h, r, first, cudaGraphConditionalHandle{}, 0);
+                if (rc) return rc;
+                first = false;
+                const int it = ctl.iter + 1;
+                const bool check = (it % check_every == 0) || it >= max_iter;
+                if (check) {
+                    CU_TRY(h, cudaMemcpyAsync(&ctl, d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, h->stream));
+                    CU_TRY(h, cudaStreamSynchronize(h->stream));
+                } else {
+                    ctl.iter = it;
+                    ctl.cont = it < max_iter;
+                }
+            } while (ctl.cont);
         }
+        if (!ctl.rho_update) break;
+        // rho rescale requested by the check (OSQP rule): rescale, clear the request, run on (re-factorising first)
+        const long long n = (long long)h->batch * h->nc_total;
+        admm_rho_scale_kernel<<<ew_blocks(n), 256, 0, h->stream>>>(h->d_rho_work, h->d_invrho_work, n, ctl.rho_scale);
         h->launches++;
         CU_TRY(h, cudaGetLastError());
-        if (check) {
-            unsigned long long bits[4];
-            CU_TRY(h, cudaMemcpyAsync(bits, h->d_res, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
-            CU_TRY(h, cudaStreamSynchronize(h->stream));
-            for (int i = 0; i < 4; ++i) std::memcpy(&res[i], &bits[i], 8);
-            converged = res[0] <= eps_abs + eps_rel * res[2] && res[1] <= eps_abs + eps_rel * res[3];
-        }
+        ctl.rho_update = 0; ctl.n_rho_updates++; ctl.rho_scale = 1.0;
+        h->admm_rho_updates_last = ctl.n_rho_updates;
+        CU_TRY(h, cudaMemcpyAsync(d_ctl, &ctl, sizeof(ctl), cudaMemcpyHostToDevice, h->stream));
+        CU_TRY(h, cudaStreamSynchronize(h->stream));   // (ctl is a stack object)
     }
-    if (iters_out) *iters_out = it;
-    if (residuals_out) { residuals_out[0] = res[0]; residuals_out[1] = res[1]; }
+    if (use_graph) {   // the graph ran backward / forward pairs: leave the protocol state as after a completed solve
+        h->factorized = true; h->backward_done = false; h->updated = false;
+        h->cur_ws = r.w; h->cur_ys = r.y; h->cur_zs = r.z; h->cur_inv_rho = h->d_invrho_work; h->cur_rho = h->d_rho_work;
+        h->sigma = sigma;
+        h->have_root = false;
+    }
+    if (h->padded) {
+        rc = repack_ws(*h, h->d_wk, w, false);
+        if (rc) return rc;
+    }
+    if (iters_out) *iters_out = ctl.iter;
+    if (residuals_out) { residuals_out[0] = ctl.res[0]; residuals_out[1] = ctl.res[1]; }
     return PDPLQR_OK;
 }
 
@@ -1243,12 +1419,12 @@ int pdplqr_admm_solve(pdplqr_handle_t h, const double* x0, double* ws, double* z
         return fail(h, PDPLQR_ERR_INVALID, "admm_solve: bad arguments");
     if (!h->cones_set) return fail(h, PDPLQR_ERR_ORDER, "admm_solve before admm_set_cones");
     cudaSetDevice(h->device);
-    const size_t B = h->batch, nct = (size_t)h->nc_total, wsl = (size_t)h->N * h->s + h->nx;
+    const size_t B = h->batch, nct = (size_t)h->nc_total, wsl = (size_t)h->N * h->su + h->nxu;   // caller's layout
     CU_TRY(h, cudaMemcpyAsync(h->d_w, ws, B * wsl * 8, cudaMemcpyHostToDevice, h->stream));
     CU_TRY(h, cudaMemcpyAsync(h->d_z, zs, B * nct * 8, cudaMemcpyHostToDevice, h->stream));
     CU_TRY(h, cudaMemcpyAsync(h->d_y, ys, B * nct * 8, cudaMemcpyHostToDevice, h->stream));
     CU_TRY(h, cudaMemcpyAsync(h->d_rho_admm, rho, B * nct * 8, cudaMemcpyHostToDevice, h->stream));
-    CU_TRY(h, cudaMemcpyAsync(h->d_x0, x0, B * h->nx * 8, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(h, cudaMemcpyAsync(h->d_x0, x0, B * h->nxu * 8, cudaMemcpyHostToDevice, h->stream));
     {   // inv_rho = 1 / rho, as the caller of the reference protocol computes it (lqr_example.cpp:42-43)
         std::vector<double> inv(B * nct);
         for (size_t i = 0; i < inv.size(); ++i) inv[i] = 1.0 / rho[i];

@@ -92,8 +92,19 @@ struct pdplqr_solver {
     int *d_cone_first = nullptr, *d_cone_type = nullptr, *d_cone_row = nullptr, *d_cone_dim = nullptr;
     double *d_elb = nullptr, *d_eub = nullptr, *d_wtilde = nullptr, *d_w = nullptr, *d_z = nullptr, *d_y = nullptr, *d_rho_admm = nullptr,
            *d_invrho_admm = nullptr;
-    unsigned long long* d_res = nullptr;
     bool cones_set = false;
+    // device-resident outer loop (pdplqr.cu, admm_kernels.cuh): control block, library-owned rho / 1/rho (rescaled by the
+    // adaptation), kernel-layout iterate of padded handles, and the CUDA graph of one conic solve with the key it was
+    // captured for
+    void* d_ctl = nullptr;
+    double *d_rho_work = nullptr, *d_invrho_work = nullptr, *d_wk = nullptr;
+    int admm_use_graph = 1, admm_adaptive = 0, admm_max_rho_updates = 10;
+    double admm_rho_tau = 5.0;
+    cudaGraph_t admm_graph = nullptr;
+    cudaGraphExec_t admm_exec = nullptr;
+    struct AdmmKey { const void *x0, *w, *z, *y; double sigma, alpha; cudaStream_t stream; } admm_key{};
+    int admm_graph_launches = 0, admm_rho_updates_last = 0;
+    int admm_fact_kernels = 0, admm_aff_kernels = 0;   // kernels per factorising / affine-only iteration inside the graph
     // pipelined host solve (H2D / compute / D2H overlapped over batch chunks)
     int chunk_b0 = 0, chunk_nb = 0;   // when chunk_nb > 0 the launchers work on problems [b0, b0 + nb)
     cudaStream_t s_in = nullptr, s_out = nullptr;

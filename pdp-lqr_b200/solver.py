@@ -157,6 +157,15 @@ class LQRCudaSolver:
                                                      _hp(np.ascontiguousarray(e_lb, dtype=np.float64)),
                                                      _hp(np.ascontiguousarray(e_ub, dtype=np.float64))))
 
+    def admm_configure(self, use_graph=True, adaptive_rho=False, rho_tau=5.0, max_rho_updates=10):
+        self._check(self._lib.pdplqr_admm_configure(self._h, int(use_graph), int(adaptive_rho), rho_tau, max_rho_updates))
+
+    def admm_stats(self):
+        """(graph launches so far, rho rescales of the last solve)."""
+        a, b = C.c_int(), C.c_int()
+        self._check(self._lib.pdplqr_admm_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def admm_solve(self, x0, ws, zs, ys, rho, sigma=1e-6, alpha=1.6, max_iter=50, eps_abs=1e-4, eps_rel=1e-4,
                    check_every=10):
         it = C.c_int()

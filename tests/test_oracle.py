@@ -153,3 +153,43 @@ def test_oracle_costates_sequential_parallel_and_kkt(oracle, S, condensed):
     wp = par.solve(ws_in=wprev, sigma=0.02)
     assert np.max(np.abs(wp - ws)) < 1e-10
     assert np.max(np.abs(par.costates(wp) - lam)) < 1e-9 * max(1.0, np.max(np.abs(lam)))
+
+
+def test_admm_dual_residual_identity_equals_stationarity_definition(oracle):
+    """The dual residual the ADMM kernel reports is computed from stage-local differences,
+        sigma (w~ - w_prev) + D^T rho ((1 - alpha)(z~ - z_prev) + (z - z_prev)),
+    which must equal the DEFINITION: the stationarity residual H w~ + h + D^T y + (dynamics multipliers) of the conic
+    problem, evaluated here with the multipliers of an independent sparse KKT solve of the same LQ sub-problem."""
+    from kkt_ref import kkt_solve
+    from oracle import admm_ref
+    p = P.problems.random_lq(5, 2, 9, batch=1, seed=12, nc=4)
+    nx, nu, N, s = p.nx, p.nu, p.N, p.s
+    rho = np.full(p.nc_total, 0.8)
+    coff, doff = p.coff(), p.doff()
+    for alpha in (1.0, 1.6):
+        K = 6
+        w0, z0, y0, _, _ = admm_ref.admm(p, 0, rho, sigma=1e-2, alpha=alpha, iters=K - 1)
+        _, _, _, _, r_dual = admm_ref.admm(p, 0, rho, sigma=1e-2, alpha=alpha, iters=K)
+        wt, lam = kkt_solve(p, 0, w0, 1e-2, y0, z0, rho, 1.0 / rho, return_costates=True)   # K-th LQ solve + costates
+        cones = [[c for c in p.cones if c[0] == k] for k in range(N + 1)]
+        worst = 0.0
+        for k in range(N + 1):
+            dim = s if k < N else nx
+            nc = int(p.ncs[k])
+            Dk = p.D[0, doff[k]:doff[k + 1]].reshape(nc, dim, order="F")
+            sl = slice(coff[k], coff[k + 1])
+            wk = wt[k * s:k * s + dim]
+            zt = Dk @ wk
+            zh = alpha * zt + (1.0 - alpha) * z0[sl]
+            zn = admm_ref.project(zh + y0[sl] / rho[sl], cones[k], p.e_lb[0, sl], p.e_ub[0, sl])
+            yn = y0[sl] + rho[sl] * (zh - zn)
+            Hk = (p.H[0, k].reshape(s, s, order="F") if k < N else p.HN[0].reshape(nx, nx, order="F"))
+            hk = p.h[0, k] if k < N else p.hN[0]
+            v = Hk @ wk + hk + Dk.T @ yn
+            if k < N:
+                v = v + p.E[0, k].reshape(nx, s, order="F").T @ lam[k]       # E_k^T lambda_{k+1}
+            if k >= 1:
+                v[dim - nx:] -= lam[k - 1]                                      # - lambda_k on the rows of x_k
+            rows = slice(0, nu) if k == 0 else slice(0, dim)
+            worst = max(worst, float(np.max(np.abs(v[rows]))))
+        assert abs(worst - r_dual) < 1e-9 * max(1.0, worst), (alpha, worst, r_dual)

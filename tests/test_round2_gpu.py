@@ -327,3 +327,67 @@ def test_admm_box_and_soc_at_c4_dimensions(oracle):
         if typ == 1:
             v = zs[0, coff[k] + r0:coff[k] + r0 + d]
             assert np.linalg.norm(v[1:]) <= v[0] + 1e-12
+
+
+# ---------------------------------------------------------------------------------- ADMM as one CUDA graph (row f1)
+def _cone_problem(nx, nu, N, batch, seed, nc):
+    p = P.problems.random_lq(nx, nu, N, batch=batch, seed=seed, nc=nc)
+    p.cones = []
+    for k in range(p.N + 1):
+        n = int(p.ncs[k])
+        p.cones += [(k, 0, 2, 0), (k, 2, n - 2, 1)] if k < p.N and n > 3 else [(k, 0, n, 0)]
+    return p
+
+
+@pytest.mark.parametrize("nx,nu,S", [(6, 3, 1), (6, 3, 3), (12, 4, 2), (5, 2, 1), (7, 3, 2)])
+def test_admm_graph_equals_host_loop_and_numpy(oracle, nx, nu, S):
+    """One conic solve = ONE CUDA graph launch (factorising iteration + WHILE node over affine-only iterations, convergence
+    test on the device); same iterates as the host-issued loop and as oracle/admm_ref.py, incl. padded (nx, nu)."""
+    from oracle import admm_ref
+    p = _cone_problem(nx, nu, 12, 2, 31 + nx, 6)
+    rho = np.full((p.batch, p.nc_total), 0.7)
+    res = {}
+    for mode in ("graph", "host"):
+        sol = P.LQRCudaSolver.from_problem(p, num_segments=S)
+        sol.admm_set_cones(p.cones, p.e_lb, p.e_ub)
+        sol.admm_configure(use_graph=(mode == "graph"))
+        ws, zs, ys = p.zeros_ws(), np.zeros((p.batch, p.nc_total)), np.zeros((p.batch, p.nc_total))
+        l0 = sol.launch_count()
+        iters, r = sol.admm_solve(p.x0, ws, zs, ys, rho, sigma=1e-4, alpha=1.6, max_iter=17, eps_abs=0.0, eps_rel=0.0,
+                                  check_every=5)
+        res[mode] = (iters, r.copy(), ws, zs, ys, sol.launch_count() - l0, sol.admm_stats())
+    (ig, rg, wg, zg, yg, lg, sg), (ih, rh, wh, zh, yh, lh, sh) = res["graph"], res["host"]
+    assert ig == ih == 17 and sg[0] == 1 and sh[0] == 0          # exactly one graph launch for the whole solve
+    assert np.array_equal(wg, wh) and np.array_equal(zg, zh) and np.array_equal(yg, yh) and np.array_equal(rg, rh)
+    assert lg == lh                                                # same kernels ran, counted from the captured graph
+    rp = rd = 0.0
+    for b in range(p.batch):
+        w, z, y, r_prim, r_dual = admm_ref.admm(p, b, rho[b], sigma=1e-4, alpha=1.6, iters=17)
+        assert rel_err(wg[b], w) < TOL and rel_err(zg[b], z) < TOL
+        rp, rd = max(rp, r_prim), max(rd, r_dual)
+    assert abs(rg[0] - rp) < 1e-9 * max(1.0, rp) and abs(rg[1] - rd) < 1e-9 * max(1.0, rd)
+
+
+def test_admm_device_convergence_test_and_rho_adaptation(oracle):
+    """Early exit decided on the device (the graph's WHILE condition), and the OSQP rho rule: a badly scaled rho is
+    rescaled (re-factorisation, one more graph launch per rescale) and the solve then converges in fewer iterations."""
+    p = P.problems.quadrotor_example(N=20, constrained=True)
+    p.x0[0, 2] = 0.0
+    lb = np.where(np.isfinite(p.e_lb), p.e_lb, -1e20)
+    ub = np.where(np.isfinite(p.e_ub), p.e_ub, 1e20)
+    out = {}
+    for adaptive in (False, True):
+        sol = P.LQRCudaSolver.from_problem(p, num_segments=2)
+        sol.admm_set_cones(p.cones, lb, ub)
+        sol.admm_configure(use_graph=True, adaptive_rho=adaptive, rho_tau=5.0, max_rho_updates=6)
+        rho = np.full((1, p.nc_total), 1e-3)          # far too small: the primal residual dominates
+        ws, zs, ys = p.zeros_ws(), np.zeros((1, p.nc_total)), np.zeros((1, p.nc_total))
+        iters, r = sol.admm_solve(p.x0, ws, zs, ys, rho, sigma=1e-6, alpha=1.6, max_iter=4000, eps_abs=1e-5, eps_rel=1e-5,
+                                  check_every=25)
+        out[adaptive] = (iters, r, sol.admm_stats(), ws.copy())
+    it0, r0, st0, w0 = out[False]
+    it1, r1, st1, w1 = out[True]
+    assert it0 % 25 == 0 and it1 % 25 == 0                       # exits happen on check iterations
+    assert st0 == (1, 0) and st1[1] >= 1 and st1[0] == 1 + st1[1]   # one launch, plus one per rescale
+    assert it1 < it0 and it1 < 4000                              # adaptation pays, and the device test stopped the loop
+    assert r1[0] <= 1e-5 + 1e-5 * 10 and rel_err(w1, w0) < 1e-2 or it0 == 4000
