@@ -277,19 +277,20 @@ class Ctx:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return [float(v) for v in t.cpu()]
 
-    def time_loop(self, fn, steps, warmup):
+    def time_loop(self, fn, steps, warmup, stream=None):
         """W untimed + K timed calls of fn() bracketed by barrier + synchronize; CUDA events on the launch stream;
         returns ms per step as the MAX over ranks."""
         torch = self.torch
+        stream = stream or self.stream
         for _ in range(warmup):
             fn()
         self.barrier()
         t0 = time.time()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(self.stream)
+        e0.record(stream)
         for _ in range(steps):
             fn()
-        e1.record(self.stream)
+        e1.record(stream)
         self.barrier()
         self.windows.append((t0, time.time()))
         return self.max_over_ranks([e0.elapsed_time(e1) / steps])[0]
@@ -555,23 +556,30 @@ def run_c3(ctx, steps, warmup, want_cpu=True, batch=C3_BATCH):
 
 
 # --------------------------------------------------------------------------------------------- C2 (latency)
-def run_single(ctx, prob, num_segments, steps, warmup, load_balancing=True):
-    """One long problem on one GPU: returns (solver, ms per device-resident step, output array, ws / x0 tensors)."""
+def run_single(ctx, prob, num_segments, steps, warmup, load_balancing=True, graph=False):
+    """One long problem on one GPU: returns (solver, ms per device-resident step, output array, ws / x0 tensors, step fn).
+    graph=True: the step is pdplqr_solve_device (one CUDA graph launch per solve) on a side stream -- stream capture is
+    not possible on the legacy default stream."""
     import pdplqr_b200 as P
     torch = ctx.torch
     sol = P.LQRCudaSolver.from_problem(prob, device=ctx.local_rank, num_segments=num_segments, load_balancing=load_balancing)
-    sol.set_stream(ctx.stream.cuda_stream)
+    stream = torch.cuda.Stream(device=ctx.dev) if graph else ctx.stream
+    sol.set_stream(stream.cuda_stream)
     rng = np.random.default_rng(17)
     ws_host = torch.from_numpy(0.01 * rng.standard_normal((1, prob.ws_len))).pin_memory()
     x0_host = torch.from_numpy(np.ascontiguousarray(prob.x0)).pin_memory()
     ws_dev, x0_dev = ws_host.to(ctx.dev), x0_host.to(ctx.dev)
     out_dev = torch.empty_like(ws_dev)
+    torch.cuda.synchronize()
 
     def step():
-        sol.update_problem_data_device(ws_dev, sigma=SIGMA)
-        sol.backward_device()
-        sol.forward_device(x0_dev, out_dev)
-    ms = ctx.time_loop(step, steps, warmup)
+        if graph:
+            sol.solve_device(ws_dev, x0_dev, out_dev, sigma=SIGMA)
+        else:
+            sol.update_problem_data_device(ws_dev, sigma=SIGMA)
+            sol.backward_device()
+            sol.forward_device(x0_dev, out_dev)
+    ms = ctx.time_loop(step, steps, warmup, stream=stream)
     return sol, ms, out_dev, ws_host, x0_host, step
 
 
@@ -581,9 +589,15 @@ def leg_c2(ctx, steps):
     torch = ctx.torch
     out = dict(workload_config("c2", ctx.world))
     prob = P.problems.quadrotor_ltv(1024)
-    sol, ms, out_dev, ws_host, x0_host, step = run_single(ctx, prob, 0, max(steps, 50), 5)
+    # the reference's 4-call protocol, one launch after the other ...
+    sol_p, ms_protocol, out_p, _, _, _ = run_single(ctx, prob, 0, max(steps, 50), 5)
+    del sol_p
+    # ... and the whole solve as one CUDA graph launch (pdplqr_solve_device): the headline latency
+    sol, ms, out_dev, ws_host, x0_host, step = run_single(ctx, prob, 0, max(steps, 50), 5, graph=True)
     l0 = sol.launch_count(); step(); launches = sol.launch_count() - l0
     torch.cuda.synchronize()
+    out["ms_per_step_protocol_calls"] = ms_protocol
+    out["graph_matches_protocol_calls"] = bool(torch.equal(out_dev, out_p))
     out_np = torch.empty(1, prob.ws_len, dtype=torch.float64).pin_memory().numpy()
     ms_e2e = ctx.time_wall(lambda: sol.solve(ws_host.numpy(), x0_host.numpy(), out_np, sigma=SIGMA), 20, 3)
     bwd_b, fwd_b = stage_bytes(12, 4, True)
@@ -601,7 +615,7 @@ def leg_c2(ctx, steps):
     lat = {}
     for n in LATENCY_NS:
         pn = P.problems.quadrotor_ltv(n) if n != 100 else P.problems.quadrotor_example()
-        sn, msn, on, wh, _, _ = run_single(ctx, pn, 0, 30, 5)
+        sn, msn, on, wh, _, _ = run_single(ctx, pn, 0, 30, 5, graph=True)
         entry = {"us": msn * 1e3, "num_segments": sn.num_segments}
         if ctx.rank == 0:
             refn = O.OracleSolver(pn, parallel=False).solve(ws_in=wh.numpy()[0].copy(), sigma=SIGMA)

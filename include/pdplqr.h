@@ -91,6 +91,11 @@ int pdplqr_update_problem_data_device(pdplqr_handle_t h, const double* ws, const
 int pdplqr_backward_device(pdplqr_handle_t h, const double* rho);
 int pdplqr_backward_without_factorization_device(pdplqr_handle_t h, const double* rho);
 int pdplqr_forward_device(pdplqr_handle_t h, const double* x0, double* ws_out);
+/* update_problem_data + backward + forward on device arrays as ONE CUDA graph launch (captured on first use and again
+ * whenever a pointer, sigma or the stream changes; PDPLQR_SOLVE_GRAPH=0 issues the launches one by one).  Returns without
+ * synchronising.  This is the call for a single latency-bound problem (BASELINE.json config 2). */
+int pdplqr_solve_device(pdplqr_handle_t h, const double* ws_in, const double* ys, const double* zs, const double* rho,
+                        const double* inv_rho, double sigma, const double* x0, double* ws_out);
 int pdplqr_synchronize(pdplqr_handle_t h);
 
 /* Options (addition).  PDPLQR_OPT_AFFINE_CACHE: keep per stage Quu^-1, P+c, F+c, F+B during the factorising

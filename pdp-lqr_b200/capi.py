@@ -31,6 +31,7 @@ SIGNATURES = {
     "pdplqr_backward_device": (C.c_int, [C.c_void_p, _dp]),
     "pdplqr_backward_without_factorization_device": (C.c_int, [C.c_void_p, _dp]),
     "pdplqr_forward_device": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "pdplqr_solve_device": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp]),
     "pdplqr_synchronize": (C.c_int, [C.c_void_p]),
     "pdplqr_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "pdplqr_summary_doubles": (C.c_int, [C.c_void_p]),

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) batch_backward_kernel(SegPar
             for (int i = 0; i < NX; ++i) sm[D::SUM_P + i + j * NX] = P[i][j];
 #pragma unroll
         for (int i = 0; i < NX; ++i) sm[D::SUM_p + i] = pv[i];
-        if (bad) p.status[b] = bad;
+        p.status[b] = bad;   // (one slot per (problem, segment): plain store, nothing to clear between solves)
     }
 }
 

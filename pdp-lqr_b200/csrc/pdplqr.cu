@@ -306,6 +306,7 @@ int set_model_common(Solver& h, const double* E, const double* c, const double* 
     h.model_set = true;
     h.factorized = false;
     if (h.admm_exec) { cudaGraphExecDestroy(h.admm_exec); h.admm_exec = nullptr; }   // sel_mode etc. are baked into the graph
+    if (h.solve_exec) { cudaGraphExecDestroy(h.solve_exec); h.solve_exec = nullptr; }
     return PDPLQR_OK;
 }
 
@@ -363,7 +364,6 @@ int run_tree_up(Solver& h, bool affine_only) {
 int run_backward(Solver& h) {
     if (!h.model_set) return fail(&h, PDPLQR_ERR_ORDER, "backward before set_model");
     if (!h.updated) return fail(&h, PDPLQR_ERR_ORDER, "backward before update_problem_data (lqr_solver_parallel.hpp:115)");
-    CU_TRY(&h, cudaMemsetAsync(h.d_status, 0, sizeof(int) * h.batch, h.stream));
     int rc = h.ops->backward(h);
     if (rc) return rc;
     if (h.S > 1) {
@@ -560,6 +560,7 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (const char* e = getenv("PDPLQR_SEG_T")) h->seg_t = atoi(e);
     if (const char* e = getenv("PDPLQR_WARP_KERNEL")) h->warp_kernel = atoi(e);
     if (const char* e = getenv("PDPLQR_ADMM_GRAPH")) h->admm_use_graph = atoi(e);
+    if (const char* e = getenv("PDPLQR_SOLVE_GRAPH")) h->solve_use_graph = atoi(e);
     if (const char* e = getenv("PDPLQR_SPARSE_D")) h->allow_sel = atoi(e);
     if (const char* e = getenv("PDPLQR_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(1, std::min(64, atoi(e)));
 
@@ -595,7 +596,7 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     rc |= dev_alloc(*h, &h->d_x0, B * nx);
     rc |= dev_alloc(*h, &h->d_seg_start, S);
     rc |= dev_alloc(*h, &h->d_seg_len, S);
-    rc |= dev_alloc(*h, &h->d_status, B);
+    rc |= dev_alloc(*h, &h->d_status, B * S);
     if (h->padded) {
         rc |= dev_alloc(*h, &h->d_wsp_in, ws_len * B);
         rc |= dev_alloc(*h, &h->d_wsp_out, ws_len * B);
@@ -627,7 +628,7 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     CREATE_TRY(cudaMemcpy(h->d_seg_len, h->seg_len.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
     CREATE_TRY(cudaMemset(h->d_fac, 0, Bpad * N * ops->FREC * sizeof(double)));
     CREATE_TRY(cudaMemset(h->d_uhat, 0, B * S * nx * sizeof(double)));
-    CREATE_TRY(cudaMemset(h->d_status, 0, B * sizeof(int)));
+    CREATE_TRY(cudaMemset(h->d_status, 0, B * S * sizeof(int)));
     // the thread-per-problem kernels write only P, p of the summary: F, C, f of a one-segment terminal slice are zero
     CREATE_TRY(cudaMemset(h->d_sum, 0, B * S * ops->SREC * sizeof(double)));
 
@@ -691,6 +692,7 @@ int pdplqr_destroy(pdplqr_handle_t h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->admm_exec) cudaGraphExecDestroy(h->admm_exec);
     if (h->admm_graph) cudaGraphDestroy(h->admm_graph);
+    if (h->solve_exec) cudaGraphExecDestroy(h->solve_exec);
     for (void* p : h->owned) cudaFree(p);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -708,6 +710,7 @@ int pdplqr_set_stream(pdplqr_handle_t h, void* cuda_stream) {
     h->stream = static_cast<cudaStream_t>(cuda_stream);
     h->own_stream = false;
     if (h->admm_exec) { cudaGraphExecDestroy(h->admm_exec); h->admm_exec = nullptr; }   // captured for the old stream
+    if (h->solve_exec) { cudaGraphExecDestroy(h->solve_exec); h->solve_exec = nullptr; }
     return PDPLQR_OK;
 }
 
@@ -799,6 +802,8 @@ int pdplqr_backward_without_factorization(pdplqr_handle_t h, const double* rho) 
 }
 int pdplqr_set_option(pdplqr_handle_t h, int option, int value) {
     if (!h) return PDPLQR_ERR_INVALID;
+    if (h->solve_exec) { cudaGraphExecDestroy(h->solve_exec); h->solve_exec = nullptr; }   // options change the launch plan
+    if (h->admm_exec) { cudaGraphExecDestroy(h->admm_exec); h->admm_exec = nullptr; }
     if (option == PDPLQR_OPT_AFFINE_CACHE) {
         if (value && !h->d_aff) {
             if (dev_alloc(*h, &h->d_aff, (size_t)h->batch * h->N * h->ops->AREC)) return PDPLQR_ERR_CUDA;
@@ -941,7 +946,6 @@ static int solve_pipelined(Solver& h, const double* ws_in, double sigma, const d
     CU_TRY(&h, cudaEventRecord(h.ev_ready, h.stream));
     CU_TRY(&h, cudaStreamWaitEvent(h.s_in, h.ev_ready, 0));
     CU_TRY(&h, cudaStreamWaitEvent(h.s_out, h.ev_ready, 0));
-    CU_TRY(&h, cudaMemsetAsync(h.d_status, 0, sizeof(int) * h.batch, h.stream));
     h.cur_ws = ws_in ? h.d_ws_in : nullptr;
     h.sigma = sigma;
     int rc = PDPLQR_OK;
@@ -978,6 +982,55 @@ int pdplqr_solve(pdplqr_handle_t h, const double* ws_in, const double* ys, const
     rc = pdplqr_backward(h, rho);
     if (rc) return rc;
     return pdplqr_forward(h, x0, ws_out);
+}
+// update_problem_data + backward + forward on device arrays, enqueued as ONE CUDA graph launch (captured on first use and
+// whenever a pointer, sigma or the stream changes).  For a single latency-bound problem the five to eight dependent
+// kernels of a solve then start back to back without a host round trip per launch.
+int pdplqr_solve_device(pdplqr_handle_t h, const double* ws_in, const double* ys, const double* zs, const double* rho,
+                        const double* inv_rho, double sigma, const double* x0, double* ws_out) {
+    if (!h || !x0 || !ws_out) return fail(h, PDPLQR_ERR_INVALID, "solve_device: null pointer");
+    if (!h->model_set) return fail(h, PDPLQR_ERR_ORDER, "solve_device before set_model");
+    cudaSetDevice(h->device);
+    auto plain = [&]() {
+        int rc = pdplqr_update_problem_data_device(h, ws_in, ys, zs, inv_rho, sigma);
+        if (rc) return rc;
+        rc = pdplqr_backward_device(h, rho);
+        if (rc) return rc;
+        return pdplqr_forward_device(h, x0, ws_out);
+    };
+    if (!h->solve_use_graph || h->interior || h->root_fresh) return plain();   // (shard boundaries change per solve)
+    const auto& k = h->solve_key;
+    const bool same = h->solve_exec && k.ws == ws_in && k.ys == ys && k.zs == zs && k.rho == rho && k.inv_rho == inv_rho &&
+                      k.x0 == x0 && k.out == ws_out && k.sigma == sigma && k.stream == h->stream;
+    if (!same) {
+        if (h->solve_exec) { cudaGraphExecDestroy(h->solve_exec); h->solve_exec = nullptr; }
+        const long long l0 = h->launches;
+        const bool was_factorized = h->factorized;
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed);
+        if (e != cudaSuccess) { cudaGetLastError(); return plain(); }
+        int rc = plain();
+        e = cudaStreamEndCapture(h->stream, &g);
+        h->solve_kernels = (int)(h->launches - l0);
+        h->launches = l0;
+        h->factorized = was_factorized; h->backward_done = false; h->updated = false;   // nothing ran during the capture
+        if (rc != PDPLQR_OK || e != cudaSuccess || !g) {
+            cudaGetLastError();
+            if (g) cudaGraphDestroy(g);
+            return rc != PDPLQR_OK ? rc : plain();
+        }
+        e = cudaGraphInstantiate(&h->solve_exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { cudaGetLastError(); h->solve_exec = nullptr; return plain(); }
+        h->solve_key = {ws_in, ys, zs, rho, inv_rho, x0, ws_out, sigma, h->stream};
+    }
+    CU_TRY(h, cudaGraphLaunch(h->solve_exec, h->stream));
+    h->launches += h->solve_kernels;
+    // host-side protocol state as after update_problem_data + backward + forward
+    h->cur_ws = (h->padded && ws_in) ? h->d_wsp_in : ws_in;
+    h->cur_ys = ys; h->cur_zs = zs; h->cur_inv_rho = inv_rho; h->cur_rho = rho; h->sigma = sigma;
+    h->updated = false; h->factorized = true; h->backward_done = false; h->have_root = false;
+    return PDPLQR_OK;
 }
 int pdplqr_synchronize(pdplqr_handle_t h) {
     if (!h) return PDPLQR_ERR_INVALID;
@@ -1117,13 +1170,16 @@ int pdplqr_get_costates(pdplqr_handle_t h, const double* ws, double* lam) {
 int pdplqr_last_status(pdplqr_handle_t h, int* status) {
     if (!h) return PDPLQR_ERR_INVALID;
     cudaSetDevice(h->device);
-    std::vector<int> host(h->batch);
+    const size_t S = h->S;
+    std::vector<int> host((size_t)h->batch * S);   // one slot per (problem, segment)
     CU_TRY(h, cudaStreamSynchronize(h->stream));
-    CU_TRY(h, cudaMemcpy(host.data(), h->d_status, sizeof(int) * h->batch, cudaMemcpyDeviceToHost));
+    CU_TRY(h, cudaMemcpy(host.data(), h->d_status, sizeof(int) * host.size(), cudaMemcpyDeviceToHost));
     int bad = 0;
     for (int b = 0; b < h->batch; ++b) {
-        bad += host[b] != 0;
-        if (status) status[b] = host[b];
+        int worst = 0;   // the latest stage with a non-positive pivot (the sweep runs backwards: the first one met)
+        for (size_t sg = 0; sg < S; ++sg) worst = std::max(worst, host[(size_t)b * S + sg]);
+        bad += worst != 0;
+        if (status) status[b] = worst;
     }
     return bad;
 }

@@ -77,7 +77,7 @@ struct SegParams {
     double sigma;
     double* fac;             // [batch][N][FREC]
     double* sum;             // [batch][S][SREC]
-    int* status;             // [batch]
+    int* status;             // [batch][S]  first non-positive pivot (1 + stage) met by each segment, 0 = none
     double* aff;             // [batch][N][AREC] affine cache, or nullptr (not kept)
     // constraints (all nullptr / 0 when the problem has none)
     const int* ncs;          // [N+1] rows per stage
@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         sm[D::SUM_p + i] = pn[i];
         sm[D::SUM_f + i] = fn[i];
     }
-    if (bad && tid == 0) atomicMax(&p.status[b], bad);
+    if (tid == 0) p.status[(size_t)b * p.S + seg] = bad;   // one slot per (problem, segment): no clearing launch needed
 }
 
 // ------------------------------------------------------------------------------------------------

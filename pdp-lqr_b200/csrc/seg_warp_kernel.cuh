@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(32, PDPLQR_WARP_MINB) seg_backward_warp_kernel
         sm[D::SUM_p + i] = pn[i];
         sm[D::SUM_f + i] = fn[i];
     }
-    if (bad && lane == 0) atomicMax(&p.status[b], bad);
+    if (lane == 0) p.status[(size_t)b * p.S + seg] = bad;
 }
 
 }  // namespace pdplqr

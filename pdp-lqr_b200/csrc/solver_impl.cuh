@@ -104,6 +104,11 @@ struct pdplqr_solver {
     cudaGraphExec_t admm_exec = nullptr;
     struct AdmmKey { const void *x0, *w, *z, *y; double sigma, alpha; cudaStream_t stream; } admm_key{};
     int admm_graph_launches = 0, admm_rho_updates_last = 0;
+    // CUDA graph of one update_problem_data + backward + forward (pdplqr_solve_device), and the pointers it was captured for
+    int solve_use_graph = 1;
+    cudaGraphExec_t solve_exec = nullptr;
+    struct SolveKey { const void *ws, *ys, *zs, *rho, *inv_rho, *x0, *out; double sigma; cudaStream_t stream; } solve_key{};
+    int solve_kernels = 0;
     int admm_fact_kernels = 0, admm_aff_kernels = 0;   // kernels per factorising / affine-only iteration inside the graph
     // pipelined host solve (H2D / compute / D2H overlapped over batch chunks)
     int chunk_b0 = 0, chunk_nb = 0;   // when chunk_nb > 0 the launchers work on problems [b0, b0 + nb)
@@ -187,7 +192,7 @@ inline SegParams seg_params(Solver& h) {
         p.batch = h.chunk_nb;
         p.model += b0 * h.N * h.mrec; p.HN += b0 * h.nx * h.nx; p.hN += b0 * h.nx;
         if (p.ws_prev) p.ws_prev += b0 * wsl;
-        p.fac += b0 * h.N * h.frec; p.sum += b0 * h.S * h.ops->SREC; p.status += b0;
+        p.fac += b0 * h.N * h.frec; p.sum += b0 * h.S * h.ops->SREC; p.status += b0 * h.S;
         p.xhat += b0 * h.S * h.nx; p.uhat += b0 * h.S * h.nx;
     }
     return p;

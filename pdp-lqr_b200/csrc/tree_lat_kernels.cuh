@@ -15,6 +15,11 @@
 //     the two buffers ping-pong (one barrier per step); the reciprocal is a Newton-refined hardware seed;
 //   * the down-sweep records are pulled into shared memory by TMA bulk copies before the level loop starts, so the
 //     dependent mat-vec chain never waits for L2.
+// Round 2 tried a register-resident alternative for the elimination (one warp, one column of [M | I] per lane, column k
+// fetched by shuffles, redundant per-lane pivot search, W = M^-1 followed by tensor-core products W F_a, W C_a): its pivot
+// step measured 625 cycles against the 610 of the scheme below (the serial argmax / select chains of a single in-order warp
+// cost what the barrier and the shared atomics cost here), and with four of them on one SM sub-partition 2.3x more -- not
+// kept (git history: "combine_fast").
 // Measured latencies that shape this (scripts/micro/lat_bench.cu, B200): LDS 30, DFMA 8, bar.sync (128 thr) 20,
 // STS->bar->LDS 55, ATOMS.MAX+LDS 51, reciprocal 48 (IEEE division 72), 64-bit shuffle 28 cycles.
 #pragma once

@@ -146,6 +146,11 @@ class LQRCudaSolver:
     def forward_device(self, x0, ws_out):
         self._check(self._lib.pdplqr_forward_device(self._h, _dptr(x0), _dptr(ws_out)))
 
+    def solve_device(self, ws_in, x0, ws_out, sigma=1e-6, ys=None, zs=None, rho=None, inv_rho=None):
+        """update_problem_data + backward + forward as one CUDA graph launch (pdplqr_solve_device); asynchronous."""
+        self._check(self._lib.pdplqr_solve_device(self._h, _dptr(ws_in), _dptr(ys), _dptr(zs), _dptr(rho), _dptr(inv_rho),
+                                                   sigma, _dptr(x0), _dptr(ws_out)))
+
     # ------------------------------------------------------------------ conic ADMM outer iteration (addition, a11)
     def admm_set_cones(self, cones, e_lb, e_ub):
         """cones: list of (stage, first_row, dim, type) sorted by stage, tiling every stage's rows."""

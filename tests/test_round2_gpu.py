@@ -391,3 +391,74 @@ def test_admm_device_convergence_test_and_rho_adaptation(oracle):
     assert st0 == (1, 0) and st1[1] >= 1 and st1[0] == 1 + st1[1]   # one launch, plus one per rescale
     assert it1 < it0 and it1 < 4000                              # adaptation pays, and the device test stopped the loop
     assert r1[0] <= 1e-5 + 1e-5 * 10 and rel_err(w1, w0) < 1e-2 or it0 == 4000
+
+
+# ---------------------------------------------------------------------------------- graph-launched solve, status slots
+@pytest.mark.parametrize("nx,nu,N,S,nc", [(12, 4, 256, 0, 0), (6, 3, 40, 4, 5), (5, 2, 30, 3, 0), (4, 1, 64, 1, 0)])
+def test_solve_device_graph_equals_protocol_calls(oracle, nx, nu, N, S, nc):
+    """pdplqr_solve_device (one CUDA graph launch: update_problem_data + backward + forward) on a side stream gives the
+    same bits as the three protocol calls, on repeated launches and after a pointer change (re-capture)."""
+    import torch
+    p = P.problems.quadrotor_ltv(N) if (nx, nu) == (12, 4) else P.problems.random_lq(nx, nu, N, batch=3, seed=nx, nc=nc)
+    dev = torch.device("cuda", 0)
+    side = torch.cuda.Stream()
+    rng = np.random.default_rng(2)
+    T = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    wprev = T(rng.standard_normal((p.batch, p.ws_len)))
+    kw = {}
+    if nc:
+        nct = p.nc_total
+        rho = rng.uniform(0.5, 2.0, (p.batch, nct))
+        kw = dict(ys=T(rng.standard_normal((p.batch, nct))), zs=T(rng.standard_normal((p.batch, nct))), rho=T(rho),
+                  inv_rho=T(1.0 / rho))
+    x0 = T(p.x0)
+    outs = []
+    for graph in (False, True):
+        sol = P.LQRCudaSolver.from_problem(p, num_segments=S)
+        sol.set_stream(side.cuda_stream)
+        out = torch.zeros_like(wprev)
+        with torch.cuda.stream(side):
+            for rep in range(3):
+                if graph:
+                    sol.solve_device(wprev, x0, out, sigma=1e-3, **kw)
+                else:
+                    sol.update_problem_data_device(wprev, kw.get("ys"), kw.get("zs"), kw.get("inv_rho"), sigma=1e-3)
+                    sol.backward_device(kw.get("rho"))
+                    sol.forward_device(x0, out)
+            if graph:   # other output pointer -> the graph is captured again
+                out2 = torch.zeros_like(wprev)
+                sol.solve_device(wprev, x0, out2, sigma=1e-3, **kw)
+                sol.synchronize()
+                assert torch.equal(out, out2)
+        sol.synchronize()
+        assert sol.last_status()[0] == 0
+        outs.append(out.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    for b in range(p.batch):
+        o = oracle.OracleSolver(p, b=b)
+        if nc:
+            o.update_problem_data(wprev.cpu().numpy()[b], kw["ys"].cpu().numpy()[b], kw["zs"].cpu().numpy()[b],
+                                  kw["inv_rho"].cpu().numpy()[b], 1e-3)
+            o.backward(kw["rho"].cpu().numpy()[b])
+            ref = o.forward(p.x0[b], np.zeros(p.ws_len))
+        else:
+            ref = o.solve(ws_in=wprev.cpu().numpy()[b], sigma=1e-3)
+        assert rel_err(outs[1][b], ref) < TOL
+
+
+def test_not_positive_definite_reported_per_problem_across_segments():
+    """Status slots are per (problem, segment) now (no clearing launch in the solve chain): a non-positive pivot in any
+    segment of a problem is reported for that problem only, and a later clean solve reports none."""
+    p = P.problems.random_lq(6, 3, 30, batch=4, seed=5)
+    bad = p.H.copy()
+    Hk = bad[2, 17].reshape(9, 9, order="F")
+    Hk[:3, :3] = -5.0 * np.eye(3)                     # indefinite R at stage 17 of problem 2
+    bad[2, 17] = Hk.reshape(-1, order="F")
+    q = P.problems.Problem(p.nx, p.nu, p.N, p.batch, p.E, p.c, bad, p.h, p.HN, p.hN, p.x0)
+    sol = P.LQRCudaSolver.from_problem(q, num_segments=5, load_balancing=False)
+    sol.solve(q.zeros_ws(), q.x0, q.zeros_ws())
+    n, st = sol.last_status()
+    assert n == 1 and st[2] == 18 and st[0] == st[1] == st[3] == 0
+    sol.set_model(p)
+    sol.solve(p.zeros_ws(), p.x0, p.zeros_ws())
+    assert sol.last_status()[0] == 0
