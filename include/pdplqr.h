@@ -125,6 +125,24 @@ int pdplqr_coupler_create(pdplqr_handle_t* out, int nx, int nu, int num_shards, 
 int pdplqr_coupler_solve_device(pdplqr_handle_t coupler, const double* summaries, const double* x0, double* xhat,
                                 double* lam);
 
+/* Single-process horizon sharding over several GPUs (addition): the same flow behind one handle.  The horizon is cut into
+ * num_devices contiguous time slices (devices[d] = CUDA ordinal of slice d, NULL = 0 .. num_devices-1), every device
+ * reduces its slice, the slice summaries are all-gathered with NCCL (ncclCommInitAll; libnccl.so.2 is loaded at run time),
+ * every device solves the interface system redundantly and rolls out its slice.  Host arrays of the FULL horizon in the
+ * flat layout above, batch = 1 (one very long problem: BASELINE.json config 5); constraint rows travel with their stages.
+ * segments_per_device = 0 lets the library choose.  C++ wrapper: include/pdplqr/lqr_cuda_sharded_solver.hpp. */
+typedef struct pdplqr_sharded* pdplqr_sharded_t;
+int pdplqr_sharded_create(pdplqr_sharded_t* out, int nx, int nu, int N, const int* ncs, int num_devices, const int* devices,
+                          int segments_per_device, int condensed_type);
+int pdplqr_sharded_set_model(pdplqr_sharded_t hs, const double* E, const double* c, const double* H, const double* hvec,
+                             const double* HN, const double* hN, const double* D);
+/* update_problem_data + backward + forward over all devices (lqr_solver_parallel.hpp:115-238); blocks until ws_out is written */
+int pdplqr_sharded_solve(pdplqr_sharded_t hs, const double* ws_in, const double* ys, const double* zs, const double* rho,
+                         const double* inv_rho, double sigma, const double* x0, double* ws_out);
+int pdplqr_sharded_num_devices(pdplqr_sharded_t hs);
+const char* pdplqr_sharded_last_error(pdplqr_sharded_t hs);
+int pdplqr_sharded_destroy(pdplqr_sharded_t hs);
+
 /* Conic ADMM outer iteration (addition -- NOT IN THE REFERENCE, which ships only the hooks: the ws/ys/zs/rho/
  * inv_rho/sigma arguments, lqr_solver_parallel.hpp:33-37, and Node::D_con/e_lb/e_ub, lqr_model.hpp:21-24, with the
  * example's constraints disabled, lqr_example.cpp:127,158).  OSQP-form ADMM on  D_k w_k in K_k  where every stage's

@@ -45,7 +45,7 @@ def stale() -> bool:
 
 
 def _units():
-    units = [("pdplqr", os.path.join(CSRC, "pdplqr.cu"), [])]
+    units = [("pdplqr", os.path.join(CSRC, "pdplqr.cu"), []), ("sharded", os.path.join(CSRC, "sharded.cu"), [])]
     for nx, nu, t in instances():
         units.append((f"inst_{nx}_{nu}", os.path.join(CSRC, "inst.cu"), [f"-DINST_NX={nx}", f"-DINST_NU={nu}", f"-DINST_T={t}"]))
     return units
@@ -67,5 +67,5 @@ def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -
         for rc in ex.map(lambda cmd: subprocess.run(cmd).returncode, todo):
             if rc != 0:
                 raise subprocess.CalledProcessError(rc, "nvcc")
-    subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs)
+    subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-o", LIB] + objs + ["-ldl"])
     return LIB

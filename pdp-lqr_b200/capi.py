@@ -39,6 +39,12 @@ SIGNATURES = {
     "pdplqr_set_root_boundary_device": (C.c_int, [C.c_void_p, _dp, _dp]),
     "pdplqr_coupler_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "pdplqr_coupler_solve_device": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp]),
+    "pdplqr_sharded_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, _ip, C.c_int, _ip, C.c_int, C.c_int]),
+    "pdplqr_sharded_set_model": (C.c_int, [C.c_void_p] + [_dp] * 7),
+    "pdplqr_sharded_solve": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp]),
+    "pdplqr_sharded_num_devices": (C.c_int, [C.c_void_p]),
+    "pdplqr_sharded_last_error": (C.c_char_p, [C.c_void_p]),
+    "pdplqr_sharded_destroy": (C.c_int, [C.c_void_p]),
     "pdplqr_admm_set_cones": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _ip, _ip, _dp, _dp]),
     "pdplqr_admm_solve": (C.c_int, [C.c_void_p, _dp, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_int, C.c_double,
                                     C.c_double, C.c_int, _ip, _dp]),

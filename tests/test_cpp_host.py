@@ -85,3 +85,38 @@ def test_cpp_mpc_example_closed_loop():
     rh = RecedingHorizon(sol, p, rho=0.1, max_iter=400, eps_abs=1e-4, eps_rel=1e-4)
     u_py, _ = rh.step()
     assert np.max(np.abs(np.array(u0) - u_py[0])) < 5e-3
+
+
+# ---------------------------------------------------------------- single-process multi-GPU solver (C ABI pdplqr_sharded_*)
+SHARDED_EXE = os.path.join(ROOT, "examples", "sharded_example_bin")
+
+
+def _compile_sharded():
+    libdir = os.path.dirname(P.capi.lib_path())
+    P.capi.load()
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "sharded_example.cpp"), "-L" + libdir, "-lpdplqr",
+                           "-Wl,-rpath," + libdir, "-o", SHARDED_EXE])
+
+
+def test_cpp_sharded_example_compiles_and_has_no_cpu_fallback():
+    import torch
+    _compile_sharded()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    r = subprocess.run([SHARDED_EXE, "2", "256"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("G", [1, 2, 4])
+def test_cpp_sharded_solver_matches_single_gpu(G):
+    """lqr::LQRCudaShardedSolver (one process, G devices, NCCL all-gather of the slice summaries) against
+    lqr::LQRCudaSolver on one device, from C++ (examples/sharded_example.cpp)."""
+    import torch
+    if torch.cuda.device_count() < G:
+        pytest.skip(f"needs {G} GPUs")
+    _compile_sharded()
+    r = subprocess.run([SHARDED_EXE, str(G), "4096"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"devices {G}" in r.stdout

@@ -462,3 +462,50 @@ def test_not_positive_definite_reported_per_problem_across_segments():
     sol.set_model(p)
     sol.solve(p.zeros_ws(), p.x0, p.zeros_ws())
     assert sol.last_status()[0] == 0
+
+
+# ---------------------------------------------------------------------------------- single-process sharded solve (C ABI)
+@pytest.mark.parametrize("G,nc", [(1, 0), (2, 0), (2, 6), (4, 0)])
+def test_sharded_c_abi_matches_oracle(oracle, G, nc):
+    """pdplqr_sharded_* : one process drives G devices (time slices, NCCL all-gather, redundant interface solve) -- host
+    arrays in, host arrays out; with and without constraint rows."""
+    import ctypes as C
+    import torch
+    if torch.cuda.device_count() < G:
+        pytest.skip(f"needs {G} GPUs")
+    lib = P.capi.load()
+    p = P.problems.quadrotor_ltv(3000) if nc == 0 else P.problems.random_lq(6, 3, 90, batch=1, seed=8, nc=nc)
+    rng = np.random.default_rng(4)
+    wprev = 0.1 * rng.standard_normal((1, p.ws_len))
+    hs = C.c_void_p()
+    ncs = None if p.ncs is None else np.ascontiguousarray(p.ncs, dtype=np.int32)
+    rc = lib.pdplqr_sharded_create(C.byref(hs), p.nx, p.nu, p.N, None if ncs is None else ncs.ctypes.data_as(C.POINTER(C.c_int)),
+                                   G, None, 0 if nc == 0 else 3, P.CHOLESKY)
+    assert rc == 0, lib.pdplqr_last_error(None)
+    dp = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64).ctypes.data
+    keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (p.E, p.c, p.H, p.h, p.HN, p.hN)]
+    D = None if p.D is None else np.ascontiguousarray(p.D, dtype=np.float64)
+    assert lib.pdplqr_sharded_set_model(hs, *[a.ctypes.data for a in keep], None if D is None else D.ctypes.data) == 0, \
+        lib.pdplqr_sharded_last_error(hs)
+    out = np.zeros_like(wprev)
+    kw = [None] * 4
+    if nc:
+        nct = p.nc_total
+        ys, zs = rng.standard_normal((1, nct)), rng.standard_normal((1, nct))
+        rho = rng.uniform(0.5, 2.0, (1, nct))
+        inv = np.ascontiguousarray(1.0 / rho)
+        kw = [ys, zs, rho, inv]
+    for _ in range(2):   # repeated solves on the same handle
+        rc = lib.pdplqr_sharded_solve(hs, wprev.ctypes.data, *[dp(a) for a in kw], 1e-4, np.ascontiguousarray(p.x0).ctypes.data,
+                                      out.ctypes.data)
+        assert rc == 0, lib.pdplqr_sharded_last_error(hs)
+    assert lib.pdplqr_sharded_num_devices(hs) == G
+    lib.pdplqr_sharded_destroy(hs)
+    o = oracle.OracleSolver(p)
+    if nc:
+        o.update_problem_data(wprev[0], kw[0][0], kw[1][0], kw[3][0], 1e-4)
+        o.backward(kw[2][0])
+        ref = o.forward(p.x0[0], np.zeros(p.ws_len))
+    else:
+        ref = o.solve(ws_in=wprev[0], sigma=1e-4)
+    assert rel_err(out[0], ref) < TOL
