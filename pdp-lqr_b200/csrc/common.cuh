@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <type_traits>
 
 namespace pdplqr {
 
@@ -65,6 +66,17 @@ PDPLQR_DEVINL void bulk_wait() {
 // order generic-proxy smem accesses before subsequent async-proxy (TMA) accesses of the same locations
 PDPLQR_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// compile-time loop: f(std::integral_constant<int, I>) for I = BEGIN .. END-1.  Indices of register arrays written this way
+// are constants by construction (a `#pragma unroll` loop that the compiler declines to unroll completely makes them
+// dynamic, and the array goes to local memory: the 10 x 10 factor of the nx30/nu10 stage did).
+template <int BEGIN, int END, class F>
+PDPLQR_DEVINL void static_for(F&& f) {
+    if constexpr (BEGIN < END) {
+        f(std::integral_constant<int, BEGIN>{});
+        static_for<BEGIN + 1, END>(f);
+    }
+}
+
 // 1/a to within an ulp or two: hardware seed (2^-23) + two Newton steps (~48 cycles against ~72 for an IEEE division
 // and ~130 for rsqrt, scripts/micro/lat_bench.cu); a must be a normal, non-zero number (a pivot)
 PDPLQR_DEVINL double rcp_newton(double a) {
@@ -87,6 +99,11 @@ PDPLQR_DEVINL double rcp_newton(double a) {
 //     (rows 0,2,4,6 | 1,3,5,7 of every full group of 8; rows 0,2,1,3 of a trailing group of 4).
 // Both are the identity for every other size.
 #define PDPLQR_HD __host__ __device__ __forceinline__
+// rows of column j of H are stored rotated by 4 (j / 2) when s is a multiple of 16: H is only ever read as the initial value
+// of a tensor-core accumulator tile (lane -> row r, columns 2 (lane % 4) + {0, 1}); with such a leading dimension the 16 lanes
+// of a half-warp would otherwise hit 4 banks 4 times each.  (Tried for every multiple of 8, i.e. also s = 40: the index
+// arithmetic of a rotation modulo 40 cost more than the conflicts, S3 of the nx30/nu10 stage 5,000 -> 7,000 cycles.)
+PDPLQR_HD constexpr bool h_rotated(int s) { return s % 16 == 0; }
 PDPLQR_HD constexpr bool warp_layout(int nx, int nu) { return nx % 4 == 0 && nx <= 16 && nu <= 8 && nx + nu + 1 <= 24; }
 PDPLQR_HD constexpr int erow_pos(int i, int nx, bool on) {       // storage position of row i
     if (!on) return i;

@@ -88,7 +88,7 @@ __global__ void pack_model_kernel(const double* __restrict__ E, const double* __
                 int j = 0;
                 while (q >= s - j) { q -= s - j; ++j; }
                 q = (j + q) + j * s;
-            } else if (s % 16 == 0) {   // SegDims::h_off: rows of column j rotated by 4 (j / 2)
+            } else if (h_rotated(s)) {   // SegDims::h_off: rows of column j rotated by 4 (j / 2)
                 const int di = q % s, j = q / s;
                 q = (((di - 4 * (j >> 1)) % s + s) % s) + j * s;
             }

@@ -40,7 +40,7 @@ struct SegDims {
     // H is only ever read as the initial value of a DMMA accumulator tile (lane -> row r, columns 2 (lane%4) + {0,1}).
     // With a leading dimension S = 0 (mod 16) the 16 lanes of a half-warp would hit 4 banks 4 times each, so for those
     // S the rows of column j are stored rotated by 4 (j / 2): element (i, j) at ((i + 4 (j/2)) mod S) + j S.
-    static constexpr bool H_ROT = (S % 16 == 0);
+    static constexpr bool H_ROT = h_rotated(S);
     PDPLQR_DEVINL static int h_off(int i, int j) { return H_ROT ? ((i + 4 * (j >> 1)) % S) + j * S : i + j * S; }
     // record order of the rows of [E c] and of the w-indices (common.cuh): identity unless the warp kernel's layout is on.
     // Everywhere below i, j are the reference's indices (w = [u; x], lqr_model.hpp:12-19); er / wi give the position.
@@ -316,6 +316,35 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         }
     };
     if (LEN > 0) fetch_w(N1 - 1);
+    // the constraint vectors of a stage (rho, z, y, 1/rho and, for selection-matrix constraints, the column and value of
+    // every row) are fetched one stage ahead into registers as well: consumed right after their loads they cost the group a
+    // DRAM round trip at the top of every stage (3,600 of 17,000 cycles per stage at nx30/nu10/nc44, profiles/r2_phase_clocks.txt)
+    constexpr int CR = CON ? 2 : 1;          // rows per thread held in registers
+    double pr_rho[CR], pr_z[CR], pr_ir[CR], pr_y[CR], pr_v[CR];
+    int pr_c[CR], pr_n = 0;
+    // (row count and offset of the stage AFTER the prefetched one are fetched yet another stage ahead: the vector loads
+    // need them for their addresses, and an address that is itself still in flight stalls the in-order group)
+    int nx_n = 0;
+    long long nx_co = 0;
+    auto fetch_con = [&](int kk) {   // vectors of stage kk (its count / offset are in nx_n / nx_co), then count / offset of kk-1
+        pr_n = nx_n;
+        const size_t co = cbase + nx_co;
+#pragma unroll
+        for (int q = 0; q < CR; ++q) {
+            const int r = tid + q * T;
+            pr_c[q] = -1; pr_v[q] = 0.0;
+            if (r < pr_n) {
+                pr_rho[q] = p.rho[co + r]; pr_z[q] = p.zs[co + r]; pr_ir[q] = p.inv_rho[co + r]; pr_y[q] = p.ys[co + r];
+                if (sel) { pr_c[q] = p.sel_col[co + r]; pr_v[q] = p.sel_val[co + r]; }
+            }
+        }
+        if (kk - 1 >= N0) { nx_n = p.ncs[kk - 1]; nx_co = p.coff[kk - 1]; }
+    };
+    if (CON && LEN > 0) {
+        nx_n = ncmax > 0 ? p.ncs[N1 - 1] : 0;
+        nx_co = ncmax > 0 ? p.coff[N1 - 1] : 0;
+        fetch_con(N1 - 1);
+    }
     constexpr bool Z_BULK = (D::FREC % 2 == 0) && ((NU * D::NRHS) % 2 == 0) && ((NU * (NX + 1)) % 2 == 0);
     PHASE_DECL
     PHASE_START();
@@ -326,23 +355,26 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         const double* R = rec;
         mbar_wait(&bar[0], it & 1);              // requested after S3 of the previous stage (or in the prologue)
         PHASE(0);
-        const int nck = ncmax > 0 ? p.ncs[k] : 0;
+        const int nck = CON ? pr_n : 0;
         if (nck > 0) {  // g = z - y/rho ; keep rho and rho.*g   (lqr_solver_parallel.hpp:134-137, lqr_kernel.hpp:110)
             const size_t co = cbase + p.coff[k];
-            for (int r = tid; r < nck; r += T) {
-                const double rr = p.rho[co + r];
+            auto row = [&](int r, double rr, double zz, double ir, double yy, int cj, double v) {
                 rho_s[r] = rr;
-                rg_s[r] = rr * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]);
-                if (sel) {   // D_k rows are scaled unit vectors: D^T rho D is diagonal
-                    const int cj = p.sel_col[co + r];
-                    const double v = p.sel_val[co + r];
-                    if (cj >= 0) {
-                        atomicAdd(&dg_s[cj], rr * v * v);
-                        atomicAdd(&dh_s[cj], v * rg_s[r]);
-                    }
+                const double rg = rr * (zz - ir * yy);
+                rg_s[r] = rg;
+                if (sel && cj >= 0) {   // D_k rows are scaled unit vectors: D^T rho D is diagonal
+                    atomicAdd(&dg_s[cj], rr * v * v);
+                    atomicAdd(&dh_s[cj], v * rg);
                 }
-            }
+            };
+#pragma unroll
+            for (int q = 0; q < CR; ++q)   // rows fetched a stage ahead (registers)
+                if (tid + q * T < nck) row(tid + q * T, pr_rho[q], pr_z[q], pr_ir[q], pr_y[q], pr_c[q], pr_v[q]);
+            for (int r = tid + CR * T; r < nck; r += T)   // (more than CR rows per thread: straight from global memory)
+                row(r, p.rho[co + r], p.zs[co + r], p.inv_rho[co + r], p.ys[co + r], sel ? p.sel_col[co + r] : -1,
+                    sel ? p.sel_val[co + r] : 0.0);
         }
+        if (CON && it + 1 < LEN) fetch_con(k - 1);
 #pragma unroll
         for (int q = 0; q < NW; ++q)
             if (tid + q * T < S) wp[tid + q * T] = wreg[q];
@@ -406,25 +438,27 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         // S4: Quu = L D L^T (unit lower L).  NU <= 12: every solving thread factorises its own register copy (no
         //     barriers, no square roots); larger NU: cooperative Cholesky of the leading block of Ma in place.
         constexpr bool REG_CHOL = NU <= 12;
-        double Lr[REG_CHOL ? NU : 1][REG_CHOL ? NU : 1];   // Lr[i][j], i > j: L(i,j)  (registers up to NU = 8; at NU = 10
-                                                            // the compiler keeps the array in L1-cached local memory)
+        double Lr[REG_CHOL ? NU : 1][REG_CHOL ? NU : 1];   // Lr[i][j], i > j: L(i,j); indexed through static_for only, so
+                                                            // it is registers at every NU (with `#pragma unroll` loops the
+                                                            // 10 x 10 factor of nx30/nu10 went to local memory)
         double dr[REG_CHOL ? NU : 1];                       // 1 / D(c)
         const int n1 = NX + 1, n2 = pdp ? NX : 0, n3 = aff_b ? NU : 0;
         if constexpr (REG_CHOL) {
             if (tid < n1 + n2 + n3) {
                 double dd[NU];                              // D(q)
-#pragma unroll
-                for (int j = 0; j < NU; ++j)
-#pragma unroll
-                    for (int i = j + 1; i < NU; ++i) Lr[i][j] = Ma[i + j * L::LDM];
-#pragma unroll
-                for (int c = 0; c < NU; ++c) {
-                    double vc[NU];                          // vc[q] = L(c,q) D(q): row c of L D (off the pivot chain for q < c-1)
-#pragma unroll
-                    for (int q = 0; q < c; ++q) vc[q] = Lr[c][q] * dd[q];
+                static_for<0, NU>([&](auto jc) {
+                    constexpr int j = jc;
+                    static_for<j + 1, NU>([&](auto ic) {
+                        constexpr int i = ic;
+                        Lr[i][j] = Ma[i + j * L::LDM];
+                    });
+                });
+                static_for<0, NU>([&](auto cc) {
+                    constexpr int c = cc;
+                    double vc[NU > 1 ? NU : 2];             // vc[q] = L(c,q) D(q): row c of L D (off the pivot chain for q < c-1)
+                    static_for<0, c>([&](auto qc) { constexpr int q = qc; vc[q] = Lr[c][q] * dd[q]; });
                     double a = Ma[c + c * L::LDM];
-#pragma unroll
-                    for (int q = 0; q < c; ++q) a = fma(-Lr[c][q], vc[q], a);
+                    static_for<0, c>([&](auto qc) { constexpr int q = qc; a = fma(-Lr[c][q], vc[q], a); });
                     double r = rcp_newton(a);              // the pivot test stays off the dependent chain
                     if (!(a > 0.0)) {                      // (rare) keep the sweep finite, report through the status word
                         if (!bad) bad = k + 1;
@@ -433,14 +467,13 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                     }
                     dr[c] = r;
                     dd[c] = a;
-#pragma unroll
-                    for (int i = c + 1; i < NU; ++i) {
+                    static_for<c + 1, NU>([&](auto ic) {
+                        constexpr int i = ic;
                         double v = Lr[i][c];
-#pragma unroll
-                        for (int q = 0; q < c; ++q) v = fma(-Lr[i][q], vc[q], v);
+                        static_for<0, c>([&](auto qc) { constexpr int q = qc; v = fma(-Lr[i][q], vc[q], v); });
                         Lr[i][c] = v * r;
-                    }
-                }
+                    });
+                });
             }
         } else {
             const int info = group_chol<NU, T>(tid, Ma, L::LDM, dinv);
@@ -467,20 +500,18 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 }
                 double z[NU];
                 if constexpr (REG_CHOL) {      // L D L^T: forward (unit lower), scale, backward
-#pragma unroll
-                    for (int m = 1; m < NU; ++m) {
+                    static_for<1, NU>([&](auto mc) {
+                        constexpr int m = mc;
                         double v = y[m];
-#pragma unroll
-                        for (int qq = 0; qq < m; ++qq) v = fma(-Lr[m][qq], y[qq], v);
+                        static_for<0, m>([&](auto qc) { constexpr int qq = qc; v = fma(-Lr[m][qq], y[qq], v); });
                         y[m] = v;
-                    }
-#pragma unroll
-                    for (int m = NU - 1; m >= 0; --m) {
+                    });
+                    static_for<0, NU>([&](auto mc) {
+                        constexpr int m = NU - 1 - mc;
                         double v = y[m] * dr[m];
-#pragma unroll
-                        for (int qq = m + 1; qq < NU; ++qq) v = fma(-Lr[qq][m], z[qq], v);
+                        static_for<m + 1, NU>([&](auto qc) { constexpr int qq = qc; v = fma(-Lr[qq][m], z[qq], v); });
                         z[m] = v;
-                    }
+                    });
                 } else {                       // Cholesky factor in Ma, reciprocal diagonal in dinv
 #pragma unroll
                     for (int m = 0; m < NU; ++m) {
@@ -733,6 +764,42 @@ __global__ void __launch_bounds__(T) seg_affine_kernel(SegParams p) {
         if (nck > 0) bulk_g2s(Dbuf + bufi * DSTRIDE, D_b + p.doff[kk], dbytes, &bar[bufi]);
     };
     if (tid == 0 && LEN > 0) issue_stage(N1 - 1, 0);
+    // w_prev and the constraint vectors of a stage are fetched one stage ahead into registers (consumed right after their
+    // loads they cost the group a DRAM round trip per stage -- this sweep is the common ADMM iteration)
+    constexpr int NWA = (S + T - 1) / T, CR = 2;
+    double wnext[NWA], pr_rho[CR], pr_z[CR], pr_ir[CR], pr_y[CR], pr_v[CR];
+    int pr_c[CR], pr_n = 0;
+    auto fetch_wa = [&](int kk) {
+#pragma unroll
+        for (int r = 0; r < NWA; ++r) {
+            const int i = tid + r * T;
+            wnext[r] = (i < S && ws_b) ? ws_b[(size_t)kk * S + i] : 0.0;
+        }
+    };
+    int nx_n = 0;          // row count / offset of the next stage to prefetch (fetched one more stage ahead: the vector
+    long long nx_co = 0;   // loads need them for their addresses)
+    auto fetch_con = [&](int kk) {
+        pr_n = nx_n;
+        const size_t co = cbase + nx_co;
+#pragma unroll
+        for (int q = 0; q < CR; ++q) {
+            const int r = tid + q * T;
+            pr_c[q] = -1; pr_v[q] = 0.0;
+            if (r < pr_n) {
+                pr_rho[q] = p.rho[co + r]; pr_z[q] = p.zs[co + r]; pr_ir[q] = p.inv_rho[co + r]; pr_y[q] = p.ys[co + r];
+                if (sel) { pr_c[q] = p.sel_col[co + r]; pr_v[q] = p.sel_val[co + r]; }
+            }
+        }
+        if (kk - 1 >= N0) { nx_n = p.ncs[kk - 1]; nx_co = p.coff[kk - 1]; }
+    };
+    if (LEN > 0) {
+        fetch_wa(N1 - 1);
+        if (ncmax > 0) {
+            nx_n = p.ncs[N1 - 1];
+            nx_co = p.coff[N1 - 1];
+            fetch_con(N1 - 1);
+        }
+    }
 #pragma unroll 1
     for (int it = 0; it < LEN; ++it) {
         const int k = N1 - 1 - it;
@@ -745,23 +812,27 @@ __global__ void __launch_bounds__(T) seg_affine_kernel(SegParams p) {
             fence_proxy_async();
             issue_stage(k - 1, buf ^ 1);
         }
-        const int nck = ncmax > 0 ? p.ncs[k] : 0;
+        const int nck = pr_n;
         if (nck > 0) {
             const size_t co = cbase + p.coff[k];
-            for (int r = tid; r < nck; r += T) {
-                const double rg = p.rho[co + r] * (p.zs[co + r] - p.inv_rho[co + r] * p.ys[co + r]);
+            auto row = [&](int r, double rr, double zz, double ir, double yy, int cj, double v) {
+                const double rg = rr * (zz - ir * yy);
                 rg_s[r] = rg;
-                if (sel) {
-                    const int cj = p.sel_col[co + r];
-                    if (cj >= 0) atomicAdd(&dh_s[cj], p.sel_val[co + r] * rg);
-                }
-            }
-        }
-        double wpv[(S + T - 1) / T];
+                if (sel && cj >= 0) atomicAdd(&dh_s[cj], v * rg);
+            };
 #pragma unroll
-        for (int r = 0; r < (S + T - 1) / T; ++r) {
-            const int i = tid + r * T;
-            wpv[r] = (i < S && ws_b) ? ws_b[(size_t)k * S + i] : 0.0;
+            for (int q = 0; q < CR; ++q)   // rows fetched a stage ahead (registers)
+                if (tid + q * T < nck) row(tid + q * T, pr_rho[q], pr_z[q], pr_ir[q], pr_y[q], pr_c[q], pr_v[q]);
+            for (int r = tid + CR * T; r < nck; r += T)
+                row(r, p.rho[co + r], p.zs[co + r], p.inv_rho[co + r], p.ys[co + r], sel ? p.sel_col[co + r] : -1,
+                    sel ? p.sel_val[co + r] : 0.0);
+        }
+        double wpv[NWA];
+#pragma unroll
+        for (int r = 0; r < NWA; ++r) wpv[r] = wnext[r];
+        if (it + 1 < LEN) {   // next stage's w_prev and constraint vectors: in flight while this stage computes
+            fetch_wa(k - 1);
+            if (ncmax > 0) fetch_con(k - 1);
         }
         mbar_wait(&bar[buf], (it >> 1) & 1);
         for (int i = tid; i < NX; i += T) tv[i] = Ak[D::AR_PC + i] + pn[i];
