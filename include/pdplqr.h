@@ -84,8 +84,9 @@ int pdplqr_solve(pdplqr_handle_t h, const double* ws_in, const double* ys, const
                  const double* inv_rho, double sigma, const double* x0, double* ws_out);
 
 /* Device-pointer variants: arguments are device arrays (same layouts), work is enqueued on the handle's stream
- * and the call returns without synchronising.  Pointers passed to update_problem_data_device must stay valid
- * until the following backward has run. */
+ * and the call returns without synchronising.  Pointers passed to update_problem_data_device are kept, not copied: the
+ * arrays must stay valid and UNMODIFIED until the following backward* has run and, if pdplqr_get_costates* is going to be
+ * called for this solve, until that call has run (it re-reads ws / ys / zs / rho through the same pointers). */
 int pdplqr_update_problem_data_device(pdplqr_handle_t h, const double* ws, const double* ys, const double* zs,
                                       const double* inv_rho, double sigma);
 int pdplqr_backward_device(pdplqr_handle_t h, const double* rho);
@@ -196,9 +197,8 @@ int pdplqr_get_summaries(pdplqr_handle_t h, double* P, double* p, double* F, dou
  * costates.  `ws` is the trajectory returned by the last forward; call after forward, before
  * the next update_problem_data with different vectors (the device variant reads the ws / ys / zs / rho arrays of the
  * last update through the pointers it was given; after pdplqr_admm_solve* those are the loop's final iterates, which
- * have moved on by one relaxation / projection step from the ones the last LQ solve used).  Segment-path handles only:
- * PDPLQR_ERR_UNSUPPORTED on the
- * thread-per-problem path (batch of tiny systems with num_segments = 1). */
+ * have moved on by one relaxation / projection step from the ones the last LQ solve used).  Works on both the segment
+ * path and the thread-per-problem path (batch of tiny systems with num_segments = 1). */
 int pdplqr_get_costates(pdplqr_handle_t h, const double* ws, double* lam);
 int pdplqr_get_costates_device(pdplqr_handle_t h, const double* ws, double* lam);
 /* Number of problems whose last factorising backward met a non-positive pivot; per-problem codes (0 = ok,

@@ -89,3 +89,29 @@ def test_gpu_equals_reference_binary(S):
     sol2 = P.LQRCudaSolver.from_problem(q, num_segments=S)
     ws2 = sol2.solve(w, q.x0, np.zeros_like(w), sigma=1e-3, ys=y, zs=z, rho=rho, inv_rho=inv)
     assert rel_err(ws2[0], ref2) < 1e-9
+
+
+REF_EXAMPLE = os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle", "_ref", "lqr_example_cuda")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(REF_EXAMPLE), reason="oracle/_ref/lqr_example_cuda not built (needs /root/reference)")
+def test_reference_example_with_cuda_solver():
+    """The reference's OWN examples/lqr_example.cpp with the 2-line integration change of INTEGRATION.md section 1
+    (oracle/Makefile target ref_example): its model code fills the reference's Node / LQRModel, its LQRSolver block
+    runs on the host, and the LQRParallelSolver block runs on LQRCudaSolver.  The two printed solutions must agree."""
+    import re
+    import subprocess
+    out = subprocess.run([REF_EXAMPLE], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.splitlines()
+
+    def rows(tag):
+        inputs = [np.array(l.split(":", 1)[1].split(), dtype=float) for l in lines if re.match(r"Input \d+ \(%s\)" % tag, l)]
+        k = next(i for i, l in enumerate(lines) if l.startswith("Final state (%s)" % tag))
+        return np.concatenate(inputs + [np.array(lines[k + 1].split(), dtype=float)])
+
+    cpu, gpu = rows("LQRSolver"), rows("LQRParallelSolver")
+    assert cpu.size == gpu.size == 5 * 4 + 12
+    assert abs(cpu[0] - (-2.898056669662)) < 1e-9          # SURVEY.md's independent probe value of u_0[0]
+    assert rel_err(gpu, cpu) < 1e-9
