@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 # PDPLQR_VARIANT=name + PDPLQR_CFLAGS="-D..." build an instrumented copy (libpdplqr_<name>.so) next to the product library
 VARIANT = os.environ.get("PDPLQR_VARIANT", "")
-OBJ = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
+OBJ = os.path.join(HERE, "build", "variant_" + VARIANT) if VARIANT else os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpdplqr" + ("_" + VARIANT if VARIANT else "") + ".so")
 NVCC = os.environ.get("PDPLQR_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",

@@ -42,6 +42,7 @@ struct AdmmParams {
     const int* cone_type;
     const int* cone_row;
     const int* cone_dim;
+    const int* row_box;        // [nc_total] (shared by the batch): 1 = the row belongs to a box cone
     const double* e_lb;        // [batch][nc_total]   box bounds (ball: radius in e_ub of the first row)
     const double* e_ub;
     const double* w_tilde;     // [batch][ws_len]   LQ solution of this iteration
@@ -79,6 +80,10 @@ PDPLQR_DEVINL void atomic_max_nonneg(unsigned long long* addr, double v) {
     atomicMax(addr, (unsigned long long)__double_as_longlong(v));
 }
 
+// Tried and dropped (measured at C4, 4096 x 257 items, 50 iterations): an L2 (or L1) prefetch of everything the next item
+// of the warp will read, one 128-byte line per lane, issued at the top of an item: 356 -> 374 ms per solve (376 with L1, the
+// same with 6 instead of 8 CTAs per SM).  With 64 resident warps per SM the loads are covered already; the kernel is bound by
+// issue slots (ncu: 70 % issue-active), and the prefetch adds 250 instructions per item.
 constexpr int ADMM_WARPS = 8;   // warps per CTA of admm_update_kernel; 8 CTAs per SM (32 registers): the kernel is a chain of
                                 // dependent global loads per item, so resident warps are what hides the latency (C4 453 -> 422 ms)
 
@@ -86,134 +91,131 @@ constexpr int ADMM_WARPS = 8;   // warps per CTA of admm_update_kernel; 8 CTAs p
 // does the work, decided on the device from the loop state, so the iteration can sit in a CUDA graph unchanged.  Kept
 // separate (not a template flag on one body): with the residual code in the same kernel the hot loop went from 1.3 to
 // 2.5 ms per iteration at C4.
-__global__ void __launch_bounds__(ADMM_WARPS * 32, 8) admm_update_kernel(AdmmParams p) {
+#ifndef PDPLQR_ADMM_MINB
+#define PDPLQR_ADMM_MINB 8
+#endif
+__global__ void __launch_bounds__(ADMM_WARPS * 32, PDPLQR_ADMM_MINB) admm_update_kernel(AdmmParams p) {
     if (admm_is_check(p.ctl)) return;
+    // ncu (profiles/r2_ncu_c4_kernels.txt): this kernel is ISSUE-bound (70 % of the issue slots at 64 resident warps per SM,
+    // 900 warp-instructions per item), not latency-bound.  So: a box row -- the common case -- is finished in the pass that
+    // forms it, in registers (one trip through z, y, rho, the bounds; no shared-memory staging, no second pass); only rows of
+    // second-order cones / balls go through shared memory; (problem, stage) advance incrementally (no 64-bit divisions per
+    // item); y / rho by a Newton reciprocal.
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int s = p.nx + p.nu;
+    const int s = p.nx + p.nu, N1 = p.N + 1;
     const size_t ws_len = (size_t)p.N * s + p.nx;
     double* wt = smem + (size_t)warp * (s + 3 * p.ncmax);   // w~ of this stage   (dim)
-    double* v = wt + s;                // z^ + y/rho         (ncmax)
-    double* zt = v + p.ncmax;          // z~                 (ncmax)
-    double* dz = zt + p.ncmax;         // rho o (z - z_prev) (ncmax)
-    double r_prim = 0.0, nrm = 0.0, r_dual = 0.0, nrm_d = 0.0;
-    const long long items = (long long)p.batch * (p.N + 1);
-#pragma unroll 1
-    for (long long item = (long long)blockIdx.x * ADMM_WARPS + warp; item < items; item += (long long)gridDim.x * ADMM_WARPS) {
-    const int k = (int)(item % (p.N + 1));
-    const int b = (int)(item / (p.N + 1));
-    const int dim = (k < p.N) ? s : p.nx;
-    const int nc = p.ncs[k];
-    const size_t wo = (size_t)b * ws_len + (size_t)k * s;
-    __syncwarp();                      // the previous item's readers of the scratch are done
-    for (int i = lane; i < dim; i += 32) {
-        const double a = p.w_tilde[wo + i];
-        wt[i] = a;
-        p.w[wo + i] = p.alpha * a + (1.0 - p.alpha) * p.w[wo + i];
-    }
-    if (nc == 0) continue;
-    __syncwarp();
-    const double* Dk = p.Dm + (size_t)b * p.d_total + p.doff[k];
-    const size_t co = (size_t)b * p.nc_total + p.coff[k];
+    double* v = wt + s;                // z^ + y/rho, then its projection   (rows of non-box cones)
+    double* zt = v + p.ncmax;          // z^                                (rows of non-box cones)
+    const double alpha = p.alpha, oma = 1.0 - p.alpha;
+    const long long items = (long long)p.batch * N1;
+    const long long stride = (long long)gridDim.x * ADMM_WARPS;
+    const int dk = (int)(stride % N1);
+    const long long db = stride / N1;
+    long long item = (long long)blockIdx.x * ADMM_WARPS + warp;
+    int k = (int)(item % N1);
+    long long b = item / N1;
     const bool sel = p.sel_col != nullptr;
-    for (int r = lane; r < nc; r += 32) {
-        double acc = 0.0;
-        if (sel) {
-            const int cj = p.sel_col[co + r];
-            if (cj >= 0) acc = p.sel_val[co + r] * wt[cj];
-        } else {
-            for (int j = 0; j < dim; ++j) acc = fma(Dk[r + (size_t)j * nc], wt[j], acc);
-        }
-        zt[r] = acc;
-        const double zh = p.alpha * acc + (1.0 - p.alpha) * p.z[co + r];
-        v[r] = zh + p.y[co + r] / p.rho[co + r];
-    }
-    __syncwarp();
-    // projections.  Few cones per stage (the usual case: one box over all variables + a cone or two): the warp walks
-    // the cones together and clamps a box row-parallel (a lane per cone left 31 lanes idle for 40 serial clamps: 1,980
-    // warp-instructions per stage at C4).  Many cones per stage: one lane per cone.
-    auto project_serial = [&](int r0, int d, int type) {     // one lane, whole cone
-        if (type == CONE_BOX) {
-            for (int r = r0; r < r0 + d; ++r) v[r] = fmin(fmax(v[r], p.e_lb[co + r]), p.e_ub[co + r]);
-        } else if (type == CONE_SOC) {
-            double nv = 0.0;
-            for (int r = r0 + 1; r < r0 + d; ++r) nv = fma(v[r], v[r], nv);
-            nv = sqrt(nv);
-            const double t = v[r0];
-            if (nv <= t) { /* inside */ }
-            else if (nv <= -t) { for (int r = r0; r < r0 + d; ++r) v[r] = 0.0; }
-            else {
-                const double a = 0.5 * (t + nv), sc = a / nv;
-                v[r0] = a;
-                for (int r = r0 + 1; r < r0 + d; ++r) v[r] *= sc;
+#pragma unroll 1
+    for (; item < items; item += stride) {
+        const int dim = (k < p.N) ? s : p.nx;
+        const int nc = p.ncs[k];
+        const long long cok = p.coff[k];
+        const size_t wo = (size_t)b * ws_len + (size_t)k * s;
+        const size_t co = (size_t)b * p.nc_total + cok;
+        const double* Dk = p.Dm + (size_t)b * p.d_total + p.doff[k];
+        const int c0 = p.cone_first[k], c1 = p.cone_first[k + 1];
+        k += dk; b += db;              // (problem, stage) of the next item
+        if (k >= N1) { k -= N1; ++b; }
+        // every load of a row is issued before the first use of any of them, and the first 32 rows' loads together with the
+        // loads of w~ and w: one DRAM round trip per item instead of four (ncu: long-scoreboard stalls at the sel_col -> wt[cj],
+        // w, z and bound loads, one after the other, were 60 % of the kernel's stall samples)
+        struct Row { int cj, box; double sv, zold, yold, rr, lb, ub; };
+        auto load_row = [&](int r, Row& q) {
+            q.cj = sel ? p.sel_col[co + r] : -1;
+            q.sv = sel ? p.sel_val[co + r] : 0.0;
+            q.zold = p.z[co + r]; q.yold = p.y[co + r]; q.rr = p.rho[co + r];
+            q.box = p.row_box[cok + r];
+            q.lb = p.e_lb[co + r]; q.ub = p.e_ub[co + r];
+        };
+        auto finish = [&](int r, double zh, double znew, double yold, double rr) {
+            p.z[co + r] = znew;
+            p.y[co + r] = yold + rr * (zh - znew);
+        };
+        auto do_row = [&](int r, const Row& q) {
+            double acc = 0.0;
+            if (sel) {
+                if (q.cj >= 0) acc = q.sv * wt[q.cj];
+            } else {
+                for (int j = 0; j < dim; ++j) acc = fma(Dk[r + (size_t)j * nc], wt[j], acc);
             }
-        } else {  // ball of radius e_ub[first row]
-            double nv = 0.0;
-            for (int r = r0; r < r0 + d; ++r) nv = fma(v[r], v[r], nv);
-            nv = sqrt(nv);
-            const double rad = p.e_ub[co + r0];
-            if (nv > rad) { const double sc = rad / nv; for (int r = r0; r < r0 + d; ++r) v[r] *= sc; }
+            const double zh = alpha * acc + oma * q.zold;
+            const double vv = fma(q.yold, rcp_newton(q.rr), zh);
+            if (q.box) {
+                finish(r, zh, fmin(fmax(vv, q.lb), q.ub), q.yold, q.rr);
+            } else {
+                v[r] = vv;
+                zt[r] = zh;
+            }
+        };
+        Row q0;
+        if (lane < nc) load_row(lane, q0);
+        __syncwarp();                  // the previous item's readers of the scratch are done
+        for (int i = lane; i < dim; i += 32) {
+            const double a = p.w_tilde[wo + i], wold = p.w[wo + i];
+            wt[i] = a;
+            p.w[wo + i] = alpha * a + oma * wold;
         }
-    };
-    const int c0 = p.cone_first[k], c1 = p.cone_first[k + 1];
-    if (c1 - c0 <= 8) {
-        for (int c = c0; c < c1; ++c) {                      // warp-uniform
-            const int r0 = p.cone_row[c], d = p.cone_dim[c], type = p.cone_type[c];
-            if (type == CONE_BOX) {
-                for (int r = r0 + lane; r < r0 + d; r += 32) v[r] = fmin(fmax(v[r], p.e_lb[co + r]), p.e_ub[co + r]);
-            } else if (lane == 0)
-                project_serial(r0, d, type);
+        if (nc == 0) continue;
+        __syncwarp();
+        if (lane < nc) do_row(lane, q0);
+        for (int r = lane + 32; r < nc; r += 32) {
+            Row q;
+            load_row(r, q);
+            do_row(r, q);
         }
-    } else {
-        for (int c = c0 + lane; c < c1; c += 32) project_serial(p.cone_row[c], p.cone_dim[c], p.cone_type[c]);
-    }
-    __syncwarp();
-    for (int r = lane; r < nc; r += 32) {
-        const double zold = p.z[co + r], znew = v[r], rr = p.rho[co + r];
-        const double zh = p.alpha * zt[r] + (1.0 - p.alpha) * zold;
-        const double ynew = p.y[co + r] + rr * (zh - znew);
-        p.z[co + r] = znew;
-        p.y[co + r] = ynew;
-        dz[r] = rr * (znew - zold);
-        v[r] = ynew;                       // reuse: y for the D^T y norm
-        r_prim = fmax(r_prim, fabs(zt[r] - znew));
-        nrm = fmax(nrm, fmax(fabs(zt[r]), fabs(znew)));
-    }
-    if (!false) continue;
-    __syncwarp();
-    for (int j = lane; j < dim; j += 32) {
-        double acc = 0.0, accy = 0.0;
-        if (sel) {
-            for (int r = 0; r < nc; ++r)
-                if (p.sel_col[co + r] == j) {
-                    const double dv = p.sel_val[co + r];
-                    acc = fma(dv, dz[r], acc);
-                    accy = fma(dv, v[r], accy);
+        auto project_serial = [&](int r0, int d, int type) {     // one lane, whole cone (second-order cone or ball)
+            if (type == CONE_SOC) {
+                double nv = 0.0;
+                for (int r = r0 + 1; r < r0 + d; ++r) nv = fma(v[r], v[r], nv);
+                nv = sqrt(nv);
+                const double t = v[r0];
+                if (nv <= t) { /* inside */ }
+                else if (nv <= -t) { for (int r = r0; r < r0 + d; ++r) v[r] = 0.0; }
+                else {
+                    const double a = 0.5 * (t + nv), sc = a / nv;
+                    v[r0] = a;
+                    for (int r = r0 + 1; r < r0 + d; ++r) v[r] *= sc;
                 }
-        } else {
-            for (int r = 0; r < nc; ++r) {
-                const double dv = Dk[r + (size_t)j * nc];
-                acc = fma(dv, dz[r], acc);
-                accy = fma(dv, v[r], accy);
+            } else {  // ball of radius e_ub[first row]
+                double nv = 0.0;
+                for (int r = r0; r < r0 + d; ++r) nv = fma(v[r], v[r], nv);
+                nv = sqrt(nv);
+                const double rad = p.e_ub[co + r0];
+                if (nv > rad) { const double sc = rad / nv; for (int r = r0; r < r0 + d; ++r) v[r] *= sc; }
+            }
+        };
+        if (c1 - c0 <= 8) {            // few cones per stage: the warp walks them together
+            for (int c = c0; c < c1; ++c) {                      // warp-uniform
+                const int type = p.cone_type[c];
+                if (type == CONE_BOX) continue;
+                const int r0 = p.cone_row[c], d = p.cone_dim[c];
+                __syncwarp();
+                if (lane == 0) project_serial(r0, d, type);
+                __syncwarp();
+                for (int r = r0 + lane; r < r0 + d; r += 32) finish(r, zt[r], v[r], p.y[co + r], p.rho[co + r]);
+            }
+        } else {                       // many cones per stage: one lane per cone
+            __syncwarp();
+            for (int c = c0 + lane; c < c1; c += 32) {
+                const int type = p.cone_type[c];
+                if (type == CONE_BOX) continue;
+                const int r0 = p.cone_row[c], d = p.cone_dim[c];
+                project_serial(r0, d, type);
+                for (int r = r0; r < r0 + d; ++r) finish(r, zt[r], v[r], p.y[co + r], p.rho[co + r]);
             }
         }
-        r_dual = fmax(r_dual, fabs(acc));
-        nrm_d = fmax(nrm_d, fabs(accy));
-    }
-    }   // items
-    if (!false) return;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        r_prim = fmax(r_prim, __shfl_xor_sync(0xffffffffu, r_prim, off));
-        r_dual = fmax(r_dual, __shfl_xor_sync(0xffffffffu, r_dual, off));
-        nrm = fmax(nrm, __shfl_xor_sync(0xffffffffu, nrm, off));
-        nrm_d = fmax(nrm_d, __shfl_xor_sync(0xffffffffu, nrm_d, off));
-    }
-    if (lane == 0) {
-        atomic_max_nonneg(&p.ctl->acc[0], r_prim);
-        atomic_max_nonneg(&p.ctl->acc[1], r_dual);
-        atomic_max_nonneg(&p.ctl->acc[2], nrm);
-        atomic_max_nonneg(&p.ctl->acc[3], nrm_d);
     }
 }
 

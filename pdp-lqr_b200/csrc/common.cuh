@@ -370,6 +370,84 @@ PDPLQR_DEVINL void group_mm_dmma_multi(int tid, LA la, LB lb, EPI epi) {
     group_mm_dmma_impl<G, M, N, T>(tid, K, la, lb, epi);
 }
 
+// [M | g] = S x (S+1) product of which only the tiles on or below the diagonal and the tile column that holds column S are
+// formed: M is symmetric and every reader of the stage kernel (L D L^T of Quu, the Qxu rows, the lower triangle of Qxx, the
+// g column) stays in that part.  The needed tiles are dealt out in equal contiguous runs, longest rows first, so that the
+// warps finish together (the rectangular 3 x 3 blocking left 9 / 9 / 6 / 6 tiles on the four warps at S = 40: 30 tiles formed,
+// 20 needed) and a run reuses the A fragment of its row.  Same k order per tile as dmma_blocks: identical results.
+// The epilogue gets the two accumulator elements of a lane at once: epi(i, j, v(i,j), v(i,j+1)), j even.
+constexpr int sym_lower_tiles(int S) {
+    const int MT = (S + 7) / 8, TG = S / 8;
+    int n = 0;
+    for (int ti = 0; ti < MT; ++ti) n += ti + 1 + (ti < TG ? 1 : 0);
+    return n;
+}
+// tile n of the enumeration "rows from the bottom, row i holds columns 0 .. i and TG": (row, column)
+constexpr int sym_tile_row(int S, int n) {
+    const int MT = (S + 7) / 8, TG = S / 8;
+    for (int i = MT - 1; i >= 0; --i) {
+        const int cnt = i + 1 + (i < TG ? 1 : 0);
+        if (n < cnt) return i;
+        n -= cnt;
+    }
+    return -1;
+}
+constexpr int sym_tile_col(int S, int n) {
+    const int MT = (S + 7) / 8, TG = S / 8;
+    for (int i = MT - 1; i >= 0; --i) {
+        const int cnt = i + 1 + (i < TG ? 1 : 0);
+        if (n < cnt) return n <= i ? n : TG;
+        n -= cnt;
+    }
+    return -1;
+}
+// the run of warp WARP: every tile index is a compile-time constant (with run-time tile indices the operand loads sat behind
+// warp-uniform branches and were no longer hoisted over the tensor ops: S3 at S = 40 went from 5,100 to 8,700 cycles)
+template <int S, int W, int WARP, class LA, class LB, class EPI>
+PDPLQR_DEVINL void dmma_sym_lower_run(int lane, int K, LA la, LB lb, EPI epi) {
+    constexpr int NEED = sym_lower_tiles(S), CH = (NEED + W - 1) / W;
+    constexpr int N0 = WARP * CH;
+    constexpr int CNT = NEED - N0 < CH ? (NEED - N0 > 0 ? NEED - N0 : 0) : CH;   // tiles of this warp
+    if constexpr (CNT > 0) {
+        const int r = lane >> 2, q = lane & 3;
+        const int KT = (K + 3) >> 2;
+        double c[CNT][2];
+        static_for<0, CNT>([&](auto tc) { c[tc][0] = c[tc][1] = 0.0; });
+#pragma unroll 2
+        for (int kt = 0; kt < KT; ++kt) {
+            const int k = kt * 4 + q;
+            const bool kin = k < K;
+            double af[CNT], bf[CNT];
+            static_for<0, CNT>([&](auto tc) {
+                constexpr int t = tc;
+                constexpr int ti = sym_tile_row(S, N0 + t), tj = sym_tile_col(S, N0 + t);
+                constexpr bool fresh = (t == 0) || sym_tile_row(S, N0 + t - 1) != ti;
+                if constexpr (fresh) {
+                    if constexpr (8 * ti + 7 < S) af[t] = kin ? la(8 * ti + r, k) : 0.0;
+                    else af[t] = (kin && 8 * ti + r < S) ? la(8 * ti + r, k) : 0.0;
+                } else
+                    af[t] = af[t > 0 ? t - 1 : 0];
+                if constexpr (8 * tj + 7 < S + 1) bf[t] = kin ? lb(k, 8 * tj + r) : 0.0;
+                else bf[t] = (kin && 8 * tj + r < S + 1) ? lb(k, 8 * tj + r) : 0.0;
+            });
+            static_for<0, CNT>([&](auto tc) { dmma_m8n8k4(c[tc][0], c[tc][1], af[tc], bf[tc]); });
+        }
+        static_for<0, CNT>([&](auto tc) {
+            constexpr int t = tc;
+            constexpr int ti = sym_tile_row(S, N0 + t), tj = sym_tile_col(S, N0 + t);
+            const int i = 8 * ti + r, j = 8 * tj + 2 * q;
+            if (i < S && j <= S) epi(i, j, c[t][0], c[t][1]);   // elements (i, j) and (i, j + 1), j even; (i, j + 1) may be
+                                                                // out of range (j + 1 > S): the epilogue checks
+        });
+    }
+}
+template <int S, int W, class LA, class LB, class EPI>
+PDPLQR_DEVINL void dmma_sym_lower(int warp, int lane, int K, LA la, LB lb, EPI epi) {
+    static_for<0, W>([&](auto wc) {
+        if (warp == wc) dmma_sym_lower_run<S, W, wc>(lane, K, la, lb, epi);
+    });
+}
+
 #ifndef PDPLQR_DMMA_MIN_MACS
 #define PDPLQR_DMMA_MIN_MACS 500     // products smaller than this stay on the register-tile FMA path.  Measured (C5,
 #endif                               // nx12/nu4, same box): 20000 -> 4.22 ms, 3000 -> 3.90 ms, 500 and 1 -> 3.58 ms

@@ -93,7 +93,9 @@ __global__ void pack_model_kernel(const double* __restrict__ E, const double* __
                 q = (((di - 4 * (j >> 1)) % s + s) % s) + j * s;
             }
             const int iu = umap(widx_inv(q % s, nx, nu, lay)), ju = umap(widx_inv(q / s, nx, nu, lay));
-            if (iu >= 0 && ju >= 0) v = H[st * (long long)(su * su) + iu + ju * su];
+            // the record's H is exactly symmetric: both halves come from the caller's LOWER triangle, the one the reference's
+            // LLT of M reads (lqr_kernel.hpp:121-126); the kernels may then read H(i,j) as H(j,i)
+            if (iu >= 0 && ju >= 0) v = H[st * (long long)(su * su) + (iu > ju ? iu : ju) + (iu > ju ? ju : iu) * su];
             else v = (q % s == q / s) ? 1.0 : 0.0;
         } else if (e < oend) {
             const int iu = umap(widx_inv(e - oh, nx, nu, lay));
@@ -1231,6 +1233,7 @@ int pdplqr_admm_set_cones(pdplqr_handle_t h, int ncones, const int* stage, const
         rc |= dev_alloc(*h, &ctl, 1);
         h->d_ctl = ctl;
     }
+    rc |= dev_alloc(*h, &h->d_row_box, nct);
     rc |= dev_alloc(*h, &h->d_cone_type, ncones);
     rc |= dev_alloc(*h, &h->d_cone_row, ncones);
     rc |= dev_alloc(*h, &h->d_cone_dim, ncones);
@@ -1240,6 +1243,15 @@ int pdplqr_admm_set_cones(pdplqr_handle_t h, int ncones, const int* stage, const
     CU_TRY(h, cudaMemcpy(h->d_cone_type, type, sizeof(int) * ncones, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(h->d_cone_row, row0, sizeof(int) * ncones, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(h->d_cone_dim, dim, sizeof(int) * ncones, cudaMemcpyHostToDevice));
+    {   // per-row flag "belongs to a box cone" (admm_update_kernel finishes those rows in one pass)
+        std::vector<long long> off(h->N + 2, 0);
+        for (int k = 0; k <= h->N; ++k) off[k + 1] = off[k] + h->ncs[k];
+        std::vector<int> box(nct, 0);
+        for (int c = 0; c < ncones; ++c)
+            if (type[c] == PDPLQR_CONE_BOX)
+                for (int r = 0; r < dim[c]; ++r) box[off[stage[c]] + row0[c] + r] = 1;
+        CU_TRY(h, cudaMemcpy(h->d_row_box, box.data(), sizeof(int) * nct, cudaMemcpyHostToDevice));
+    }
     CU_TRY(h, cudaMemcpy(h->d_elb, e_lb, B * nct * 8, cudaMemcpyHostToDevice));
     CU_TRY(h, cudaMemcpy(h->d_eub, e_ub, B * nct * 8, cudaMemcpyHostToDevice));
     h->cones_set = true;
@@ -1285,7 +1297,7 @@ int admm_iteration(Solver& h, const AdmmRun& r, bool factorize, cudaGraphConditi
     ap.ncs = h.d_ncs; ap.coff = h.d_coff; ap.doff = h.d_doff; ap.Dm = h.d_D;
     ap.d_total = h.d_total_dev; ap.nc_total = h.nc_total;
     ap.sel_col = h.sel_mode ? h.d_sel_col : nullptr; ap.sel_val = h.sel_mode ? h.d_sel_val : nullptr;
-    ap.cone_first = h.d_cone_first; ap.cone_type = h.d_cone_type; ap.cone_row = h.d_cone_row; ap.cone_dim = h.d_cone_dim;
+    ap.cone_first = h.d_cone_first; ap.cone_type = h.d_cone_type; ap.cone_row = h.d_cone_row; ap.cone_dim = h.d_cone_dim; ap.row_box = h.d_row_box;
     ap.e_lb = h.d_elb; ap.e_ub = h.d_eub;
     ap.w_tilde = h.d_wtilde; ap.w = r.w; ap.z = r.z; ap.y = r.y; ap.rho = h.d_rho_work;
     ap.alpha = r.alpha; ap.sigma = r.sigma; ap.ctl = static_cast<AdmmCtl*>(h.d_ctl);

@@ -157,10 +157,10 @@ struct BwdSmem {
     static constexpr size_t BYTES = (size_t)DOUBLES * 8;
     // run-time tail (only when the problem has constraints):
     //   dense D:      D[even(ncmax*S)] | rho[ncmax] | rho.*g[ncmax]
-    //   selection D:                     rho[ncmax] | rho.*g[ncmax] | val[ncmax] | dg[S] | dh[S] | col[ncmax] (int)
+    //   selection D:                     rho[ncmax] | rho.*g[ncmax] | val[ncmax] | 2 x (dg[S] | dh[S]) | col[ncmax] (int)
     static size_t bytes(int ncmax, bool sel = false) {
         if (ncmax <= 0) return BYTES;
-        return BYTES + (size_t)((sel ? 0 : even_up(ncmax * S)) + 2 * ncmax + (sel ? ncmax + even_up(ncmax) / 2 + 1 + 2 * S : 0)) * 8;
+        return BYTES + (size_t)((sel ? 0 : even_up(ncmax * S)) + 2 * ncmax + (sel ? ncmax + even_up(ncmax) / 2 + 1 + 4 * S : 0)) * 8;
     }
 };
 
@@ -169,6 +169,15 @@ struct BwdSmem {
 // CON = false compiles every constraint path out (unconstrained problems pay nothing for them).
 // -DPDPLQR_PHASE_CLOCKS: thread 0 of two CTAs accumulates clock64() per phase of the stage loop and prints cycles per
 // stage at the end (instrumented builds only: PDPLQR_VARIANT=prof PDPLQR_CFLAGS=-DPDPLQR_PHASE_CLOCKS, scripts/prof_phases.py)
+#ifndef PDPLQR_SYM_S3
+#define PDPLQR_SYM_S3 1
+#endif
+#ifndef PDPLQR_S3_VEC
+#define PDPLQR_S3_VEC 1
+#endif
+#ifndef PDPLQR_FOLD_AHEAD
+#define PDPLQR_FOLD_AHEAD 1
+#endif
 #ifdef PDPLQR_PHASE_CLOCKS
 #define PHASE_DECL long long ph_acc[12] = {0}, ph_t = 0; const bool ph_on = (threadIdx.x == 0) && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2);
 #define PHASE_START() do { if (ph_on) ph_t = clock64(); } while (0)
@@ -215,9 +224,10 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
     double* rho_s = Dbuf + DSTRIDE;
     double* rg_s = rho_s + ncmax;
     double* sval_s = rg_s + ncmax;
-    double* dg_s = sval_s + ncmax;                  // selection mode: diag(D^T rho D) and D^T (rho o g) of the stage,
-    double* dh_s = dg_s + S;                        // scatter-added by the row threads (shared-memory atomics)
-    int* scol_s = reinterpret_cast<int*>(dh_s + S);
+    double* dg_s = sval_s + ncmax;                  // selection mode: diag(D^T rho D) | D^T (rho o g) of a stage, scatter-added
+                                                    // by the row threads (shared-memory atomics); two buffers: the rows of the
+                                                    // NEXT stage are folded while this stage's factorisation runs
+    int* scol_s = reinterpret_cast<int*>(dg_s + 4 * S);
 
     const size_t ws_len = (size_t)p.N * S + NX;
     const double* model_b = p.model + (size_t)b * p.N * D::REC;
@@ -285,7 +295,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         }
     }
     if (sel)
-        for (int i = tid; i < 2 * S; i += T) dg_s[i] = 0.0;
+        for (int i = tid; i < 4 * S; i += T) dg_s[i] = 0.0;
     group_sync<T>();
     auto issue_stage = [&](int kk, int bufi) {   // one elected thread: stage record (+ constraint matrix) of stage kk
         const int nck = (ncmax > 0 && !sel) ? p.ncs[kk] : 0;
@@ -331,7 +341,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         const size_t co = cbase + nx_co;
 #pragma unroll
         for (int q = 0; q < CR; ++q) {
-            const int r = tid + q * T;
+            const int r = (tid + T - T / 2) % T + q * T;
             pr_c[q] = -1; pr_v[q] = 0.0;
             if (r < pr_n) {
                 pr_rho[q] = p.rho[co + r]; pr_z[q] = p.zs[co + r]; pr_ir[q] = p.inv_rho[co + r]; pr_y[q] = p.ys[co + r];
@@ -340,10 +350,43 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         }
         if (kk - 1 >= N0) { nx_n = p.ncs[kk - 1]; nx_co = p.coff[kk - 1]; }
     };
+    // fold of one stage's rows: g = z - y/rho ; keep rho and rho.*g (lqr_solver_parallel.hpp:134-137, lqr_kernel.hpp:110);
+    // selection-matrix rows scatter-add diag(D^T rho D) and D^T (rho o g) into dgb | dgb + S.  It runs one stage AHEAD, right
+    // after S3 of the previous stage, on the threads that have no right-hand side in S4 / S5 (rows are dealt out from the
+    // middle of the group): at the top of the stage it cost 2,000 of 13,000 cycles at nx30/nu10/nc44.
+    const int ctid = (tid + T - T / 2) % T;
+    auto fold_stage = [&](int kk, double* dgb) {
+        const int n = pr_n;
+        if (n <= 0) return;
+        auto row = [&](int r, double rr, double zz, double ir, double yy, int cj, double v) {
+            rho_s[r] = rr;
+            const double rg = rr * (zz - ir * yy);
+            rg_s[r] = rg;
+            if (sel && cj >= 0) {   // D_k rows are scaled unit vectors: D^T rho D is diagonal
+                atomicAdd(&dgb[cj], rr * v * v);
+                atomicAdd(&dgb[S + cj], v * rg);
+            }
+        };
+#pragma unroll
+        for (int q = 0; q < CR; ++q)   // rows fetched a stage ahead (registers)
+            if (ctid + q * T < n) row(ctid + q * T, pr_rho[q], pr_z[q], pr_ir[q], pr_y[q], pr_c[q], pr_v[q]);
+        if (n > CR * T) {              // (more than CR rows per thread: straight from global memory)
+            const size_t co = cbase + p.coff[kk];
+            for (int r = ctid + CR * T; r < n; r += T)
+                row(r, p.rho[co + r], p.zs[co + r], p.inv_rho[co + r], p.ys[co + r], sel ? p.sel_col[co + r] : -1,
+                    sel ? p.sel_val[co + r] : 0.0);
+        }
+    };
+    int nck_next = 0;
     if (CON && LEN > 0) {
         nx_n = ncmax > 0 ? p.ncs[N1 - 1] : 0;
         nx_co = ncmax > 0 ? p.coff[N1 - 1] : 0;
         fetch_con(N1 - 1);
+        if constexpr (PDPLQR_FOLD_AHEAD) {
+            fold_stage(N1 - 1, dg_s);
+            nck_next = pr_n;
+            if (LEN > 1) fetch_con(N1 - 2);
+        }
     }
     constexpr bool Z_BULK = (D::FREC % 2 == 0) && ((NU * D::NRHS) % 2 == 0) && ((NU * (NX + 1)) % 2 == 0);
     PHASE_DECL
@@ -355,26 +398,14 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         const double* R = rec;
         mbar_wait(&bar[0], it & 1);              // requested after S3 of the previous stage (or in the prologue)
         PHASE(0);
-        const int nck = CON ? pr_n : 0;
-        if (nck > 0) {  // g = z - y/rho ; keep rho and rho.*g   (lqr_solver_parallel.hpp:134-137, lqr_kernel.hpp:110)
-            const size_t co = cbase + p.coff[k];
-            auto row = [&](int r, double rr, double zz, double ir, double yy, int cj, double v) {
-                rho_s[r] = rr;
-                const double rg = rr * (zz - ir * yy);
-                rg_s[r] = rg;
-                if (sel && cj >= 0) {   // D_k rows are scaled unit vectors: D^T rho D is diagonal
-                    atomicAdd(&dg_s[cj], rr * v * v);
-                    atomicAdd(&dh_s[cj], v * rg);
-                }
-            };
-#pragma unroll
-            for (int q = 0; q < CR; ++q)   // rows fetched a stage ahead (registers)
-                if (tid + q * T < nck) row(tid + q * T, pr_rho[q], pr_z[q], pr_ir[q], pr_y[q], pr_c[q], pr_v[q]);
-            for (int r = tid + CR * T; r < nck; r += T)   // (more than CR rows per thread: straight from global memory)
-                row(r, p.rho[co + r], p.zs[co + r], p.inv_rho[co + r], p.ys[co + r], sel ? p.sel_col[co + r] : -1,
-                    sel ? p.sel_val[co + r] : 0.0);
+        double* dg_c = dg_s + (it & 1) * 2 * S;
+        double* dh_c = dg_c + S;
+        if constexpr (CON && !PDPLQR_FOLD_AHEAD) {   // (debug switch: fold at the top of the stage)
+            nck_next = pr_n;
+            fold_stage(k, dg_c);
+            if (it + 1 < LEN) fetch_con(k - 1);
         }
-        if (CON && it + 1 < LEN) fetch_con(k - 1);
+        const int nck = CON ? nck_next : 0;      // (this stage's rows were folded while the previous stage factorised)
 #pragma unroll
         for (int q = 0; q < NW; ++q)
             if (tid + q * T < S) wp[tid + q * T] = wreg[q];
@@ -411,12 +442,44 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 if (j < S) base = R[D::H_at(i, j)] + ((i == j) ? sigma : 0.0);
                 else base = R[D::h_at(i)] - sigma * wp[i];
                 if (sel && nck > 0) {   // selection-matrix fold-in (dg, dh were scatter-added at the top of the stage)
-                    if (i == j) base += dg_s[i];
-                    else if (j == S) base -= dh_s[i];
+                    if (i == j) base += dg_c[i];
+                    else if (j == S) base -= dh_c[i];
                 }
                 Ma[i + j * L::LDM] = base + v;
             };
-            gmm<S, S + 1, NX, tl.tm, tl.tn, T>(tid, la, lb, epi);
+            // only the tiles on / below the diagonal + the g column where the product runs on the tensor cores (every reader
+            // of Ma below -- S4, S5, S6 -- stays in that part)
+            constexpr bool SYM = PDPLQR_SYM_S3 && (long long)S * (S + 1) * NX >= PDPLQR_DMMA_MIN_MACS &&
+                                 (sym_lower_tiles(S) + T / 32 - 1) / (T / 32) <= 10;
+            if constexpr (SYM) {
+                // H is symmetric in the record (pack_model_kernel mirrors the lower triangle, the one the reference's LLT
+                // reads): the lane's pair H(i,j), H(i,j+1) is read as the contiguous H(j,i), H(j+1,i) with one 16-byte load --
+                // conflict-free, where two 8-byte loads down a column pair cost 4 wavefronts each at S = 0 (mod 8)
+                constexpr bool VEC = PDPLQR_S3_VEC && !D::WLAY && !D::H_ROT && (S % 2 == 0) && (D::REC_H % 2 == 0);
+                auto epi2 = [&](int i, int j, double v0, double v1) {
+                    double b0, b1 = 0.0;
+                    const bool in1 = j + 1 <= S;
+                    if (VEC && j + 1 < S) {
+                        const double2 hv = *reinterpret_cast<const double2*>(R + D::REC_H + j + i * S);
+                        b0 = hv.x; b1 = hv.y;
+                    } else {
+                        b0 = (j < S) ? R[D::H_at(i, j)] : R[D::h_at(i)] - sigma * wp[i];
+                        if (in1) b1 = (j + 1 < S) ? R[D::H_at(i, j + 1)] : R[D::h_at(i)] - sigma * wp[i];
+                    }
+                    if (i == j) b0 += sigma;
+                    if (i == j + 1 && j + 1 < S) b1 += sigma;
+                    if (sel && nck > 0) {
+                        if (i == j) b0 += dg_c[i];
+                        else if (j == S) b0 -= dh_c[i];
+                        if (i == j + 1 && j + 1 < S) b1 += dg_c[i];
+                        else if (j + 1 == S) b1 -= dh_c[i];
+                    }
+                    Ma[i + j * L::LDM] = b0 + v0;
+                    if (in1) Ma[i + (j + 1) * L::LDM] = b1 + v1;
+                };
+                dmma_sym_lower<S, T / 32>(tid >> 5, tid & 31, NX, la, lb, epi2);
+            } else
+                gmm<S, S + 1, NX, tl.tm, tl.tn, T>(tid, la, lb, epi);
             if (nck > 0 && !sel) {  // M += D^T diag(rho) D ; g -= D^T (rho o g_c)      (lqr_kernel.hpp:106-112)
                 const double* Dk = Dbuf + buf * DSTRIDE;
                 auto lda = [&](int i, int r) { return Dk[r + i * nck]; };
@@ -432,7 +495,12 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
             issue_stage(k - 1, 0);
         }
         if (sel && nck > 0)
-            for (int i = tid; i < 2 * S; i += T) dg_s[i] = 0.0;   // ready for the next stage's scatter-add
+            for (int i = tid; i < 2 * S; i += T) dg_c[i] = 0.0;   // ready for the scatter-add of the stage after the next
+        if (CON && PDPLQR_FOLD_AHEAD && it + 1 < LEN) {    // the next stage's rows (fetched a stage ago), then the fetch for the stage after it
+            fold_stage(k - 1, dg_s + ((it + 1) & 1) * 2 * S);
+            nck_next = pr_n;
+            if (it + 2 < LEN) fetch_con(k - 2);
+        }
 
         PHASE(5);
         // S4: Quu = L D L^T (unit lower L).  NU <= 12: every solving thread factorises its own register copy (no
@@ -679,7 +747,7 @@ struct AffSmem {
     static constexpr size_t BYTES = (size_t)DOUBLES * 8;
     static size_t bytes(int ncmax, bool sel = false) {
         if (ncmax <= 0) return BYTES;
-        return BYTES + (size_t)((sel ? 0 : 2 * even_up(ncmax * S)) + ncmax + (sel ? ncmax + even_up(ncmax) / 2 + 1 + 2 * S : 0)) * 8;
+        return BYTES + (size_t)((sel ? 0 : 2 * even_up(ncmax * S)) + ncmax + (sel ? ncmax + even_up(ncmax) / 2 + 1 + 4 * S : 0)) * 8;
     }
 };
 

@@ -89,7 +89,7 @@ struct pdplqr_solver {
     double* d_aff = nullptr;
     // conic ADMM outer loop (a11)
     int ncones = 0;
-    int *d_cone_first = nullptr, *d_cone_type = nullptr, *d_cone_row = nullptr, *d_cone_dim = nullptr;
+    int *d_cone_first = nullptr, *d_cone_type = nullptr, *d_cone_row = nullptr, *d_cone_dim = nullptr, *d_row_box = nullptr;
     double *d_elb = nullptr, *d_eub = nullptr, *d_wtilde = nullptr, *d_w = nullptr, *d_z = nullptr, *d_y = nullptr, *d_rho_admm = nullptr,
            *d_invrho_admm = nullptr;
     bool cones_set = false;

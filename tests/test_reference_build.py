@@ -111,7 +111,7 @@ def test_reference_example_with_cuda_solver():
         k = next(i for i, l in enumerate(lines) if l.startswith("Final state (%s)" % tag))
         return np.concatenate(inputs + [np.array(lines[k + 1].split(), dtype=float)])
 
-    cpu, gpu = rows("LQRSolver"), rows("LQRParallelSolver")
+    cpu, gpu = rows("LQRSolver"), rows("LQRCudaSolver")   # (the patch also renames the printed tag)
     assert cpu.size == gpu.size == 5 * 4 + 12
     assert abs(cpu[0] - (-2.898056669662)) < 1e-9          # SURVEY.md's independent probe value of u_0[0]
     assert rel_err(gpu, cpu) < 1e-9
