@@ -84,6 +84,11 @@ PDPLQR_DEVINL void atomic_max_nonneg(unsigned long long* addr, double v) {
 // of the warp will read, one 128-byte line per lane, issued at the top of an item: 356 -> 374 ms per solve (376 with L1, the
 // same with 6 instead of 8 CTAs per SM).  With 64 resident warps per SM the loads are covered already; the kernel is bound by
 // issue slots (ncu: 70 % issue-active), and the prefetch adds 250 instructions per item.
+// Also tried on the lean kernel below (590 instructions per item, where ncu shows long-scoreboard stalls at the sel_col ->
+// wt[cj], w, z and bound loads one after the other): all loads of a row -- and the first 32 rows' together with w~ and w --
+// issued before the first use.  The 14 more live registers spill at the 32 the 8-CTA residency leaves (C4 349 -> 385 ms), and
+// with 40 / 48 / 64 registers (6 / 5 / 4 CTAs per SM) it measured 373 / 361 / 349 ms: what the single round trip gains, the
+// lost warps give back.
 constexpr int ADMM_WARPS = 8;   // warps per CTA of admm_update_kernel; 8 CTAs per SM (32 registers): the kernel is a chain of
                                 // dependent global loads per item, so resident warps are what hides the latency (C4 453 -> 422 ms)
 

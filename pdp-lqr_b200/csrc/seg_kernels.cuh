@@ -489,6 +489,9 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
             }
         }
         PHASE(4);
+        if constexpr (Z_BULK) {          // the previous stage's factor record has left shared memory long ago: S5 may write Z
+            if (tid == 0 && it > 0) bulk_wait_read<0>();   // (waited for at the end of S6 it held thread 0, and with it the
+        }                                                  //  end-of-stage barrier, for the drain time of the store)
         group_sync<T>();
         if (tid == 0 && it + 1 < LEN) {  // the record (H, h) and D had their last readers in S3: fetch stage k-1 into
             fence_proxy_async();         // the same buffer; it lands while S4-S6 run and is waited for at the top of the next stage
@@ -672,8 +675,7 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
                 double* fk = fac_b + (size_t)k * D::FREC;
                 const int nz = pdp ? NU * D::NRHS : NU * (NX + 1);
                 for (int e = tid; e < nz; e += T) fk[e] = Z[e];
-            } else if (tid == 0)
-                bulk_wait_read<0>();   // Z may be overwritten by the next stage
+            }   // (Z_BULK: the bulk store's read of Z is waited for just before Z is written again, after S3 of the next stage)
             if (aff_b) {  // what backward_without_factorization needs: Quu^-1, P+c, F+c, F+B
                 double* ak = aff_b + (size_t)k * D::AREC;
                 for (int e = tid; e < NU * NU; e += T) ak[D::AR_QI + e] = Qi[e];
@@ -690,6 +692,9 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
         PHASE(10);
     }
     PHASE_PRINT("seg_backward", LEN);
+    if constexpr (Z_BULK) {
+        if (tid == 0 && LEN > 0) bulk_wait_read<0>();   // shared memory must outlive the last bulk store's read
+    }
 
     // segment summary (lqr_solver_parallel.hpp:180-187): P, F, C, p, f at the segment entry
     double* sm = p.sum + ((size_t)b * p.S + seg) * D::SREC;

@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(LatSmem<NX>::TOP_THREADS) tree_sub_up_lat_kern
         int tt = THREADS / ng;
         if (tt > p.tt_cap) tt = p.tt_cap;
         const int grp = tid / tt, t = tid % tt;
+        bool issued = false;                    // this thread committed a bulk store at this level
         if (grp < groups) {
             const double* in_b = p.sum[l] + ((size_t)b * cnt + n0) * D::SREC;
             double* out = p.sum[l + 1] + ((size_t)b * cnt_up + (n0 >> 1) + grp) * D::SREC;
@@ -336,15 +337,23 @@ __global__ void __launch_bounds__(LatSmem<NX>::TOP_THREADS) tree_sub_up_lat_kern
                     if (t == 0) {
                         bulk_s2g(out, outs, D::SREC * 8);
                         bulk_commit();
-                        bulk_wait_read<0>();    // before anyone overwrites `outs` (two levels on) or the CTA exits
+                        issued = true;
                     }
                 } else
                     for (int e = t; e < D::SREC; e += tt) out[e] = outs[e];
             }
         }
+        // `outs` is an input of the next level and is overwritten two levels on: what has to be over before the barrier below
+        // is the read of the PREVIOUS level's store, not of the one just issued (waiting for that one held the whole CTA for
+        // the drain time of the copy at every level of the chain)
+        if constexpr (BULK_OUT) {
+            if (issued) bulk_wait_read<1>();
+            else bulk_wait_read<0>();
+        }
         __threadfence_block();
         __syncthreads();
     }
+    if constexpr (BULK_OUT) bulk_wait_read<0>();   // shared memory must outlive the last store's read
 }
 
 template <int NX>
