@@ -133,52 +133,35 @@ __global__ void __launch_bounds__(ADMM_WARPS * 32, PDPLQR_ADMM_MINB) admm_update
         const int c0 = p.cone_first[k], c1 = p.cone_first[k + 1];
         k += dk; b += db;              // (problem, stage) of the next item
         if (k >= N1) { k -= N1; ++b; }
-        // every load of a row is issued before the first use of any of them, and the first 32 rows' loads together with the
-        // loads of w~ and w: one DRAM round trip per item instead of four (ncu: long-scoreboard stalls at the sel_col -> wt[cj],
-        // w, z and bound loads, one after the other, were 60 % of the kernel's stall samples)
-        struct Row { int cj, box; double sv, zold, yold, rr, lb, ub; };
-        auto load_row = [&](int r, Row& q) {
-            q.cj = sel ? p.sel_col[co + r] : -1;
-            q.sv = sel ? p.sel_val[co + r] : 0.0;
-            q.zold = p.z[co + r]; q.yold = p.y[co + r]; q.rr = p.rho[co + r];
-            q.box = p.row_box[cok + r];
-            q.lb = p.e_lb[co + r]; q.ub = p.e_ub[co + r];
-        };
+        __syncwarp();                  // the previous item's readers of the scratch are done
+        for (int i = lane; i < dim; i += 32) {
+            const double a = p.w_tilde[wo + i];
+            wt[i] = a;
+            p.w[wo + i] = alpha * a + oma * p.w[wo + i];
+        }
+        if (nc == 0) continue;
+        __syncwarp();
         auto finish = [&](int r, double zh, double znew, double yold, double rr) {
             p.z[co + r] = znew;
             p.y[co + r] = yold + rr * (zh - znew);
         };
-        auto do_row = [&](int r, const Row& q) {
+        for (int r = lane; r < nc; r += 32) {
             double acc = 0.0;
             if (sel) {
-                if (q.cj >= 0) acc = q.sv * wt[q.cj];
+                const int cj = p.sel_col[co + r];
+                if (cj >= 0) acc = p.sel_val[co + r] * wt[cj];
             } else {
                 for (int j = 0; j < dim; ++j) acc = fma(Dk[r + (size_t)j * nc], wt[j], acc);
             }
-            const double zh = alpha * acc + oma * q.zold;
-            const double vv = fma(q.yold, rcp_newton(q.rr), zh);
-            if (q.box) {
-                finish(r, zh, fmin(fmax(vv, q.lb), q.ub), q.yold, q.rr);
+            const double zold = p.z[co + r], yold = p.y[co + r], rr = p.rho[co + r];
+            const double zh = alpha * acc + oma * zold;
+            const double vv = fma(yold, rcp_newton(rr), zh);
+            if (p.row_box[cok + r]) {
+                finish(r, zh, fmin(fmax(vv, p.e_lb[co + r]), p.e_ub[co + r]), yold, rr);
             } else {
                 v[r] = vv;
                 zt[r] = zh;
             }
-        };
-        Row q0;
-        if (lane < nc) load_row(lane, q0);
-        __syncwarp();                  // the previous item's readers of the scratch are done
-        for (int i = lane; i < dim; i += 32) {
-            const double a = p.w_tilde[wo + i], wold = p.w[wo + i];
-            wt[i] = a;
-            p.w[wo + i] = alpha * a + oma * wold;
-        }
-        if (nc == 0) continue;
-        __syncwarp();
-        if (lane < nc) do_row(lane, q0);
-        for (int r = lane + 32; r < nc; r += 32) {
-            Row q;
-            load_row(r, q);
-            do_row(r, q);
         }
         auto project_serial = [&](int r0, int d, int type) {     // one lane, whole cone (second-order cone or ball)
             if (type == CONE_SOC) {
