@@ -84,11 +84,21 @@ PDPLQR_DEVINL void combine_lat_init(int t, int tt, double* wk) {
 // (shared); wk: LatSmem::WORK doubles of shared workspace (16-byte aligned) whose pivot keys are zero (they are again on
 // exit); out: combined summary (shared or global, distinct from sa, sb); ddi: down-sweep record of member a (global).
 // Ends with a group barrier.
+#ifdef PDPLQR_PHASE_CLOCKS
+#define TPH_DECL long long tph[8]; const bool tph_on = (t == 0 && bar_id == 1 && blockIdx.x == 0); int tph_n = 0; if (tph_on) tph[tph_n++] = clock64();
+#define TPH() do { if (tph_on) tph[tph_n++] = clock64(); } while (0)
+#define TPH_PRINT() do { if (tph_on) printf("combine_lat tt %d | form %lld gj %lld unperm %lld prod3 %lld prod4 %lld p %lld | total %lld\n", tt, tph[1]-tph[0], tph[2]-tph[1], tph[3]-tph[2], tph[4]-tph[3], tph[5]-tph[4], tph[6]-tph[5], tph[6]-tph[0]); } while (0)
+#else
+#define TPH_DECL
+#define TPH() do {} while (0)
+#define TPH_PRINT() do {} while (0)
+#endif
 template <int NX>
 PDPLQR_DEVINL void combine_lat(int t, int tt, int bar_id, const double* sa, const double* sb, double* wk, double* out,
                                double* ddi) {
     using D = TreeDims<NX>;
     using L = LatSmem<NX>;
+    TPH_DECL
     constexpr int N2 = D::N2, LDG = L::LDG, NCOL = D::NCOL, NRCH = L::NRCH, ITEMS = L::ITEMS, MAXQ = L::MAXQ;
     const double *Pa = sa + D::SUM_P, *Fa = sa + D::SUM_F, *Ca = sa + D::SUM_C, *pa = sa + D::SUM_p, *fa = sa + D::SUM_f;
     const double *Pb = sb + D::SUM_P, *Fb = sb + D::SUM_F, *Cb = sb + D::SUM_C, *pb = sb + D::SUM_p, *fb = sb + D::SUM_f;
@@ -122,6 +132,7 @@ PDPLQR_DEVINL void combine_lat(int t, int tt, int bar_id, const double* sa, cons
     if constexpr (LDG > NX)                                      // padding rows: keep them finite
         for (int e = t; e < NCOL * (LDG - NX); e += tt) cur[NX + e % (LDG - NX) + (e / (LDG - NX)) * LDG] = 0.0;
     rt_sync(tt, bar_id);
+    TPH();
     // ---- phase 2: Gauss-Jordan, implicit partial (row) pivoting.  Step k: pivot row piv (largest |a(i,k)| among the
     //      rows not used yet), a(piv, :) /= a(piv,k), every other row i: a(i, :) -= a(i,k) a(piv, :).  Row piv then
     //      holds component k of the solution.  Work item id = (column j = 1 + id / NRCH, rows 4c .. 4c+3, c = id % NRCH)
@@ -178,6 +189,7 @@ PDPLQR_DEVINL void combine_lat(int t, int tt, int bar_id, const double* sa, cons
         double* sw = cur; cur = nxt; nxt = sw;
         if (k + 1 < NX) piv = 31 - (pivkey[k + 1] & 31);
     }
+    TPH();
     // un-permute: solution row k is row i with rowof[i] == k; the result goes to the idle buffer
 #pragma unroll
     for (int q = 0; q < MAXQ; ++q) {
@@ -190,6 +202,7 @@ PDPLQR_DEVINL void combine_lat(int t, int tt, int bar_id, const double* sa, cons
     }
     for (int r = t; r < NX; r += tt) pivkey[r] = 0;          // ready for the next combine on this workspace
     rt_sync(tt, bar_id);
+    TPH();
     // nxt holds [ . | X_F | X_C | w_f ] ; cur is scratch
     const double* XF = nxt + NX * LDG;
     const double* XC = nxt + 2 * NX * LDG;
@@ -226,6 +239,7 @@ PDPLQR_DEVINL void combine_lat(int t, int tt, int bar_id, const double* sa, cons
         ddi[D::DD_XC + e] = XC[r + c * LDG];
     }
     rt_sync(tt, bar_id);
+    TPH();
     // ---- phase 4: P = P_a + F_a^T T1 ; C = C_b + T2 F_b^T ; lv = P_b x_f + p_b ; f = F_b x_f + f_b
     {
         auto la = [&](int g, int r, int k) { return g == 0 ? Fa[k + r * NX] : T2[r + k * NX]; };
@@ -247,6 +261,7 @@ PDPLQR_DEVINL void combine_lat(int t, int tt, int bar_id, const double* sa, cons
         out[D::SUM_f + r] = af;
     }
     rt_sync(tt, bar_id);
+    TPH();
     // ---- phase 5: p = p_a + F_a^T lv   (then: `out` may be picked up by a bulk copy -> async-proxy fence)
     for (int r = t; r < NX; r += tt) {
         double ap0 = pa[r], ap1 = 0.0;
@@ -260,6 +275,8 @@ PDPLQR_DEVINL void combine_lat(int t, int tt, int bar_id, const double* sa, cons
     }
     fence_proxy_async();
     rt_sync(tt, bar_id);
+    TPH();
+    TPH_PRINT();
 }
 
 // ---------------------------------------------------------------- binary sub-trees: one CTA per (problem, block of
