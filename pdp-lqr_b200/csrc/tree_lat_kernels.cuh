@@ -20,6 +20,15 @@
 // step measured 625 cycles against the 610 of the scheme below (the serial argmax / select chains of a single in-order warp
 // cost what the barrier and the shared atomics cost here), and with four of them on one SM sub-partition 2.3x more -- not
 // kept (git history: "combine_fast").
+// A second round-2 experiment, "gj_blocked": two pivot steps per barrier, blocked like an LU panel factorisation -- a group of
+// 3 lanes owns a pair of columns in registers (rows in 4-row chunks), the warp holding the panel finds both pivots with
+// shuffles, publishes the two multiplier columns + reciprocals once, and every group applies the rank-2 update with the
+// pivot-row entries shuffled inside the group (57 threads instead of 256, one barrier per two steps).  Parity-identical, and
+// again no faster: per pair  step A 455 + step B / publish 424 + barrier 14 + rank-2 update 366 = 1,259 cycles = 630 per pivot
+// step (clock64, C2), C2 94.3 against 94.1 us.  (A first version whose run-time register selects `x[piv & 3]` the compiler
+// turned into branches with reconvergence barriers measured 950 per step; selp.f64 in inline PTX fixed that.)  Three
+// formulations, 610 - 630 cycles per step each: the step is a chain of ~100 dependent instructions -- key, reduce, select,
+// fetch, reciprocal, scale, fetch, update -- on an in-order warp, and none of them shortens that chain.
 // Measured latencies that shape this (scripts/micro/lat_bench.cu, B200): LDS 30, DFMA 8, bar.sync (128 thr) 20,
 // STS->bar->LDS 55, ATOMS.MAX+LDS 51, reciprocal 48 (IEEE division 72), 64-bit shuffle 28 cycles.
 #pragma once
