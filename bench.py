@@ -157,10 +157,11 @@ def c4_traffic(batch: int):
 
 
 def c5_segments(world: int = 1) -> int:
-    """Segments per rank for the 2^20-stage problem: whole waves of the stage kernel, ~200-stage segments at 1 GPU, never
-    less than one full wave per rank."""
+    """Segments per rank for the 2^20-stage problem: whole waves of the stage kernel, never less than one full wave per rank.
+    Measured at 1 GPU (scripts/sweep_c5_seglen.sh): one wave (2,368 segments of 443 stages) 2.057 ms, two waves 2.110, three
+    2.117, four 2.165 ms -- the stage sweep does not care, the interface tree gets shorter."""
     wave = stage_wave()
-    per_rank = wave_aligned(max(C5_N // 200, wave), wave)
+    per_rank = wave_aligned(max(C5_N // int(os.environ.get("BENCH_C5_SEG_LEN", "450")), wave), wave)
     return wave_aligned(max(per_rank // world, wave), wave)
 
 

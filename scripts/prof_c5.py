@@ -8,7 +8,7 @@ import pdplqr_b200 as P
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 wave = P.wave_size(12, 4)
-S = max(1, (max(N // 200, wave) // wave) * wave)
+S = max(1, (max(N // 450, wave) // wave) * wave)
 p = P.problems.quadrotor_ltv(N)
 sol = P.LQRCudaSolver.from_problem(p, num_segments=S, load_balancing=2)
 ws = 0.01 * np.random.default_rng(17).standard_normal((1, p.ws_len))
