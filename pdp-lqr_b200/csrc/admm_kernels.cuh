@@ -386,6 +386,11 @@ __global__ void admm_ctl_kernel(AdmmCtl* c, cudaGraphConditionalHandle handle, i
     if (use_handle) cudaGraphSetConditional(handle, (unsigned)cont);
 }
 
+__global__ void admm_inv_kernel(const double* __restrict__ rho, double* __restrict__ inv_rho, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        inv_rho[i] = 1.0 / rho[i];
+}
+
 __global__ void admm_rho_scale_kernel(double* __restrict__ rho, double* __restrict__ inv_rho, long long n, double scale) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const double r = fmin(fmax(rho[i] * scale, 1e-6), 1e6);
