@@ -175,6 +175,9 @@ struct BwdSmem {
 #ifndef PDPLQR_S3_VEC
 #define PDPLQR_S3_VEC 1
 #endif
+#ifndef PDPLQR_AFF_PSHIFT
+#define PDPLQR_AFF_PSHIFT 1
+#endif
 #ifndef PDPLQR_FOLD_AHEAD
 #define PDPLQR_FOLD_AHEAD 1
 #endif
@@ -739,20 +742,30 @@ struct AffSmem {
     static constexpr int H_OFF = D::REC_h & ~1;              // 16-byte aligned start of the h chunk inside the record
     static constexpr int H_LEN = (D::REC - H_OFF);           // doubles copied (h plus at most one neighbour)
     static constexpr int RLITE = D::REC_EC + H_LEN;          // doubles per ring slot
-    static constexpr int o_rec = 0;                          // 2 x RLITE (TMA)
-    static constexpr int o_fac = o_rec + 2 * RLITE;          // 2 x FREC  (TMA)
-    static constexpr int o_aff = o_fac + 2 * D::FREC;        // 2 x AREC  (TMA)
-    static constexpr int o_t = o_aff + 2 * D::AREC;          // t (NX)
-    static constexpr int o_g = o_t + NX;                     // g (S)
-    static constexpr int o_d = o_g + S;                      // d (NU)
-    static constexpr int o_pn = o_d + NU;
-    static constexpr int o_fn = o_pn + NX;
-    static constexpr int o_bar = even_up(o_fn + NX);
-    static constexpr int DOUBLES = even_up(o_bar + 2);
-    static constexpr size_t BYTES = (size_t)DOUBLES * 8;
-    static size_t bytes(int ncmax, bool sel = false) {
-        if (ncmax <= 0) return BYTES;
-        return BYTES + (size_t)((sel ? 0 : 2 * even_up(ncmax * S)) + ncmax + (sel ? ncmax + even_up(ncmax) / 2 + 1 + 4 * S : 0)) * 8;
+    // Ring slots of the factor record and of the affine cache: a launch whose groups are all last / only segments (one segment
+    // per problem: the ADMM batch) needs only [K | d] and [Quu^-1 | P+c] of them -- 29 instead of 39 KB per group at nx30/nu10,
+    // 7 instead of 5 resident groups per SM ("lite" layout, chosen by the launcher, recomputed by the kernel from p.S)
+    static constexpr int FSL_LITE = even_up(NU * (NX + 1)), ASL_LITE = even_up(D::AR_FC);
+    struct Layout { int fsl, asl, o_fac, o_aff, o_t, o_g, o_d, o_pn, o_fn, o_bar, doubles; };
+    PDPLQR_HD static constexpr Layout layout(bool lite) {
+        Layout l{};
+        l.fsl = lite ? FSL_LITE : D::FREC;
+        l.asl = lite ? ASL_LITE : D::AREC;
+        l.o_fac = 2 * RLITE;                 // rec: 2 x RLITE (TMA) at 0
+        l.o_aff = l.o_fac + 2 * l.fsl;       // 2 x fsl  (TMA)
+        l.o_t = l.o_aff + 2 * l.asl;         // 2 x asl  (TMA); t (NX)
+        l.o_g = l.o_t + NX;                  // g (S)
+        l.o_d = l.o_g + S;                   // d (NU)
+        l.o_pn = l.o_d + NU;
+        l.o_fn = l.o_pn + NX;
+        l.o_bar = even_up(l.o_fn + NX);
+        l.doubles = even_up(l.o_bar + 2);
+        return l;
+    }
+    static size_t bytes(int ncmax, bool sel = false, bool lite = false) {
+        const size_t base = (size_t)layout(lite).doubles * 8;
+        if (ncmax <= 0) return base;
+        return base + (size_t)((sel ? 0 : 2 * even_up(ncmax * S)) + ncmax + (sel ? ncmax + even_up(ncmax) / 2 + 1 + 4 * S : 0)) * 8;
     }
 };
 
@@ -769,19 +782,20 @@ __global__ void __launch_bounds__(T) seg_affine_kernel(SegParams p) {
     const bool is_last = (seg == p.S - 1) && !p.interior;
     const bool pdp = !is_last;
 
-    double* rec = smem + L::o_rec;
-    double* fac = smem + L::o_fac;
-    double* aff = smem + L::o_aff;
-    double* tv = smem + L::o_t;
-    double* gv = smem + L::o_g;
-    double* dv = smem + L::o_d;
-    double* pn = smem + L::o_pn;
-    double* fn = smem + L::o_fn;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::o_bar);
+    const typename L::Layout lay = L::layout(p.S == 1 && !p.interior);   // (the launcher sized the allocation the same way)
+    const int FSL = lay.fsl, ASL = lay.asl;
+    double* rec = smem;
+    double* fac = smem + lay.o_fac;
+    double* aff = smem + lay.o_aff;
+    double* gv = smem + lay.o_g;
+    double* dv = smem + lay.o_d;
+    double* pn = smem + lay.o_pn;
+    double* fn = smem + lay.o_fn;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.o_bar);
     const int ncmax = p.ncmax;
     const bool sel = p.sel_col != nullptr;
     const int DSTRIDE = sel ? 0 : even_up(ncmax * S);
-    double* Dbuf = smem + L::DOUBLES;
+    double* Dbuf = smem + lay.doubles;
     double* rg_s = Dbuf + 2 * DSTRIDE;
     double* sval_s = rg_s + ncmax;
     double* dh_s = sval_s + ncmax + S;              // (same tail layout as the factorising kernel: dg unused here)
@@ -832,8 +846,8 @@ __global__ void __launch_bounds__(T) seg_affine_kernel(SegParams p) {
         mbar_expect_tx(&bar[bufi], (L::RLITE + fdoubles + adoubles) * 8 + dbytes);
         bulk_g2s(rec + bufi * L::RLITE, model_b + (size_t)kk * D::REC, D::REC_EC * 8, &bar[bufi]);
         bulk_g2s(rec + bufi * L::RLITE + D::REC_EC, model_b + (size_t)kk * D::REC + L::H_OFF, L::H_LEN * 8, &bar[bufi]);
-        bulk_g2s(fac + bufi * D::FREC, fac_b + (size_t)kk * D::FREC, fdoubles * 8, &bar[bufi]);
-        bulk_g2s(aff + bufi * D::AREC, aff_b + (size_t)kk * D::AREC, adoubles * 8, &bar[bufi]);
+        bulk_g2s(fac + bufi * FSL, fac_b + (size_t)kk * D::FREC, fdoubles * 8, &bar[bufi]);
+        bulk_g2s(aff + bufi * ASL, aff_b + (size_t)kk * D::AREC, adoubles * 8, &bar[bufi]);
         if (nck > 0) bulk_g2s(Dbuf + bufi * DSTRIDE, D_b + p.doff[kk], dbytes, &bar[bufi]);
     };
     if (tid == 0 && LEN > 0) issue_stage(N1 - 1, 0);
@@ -849,6 +863,9 @@ __global__ void __launch_bounds__(T) seg_affine_kernel(SegParams p) {
             wnext[r] = (i < S && ws_b) ? ws_b[(size_t)kk * S + i] : 0.0;
         }
     };
+    // constraint rows are dealt out from the middle of the group: with 128 threads the rows of the next stage are then folded by
+    // warps 2-3 while warp 0 forms d and warp 1 forms p
+    const int ctid = (T >= 128) ? (tid + T - T / 2) % T : tid;
     int nx_n = 0;          // row count / offset of the next stage to prefetch (fetched one more stage ahead: the vector
     long long nx_co = 0;   // loads need them for their addresses)
     auto fetch_con = [&](int kk) {
@@ -856,7 +873,7 @@ __global__ void __launch_bounds__(T) seg_affine_kernel(SegParams p) {
         const size_t co = cbase + nx_co;
 #pragma unroll
         for (int q = 0; q < CR; ++q) {
-            const int r = tid + q * T;
+            const int r = ctid + q * T;
             pr_c[q] = -1; pr_v[q] = 0.0;
             if (r < pr_n) {
                 pr_rho[q] = p.rho[co + r]; pr_z[q] = p.zs[co + r]; pr_ir[q] = p.inv_rho[co + r]; pr_y[q] = p.ys[co + r];
@@ -865,52 +882,64 @@ __global__ void __launch_bounds__(T) seg_affine_kernel(SegParams p) {
         }
         if (kk - 1 >= N0) { nx_n = p.ncs[kk - 1]; nx_co = p.coff[kk - 1]; }
     };
+    // rows of one stage (vectors in the prefetch registers): rho o g -> rg_s, selection rows scatter-add D^T (rho o g) into dh_s.
+    // Done one stage AHEAD, in the d / p phase of the previous stage (after its g phase has consumed and cleared rg_s / dh_s),
+    // so that no barrier of its own separates it from the g phase that reads the result.
+    auto fold_rows = [&](int kk) {
+        const int n = pr_n;
+        if (n <= 0) return;
+        auto row = [&](int r, double rr, double zz, double ir, double yy, int cj, double v) {
+            const double rg = rr * (zz - ir * yy);
+            rg_s[r] = rg;
+            if (sel && cj >= 0) atomicAdd(&dh_s[cj], v * rg);
+        };
+#pragma unroll
+        for (int q = 0; q < CR; ++q)   // rows fetched a stage ahead (registers)
+            if (ctid + q * T < n) row(ctid + q * T, pr_rho[q], pr_z[q], pr_ir[q], pr_y[q], pr_c[q], pr_v[q]);
+        if (n > CR * T) {
+            const size_t co = cbase + p.coff[kk];
+            for (int r = ctid + CR * T; r < n; r += T)
+                row(r, p.rho[co + r], p.zs[co + r], p.inv_rho[co + r], p.ys[co + r], sel ? p.sel_col[co + r] : -1,
+                    sel ? p.sel_val[co + r] : 0.0);
+        }
+    };
+    int nck_cur = 0;
     if (LEN > 0) {
         fetch_wa(N1 - 1);
         if (ncmax > 0) {
             nx_n = p.ncs[N1 - 1];
             nx_co = p.coff[N1 - 1];
             fetch_con(N1 - 1);
+            fold_rows(N1 - 1);
+            nck_cur = pr_n;
+            if (LEN > 1) fetch_con(N1 - 2);
         }
     }
+    group_sync<T>();
 #pragma unroll 1
     for (int it = 0; it < LEN; ++it) {
         const int k = N1 - 1 - it;
         const int buf = it & 1;
         const double* R = rec + buf * L::RLITE;
         const double* hrec = R + D::REC_EC + (D::REC_h - L::H_OFF);   // h of this stage
-        const double* Zk = fac + buf * D::FREC;
-        const double* Ak = aff + buf * D::AREC;
+        const double* Zk = fac + buf * FSL;
+        const double* Ak = aff + buf * ASL;
         if (tid == 0 && it + 1 < LEN) {
             fence_proxy_async();
             issue_stage(k - 1, buf ^ 1);
         }
-        const int nck = pr_n;
-        if (nck > 0) {
-            const size_t co = cbase + p.coff[k];
-            auto row = [&](int r, double rr, double zz, double ir, double yy, int cj, double v) {
-                const double rg = rr * (zz - ir * yy);
-                rg_s[r] = rg;
-                if (sel && cj >= 0) atomicAdd(&dh_s[cj], v * rg);
-            };
-#pragma unroll
-            for (int q = 0; q < CR; ++q)   // rows fetched a stage ahead (registers)
-                if (tid + q * T < nck) row(tid + q * T, pr_rho[q], pr_z[q], pr_ir[q], pr_y[q], pr_c[q], pr_v[q]);
-            for (int r = tid + CR * T; r < nck; r += T)
-                row(r, p.rho[co + r], p.zs[co + r], p.inv_rho[co + r], p.ys[co + r], sel ? p.sel_col[co + r] : -1,
-                    sel ? p.sel_val[co + r] : 0.0);
-        }
+        const int nck = nck_cur;
         double wpv[NWA];
 #pragma unroll
         for (int r = 0; r < NWA; ++r) wpv[r] = wnext[r];
-        if (it + 1 < LEN) {   // next stage's w_prev and constraint vectors: in flight while this stage computes
-            fetch_wa(k - 1);
-            if (ncmax > 0) fetch_con(k - 1);
-        }
+        if (it + 1 < LEN) fetch_wa(k - 1);   // next stage's w_prev: in flight while this stage computes
         mbar_wait(&bar[buf], (it >> 1) & 1);
-        for (int i = tid; i < NX; i += T) tv[i] = Ak[D::AR_PC + i] + pn[i];
-        group_sync<T>();
-        // g = h - sigma w - D^T (rho o g_c) + E^T t
+        // The stage is a chain of dependent mat-vecs between group barriers, and that chain -- not the 17 GB the sweep reads -- is
+        // what the (problem, segment) groups resident on an SM spend their time in (ncu: 5.2 TB/s, half of all stall samples at
+        // the barriers, a 30-term FMA chain on 40 of 128 threads).  So: t = P+c + p+ is formed inside the product (no barrier of
+        // its own), every dot product runs on four independent accumulators, and d and p -- which both need only g -- share
+        // one phase on different warps.
+        // g = h - sigma w - D^T (rho o g_c) + E^T t ,  t = P+c + p+
 #pragma unroll
         for (int r = 0; r < (S + T - 1) / T; ++r) {
             const int i = tid + r * T;
@@ -923,35 +952,59 @@ __global__ void __launch_bounds__(T) seg_affine_kernel(SegParams p) {
                     const double* Dk = Dbuf + buf * DSTRIDE;
                     for (int q = 0; q < nck; ++q) acc = fma(-Dk[q + i * nck], rg_s[q], acc);
                 }
-#pragma unroll 4
-                for (int q = 0; q < NX; ++q) acc = fma(R[q + D::wi(i) * NX], tv[D::eri(q)], acc);
-                gv[i] = acc;
+                double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                const double* Ei = R + D::wi(i) * NX;
+#pragma unroll
+                for (int q = 0; q + 3 < NX; q += 4) {
+                    acc = fma(Ei[q], Ak[D::AR_PC + D::eri(q)] + pn[D::eri(q)], acc);
+                    a1 = fma(Ei[q + 1], Ak[D::AR_PC + D::eri(q + 1)] + pn[D::eri(q + 1)], a1);
+                    a2 = fma(Ei[q + 2], Ak[D::AR_PC + D::eri(q + 2)] + pn[D::eri(q + 2)], a2);
+                    a3 = fma(Ei[q + 3], Ak[D::AR_PC + D::eri(q + 3)] + pn[D::eri(q + 3)], a3);
+                }
+#pragma unroll
+                for (int q = NX & ~3; q < NX; ++q) acc = fma(Ei[q], Ak[D::AR_PC + D::eri(q)] + pn[D::eri(q)], acc);
+                gv[i] = (acc + a1) + (a2 + a3);
             }
         }
         group_sync<T>();
-        // d = -Quu^-1 g_u
+        if (ncmax > 0 && it + 1 < LEN) {   // the next stage's rows, then the fetch for the stage after it
+            fold_rows(k - 1);
+            nck_cur = pr_n;
+            if (it + 2 < LEN) fetch_con(k - 2);
+        }
+        // d = -Quu^-1 g_u   |   p = g_x + K^T g_u          (the latter one warp further on when the group has one)
         for (int m = tid; m < NU; m += T) {
-            double acc = 0.0;
+            double acc = 0.0, a1 = 0.0;
 #pragma unroll
-            for (int q = 0; q < NU; ++q) acc = fma(-Ak[D::AR_QI + m + q * NU], gv[q], acc);
+            for (int q = 0; q + 1 < NU; q += 2) {
+                acc = fma(-Ak[D::AR_QI + m + q * NU], gv[q], acc);
+                a1 = fma(-Ak[D::AR_QI + m + (q + 1) * NU], gv[q + 1], a1);
+            }
+            if constexpr (NU & 1) acc = fma(-Ak[D::AR_QI + m + (NU - 1) * NU], gv[NU - 1], acc);
+            acc += a1;
             dv[m] = acc;
             fac_b[(size_t)k * D::FREC + NU * NX + m] = acc;   // the d slot of Z = [K | d | Gt]
         }
-        group_sync<T>();
-        // p = g_x + K^T g_u ;  f = F+c + (F+B) d + f+
-        for (int i = tid; i < NX; i += T) {
-            double acc = gv[NU + i];
+        for (int i = ((T >= 64 && PDPLQR_AFF_PSHIFT) ? (tid + T - 32) % T : tid); i < NX; i += T) {   // (p+ had its last readers in the g phase)
+            double acc = gv[NU + i], a1 = 0.0;
 #pragma unroll
-            for (int m = 0; m < NU; ++m) acc = fma(Zk[m + i * NU], gv[m], acc);
-            pn[i] = acc;
-            if (pdp) {
+            for (int m = 0; m + 1 < NU; m += 2) {
+                acc = fma(Zk[m + i * NU], gv[m], acc);
+                a1 = fma(Zk[m + 1 + i * NU], gv[m + 1], a1);
+            }
+            if constexpr (NU & 1) acc = fma(Zk[NU - 1 + i * NU], gv[NU - 1], acc);
+            pn[i] = acc + a1;
+        }
+        group_sync<T>();
+        if (pdp) {           // f = F+c + (F+B) d + f+
+            for (int i = tid; i < NX; i += T) {
                 double af = Ak[D::AR_FC + i] + fn[i];
 #pragma unroll
                 for (int m = 0; m < NU; ++m) af = fma(Ak[D::AR_FB + i + m * NX], dv[m], af);
                 fn[i] = af;
             }
+            group_sync<T>();
         }
-        group_sync<T>();
     }
     double* sm = p.sum + ((size_t)b * p.S + seg) * D::SREC;
     for (int i = tid; i < NX; i += T) {
@@ -1030,14 +1083,23 @@ __global__ void __launch_bounds__(T) seg_forward_kernel(SegParams p) {
         }
         mbar_wait(&bar[buf], (it >> 1) & 1);
         // u = K x + d (+ Gt uhat)
-        for (int i = tid; i < NU; i += T) {
-            double acc = Zk[NU * NX + i];
-#pragma unroll 4
-            for (int j = 0; j < NX; ++j) acc = fma(Zk[i + j * NU], xs[j], acc);
-            if (!is_last) {
-#pragma unroll 4
-                for (int j = 0; j < NX; ++j) acc = fma(Zk[NU * (NX + 1) + i + j * NU], uh[j], acc);
+        for (int i = tid; i < NU; i += T) {   // (independent accumulators: the rollout is a chain of dependent mat-vecs)
+            double acc = Zk[NU * NX + i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int j = 0; j + 1 < NX; j += 2) {
+                acc = fma(Zk[i + j * NU], xs[j], acc);
+                a1 = fma(Zk[i + (j + 1) * NU], xs[j + 1], a1);
             }
+            if constexpr (NX & 1) acc = fma(Zk[i + (NX - 1) * NU], xs[NX - 1], acc);
+            if (!is_last) {
+#pragma unroll
+                for (int j = 0; j + 1 < NX; j += 2) {
+                    a2 = fma(Zk[NU * (NX + 1) + i + j * NU], uh[j], a2);
+                    a3 = fma(Zk[NU * (NX + 1) + i + (j + 1) * NU], uh[j + 1], a3);
+                }
+                if constexpr (NX & 1) a2 = fma(Zk[NU * (NX + 1) + i + (NX - 1) * NU], uh[NX - 1], a2);
+            }
+            acc = (acc + a1) + (a2 + a3);
             us[i] = acc;
             ws_b[(size_t)k * S + i] = acc;
         }
@@ -1049,12 +1111,20 @@ __global__ void __launch_bounds__(T) seg_forward_kernel(SegParams p) {
         for (int r = 0; r < (NX + T - 1) / T; ++r) {
             const int i = tid + r * T;
             if (i < NX) {
-                double acc = R[D::REC_C + D::er(i)];
+                double acc = R[D::REC_C + D::er(i)], a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-                for (int j = 0; j < NU; ++j) acc = fma(R[D::er(i) + D::wi(j) * NX], us[j], acc);
-#pragma unroll 4
-                for (int j = 0; j < NX; ++j) acc = fma(R[D::er(i) + D::wi(NU + j) * NX], xs[j], acc);
-                xn[r] = acc;
+                for (int j = 0; j + 1 < NU; j += 2) {
+                    acc = fma(R[D::er(i) + D::wi(j) * NX], us[j], acc);
+                    a1 = fma(R[D::er(i) + D::wi(j + 1) * NX], us[j + 1], a1);
+                }
+                if constexpr (NU & 1) acc = fma(R[D::er(i) + D::wi(NU - 1) * NX], us[NU - 1], acc);
+#pragma unroll
+                for (int j = 0; j + 1 < NX; j += 2) {
+                    a2 = fma(R[D::er(i) + D::wi(NU + j) * NX], xs[j], a2);
+                    a3 = fma(R[D::er(i) + D::wi(NU + j + 1) * NX], xs[j + 1], a3);
+                }
+                if constexpr (NX & 1) a2 = fma(R[D::er(i) + D::wi(NU + NX - 1) * NX], xs[NX - 1], a2);
+                xn[r] = (acc + a1) + (a2 + a3);
             }
         }
         group_sync<T>();

@@ -350,7 +350,7 @@ int affine_impl(Solver& h) {
     SegParams p = seg_params(h);
     constexpr int TA = (NX + NU >= 32) ? 128 : 32;   // the sweep is latency-bound: more warps per SM for big stages
     auto kern = seg_affine_kernel<NX, NU, TA>;
-    const size_t bytes = AffSmem<NX, NU>::bytes(h.ncmax, h.sel_mode);
+    const size_t bytes = AffSmem<NX, NU>::bytes(h.ncmax, h.sel_mode, p.S == 1 && !p.interior);
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
     kern<<<h.batch * h.S, TA, bytes, h.stream>>>(p);

@@ -509,3 +509,17 @@ def test_sharded_c_abi_matches_oracle(oracle, G, nc):
     else:
         ref = o.solve(ws_in=wprev[0], sigma=1e-4)
     assert rel_err(out[0], ref) < TOL
+
+
+@pytest.mark.gpu
+def test_wave_size_is_whole_sms_and_default_segmentation_uses_it():
+    """pdplqr_wave_size: (problem, segment) groups resident at once in the throughput-mode stage sweep = SMs x CTAs per SM of
+    the kernel that would run; num_segments = 0 on a long horizon picks whole waves."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for nx, nu in [(12, 4), (30, 10), (6, 3)]:
+        w = P.wave_size(nx, nu)
+        assert w > 0 and w % sms == 0, (nx, nu, w)
+    p = P.problems.quadrotor_ltv(1 << 16)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=0, load_balancing=2)
+    assert sol.num_segments % P.wave_size(12, 4) == 0 or sol.num_segments < P.wave_size(12, 4)
