@@ -96,9 +96,32 @@ constexpr int ADMM_WARPS = 8;   // warps per CTA of admm_update_kernel; 8 CTAs p
 // does the work, decided on the device from the loop state, so the iteration can sit in a CUDA graph unchanged.  Kept
 // separate (not a template flag on one body): with the residual code in the same kernel the hot loop went from 1.3 to
 // 2.5 ms per iteration at C4.
+#ifndef PDPLQR_ADMM_HOIST
+#define PDPLQR_ADMM_HOIST 0      // 1: the first 32 rows' loads issued together with w~ (measured: 338 vs 308 ms per C4 solve at 8
+#endif                           // CTAs per SM, 326 / 310 ms at 6 / 4 -- the extra live registers spill or cost residency)
 #ifndef PDPLQR_ADMM_MINB
 #define PDPLQR_ADMM_MINB 8
 #endif
+// ORDINARY iterations, part 1: relaxation w = alpha w~ + (1 - alpha) w.  No per-stage structure: a flat coalesced pass of its
+// own (inside the per-stage kernel it cost that kernel its registers; the rows below need w~ only).
+__global__ void __launch_bounds__(256) admm_relax_kernel(AdmmParams p) {
+    if (admm_is_check(p.ctl)) return;
+    const double alpha = p.alpha, oma = 1.0 - p.alpha;
+    const long long nw = (long long)p.batch * ((long long)p.N * (p.nx + p.nu) + p.nx);
+    const long long tstride = (long long)gridDim.x * blockDim.x;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; idx + 3 * tstride < nw; idx += 4 * tstride) {
+        const double a0 = p.w_tilde[idx], a1 = p.w_tilde[idx + tstride], a2 = p.w_tilde[idx + 2 * tstride],
+                     a3 = p.w_tilde[idx + 3 * tstride];
+        const double w0 = p.w[idx], w1 = p.w[idx + tstride], w2 = p.w[idx + 2 * tstride], w3 = p.w[idx + 3 * tstride];
+        p.w[idx] = alpha * a0 + oma * w0;
+        p.w[idx + tstride] = alpha * a1 + oma * w1;
+        p.w[idx + 2 * tstride] = alpha * a2 + oma * w2;
+        p.w[idx + 3 * tstride] = alpha * a3 + oma * w3;
+    }
+    for (; idx < nw; idx += tstride) p.w[idx] = alpha * p.w_tilde[idx] + oma * p.w[idx];
+}
+
 __global__ void __launch_bounds__(ADMM_WARPS * 32, PDPLQR_ADMM_MINB) admm_update_kernel(AdmmParams p) {
     if (admm_is_check(p.ctl)) return;
     // ncu (profiles/r2_ncu_c4_kernels.txt): this kernel is ISSUE-bound (70 % of the issue slots at 64 resident warps per SM,
@@ -133,35 +156,45 @@ __global__ void __launch_bounds__(ADMM_WARPS * 32, PDPLQR_ADMM_MINB) admm_update
         const int c0 = p.cone_first[k], c1 = p.cone_first[k + 1];
         k += dk; b += db;              // (problem, stage) of the next item
         if (k >= N1) { k -= N1; ++b; }
-        __syncwarp();                  // the previous item's readers of the scratch are done
-        for (int i = lane; i < dim; i += 32) {
-            const double a = p.w_tilde[wo + i];
-            wt[i] = a;
-            p.w[wo + i] = alpha * a + oma * p.w[wo + i];
-        }
-        if (nc == 0) continue;
-        __syncwarp();
+        if (nc == 0) continue;         // (the relaxation of w is the flat pass above)
+        struct Row { int cj, box; double sv, zold, yold, rr, lb, ub; };
+        auto load_row = [&](int r, Row& q) {
+            q.cj = sel ? p.sel_col[co + r] : -1;
+            q.sv = sel ? p.sel_val[co + r] : 0.0;
+            q.zold = p.z[co + r]; q.yold = p.y[co + r]; q.rr = p.rho[co + r];
+            q.box = p.row_box[cok + r];
+            q.lb = p.e_lb[co + r]; q.ub = p.e_ub[co + r];
+        };
         auto finish = [&](int r, double zh, double znew, double yold, double rr) {
             p.z[co + r] = znew;
             p.y[co + r] = yold + rr * (zh - znew);
         };
-        for (int r = lane; r < nc; r += 32) {
+        auto do_row = [&](int r, const Row& q) {
             double acc = 0.0;
             if (sel) {
-                const int cj = p.sel_col[co + r];
-                if (cj >= 0) acc = p.sel_val[co + r] * wt[cj];
+                if (q.cj >= 0) acc = q.sv * wt[q.cj];
             } else {
                 for (int j = 0; j < dim; ++j) acc = fma(Dk[r + (size_t)j * nc], wt[j], acc);
             }
-            const double zold = p.z[co + r], yold = p.y[co + r], rr = p.rho[co + r];
-            const double zh = alpha * acc + oma * zold;
-            const double vv = fma(yold, rcp_newton(rr), zh);
-            if (p.row_box[cok + r]) {
-                finish(r, zh, fmin(fmax(vv, p.e_lb[co + r]), p.e_ub[co + r]), yold, rr);
+            const double zh = alpha * acc + oma * q.zold;
+            const double vv = fma(q.yold, rcp_newton(q.rr), zh);
+            if (q.box) {
+                finish(r, zh, fmin(fmax(vv, q.lb), q.ub), q.yold, q.rr);
             } else {
                 v[r] = vv;
                 zt[r] = zh;
             }
+        };
+        Row q0;
+        if (PDPLQR_ADMM_HOIST && lane < nc) load_row(lane, q0);   // in flight together with w~ (one round trip for the first 32 rows)
+        __syncwarp();                  // the previous item's readers of the scratch are done
+        for (int i = lane; i < dim; i += 32) wt[i] = p.w_tilde[wo + i];
+        __syncwarp();
+        if (PDPLQR_ADMM_HOIST && lane < nc) do_row(lane, q0);
+        for (int r = lane + (PDPLQR_ADMM_HOIST ? 32 : 0); r < nc; r += 32) {
+            Row q;
+            load_row(r, q);
+            do_row(r, q);
         }
         auto project_serial = [&](int r0, int d, int type) {     // one lane, whole cone (second-order cone or ball)
             if (type == CONE_SOC) {

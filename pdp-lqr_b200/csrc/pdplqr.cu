@@ -1311,9 +1311,10 @@ int admm_iteration(Solver& h, const AdmmRun& r, bool factorize, cudaGraphConditi
     rc = set_smem(h, admm_update_res_kernel, smem_res);
     if (rc) return rc;
     // both kernels are enqueued; the one whose turn it is not returns at once (decided on the device)
+    admm_relax_kernel<<<148 * 8, 256, 0, h.stream>>>(ap);
     admm_update_kernel<<<ctas, ADMM_WARPS * 32, smem, h.stream>>>(ap);
     admm_update_res_kernel<<<ctas, ADMM_WARPS * 32, smem_res, h.stream>>>(ap);
-    h.launches += 2;
+    h.launches += 3;
     CU_TRY(&h, cudaGetLastError());
     admm_ctl_kernel<<<1, 1, 0, h.stream>>>(static_cast<AdmmCtl*>(h.d_ctl), handle, use_handle);
     h.launches++;
