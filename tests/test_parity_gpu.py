@@ -236,7 +236,8 @@ def test_c1_with_box_constraints_enabled(oracle):
         assert rel_err(ws[0], ref) < TOL
 
 
-@pytest.mark.parametrize("nx,nu,nc,S", [(6, 3, 5, 1), (6, 3, 5, 4), (12, 4, 8, 3), (12, 4, 0, 5), (4, 1, 0, 1), (30, 10, 12, 2)])
+@pytest.mark.parametrize("nx,nu,nc,S", [(6, 3, 5, 1), (6, 3, 5, 4), (12, 4, 8, 3), (12, 4, 0, 5), (4, 1, 0, 1), (30, 10, 12, 2),
+                                        (30, 10, 12, 1), (30, 10, 0, 3), (16, 4, 6, 1)])
 def test_backward_without_factorization(oracle, nx, nu, nc, S):
     """Affine-only re-solve with cached factors (lqr_kernel.hpp:149-178, lqr_solver_parallel.hpp:148-154, :190-211):
     same protocol on the oracle and on the GPU; also against a fresh factorising solve of the second iterate."""
