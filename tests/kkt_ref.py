@@ -1,6 +1,8 @@
-"""Independent numpy/scipy check: assemble the equality-constrained LQ KKT system (rho_dyn = 0, i.e. the exact
-system -- NOT QDLDLSolver's perturbed one, qdldl_solver.hpp:40) and solve it with a sparse LU.
-Variable order [w_0 .. w_{N-1}, x_N | lambda_1 .. lambda_N]; x_0 is eliminated by fixing it in w_0."""
+"""Independent numpy/scipy check: assemble the equality-constrained LQ KKT system and solve it with a sparse LU.
+rho_dyn = 0 (default) is the exact system; rho_dyn = 1e-6 reproduces the semantics of the reference's QDLDLSolver, which
+puts -rho_dyn I on the diagonal of the dynamics rows (kkt.hpp:196-203, qdldl_solver.hpp:40-42) -- the baseline the reference's
+example prints next to the Riccati solvers (lqr_example.cpp:173-190), about 2e-5 away from the exact solution on config 1.
+Variable order [w_0 .. w_{N-1}, x_N | lambda_1 .. lambda_N]; x_0 is fixed by its own (unperturbed) rows."""
 import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
@@ -30,7 +32,7 @@ def augmented_cost(prob, b, ws_prev, sigma, ys=None, zs=None, rho=None, inv_rho=
 
 
 def kkt_solve(prob, b=0, ws_prev=None, sigma=1e-6, ys=None, zs=None, rho=None, inv_rho=None, x0=None,
-              return_costates=False):
+              return_costates=False, rho_dyn=0.0):
     nx, nu, N, s = prob.nx, prob.nu, prob.N, prob.s
     ws_prev = np.zeros(prob.ws_len) if ws_prev is None else ws_prev
     x0 = prob.x0[b] if x0 is None else x0
@@ -54,7 +56,10 @@ def kkt_solve(prob, b=0, ws_prev=None, sigma=1e-6, ys=None, zs=None, rho=None, i
     rhs_c[N * nx:] = x0
     Cm = sp.csc_matrix((vals, (rows, cols)), shape=(N * nx + nx, nw))
     Hb = sp.block_diag([sp.csc_matrix(Hk) for Hk in Hs], format="csc")
-    K = sp.bmat([[Hb, Cm.T], [Cm, None]], format="csc")
+    reg = None
+    if rho_dyn != 0.0:   # QDLDLSolver semantics: -rho_dyn on the dynamics rows only (x_0 is eliminated exactly there)
+        reg = sp.diags(np.concatenate([np.full(N * nx, -rho_dyn), np.zeros(nx)]), format="csc")
+    K = sp.bmat([[Hb, Cm.T], [Cm, reg]], format="csc")
     rhs = np.concatenate([-np.concatenate(hs), rhs_c])
     lu = spla.splu(K)
     sol = lu.solve(rhs)

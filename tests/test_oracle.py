@@ -28,6 +28,25 @@ def test_c1_golden_and_survey_probe(oracle):
     assert abs(xN[2] - 0.9999999) < 1e-9 and np.max(np.abs(np.delete(xN, 2))) < 1e-13
 
 
+def test_c1_qdldl_semantics_printout(oracle, capsys):
+    """SURVEY.md section 8 (f3), optional part: the reference's example prints its QDLDL baseline next to the Riccati solvers
+    (lqr_example.cpp:173-190).  QDLDLSolver regularises the dynamics rows with rho_dyn = 1e-6 (qdldl_solver.hpp:40-42,
+    kkt.hpp:196-203), so its solution is NOT the exact one: reproduce that system and print the like-for-like comparison
+    (the survey's probe: 1.9e-5 between the two on config 1; exact vs the Riccati solvers: 2e-15)."""
+    p = P.problems.quadrotor_example()
+    ws = oracle.OracleSolver(p).solve()
+    exact = kkt_solve(p, rho_dyn=0.0)
+    qdldl = kkt_solve(p, rho_dyn=1e-6)
+    e_exact, e_qdldl = rel_err(ws, exact), rel_err(ws, qdldl)
+    with capsys.disabled():
+        print("\nconfig 1 (lqr_example.cpp): Riccati vs exact KKT (rho_dyn = 0): %.2e | vs QDLDLSolver semantics "
+              "(rho_dyn = 1e-6): %.2e" % (e_exact, e_qdldl))
+        for k in range(5):   # the five controls the example prints (lqr_example.cpp:206-209)
+            print("  u_%d  riccati % .12f   qdldl-semantics % .12f" % (k, ws[k * 16], qdldl[k * 16]))
+    assert e_exact < 1e-12
+    assert 1e-6 < e_qdldl < 1e-4
+
+
 @pytest.mark.parametrize("S", [2, 4, 8])
 @pytest.mark.parametrize("ctype", [0, 1])
 @pytest.mark.parametrize("lb", [True, False])
