@@ -213,6 +213,15 @@ int pdplqr_record_doubles(pdplqr_handle_t h, int* model_rec, int* factor_rec);
  * stage kernel for this (nx, nu), from the CUDA occupancy calculator): a segment count that is a whole multiple of it
  * avoids a trailing partial wave.  num_segments = 0 in pdplqr_create uses it. */
 int pdplqr_wave_size(int nx, int nu, int device);
+/* Debug aid (addition; the memcheck substitute where compute-sanitizer is not available).  With PDPLQR_DEBUG_GUARDS=1 in the
+ * environment at pdplqr_create, every device allocation of the handle is pre-filled with 0xFF bytes (a double read before the
+ * library wrote it is a NaN and surfaces in the results) and placed between two 4 KiB guard bands; this call synchronises
+ * the handle's stream and counts guard bytes that were overwritten (out-of-bounds device writes) into *corrupted_bytes
+ * (0 = clean, -1 = the handle was created without guards).
+ * Self-test: called with *corrupted_bytes == PDPLQR_GUARD_SELF_TEST the library first writes 3 bytes just past its first
+ * allocation, so the call must report 3 (the handle should be destroyed afterwards). */
+#define PDPLQR_GUARD_SELF_TEST (-12345LL)
+int pdplqr_debug_check_guards(pdplqr_handle_t h, long long* corrupted_bytes);
 int pdplqr_version(void);
 
 #ifdef __cplusplus

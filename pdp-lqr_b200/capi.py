@@ -62,6 +62,7 @@ SIGNATURES = {
     "pdplqr_last_status": (C.c_int, [C.c_void_p, _ip]),
     "pdplqr_last_error": (C.c_char_p, [C.c_void_p]),
     "pdplqr_launch_count": (C.c_longlong, [C.c_void_p]),
+    "pdplqr_debug_check_guards": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong)]),
     "pdplqr_record_doubles": (C.c_int, [C.c_void_p, _ip, _ip]),
     "pdplqr_wave_size": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "pdplqr_version": (C.c_int, []),

@@ -63,6 +63,14 @@ template <int N>
 PDPLQR_DEVINL void bulk_wait() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be
+// scheduled while its predecessor in the stream (or graph) is still running; pdl_wait() returns when the predecessor grid
+// has COMPLETED and its memory operations are visible -- placed before the first global access, the kernel is as safe as
+// an ordinary launch and only its launch latency / CTA scheduling overlaps the predecessor's tail.  pdl_trigger() lets the
+// NEXT kernel of the chain be scheduled from this point on.  Both are no-ops in a kernel launched without the attribute.
+PDPLQR_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+PDPLQR_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // order generic-proxy smem accesses before subsequent async-proxy (TMA) accesses of the same locations
 PDPLQR_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

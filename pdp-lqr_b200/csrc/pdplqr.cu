@@ -213,7 +213,20 @@ __global__ void detect_selection_kernel(const double* __restrict__ D, const long
 template <class Tp>
 int dev_alloc(Solver& h, Tp** p, size_t count) {
     void* q = nullptr;
-    CU_TRY(&h, cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(Tp)));
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(Tp);
+    if (h.guards) {   // [guard | payload (0xFF) | guard], see Solver::guards
+        constexpr size_t G = Solver::GUARD_BYTES;
+        CU_TRY(&h, cudaMalloc(&q, bytes + 2 * G));
+        h.owned.push_back(q);
+        char* base = static_cast<char*>(q);
+        CU_TRY(&h, cudaMemset(base, 0xA5, G));
+        CU_TRY(&h, cudaMemset(base + G, 0xFF, bytes));
+        CU_TRY(&h, cudaMemset(base + G + bytes, 0xA5, G));
+        h.guarded.push_back({base, bytes});
+        *p = reinterpret_cast<Tp*>(base + G);
+        return PDPLQR_OK;
+    }
+    CU_TRY(&h, cudaMalloc(&q, bytes));
     h.owned.push_back(q);
     *p = static_cast<Tp*>(q);
     return PDPLQR_OK;
@@ -552,6 +565,7 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     h->thread_path = (S == 1) && ops->has_thread_path && h->nc_total == 0;   // (interior shards switch it off)
     h->frec = h->thread_path ? ops->FRECT : ops->FREC;
     h->mrec = h->thread_path ? ops->TREC : ops->REC;
+    if (const char* e = getenv("PDPLQR_DEBUG_GUARDS")) h->guards = atoi(e) != 0;
     if (const char* e = getenv("PDPLQR_BWD_VARIANT")) h->bwd_variant = atoi(e);
     if (const char* e = getenv("PDPLQR_FWD_VARIANT")) h->fwd_variant = atoi(e);
     if (const char* e = getenv("PDPLQR_LAT_THREADS")) h->lat_threads = atoi(e);
@@ -565,6 +579,8 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (const char* e = getenv("PDPLQR_SOLVE_GRAPH")) h->solve_use_graph = atoi(e);
     if (const char* e = getenv("PDPLQR_SPARSE_D")) h->allow_sel = atoi(e);
     if (const char* e = getenv("PDPLQR_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(1, std::min(64, atoi(e)));
+    h->use_pdl = ((long long)batch * S <= 2 * 148) ? 1 : 0;   // latency regime: a solve is a chain of short dependent kernels
+    if (const char* e = getenv("PDPLQR_PDL")) h->use_pdl = atoi(e) != 0;
 
     auto bail = [&](int rc) {   // keep the error text: the handle does not survive
         g_create_error = h->err.empty() ? std::string("pdplqr_create: ") + cudaGetErrorString(cudaGetLastError()) : h->err;
@@ -1188,6 +1204,27 @@ int pdplqr_last_status(pdplqr_handle_t h, int* status) {
 // h == NULL: the reason the last pdplqr_create / pdplqr_coupler_create on this thread failed
 const char* pdplqr_last_error(pdplqr_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 long long pdplqr_launch_count(pdplqr_handle_t h) { return h ? h->launches : 0; }
+int pdplqr_debug_check_guards(pdplqr_handle_t h, long long* corrupted_bytes) {
+    if (!h || !corrupted_bytes) return PDPLQR_ERR_INVALID;
+    const bool self_test = (*corrupted_bytes == PDPLQR_GUARD_SELF_TEST);
+    *corrupted_bytes = -1;
+    if (!h->guards) return PDPLQR_OK;
+    if (self_test && !h->guarded.empty())   // prove the detector: 3 bytes written just past the first allocation
+        CU_TRY(h, cudaMemset(h->guarded[0].base + Solver::GUARD_BYTES + h->guarded[0].bytes, 0, 3));
+    cudaSetDevice(h->device);
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaDeviceSynchronize());   // the copy streams of the pipelined host solve as well
+    constexpr size_t G = Solver::GUARD_BYTES;
+    std::vector<unsigned char> host(2 * G);
+    long long bad = 0;
+    for (const Solver::GuardedAlloc& a : h->guarded) {
+        CU_TRY(h, cudaMemcpy(host.data(), a.base, G, cudaMemcpyDeviceToHost));
+        CU_TRY(h, cudaMemcpy(host.data() + G, a.base + G + a.bytes, G, cudaMemcpyDeviceToHost));
+        for (unsigned char v : host) bad += (v != 0xA5);
+    }
+    *corrupted_bytes = bad;
+    return PDPLQR_OK;
+}
 int pdplqr_record_doubles(pdplqr_handle_t h, int* model_rec, int* factor_rec) {
     if (!h) return PDPLQR_ERR_INVALID;
     if (model_rec) *model_rec = h->mrec;
@@ -1402,6 +1439,8 @@ int pdplqr_admm_solve_device(pdplqr_handle_t h, const double* x0, double* w, dou
     if (!h->model_set) return fail(h, PDPLQR_ERR_ORDER, "admm_solve before set_model");
     cudaSetDevice(h->device);
     if (check_every < 1) check_every = 1;
+    // the iterations live inside a WHILE conditional node: plain kernel dependencies there (no programmatic edges)
+    struct PdlOff { Solver* s; int saved; PdlOff(Solver* q) : s(q), saved(q->use_pdl) { q->use_pdl = 0; } ~PdlOff() { s->use_pdl = saved; } } pdl_off(h);
     const size_t nb = (size_t)h->batch * h->nc_total * 8;
     // rho and 1/rho are copied: the adaptation rescales the library's copies, the caller's arrays stay as given
     CU_TRY(h, cudaMemcpyAsync(h->d_rho_work, rho, nb, cudaMemcpyDeviceToDevice, h->stream));

@@ -199,6 +199,8 @@ __global__ void __launch_bounds__(T) seg_backward_kernel(SegParams p) {
     using L = BwdSmem<NX, NU>;
     constexpr int S = D::S;
     extern __shared__ __align__(16) double smem[];
+    pdl_wait();      // the predecessor kernel of the solve chain has completed (no-op without the launch attribute)
+    pdl_trigger();   // the next kernel of the chain may be scheduled from here on
     const int tid = threadIdx.x;
     const int g = blockIdx.x;
     const int b = g / p.S, seg = g % p.S;
@@ -1034,6 +1036,8 @@ __global__ void __launch_bounds__(T) seg_forward_kernel(SegParams p) {
     using L = FwdSmem<NX, NU>;
     constexpr int S = D::S;
     extern __shared__ __align__(16) double smem[];
+    pdl_wait();      // the predecessor kernel of the solve chain has completed (no-op without the launch attribute)
+    pdl_trigger();   // the next kernel of the chain may be scheduled from here on
     const int tid = threadIdx.x;
     const int g = blockIdx.x;
     const int b = g / p.S, seg = g % p.S;

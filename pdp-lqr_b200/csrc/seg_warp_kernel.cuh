@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(32, PDPLQR_WARP_MINB) seg_backward_warp_kernel
     constexpr bool AFX = (S % 8 == 0);
     constexpr int TT = AFX ? ST : S1T;      // tiles over the record columns that ride on the tensor pipe
     extern __shared__ __align__(16) double smem[];
+    pdl_wait();      // the predecessor kernel of the solve chain has completed (no-op without the launch attribute)
+    pdl_trigger();   // the next kernel of the chain may be scheduled from here on
     const int lane = threadIdx.x, r = lane >> 2, q = lane & 3;
     const int g = blockIdx.x;
     const int b = g / p.S, seg = g % p.S;

@@ -57,6 +57,8 @@ struct pdplqr_solver {
     int lat_threads = 128;     // 0 disables the 128-thread latency mode of the segment backward kernel
     int seg_t = 0;             // PDPLQR_SEG_T: threads per (problem, segment) in throughput mode (0 = default 32)
     int warp_kernel = 1;       // PDPLQR_WARP_KERNEL: register-resident warp kernel (0 off, 1 throughput mode, 2 always)
+    int use_pdl = 0;           // programmatic dependent launch of the solve chain (launch_chain); set at create: on in the
+                               // latency regime (batch * segments <= 2 x 148), PDPLQR_PDL = 0 / 1 overrides
     int tree_lat = 1;          // latency-mode tree kernels when a level has few groups (PDPLQR_TREE_LAT=0 disables)
     int tree_lat_max = 296;    // ... "few" = at most this many CTAs (PDPLQR_TREE_LAT_MAX)
     int lat_width = 0, lat_tt_cap = 0;   // PDPLQR_TREE_LAT_WIDTH / PDPLQR_TREE_LAT_TT: tuning overrides (0 = default)
@@ -123,6 +125,14 @@ struct pdplqr_solver {
     bool have_root = false;
     std::vector<TreeLevel> levels;
     std::vector<void*> owned;  // everything to cudaFree
+    // PDPLQR_DEBUG_GUARDS=1 (read at create): every device allocation of the handle is filled with 0xFF bytes (NaN as a
+    // double, -1 as an int: a read of memory the library never wrote shows up in the results) and sits between two
+    // GUARD_BYTES bands of 0xA5 that pdplqr_debug_check_guards inspects (out-of-bounds writes).  compute-sanitizer is closed
+    // on the pool this was developed on; the parity suite run in this mode is the memcheck substitute.
+    bool guards = false;
+    static constexpr size_t GUARD_BYTES = 4096;
+    struct GuardedAlloc { char* base; size_t bytes; };
+    std::vector<GuardedAlloc> guarded;
     // per-iteration state
     const double* cur_ws = nullptr;  // device pointer used by the next backward (nullptr == zeros)
     double sigma = 0.0;
@@ -170,6 +180,29 @@ template <class K>
 int set_smem(Solver& h, K kernel, size_t bytes) {
     if (bytes > 48 * 1024) CU_TRY(&h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return PDPLQR_OK;
+}
+
+// Launch of a solve-chain kernel whose body starts with pdl_wait() (common.cuh).  In the latency regime (h.use_pdl: few
+// (problem, segment) groups, a solve is a chain of 5 - 10 short dependent kernels) the launch carries the programmatic
+// stream serialization attribute, so that the kernel is scheduled while its predecessor drains; stream capture turns the
+// attribute into a programmatic edge of the solve graph.
+template <class K, class Prm>
+inline void launch_chain(Solver& h, K kern, int grid, int block, size_t smem, const Prm& prm) {
+    if (!h.use_pdl) {
+        kern<<<grid, block, smem, h.stream>>>(prm);
+        return;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, prm);   // the caller checks cudaGetLastError() as after a <<< >>> launch
 }
 
 inline SegParams seg_params(Solver& h) {
@@ -231,7 +264,7 @@ int launch_seg_bwd(Solver& h, const SegParams& p, size_t bytes) {
     auto kern = seg_backward_kernel<NX, NU, TT, CON>;
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
-    kern<<<h.batch * h.S, TT, bytes, h.stream>>>(p);
+    launch_chain(h, kern, h.batch * h.S, TT, bytes, p);
     return PDPLQR_OK;
 }
 
@@ -260,7 +293,7 @@ int backward_impl(Solver& h) {
             constexpr size_t wbytes = WarpSmem<NX, NU>::BYTES;
             int rc = set_smem(h, kern, wbytes);
             if (rc) return rc;
-            kern<<<h.batch * h.S, 32, wbytes, h.stream>>>(p);
+            launch_chain(h, kern, h.batch * h.S, 32, wbytes, p);
             h.launches++;
             CU_TRY(&h, cudaGetLastError());
             return PDPLQR_OK;
@@ -319,7 +352,7 @@ int forward_impl(Solver& h, const double* d_x0, double* d_ws_out) {
     constexpr size_t bytes = FwdSmem<NX, NU>::BYTES;
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
-    kern<<<h.batch * h.S, TF, bytes, h.stream>>>(p);
+    launch_chain(h, kern, h.batch * h.S, TF, bytes, p);
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -396,7 +429,7 @@ int tree_sub_up_impl(Solver& h, const TreeTopParams& p) {
         auto kern = tree_sub_up_lat_kernel<NX>;
         int rc = set_smem(h, kern, LatSmem<NX>::TOP_BYTES);
         if (rc) return rc;
-        kern<<<p.batch * p.ngroups, LatSmem<NX>::TOP_THREADS, LatSmem<NX>::TOP_BYTES, h.stream>>>(p);
+        launch_chain(h, kern, p.batch * p.ngroups, LatSmem<NX>::TOP_THREADS, LatSmem<NX>::TOP_BYTES, p);
         h.launches++;
         CU_TRY(&h, cudaGetLastError());
         return PDPLQR_OK;
@@ -409,7 +442,7 @@ int tree_sub_down_impl(Solver& h, const TreeTopParams& p) {
         auto kern = tree_sub_down_lat_kernel<NX>;
         int rc = set_smem(h, kern, LatSmem<NX>::DOWN_BYTES);
         if (rc) return rc;
-        kern<<<p.batch * p.ngroups, LatSmem<NX>::TOP_THREADS, LatSmem<NX>::DOWN_BYTES, h.stream>>>(p);
+        launch_chain(h, kern, p.batch * p.ngroups, LatSmem<NX>::TOP_THREADS, LatSmem<NX>::DOWN_BYTES, p);
         h.launches++;
         CU_TRY(&h, cudaGetLastError());
         return PDPLQR_OK;

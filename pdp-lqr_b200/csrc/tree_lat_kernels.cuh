@@ -299,6 +299,8 @@ __global__ void __launch_bounds__(LatSmem<NX>::TOP_THREADS) tree_sub_up_lat_kern
     constexpr int THREADS = L::TOP_THREADS;
     constexpr bool BULK_OUT = (D::SREC % 2 == 0);   // 16-byte granularity of cp.async.bulk
     extern __shared__ __align__(16) double smem[];
+    pdl_wait();      // the predecessor kernel of the solve chain has completed (no-op without the launch attribute)
+    pdl_trigger();   // the next kernel of the chain may be scheduled from here on
     const int tid = threadIdx.x;
     const int b = blockIdx.x / p.ngroups, g0 = blockIdx.x % p.ngroups;
 #pragma unroll 1
@@ -417,6 +419,8 @@ __global__ void __launch_bounds__(LatSmem<NX>::TOP_THREADS) tree_sub_down_lat_ke
     using D = TreeDims<NX>;
     using L = LatSmem<NX>;
     extern __shared__ __align__(16) double smem[];
+    pdl_wait();      // the predecessor kernel of the solve chain has completed (no-op without the launch attribute)
+    pdl_trigger();   // the next kernel of the chain may be scheduled from here on
     __shared__ __align__(8) uint64_t bar[TREE_TOP_MAX_LEVELS];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int b = blockIdx.x / p.ngroups, g0 = blockIdx.x % p.ngroups;

@@ -13,12 +13,18 @@ PyTorch is used only for device memory / streams in the *_device variants.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
 from . import capi
 
 LU, CHOLESKY = capi.CONDENSED_LU, capi.CONDENSED_CHOLESKY
+
+
+# filled by LQRCudaSolver.close() when PDPLQR_DEBUG_GUARDS=1 (tests/conftest.py asserts on it after every test)
+GUARD_STATS = {"enabled": os.environ.get("PDPLQR_DEBUG_GUARDS", "0") not in ("", "0"), "handles": 0, "corrupted_bytes": 0,
+               "unguarded": 0}
 
 
 class PdplqrError(RuntimeError):
@@ -83,8 +89,20 @@ class LQRCudaSolver:
     # ------------------------------------------------------------------ lifetime
     def close(self):
         if getattr(self, "_h", None):
+            if GUARD_STATS["enabled"]:   # PDPLQR_DEBUG_GUARDS=1: out-of-bounds device writes of this handle's lifetime
+                n = self.debug_check_guards()
+                GUARD_STATS["handles"] += 1
+                GUARD_STATS["corrupted_bytes"] += max(n, 0)
+                GUARD_STATS["unguarded"] += n < 0
             self._lib.pdplqr_destroy(self._h)
             self._h = None
+
+    def debug_check_guards(self) -> int:
+        """Guard bytes around this handle's device allocations that were overwritten (pdplqr_debug_check_guards):
+        0 = clean, -1 = created without PDPLQR_DEBUG_GUARDS=1."""
+        n = C.c_longlong()
+        self._check(self._lib.pdplqr_debug_check_guards(self._h, C.byref(n)))
+        return int(n.value)
 
     def __del__(self):
         try:
@@ -278,6 +296,12 @@ class Coupler:
 
     def close(self):
         if getattr(self, "_h", None):
+            if GUARD_STATS["enabled"]:
+                n = C.c_longlong()
+                self._lib.pdplqr_debug_check_guards(self._h, C.byref(n))
+                GUARD_STATS["handles"] += 1
+                GUARD_STATS["corrupted_bytes"] += max(int(n.value), 0)
+                GUARD_STATS["unguarded"] += n.value < 0
             self._lib.pdplqr_destroy(self._h)
             self._h = None
 

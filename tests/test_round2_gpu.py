@@ -523,3 +523,42 @@ def test_wave_size_is_whole_sms_and_default_segmentation_uses_it():
     p = P.problems.quadrotor_ltv(1 << 16)
     sol = P.LQRCudaSolver.from_problem(p, num_segments=0, load_balancing=2)
     assert sol.num_segments % P.wave_size(12, 4) == 0 or sol.num_segments < P.wave_size(12, 4)
+
+
+# ---------------------------------------------------------------------------------- memcheck substitute (guard bands)
+def test_debug_guard_bands_detect_and_stay_clean(oracle, monkeypatch):
+    """PDPLQR_DEBUG_GUARDS=1: allocations are NaN-filled and sit between guard bands.  A full protocol run (segments, tree,
+    constraints, no-refactor, costates) still matches the oracle (nothing reads memory the library did not write), leaves
+    every band intact, and the detector reports a deliberate 3-byte overrun (self-test).  The whole GPU suite is also run
+    once in this mode (profiles/r2_pytest_gpu_guards.log)."""
+    import ctypes as C
+    p = P.problems.random_lq(6, 3, 40, batch=3, seed=5, nc=5)
+    plain = P.LQRCudaSolver.from_problem(p, num_segments=4)
+    assert plain.debug_check_guards() == -1 or P.solver.GUARD_STATS["enabled"]
+    monkeypatch.setenv("PDPLQR_DEBUG_GUARDS", "1")
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=4)
+    sol.set_option(P.capi.OPT_AFFINE_CACHE, 1)
+    rng = np.random.default_rng(3)
+    nct = p.nc_total
+    rho = np.full((p.batch, nct), 0.5)
+    for it in range(2):
+        ws_prev = rng.standard_normal((p.batch, p.ws_len))
+        ys, zs = rng.standard_normal((p.batch, nct)), rng.standard_normal((p.batch, nct))
+        sol.update_problem_data(ws_prev, ys, zs, 1.0 / rho, sigma=1e-3)
+        if it == 0:
+            sol.backward(rho)
+        else:
+            sol.backward_without_factorization(rho)
+        out = sol.forward(p.x0, np.zeros((p.batch, p.ws_len)))
+        lam = sol.costates(out)
+        assert np.all(np.isfinite(out)) and np.all(np.isfinite(lam))
+        for b in range(p.batch):
+            ref = oracle.OracleSolver(p, b=b).solve(ws_in=ws_prev[b], sigma=1e-3, ys=ys[b], zs=zs[b], rho=rho[b],
+                                                    inv_rho=1.0 / rho[b])
+            assert rel_err(out[b], ref) < 1e-9
+    assert sol.debug_check_guards() == 0
+    n = C.c_longlong(-12345)
+    assert sol._lib.pdplqr_debug_check_guards(sol._h, C.byref(n)) == 0 and n.value == 3
+    if P.solver.GUARD_STATS["enabled"]:   # the suite-wide fixture would (rightly) flag the deliberate overrun
+        sol._lib.pdplqr_destroy(sol._h)
+        sol._h = None
