@@ -237,6 +237,7 @@ inline int ew_blocks(long long total) { return (int)std::max<long long>(1, std::
 
 // caller-layout trajectory -> kernel layout (or back): only used by padded handles
 int repack_ws(Solver& h, const double* src, double* dst, bool to_kernel) {
+    h.chain_tail = false;
     const long long total = (long long)h.batch * ((long long)h.N * (to_kernel ? h.s : h.su) + (to_kernel ? h.nx : h.nxu));
     if (to_kernel) repack_ws_kernel<<<ew_blocks(total), 256, 0, h.stream>>>(src, dst, h.batch, h.N, h.nxu, h.nuu, h.nx, h.nu);
     else repack_ws_kernel<<<ew_blocks(total), 256, 0, h.stream>>>(src, dst, h.batch, h.N, h.nx, h.nu, h.nxu, h.nuu);
@@ -247,6 +248,7 @@ int repack_ws(Solver& h, const double* src, double* dst, bool to_kernel) {
 // [items][n_src (x n_src)] -> [items][n_dst (x n_dst)]
 int repack_vec(Solver& h, const double* src, double* dst, long long items, int n_src, int n_dst, bool square = false,
                double fill = 0.0) {
+    h.chain_tail = false;
     const long long total = items * (square ? (long long)n_dst * n_dst : n_dst);
     repack_vec_kernel<<<ew_blocks(total), 256, 0, h.stream>>>(src, dst, items, n_src, n_dst, square ? 1 : 0, fill);
     h.launches++;
@@ -377,6 +379,7 @@ int run_tree_up(Solver& h, bool affine_only) {
 }
 
 int run_backward(Solver& h) {
+    if (!h.fused) h.chain_tail = false;   // work the caller enqueued since the last API call is unknown (launch_chain)
     if (!h.model_set) return fail(&h, PDPLQR_ERR_ORDER, "backward before set_model");
     if (!h.updated) return fail(&h, PDPLQR_ERR_ORDER, "backward before update_problem_data (lqr_solver_parallel.hpp:115)");
     int rc = h.ops->backward(h);
@@ -395,6 +398,7 @@ int run_backward(Solver& h) {
 // (thread-per-problem path, or PDPLQR_OPT_AFFINE_CACHE = 0) the full factorising sweep is run instead -- same
 // result, since only affine data may have changed between the two calls.
 int run_backward_nofact(Solver& h) {
+    if (!h.fused) h.chain_tail = false;   // work the caller enqueued since the last API call is unknown (launch_chain)
     if (!h.factorized)
         return fail(&h, PDPLQR_ERR_ORDER, "backward_without_factorization before any backward (lqr_solver_parallel.hpp:148)");
     if (!h.keep_affine || h.thread_path) return run_backward(h);
@@ -440,6 +444,7 @@ int run_tree_down(Solver& h, const double* d_x0, const double* d_lam0) {
 }
 
 int run_forward(Solver& h, const double* d_x0, double* d_ws_out) {
+    if (!h.fused) h.chain_tail = false;   // work the caller enqueued since the last API call is unknown (launch_chain)
     if (!h.backward_done) return fail(&h, PDPLQR_ERR_ORDER, "forward before backward (one forward per backward)");
     if (h.interior && !h.root_fresh)
         return fail(&h, PDPLQR_ERR_ORDER, "forward on an interior horizon shard needs a fresh pdplqr_set_root_boundary_device");
@@ -579,8 +584,12 @@ int pdplqr_create(pdplqr_handle_t* out, int nx, int nu, int N, const int* ncs, i
     if (const char* e = getenv("PDPLQR_SOLVE_GRAPH")) h->solve_use_graph = atoi(e);
     if (const char* e = getenv("PDPLQR_SPARSE_D")) h->allow_sel = atoi(e);
     if (const char* e = getenv("PDPLQR_PIPELINE_CHUNKS")) h->pipeline_chunks = std::max(1, std::min(64, atoi(e)));
-    h->use_pdl = ((long long)batch * S <= 2 * 148) ? 1 : 0;   // latency regime: a solve is a chain of short dependent kernels
+    // Programmatic dependent launch of the solve chain: OFF unless PDPLQR_PDL=1 (experimental, see launch_chain in
+    // solver_impl.cuh: one edge of the chain is not safe behind asynchronous H2D copies, and the graph-launched solve gains
+    // only 1.3 us from it).
+    h->use_pdl = 0;
     if (const char* e = getenv("PDPLQR_PDL")) h->use_pdl = atoi(e) != 0;
+    if (const char* e = getenv("PDPLQR_PDL_MASK")) h->pdl_mask = atoi(e);
 
     auto bail = [&](int rc) {   // keep the error text: the handle does not survive
         g_create_error = h->err.empty() ? std::string("pdplqr_create: ") + cudaGetErrorString(cudaGetLastError()) : h->err;
@@ -918,6 +927,7 @@ int pdplqr_coupler_solve_device(pdplqr_handle_t c, const double* summaries, cons
         if (rc) return rc;
         x0 = c->d_x0p;
     }
+    c->chain_tail = false;   // (the D2D copy above precedes the first tree kernel: ordinary launch, see launch_chain)
     rc = run_tree_up(*c, false);
     if (rc) return rc;
     rc = run_tree_down(*c, x0, nullptr);
@@ -1010,6 +1020,8 @@ int pdplqr_solve_device(pdplqr_handle_t h, const double* ws_in, const double* ys
     if (!h->model_set) return fail(h, PDPLQR_ERR_ORDER, "solve_device before set_model");
     cudaSetDevice(h->device);
     auto plain = [&]() {
+        // one chain from the stage sweep to the rollout: nothing the caller does can come between backward and forward here
+        struct Fused { Solver* s; Fused(Solver* q) : s(q) { q->fused = 1; q->chain_tail = false; } ~Fused() { s->fused = 0; s->chain_tail = false; } } fused(h);
         int rc = pdplqr_update_problem_data_device(h, ws_in, ys, zs, inv_rho, sigma);
         if (rc) return rc;
         rc = pdplqr_backward_device(h, rho);

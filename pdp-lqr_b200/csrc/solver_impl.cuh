@@ -57,6 +57,10 @@ struct pdplqr_solver {
     int lat_threads = 128;     // 0 disables the 128-thread latency mode of the segment backward kernel
     int seg_t = 0;             // PDPLQR_SEG_T: threads per (problem, segment) in throughput mode (0 = default 32)
     int warp_kernel = 1;       // PDPLQR_WARP_KERNEL: register-resident warp kernel (0 off, 1 throughput mode, 2 always)
+    bool chain_tail = false;   // the last operation this library enqueued on the stream is a launch_chain kernel of the current call
+    int fused = 0;             // inside pdplqr_solve_device: backward and forward are one chain (no API boundary in between)
+    int pdl_mask = 0x1f;       // PDPLQR_PDL_MASK: launch sites that may carry the attribute (bit 0 stage sweep, 1 warp stage sweep,
+                               // 2 rollout, 3 tree up, 4 tree down)
     int use_pdl = 0;           // programmatic dependent launch of the solve chain (launch_chain); set at create: on in the
                                // latency regime (batch * segments <= 2 x 148), PDPLQR_PDL = 0 / 1 overrides
     int tree_lat = 1;          // latency-mode tree kernels when a level has few groups (PDPLQR_TREE_LAT=0 disables)
@@ -182,13 +186,25 @@ int set_smem(Solver& h, K kernel, size_t bytes) {
     return PDPLQR_OK;
 }
 
-// Launch of a solve-chain kernel whose body starts with pdl_wait() (common.cuh).  In the latency regime (h.use_pdl: few
-// (problem, segment) groups, a solve is a chain of 5 - 10 short dependent kernels) the launch carries the programmatic
-// stream serialization attribute, so that the kernel is scheduled while its predecessor drains; stream capture turns the
-// attribute into a programmatic edge of the solve graph.
+// Launch of a solve-chain kernel whose body starts with pdl_wait() (common.cuh).  EXPERIMENTAL, off by default (PDPLQR_PDL=1):
+// with h.use_pdl the launch carries the programmatic stream serialization attribute, so that the kernel is scheduled while
+// its predecessor drains; stream capture turns the attribute into a programmatic edge of the solve graph.
+// Measured on B200 (C2, N = 1024, S = 128; gpurun_out r14 / r15 / r16 of round 2, summarised in DESIGN.md section 9):
+//   graph-launched solve 93.5 -> 92.3 us (graph edges are already tight), protocol calls 104.7 -> 92.6 us.
+//   With the attribute on every chain launch, constrained handles with host buffers failed parity (rel. error 0.07 - 0.12, timing
+//   dependent: nx12/nu4/nc8/S3 in test_backward_without_factorization and test_horizon_shards_with_constraints).  A per-site
+//   mask (PDPLQR_PDL_MASK) pins it on ONE edge: stage sweep -> first tree launch (bit 3); rollout (bit 2) and tree-down
+//   (bit 4) edges pass.  The stage sweep there is queued behind the asynchronous H2D copies of ys / zs / rho / 1/rho, and the
+//   tree kernel, whose only dependency is the programmatic one, read summaries the sweep had not finished writing although it
+//   starts with griddepcontrol.wait.  Not root-caused within the GPU budget of the round, so the default stays the ordinary
+//   launch; the wait / trigger instructions in the kernels are no-ops then.
 template <class K, class Prm>
-inline void launch_chain(Solver& h, K kern, int grid, int block, size_t smem, const Prm& prm) {
-    if (!h.use_pdl) {
+inline void launch_chain(Solver& h, int site, K kern, int grid, int block, size_t smem, const Prm& prm) {
+    // Only behind another launch_chain kernel of the same API call: griddepcontrol.wait waits for prerequisite GRIDS only, and
+    // work the caller enqueued between two API calls is unknown -- every call starts its chain with an ordinary launch.
+    const bool pdl = h.use_pdl && h.chain_tail && ((h.pdl_mask >> site) & 1);
+    h.chain_tail = true;
+    if (!pdl) {
         kern<<<grid, block, smem, h.stream>>>(prm);
         return;
     }
@@ -242,6 +258,7 @@ int launch_batch_bwd(Solver& h, const SegParams& p) {
     if (rc) return rc;
     const int blocks = (p.batch + WARPS * 32 - 1) / (WARPS * 32);
     kern<<<blocks, WARPS * 32, bytes, h.stream>>>(p);
+    h.chain_tail = false;
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -254,6 +271,7 @@ int launch_batch_fwd(Solver& h, const SegParams& p) {
     if (rc) return rc;
     const int blocks = (p.batch + WARPS * 32 - 1) / (WARPS * 32);
     kern<<<blocks, WARPS * 32, bytes, h.stream>>>(p);
+    h.chain_tail = false;
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -264,7 +282,7 @@ int launch_seg_bwd(Solver& h, const SegParams& p, size_t bytes) {
     auto kern = seg_backward_kernel<NX, NU, TT, CON>;
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
-    launch_chain(h, kern, h.batch * h.S, TT, bytes, p);
+    launch_chain(h, 0, kern, h.batch * h.S, TT, bytes, p);
     return PDPLQR_OK;
 }
 
@@ -293,7 +311,7 @@ int backward_impl(Solver& h) {
             constexpr size_t wbytes = WarpSmem<NX, NU>::BYTES;
             int rc = set_smem(h, kern, wbytes);
             if (rc) return rc;
-            launch_chain(h, kern, h.batch * h.S, 32, wbytes, p);
+            launch_chain(h, 1, kern, h.batch * h.S, 32, wbytes, p);
             h.launches++;
             CU_TRY(&h, cudaGetLastError());
             return PDPLQR_OK;
@@ -352,7 +370,7 @@ int forward_impl(Solver& h, const double* d_x0, double* d_ws_out) {
     constexpr size_t bytes = FwdSmem<NX, NU>::BYTES;
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
-    launch_chain(h, kern, h.batch * h.S, TF, bytes, p);
+    launch_chain(h, 2, kern, h.batch * h.S, TF, bytes, p);
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -365,6 +383,7 @@ int tree_up_impl(Solver& h, const TreeParams& p) {
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
     kern<<<p.batch * p.groups, 32, bytes, h.stream>>>(p);
+    h.chain_tail = false;
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -373,6 +392,7 @@ template <int NX>
 int tree_down_impl(Solver& h, const TreeParams& p) {
     auto kern = tree_down_kernel<NX>;
     kern<<<p.batch * p.groups, 32, 4 * NX * sizeof(double), h.stream>>>(p);
+    h.chain_tail = false;
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -387,6 +407,7 @@ int affine_impl(Solver& h) {
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
     kern<<<h.batch * h.S, TA, bytes, h.stream>>>(p);
+    h.chain_tail = false;
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -396,6 +417,7 @@ int tree_up_affine_impl(Solver& h, const TreeParams& p) {
     static_assert(NX <= 32, "tree_up_affine_kernel keeps one row per lane");
     auto kern = tree_up_affine_kernel<NX>;
     kern<<<p.batch * p.groups, 32, 5 * NX * sizeof(double), h.stream>>>(p);
+    h.chain_tail = false;
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -409,6 +431,7 @@ int tree_top_up_impl(Solver& h, const TreeTopParams& p) {
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
     kern<<<p.batch, WARPS * 32, bytes, h.stream>>>(p);
+    h.chain_tail = false;
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -417,6 +440,7 @@ template <int NX>
 int tree_top_down_impl(Solver& h, const TreeTopParams& p) {
     auto kern = tree_top_down_kernel<NX>;
     kern<<<p.batch, TreeTopSmem<NX>::WARPS * 32, TreeTopSmem<NX>::WARPS * 4 * NX * sizeof(double), h.stream>>>(p);
+    h.chain_tail = false;
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;
@@ -429,7 +453,7 @@ int tree_sub_up_impl(Solver& h, const TreeTopParams& p) {
         auto kern = tree_sub_up_lat_kernel<NX>;
         int rc = set_smem(h, kern, LatSmem<NX>::TOP_BYTES);
         if (rc) return rc;
-        launch_chain(h, kern, p.batch * p.ngroups, LatSmem<NX>::TOP_THREADS, LatSmem<NX>::TOP_BYTES, p);
+        launch_chain(h, 3, kern, p.batch * p.ngroups, LatSmem<NX>::TOP_THREADS, LatSmem<NX>::TOP_BYTES, p);
         h.launches++;
         CU_TRY(&h, cudaGetLastError());
         return PDPLQR_OK;
@@ -442,7 +466,7 @@ int tree_sub_down_impl(Solver& h, const TreeTopParams& p) {
         auto kern = tree_sub_down_lat_kernel<NX>;
         int rc = set_smem(h, kern, LatSmem<NX>::DOWN_BYTES);
         if (rc) return rc;
-        launch_chain(h, kern, p.batch * p.ngroups, LatSmem<NX>::TOP_THREADS, LatSmem<NX>::DOWN_BYTES, p);
+        launch_chain(h, 4, kern, p.batch * p.ngroups, LatSmem<NX>::TOP_THREADS, LatSmem<NX>::DOWN_BYTES, p);
         h.launches++;
         CU_TRY(&h, cudaGetLastError());
         return PDPLQR_OK;
@@ -460,6 +484,7 @@ int costates_impl(Solver& h, const double* traj, double* lam) {
     if constexpr (BatchDims<NX, NU>::ENABLED) {
         if (h.thread_path) {
             batch_costate_kernel<NX, NU><<<(h.batch + 127) / 128, 128, 0, h.stream>>>(q);
+            h.chain_tail = false;
             h.launches++;
             CU_TRY(&h, cudaGetLastError());
             return PDPLQR_OK;
@@ -470,6 +495,7 @@ int costates_impl(Solver& h, const double* traj, double* lam) {
     int rc = set_smem(h, kern, bytes);
     if (rc) return rc;
     kern<<<h.batch * h.S, 32, bytes, h.stream>>>(q);
+    h.chain_tail = false;
     h.launches++;
     CU_TRY(&h, cudaGetLastError());
     return PDPLQR_OK;

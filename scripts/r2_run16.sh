@@ -1,18 +1,10 @@
 #!/bin/bash
-# rollout kernel ring depth: C5 / C2 timing per variant + parity suite of the default
+# which programmatic edge breaks the constrained latency-path tests?  (mask bits: 0 stage sweep, 2 rollout, 3 tree up, 4 tree down)
 mkdir -p gpurun_out
-for v in "" fd2 fd3 fd6; do
-  if [ -n "$v" ]; then export PDPLQR_VARIANT=$v; else unset PDPLQR_VARIANT; fi
-  for w in c5 c2; do
-  timeout 300 python bench.py --workload $w --no-cpu-baseline > gpurun_out/r16_${w}_${v:-default}.json 2> gpurun_out/r16_${w}_${v:-default}.err
-  python - <<PY
-import json
-try:
-    d=json.load(open("gpurun_out/r16_${w}_${v:-default}.json")); x=d["detail"]
-    print("variant ${v:-default} $w: step", round(x["ms_per_step"],4), "parity", x.get("parity_rel_err"))
-except Exception as e: print("${v:-default} $w failed", e)
-PY
+K="backward_without_factorization or arbitrary_dimensions_with_constraints or horizon_shards_with_constraints or constraint"
+for m in 0 4 8 16 12 28 31; do
+  for rep in 1 2; do
+    PDPLQR_PDL=1 PDPLQR_PDL_MASK=$m timeout 300 python -m pytest tests -m gpu -q -k "$K" -p no:cacheprovider > gpurun_out/r16_mask${m}_$rep.log 2>&1
+    echo "mask $m rep $rep: $(tail -1 gpurun_out/r16_mask${m}_$rep.log) | $(grep -c FAILED gpurun_out/r16_mask${m}_$rep.log) failed: $(grep FAILED gpurun_out/r16_mask${m}_$rep.log | sed 's/.*:://' | tr '\n' ' ')"
   done
 done
-unset PDPLQR_VARIANT
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r16_pytest.log 2>&1; tail -2 gpurun_out/r16_pytest.log
