@@ -175,6 +175,13 @@ public:
         check(pdplqr_get_costates(h_, out_flat_.data(), lam.data()));
     }
     bool not_positive_definite() { return pdplqr_last_status(h_, nullptr) > 0; }
+    // Debug aid (PDPLQR_DEBUG_GUARDS=1 in the environment when the solver is constructed): guard bytes around the solver's
+    // device allocations that were overwritten; 0 = clean, -1 = constructed without guards (include/pdplqr.h).
+    long long debug_check_guards() {
+        long long n = 0;
+        check(pdplqr_debug_check_guards(h_, &n));
+        return n;
+    }
     pdplqr_handle_t handle() { return h_; }
 
 private:

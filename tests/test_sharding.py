@@ -107,3 +107,17 @@ def test_bench_wave_alignment_helpers():
     assert bench.wave_aligned((1 << 20) // 250) == 2 * W
     t = bench.c4_traffic(4096)
     assert t is None or abs(bench.c4_traffic(2048) - t / 2) < 1.0
+
+
+def test_bench_cpu_latency_leg(oracle):
+    """bench.py's per-N CPU latency (the number printed beside every entry of latency_vs_N_us): the faster of the sequential
+    LQRSolver port and the PDP port on 2 / 4 / 8 threads, with the sequential time kept next to it."""
+    import importlib.util
+    import os
+    import pdplqr_b200 as P
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    r = bench.cpu_latency(P.problems.quadrotor_example(), seconds=0.2)
+    assert r["cpu_us"] > 0 and r["cpu_us"] <= r["cpu_sequential_us"] and r["cpu_threads"] in (1, 2, 4, 8)
+    assert 10 < r["cpu_sequential_us"] < 1e6      # a 100-stage nx12/nu4 solve is tens to hundreds of microseconds on any host
