@@ -1,7 +1,9 @@
 """numpy restatement of the conic ADMM outer iteration of pdp-lqr_b200/csrc/admm_kernels.cuh, with the LQ solves done
 by the CPU oracle (sequential LQRSolver semantics).  TEST INFRASTRUCTURE ONLY.  The outer iteration is NOT in the
 reference (hooks only), so this file is what pins it: "parity unpinned" by the
-reference, pinned against this restatement + solution properties (feasibility, KKT residuals)."""
+reference, pinned against this restatement + solution properties (feasibility, KKT residuals): tests/test_oracle.py::
+test_admm_restatement_converges_to_a_kkt_point_of_the_conic_qp / ..._second_order_cone_optimality check the converged
+(w, y, z) of THIS file against the optimality conditions of the conic problem with the independent sparse KKT solve."""
 import numpy as np
 
 from . import oracle as O

@@ -212,3 +212,77 @@ def test_admm_dual_residual_identity_equals_stationarity_definition(oracle):
             rows = slice(0, nu) if k == 0 else slice(0, dim)
             worst = max(worst, float(np.max(np.abs(v[rows]))))
         assert abs(worst - r_dual) < 1e-9 * max(1.0, worst), (alpha, worst, r_dual)
+
+
+def test_admm_restatement_converges_to_a_kkt_point_of_the_conic_qp(oracle):
+    """Row a11 has no reference to pin against (the outer iteration is not in the reference), so oracle/admm_ref.py -- the
+    restatement the CUDA loop is compared with -- is pinned against the optimality conditions of the problem it solves:
+    box-constrained quadrotor (the example's own bounds), run to convergence, then checked WITHOUT the Riccati oracle:
+    primal feasibility, stationarity through the independent sparse KKT solve, dual sign / complementarity per row, and
+    independence of the fixed point from rho."""
+    from oracle import admm_ref
+    p = P.problems.quadrotor_example(N=20, constrained=True)
+    nct, s, nx, N = p.nc_total, p.s, p.nx, p.N
+    lb, ub = p.e_lb[0], p.e_ub[0]
+    sols = {}
+    for rho0 in (1.0, 10.0):
+        rho = np.full(nct, rho0)
+        w, z, y, r_prim, r_dual = admm_ref.admm(p, 0, rho, sigma=1e-6, alpha=1.6, iters=1500)
+        assert r_prim < 1e-10 and r_dual < 1e-9
+        sols[rho0] = (w, z, y, rho)
+    w, z, y, rho = sols[1.0]
+    # (i) primal feasibility: z = D w inside the box, dynamics exact
+    coff, doff = p.coff(), p.doff()
+    for k in range(N + 1):
+        dim = s if k < N else nx
+        nc = int(p.ncs[k])
+        if nc:
+            Dk = p.D[0, doff[k]:doff[k + 1]].reshape(nc, dim, order="F")
+            assert np.max(np.abs(Dk @ w[k * s:k * s + dim] - z[coff[k]:coff[k + 1]])) < 1e-9
+        if k < N:
+            Ek = p.E[0, k].reshape(nx, s, order="F")
+            xn = w[(k + 1) * s + p.nu:(k + 1) * s + p.nu + nx] if k + 1 < N else w[N * s:]
+            assert np.max(np.abs(Ek @ w[k * s:(k + 1) * s] + p.c[0, k] - xn)) < 1e-10
+    assert np.all(z <= ub + 1e-9) and np.all(z >= lb - 1e-9)
+    # (ii) stationarity of the ORIGINAL problem, H w + h + D^T y + (dynamics multipliers) = 0: at z = D w the augmented data
+    #      reduce to it, so the independent sparse KKT solve with (w, y, z) folded in must return w itself
+    w_kkt = kkt_solve(p, ws_prev=w, sigma=1e-6, ys=y, zs=z, rho=rho, inv_rho=1.0 / rho)
+    assert rel_err(w_kkt, w) < 1e-8
+    # (iii) dual feasibility and complementarity of the box rows: y > 0 only at the upper bound, y < 0 only at the lower one
+    act = np.abs(y) > 1e-7
+    assert 0 < np.sum(act) < nct                                    # the bounds bite somewhere, not everywhere
+    assert np.all(np.abs(z[y > 1e-7] - ub[y > 1e-7]) < 1e-8)
+    assert np.all(np.abs(z[y < -1e-7] - lb[y < -1e-7]) < 1e-8)
+    # (iv) the fixed point does not depend on the penalty
+    w10, z10, y10, _ = sols[10.0]
+    assert rel_err(w10, w) < 1e-7 and rel_err(y10, y) < 1e-6
+
+
+def test_admm_restatement_second_order_cone_optimality(oracle):
+    """The same pin for second-order cones (the C4 problem family at a short horizon, box + SOC rows): at convergence every
+    cone's z lies in K, the multiplier in the normal cone of K at z (-y in K = K*, y^T z = 0), and (w, y, z) satisfy the
+    stationarity of the original problem through the independent sparse KKT solve."""
+    from oracle import admm_ref
+    p = P.problems.random_conic_batch(batch=1, N=12, seed=5)
+    nct = p.nc_total
+    rho = np.full(nct, 10.0)
+    w, z, y, r_prim, r_dual = admm_ref.admm(p, 0, rho, sigma=1e-6, alpha=1.6, iters=3000)
+    assert r_prim < 1e-10 and r_dual < 1e-9
+    coff = p.coff()
+    n_soc = n_apex_or_boundary = 0
+    for (k, r0, d, typ) in p.cones:
+        sl = slice(coff[k] + r0, coff[k] + r0 + d)
+        if typ == 0:
+            assert np.all(z[sl] <= p.e_ub[0, sl] + 1e-9) and np.all(z[sl] >= p.e_lb[0, sl] - 1e-9)
+            assert np.all(np.abs(z[sl][y[sl] > 1e-7] - p.e_ub[0, sl][y[sl] > 1e-7]) < 1e-8)
+            assert np.all(np.abs(z[sl][y[sl] < -1e-7] - p.e_lb[0, sl][y[sl] < -1e-7]) < 1e-8)
+        elif typ == 1:
+            n_soc += 1
+            zt, zx, yt, yx = z[sl][0], z[sl][1:], y[sl][0], y[sl][1:]
+            assert zt >= np.linalg.norm(zx) - 1e-9                  # z in K
+            assert -yt >= np.linalg.norm(yx) - 1e-8                 # -y in K* = K
+            assert abs(float(y[sl] @ z[sl])) < 1e-8                 # complementarity
+            n_apex_or_boundary += (zt - np.linalg.norm(zx)) < 1e-8
+    assert n_soc >= 10 and n_apex_or_boundary >= 1                  # the cones are there, and at least one of them is active
+    w_kkt = kkt_solve(p, ws_prev=w, sigma=1e-6, ys=y, zs=z, rho=rho, inv_rho=1.0 / rho)
+    assert rel_err(w_kkt, w) < 1e-8
