@@ -286,3 +286,23 @@ def test_admm_restatement_second_order_cone_optimality(oracle):
     assert n_soc >= 10 and n_apex_or_boundary >= 1                  # the cones are there, and at least one of them is active
     w_kkt = kkt_solve(p, ws_prev=w, sigma=1e-6, ys=y, zs=z, rho=rho, inv_rho=1.0 / rho)
     assert rel_err(w_kkt, w) < 1e-8
+
+
+def test_admm_adaptive_restatement_rescales_and_reaches_the_same_optimum(oracle):
+    """oracle/admm_ref.py::admm_adaptive (the restatement of the device loop with OSQP's rho rule, which the GPU test
+    test_admm_rho_adaptation_matches_the_numpy_restatement compares iteration counts with): from a rho that is far too small it
+    rescales, stops on its own test well before the iteration cap, and ends at the optimum a well-scaled fixed rho gives."""
+    from oracle import admm_ref
+    p = P.problems.quadrotor_example(N=20, constrained=True)
+    p.x0[0, 2] = 0.0
+    nct = p.nc_total
+    w, z, y, it, n_upd, res, rho_end = admm_ref.admm_adaptive(p, 0, np.full(nct, 1e-3), sigma=1e-6, alpha=1.6, max_iter=4000,
+                                                               eps_abs=1e-5, eps_rel=1e-5, check_every=25, rho_tau=5.0,
+                                                               max_rho_updates=6)
+    assert it % 25 == 0 and it < 4000 and 1 <= n_upd <= 6 and rho_end[0] > 1e-3
+    w_opt, _, _, rp, rd = admm_ref.admm(p, 0, np.full(nct, 1.0), sigma=1e-6, alpha=1.6, iters=1500)
+    assert rp < 1e-10 and rd < 1e-9
+    assert rel_err(w, w_opt) < 1e-3
+    # with the same small rho held fixed the primal residual is still far from the tolerance after as many iterations
+    _, _, _, rp_fixed, _ = admm_ref.admm(p, 0, np.full(nct, 1e-3), sigma=1e-6, alpha=1.6, iters=it)
+    assert rp_fixed > 100 * res[0]
