@@ -564,26 +564,33 @@ def test_debug_guard_bands_detect_and_stay_clean(oracle, monkeypatch):
         sol._h = None
 
 
-def test_admm_rho_adaptation_matches_the_numpy_restatement(oracle):
+@pytest.mark.parametrize("family", ["quadrotor-box", "conic-soc"])
+def test_admm_rho_adaptation_matches_the_numpy_restatement(oracle, family):
     """The rho-adaptation policy pinned numerically, not only behaviourally: the device loop with
     OSQP's rule on (convergence test and rescale decision on the device, re-factorisation per rescale) takes the same
-    number of iterations and rescales as oracle/admm_ref.py::admm_adaptive and ends at the same iterate."""
+    number of iterations and rescales as oracle/admm_ref.py::admm_adaptive and ends at the same iterate -- on the example's
+    box-constrained quadrotor (segment path, S = 2) and on the C4 family (nx30 / nu10, box + second-order cones, selection-matrix
+    constraint rows) at a short horizon."""
     from oracle import admm_ref
-    p = P.problems.quadrotor_example(N=20, constrained=True)
-    p.x0[0, 2] = 0.0
+    if family == "quadrotor-box":
+        p = P.problems.quadrotor_example(N=20, constrained=True)
+        p.x0[0, 2] = 0.0
+        S, rho0, kw = 2, 1e-3, dict(max_iter=4000, eps_abs=1e-5, eps_rel=1e-5, check_every=25)
+    else:
+        p = P.problems.random_conic_batch(batch=1, N=12, seed=5)
+        S, rho0, kw = 1, 0.1, dict(max_iter=3000, eps_abs=1e-6, eps_rel=1e-6, check_every=20)
     lb = np.where(np.isfinite(p.e_lb), p.e_lb, -1e20)
     ub = np.where(np.isfinite(p.e_ub), p.e_ub, 1e20)
-    sol = P.LQRCudaSolver.from_problem(p, num_segments=2)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=S)
     sol.admm_set_cones(p.cones, lb, ub)
     sol.admm_configure(use_graph=True, adaptive_rho=True, rho_tau=5.0, max_rho_updates=6)
-    rho = np.full((1, p.nc_total), 1e-3)
+    rho = np.full((1, p.nc_total), rho0)
     ws, zs, ys = p.zeros_ws(), np.zeros((1, p.nc_total)), np.zeros((1, p.nc_total))
-    iters, r = sol.admm_solve(p.x0, ws, zs, ys, rho, sigma=1e-6, alpha=1.6, max_iter=4000, eps_abs=1e-5, eps_rel=1e-5,
-                              check_every=25)
+    iters, r = sol.admm_solve(p.x0, ws, zs, ys, rho, sigma=1e-6, alpha=1.6, **kw)
     _, n_upd = sol.admm_stats()
-    w, z, y, it_ref, n_ref, res_ref, _ = admm_ref.admm_adaptive(p, 0, rho[0], sigma=1e-6, alpha=1.6, max_iter=4000,
-                                                                eps_abs=1e-5, eps_rel=1e-5, check_every=25, rho_tau=5.0,
-                                                                max_rho_updates=6)
+    w, z, y, it_ref, n_ref, res_ref, _ = admm_ref.admm_adaptive(p, 0, rho[0], sigma=1e-6, alpha=1.6, rho_tau=5.0,
+                                                                max_rho_updates=6, **kw)
+    assert n_ref >= 1 and it_ref < kw["max_iter"]
     assert (iters, n_upd) == (it_ref, n_ref), ((iters, n_upd, list(r)), (it_ref, n_ref, res_ref))
     assert rel_err(ws[0], w) < 1e-8 and rel_err(zs[0], z) < 1e-8 and rel_err(ys[0], y) < 1e-7
     assert abs(r[0] - res_ref[0]) < 1e-6 * max(1.0, res_ref[0]) and abs(r[1] - res_ref[1]) < 1e-6 * max(1.0, res_ref[1])
