@@ -68,3 +68,55 @@ def kkt_solve(prob, b=0, ws_prev=None, sigma=1e-6, ys=None, zs=None, rho=None, i
     if return_costates:   # multiplier mu_{k+1} of x_{k+1} - E_k w_k = c_k; the costate convention of pdplqr.h is -mu
         return sol[:nw], -sol[nw:nw + N * nx].reshape(N, nx)
     return sol[:nw]
+
+
+def conic_kkt_violations(prob, b, w, z, y, rho, sigma=1e-6):
+    """Optimality conditions of  min 1/2 w'Hw + h'w  s.t. dynamics, D_k w_k = z_k in K_k  at a candidate (w, z, y) -- the problem
+    the conic outer iteration solves (not in the reference).  Returns the largest violation of each:
+      link         |D w - z|                         dynamics     |x+ - E w - c|
+      cone         distance-like violation of z in K (box: outside [lb, ub]; second-order cone: ||z_x|| - z_t; ball: ||z|| - radius)
+      normal_cone  y in N_K(z): box: y > 0 only at ub, y < 0 only at lb (reported as |z - bound| of the offending rows);
+                   second-order cone: ||y_x|| + y_t  (i.e. -y in K* = K) and |y'z|
+      stationarity relative distance between w and the solution of the equality-constrained QP with (y, z, rho) folded in
+                   (independent sparse KKT solve: at z = D w it is  H w + h + D'y + dynamics multipliers = 0)."""
+    nx, nu, N, s = prob.nx, prob.nu, prob.N, prob.s
+    coff, doff = prob.coff(), prob.doff()
+    lb, ub = prob.e_lb[b], prob.e_ub[b]
+    v = dict(link=0.0, dynamics=0.0, cone=0.0, normal_cone=0.0)
+    for k in range(N + 1):
+        dim = s if k < N else nx
+        nc = int(prob.ncs[k])
+        if nc:
+            Dk = prob.D[b, doff[k]:doff[k + 1]].reshape(nc, dim, order="F")
+            v["link"] = max(v["link"], float(np.max(np.abs(Dk @ w[k * s:k * s + dim] - z[coff[k]:coff[k + 1]]))))
+        if k < N:
+            Ek = prob.E[b, k].reshape(nx, s, order="F")
+            xn = w[(k + 1) * s + nu:(k + 1) * s + nu + nx] if k + 1 < N else w[N * s:]
+            v["dynamics"] = max(v["dynamics"], float(np.max(np.abs(Ek @ w[k * s:(k + 1) * s] + prob.c[b, k] - xn))))
+    tol_act = 1e-7
+    for (k, r0, d, typ) in prob.cones:
+        sl = slice(coff[k] + r0, coff[k] + r0 + d)
+        zz, yy = z[sl], y[sl]
+        if typ == 0:
+            v["cone"] = max(v["cone"], float(np.max(np.maximum(zz - ub[sl], 0.0))), float(np.max(np.maximum(lb[sl] - zz, 0.0))))
+            up, lo = yy > tol_act, yy < -tol_act
+            if np.any(up):
+                v["normal_cone"] = max(v["normal_cone"], float(np.max(np.abs(zz[up] - ub[sl][up]))))
+            if np.any(lo):
+                v["normal_cone"] = max(v["normal_cone"], float(np.max(np.abs(zz[lo] - lb[sl][lo]))))
+        elif typ == 1:
+            v["cone"] = max(v["cone"], float(np.linalg.norm(zz[1:]) - zz[0]))
+            v["normal_cone"] = max(v["normal_cone"], float(np.linalg.norm(yy[1:]) + yy[0]), abs(float(yy @ zz)))
+        else:
+            rad = ub[sl][0]
+            nz = float(np.linalg.norm(zz))
+            v["cone"] = max(v["cone"], nz - rad)
+            # y = t z with t >= 0, and y = 0 strictly inside the ball
+            if nz < rad - 1e-8:
+                v["normal_cone"] = max(v["normal_cone"], float(np.max(np.abs(yy))))
+            else:
+                v["normal_cone"] = max(v["normal_cone"], float(np.linalg.norm(yy - (yy @ zz) / max(nz * nz, 1e-300) * zz)),
+                                       max(0.0, -float(yy @ zz)))
+    w_kkt = kkt_solve(prob, b=b, ws_prev=w, sigma=sigma, ys=y, zs=z, rho=rho, inv_rho=1.0 / rho)
+    v["stationarity"] = float(np.max(np.abs(w_kkt - w)) / max(np.max(np.abs(w)), 1e-300))
+    return v

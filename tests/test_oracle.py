@@ -8,7 +8,7 @@ import pytest
 
 import pdplqr_b200 as P
 from conftest import rel_err
-from kkt_ref import augmented_cost, kkt_solve
+from kkt_ref import augmented_cost, conic_kkt_violations, kkt_solve
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -306,3 +306,23 @@ def test_admm_adaptive_restatement_rescales_and_reaches_the_same_optimum(oracle)
     # with the same small rho held fixed the primal residual is still far from the tolerance after as many iterations
     _, _, _, rp_fixed, _ = admm_ref.admm(p, 0, np.full(nct, 1e-3), sigma=1e-6, alpha=1.6, iters=it)
     assert rp_fixed > 100 * res[0]
+
+
+@pytest.mark.parametrize("family", ["quadrotor-box", "conic-soc"])
+def test_conic_kkt_checker_on_the_restatement(oracle, family):
+    """tests/kkt_ref.py::conic_kkt_violations (the checker the GPU test test_admm_solution_satisfies_the_conic_kkt_conditions
+    applies to the CUDA result) on the converged numpy restatement, and its sensitivity: a perturbed multiplier or iterate is flagged."""
+    from oracle import admm_ref
+    if family == "quadrotor-box":
+        p, rho0, iters = P.problems.quadrotor_example(N=20, constrained=True), 1.0, 1500
+    else:
+        p, rho0, iters = P.problems.random_conic_batch(batch=1, N=12, seed=5), 10.0, 3000
+    rho = np.full(p.nc_total, rho0)
+    w, z, y, _, _ = admm_ref.admm(p, 0, rho, sigma=1e-6, alpha=1.6, iters=iters)
+    v = conic_kkt_violations(p, 0, w, z, y, rho)
+    assert v["link"] < 1e-9 and v["dynamics"] < 1e-10 and v["cone"] < 1e-9 and v["normal_cone"] < 1e-7 and v["stationarity"] < 1e-8, v
+    act = np.argmax(np.abs(y))
+    y_bad = y.copy(); y_bad[act] *= 1.01
+    assert conic_kkt_violations(p, 0, w, z, y_bad, rho)["stationarity"] > 1e-6
+    w_bad = w.copy(); w_bad[p.nu + 1] += 1e-3       # a state entry of stage 0 ... which is data: dynamics then fail at stage 0
+    assert conic_kkt_violations(p, 0, w_bad, z, y, rho)["dynamics"] > 1e-6

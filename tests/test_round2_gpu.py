@@ -594,3 +594,29 @@ def test_admm_rho_adaptation_matches_the_numpy_restatement(oracle, family):
     assert (iters, n_upd) == (it_ref, n_ref), ((iters, n_upd, list(r)), (it_ref, n_ref, res_ref))
     assert rel_err(ws[0], w) < 1e-8 and rel_err(zs[0], z) < 1e-8 and rel_err(ys[0], y) < 1e-7
     assert abs(r[0] - res_ref[0]) < 1e-6 * max(1.0, res_ref[0]) and abs(r[1] - res_ref[1]) < 1e-6 * max(1.0, res_ref[1])
+
+
+@pytest.mark.parametrize("family", ["quadrotor-box", "conic-soc"])
+def test_admm_solution_satisfies_the_conic_kkt_conditions(oracle, family):
+    """Row a11 is 'parity unpinned' by the reference (the outer iteration is not in it): besides the comparison with the numpy
+    restatement, the CUDA result itself is checked against the optimality conditions of the conic problem, with no Riccati oracle
+    and no ADMM restatement in the loop (tests/kkt_ref.py::conic_kkt_violations: constraint link, dynamics, cone membership,
+    multiplier in the normal cone, stationarity through the independent sparse KKT solve)."""
+    from kkt_ref import conic_kkt_violations
+    if family == "quadrotor-box":
+        p, S, rho0, iters = P.problems.quadrotor_example(N=20, constrained=True), 2, 1.0, 1500
+    else:
+        p, S, rho0, iters = P.problems.random_conic_batch(batch=2, N=12, seed=5), 1, 10.0, 3000
+    lb = np.where(np.isfinite(p.e_lb), p.e_lb, -1e20)
+    ub = np.where(np.isfinite(p.e_ub), p.e_ub, 1e20)
+    sol = P.LQRCudaSolver.from_problem(p, num_segments=S)
+    sol.admm_set_cones(p.cones, lb, ub)
+    rho = np.full((p.batch, p.nc_total), rho0)
+    ws, zs, ys = p.zeros_ws(), np.zeros((p.batch, p.nc_total)), np.zeros((p.batch, p.nc_total))
+    it, r = sol.admm_solve(p.x0, ws, zs, ys, rho, sigma=1e-6, alpha=1.6, max_iter=iters, eps_abs=0.0, eps_rel=0.0,
+                           check_every=iters)
+    assert it == iters and r[0] < 1e-9 and r[1] < 1e-8
+    for b in range(p.batch):
+        v = conic_kkt_violations(p, b, ws[b], zs[b], ys[b], rho[b])
+        assert v["link"] < 1e-9 and v["dynamics"] < 1e-10 and v["cone"] < 1e-9 and v["normal_cone"] < 1e-7 \
+            and v["stationarity"] < 1e-8, (b, v)
