@@ -12,10 +12,13 @@ that shards across 1/2/4/8 GPUs without a collective (weak scaling: 65,536 probl
 `configs` block: the other BASELINE.json configurations measured in the SAME run, each with its own ms_per_step,
 roofline (HBM and FP64-pipe fractions), cpu_baseline, e2e and `parity_rel_err` (max relative error of THIS run's
 output against the CPU oracle):
-    c2  quadrotor nx12/nu4 N=1024, one problem, segment-parallel: per-solve latency, and latency vs N
+    c2  quadrotor nx12/nu4 N=1024, one problem, segment-parallel: per-solve latency (one CUDA graph launch), and latency vs N
+        (`latency_vs_N_us`: GPU us, parity, and the CPU path timed beside every N -- the faster of the sequential and the
+        PDP oracle port on 2 / 4 / 8 threads)
     c5  quadrotor N=2^20: at N GPUs > 1 the horizon is split into per-rank time slices with ONE NCCL all_gather of a
-        3,648-byte summary per solve (strong scaling) + a per-phase breakdown and `parity_vs_1gpu`
-    c4  conic (box + SOC) LQ MPC nx30/nu10 N=256, batch 4096 per GPU, full ADMM outer iterations
+        3,648-byte summary per solve (strong scaling) + a per-phase breakdown and `parity_vs_1gpu`; best of three K-step loops
+    c4  conic (box + SOC) LQ MPC nx30/nu10 N=256, batch 4096 per GPU, full ADMM outer iterations: 50 fixed iterations per
+        solve (the step; one CUDA graph launch, on a side stream), and once to tolerance 1e-4 with rho adaptation (`to_tolerance`)
 `value`   : whole-job solves/s with model + iterates resident in HBM (CUDA events on the launch stream, max over ranks).
 `e2e`     : the same metric through the host-buffer C-ABI call pdplqr_solve() -- H2D of the iterate ws / x0 from pinned
             host memory and D2H of the solution inside the timed region (model resident, uploaded once by
